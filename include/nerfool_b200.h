@@ -1,0 +1,138 @@
+/*
+ * nerfool_b200 — C ABI of the B200-native per-ray generalizable-NeRF hot path.
+ *
+ * The reference (GATECH-EIC/NeRFool) is pure Python/PyTorch and has no FFI of its own; every entry point
+ * below replaces one reference Python function on the path and cites it.  The reference-side binding a
+ * maintainer would add is a ctypes stub; nerfool_b200/_lib.py is exactly that stub.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers (fp32 unless noted) owned by the caller (PyTorch's allocator).
+ *     The library never allocates or frees device memory and keeps no mutable global state.
+ *   - `stream` is a cudaStream_t passed as void*.  Calls are asynchronous and stream-ordered; no host sync.
+ *   - Return value: NFB_OK (0) or a negative NfbStatus; nfb_last_error_string() gives the text
+ *     (thread-local).  No exceptions cross the ABI.  There is no CPU fallback.
+ *   - Row order everywhere is the reference's: points p = r*S + s (ray-major), rows (p, v) view-minor.
+ *   - Feature maps are consumed CHANNEL-LAST: feat[V][fh][fw][32]; source images as the reference stores
+ *     them: imgs[V][H][W][3] (sample_ray.py:124).
+ *
+ * Camera block `cam` (device, fp32): for each source view v, 16 floats at cam[16*v]:
+ *     [0..11]  rows 0..2 of P_v = K_v * inverse(c2w_v), row-major 3x4   (projection.py:52-56)
+ *     [12..14] camera centre c2w_v[:3,3]                                 (projection.py:76,80)
+ *     [15]     unused
+ *   followed by cam[16*V .. 16*V+2] = centre of the target (query) camera (projection.py:77-78).
+ *   P_v is computed on the host with the same torch ops as the reference so that the in-frustum masks are
+ *   bit-identical; the kernels evaluate P*[x,y,z,1] as the FMA chain measured to reproduce the CPU bmm.
+ *
+ * IBRNet parameter blob `params` (device, fp32, NFB_IBRNET_PARAM_FLOATS floats): the tensors of
+ *   IBRNet.state_dict() (mlp_network.py:153-208) in torch's native [out][in] row-major layout, concatenated
+ *   in the order of nfb_ibrnet_param_offset() / NFB_PARAM_* below.
+ */
+#ifndef NERFOOL_B200_H_
+#define NERFOOL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  NFB_OK = 0,
+  NFB_EINVAL = -1,        /* bad shape / null pointer / misaligned buffer */
+  NFB_EUNSUPPORTED = -2,  /* shape outside what the kernels are built for (e.g. C != 35, S > 256, V > 32) */
+  NFB_ECUDA = -3          /* a CUDA runtime call or launch failed; text carries cudaGetErrorString */
+} NfbStatus;
+
+#define NFB_FEAT_CH 32            /* deep-feature channels per level (config.py:57-58)          */
+#define NFB_ROW_CH 35             /* 3 RGB + 32 features per (sample, view) row                  */
+#define NFB_PS_STRIDE 72          /* floats per sample in the view-stage -> ray-stage buffer     */
+#define NFB_MAX_SAMPLES 256
+#define NFB_MAX_VIEWS 32
+#define NFB_IBRNET_PARAM_FLOATS 20136
+
+/* per-sample interface buffer `ps` [N][NFB_PS_STRIDE]:
+ *   [0,32) weighted mean of x over views   [32,64) weighted variance   [64] mean_v(weight)
+ *   [65,68) blended RGB (rgb_out)          [68] number of valid views  [69,72) unused
+ * (mlp_network.py:257-258,262,272).  The backward twin `d_ps` holds the cotangents of [0,68). */
+
+int nfb_version(void);
+const char* nfb_last_error_string(void);
+/* offset (in floats) of parameter tensor `name` (e.g. "base_fc.0.weight", "s") inside the blob, or -1 */
+int nfb_ibrnet_param_offset(const char* name);
+
+/* ---- sample_along_camera_ray  (render_ray.py:73-116) -------------------------------------------------
+ * z_out[R][S].  inv_uniform: uniform in 1/z.  t_rand: NULL for det=True, else [R][S] uniforms in [0,1)
+ * (the host draws them with torch.rand_like so the stream matches the reference's).                    */
+int nfb_coarse_depths(int R, int S, float near_depth, float far_depth, int inv_uniform,
+                      const float* t_rand, float* z_out, void* stream);
+
+/* ---- Projector.compute  (projection.py:89-132) -------------------------------------------------------
+ * Points are given either explicitly (xyz[N][3], ray_o = ray_d = z = NULL, S ignored) or implicitly as
+ * pts = z*ray_d + ray_o (xyz = NULL; ray_o, ray_d [R][3], z [R][S], N = R*S).
+ * Outputs rgb_feat[N][V][35], ray_diff[N][V][4], mask[N][V] (0/1 floats).                               */
+int nfb_project_gather_fwd(int N, int S, int V, int H, int W, int fh, int fw,
+                           const float* xyz, const float* ray_o, const float* ray_d, const float* z,
+                           const float* cam, const float* imgs, const float* feat,
+                           float* rgb_feat, float* ray_diff, float* mask, void* stream);
+/* Backward of the two bilinear gathers (grid_sampler_2d backward w.r.t. input, projection.py:119,123):
+ * d_feat[V][fh][fw][32] += ..., d_imgs[V][H][W][3] += ... (either may be NULL; caller zero-fills).      */
+int nfb_project_gather_bwd(int N, int S, int V, int H, int W, int fh, int fw,
+                           const float* xyz, const float* ray_o, const float* ray_d, const float* z,
+                           const float* cam, const float* d_rgb_feat, float* d_feat, float* d_imgs,
+                           void* stream);
+
+/* ---- IBRNet.forward  (mlp_network.py:222-274) --------------------------------------------------------
+ * Two kernels: the view stage (per (sample,view) rows: ray_dir_fc, pooling, base_fc, vis_fc, vis_fc2,
+ * rgb_fc + blending) writes ps[N][72]; the ray stage (per ray: geometry_fc, pos-enc, ray attention,
+ * LayerNorm, sigma head) turns it into raw[R][S][4].
+ * View-stage input is EITHER the materialised tensors (rgb_feat/ray_diff/mask as Projector.compute
+ * returns them) OR, in fused mode (rgb_feat == NULL), the geometry arguments of nfb_project_gather_fwd:
+ * the kernel then projects and gathers on the fly and [N][V][35] is never written.                     */
+int nfb_ibrnet_view_fwd(int N, int S, int V, int anti_alias,
+                        const float* rgb_feat, const float* ray_diff, const float* mask,
+                        int H, int W, int fh, int fw,
+                        const float* xyz, const float* ray_o, const float* ray_d, const float* z,
+                        const float* cam, const float* imgs, const float* feat,
+                        const float* params, float* ps, void* stream);
+int nfb_ibrnet_ray_fwd(int R, int S, const float* ps, const float* params, const float* pos_enc /*[S][16]*/,
+                       float* raw /*[R][S][4]*/, void* stream);
+/* Backward (data gradients): d_raw[R][S][4] -> d_ps[N][72] -> d_rgb_feat[N][V][35] (tensor mode) or a
+ * scatter into d_feat / d_imgs (fused mode, rgb_feat == NULL).                                         */
+int nfb_ibrnet_ray_bwd(int R, int S, const float* ps, const float* params, const float* pos_enc,
+                       const float* d_raw, float* d_ps, void* stream);
+int nfb_ibrnet_view_bwd(int N, int S, int V, int anti_alias,
+                        const float* rgb_feat, const float* ray_diff, const float* mask,
+                        int H, int W, int fh, int fw,
+                        const float* xyz, const float* ray_o, const float* ray_d, const float* z,
+                        const float* cam, const float* imgs, const float* feat,
+                        const float* params, const float* ps, const float* d_ps,
+                        float* d_rgb_feat, float* d_feat, float* d_imgs, void* stream);
+
+/* ---- raw2outputs  (render_ray.py:123-170) ------------------------------------------------------------
+ * pixel_mask: uint8 [R][S] (the `mask` argument), or NULL with n_valid (stride n_valid_stride floats per
+ * sample) from which pixel_mask = n_valid > 1 (render_ray.py:210).  Outputs rgb[R][3], depth[R],
+ * weights[R][S], alpha[R][S], ray_mask uint8 [R].                                                      */
+int nfb_composite_fwd(int R, int S, int white_bkgd, const float* raw, const float* z,
+                      const uint8_t* pixel_mask, const float* n_valid, int n_valid_stride,
+                      float* rgb, float* depth, float* weights, float* alpha, uint8_t* ray_mask,
+                      void* stream);
+/* any of d_rgb[R][3], d_depth[R], d_weights[R][S], d_alpha[R][S] may be NULL -> d_raw[R][S][4] */
+int nfb_composite_bwd(int R, int S, int white_bkgd, const float* raw, const float* z,
+                      const float* d_rgb, const float* d_depth, const float* d_weights,
+                      const float* d_alpha, float* d_raw, void* stream);
+
+/* ---- sample_pdf  (render_ray.py:24-70) ---------------------------------------------------------------
+ * bins[R][M+1], weights[R][M] (NOT modified; the +1e-5 is applied internally), u[u_rows][n] with
+ * u_rows in {1, R}.  Outputs samples[R][n] and (optional) above[R][n] int64 bin indices.               */
+int nfb_sample_pdf(int R, int M, int n, const float* bins, const float* weights, const float* u,
+                   int u_rows, float* samples, int64_t* above, void* stream);
+/* ---- fine depths: the whole of render_ray.py:216-238 -------------------------------------------------
+ * z_coarse[R][S], weights_coarse[R][S] -> z_fine[R][S+n_imp] sorted ascending.                         */
+int nfb_fine_depths(int R, int S, int n_imp, int inv_uniform, const float* z_coarse,
+                    const float* weights_coarse, const float* u, int u_rows, float* z_fine, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERFOOL_B200_H_ */

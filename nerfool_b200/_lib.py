@@ -1,0 +1,95 @@
+"""ctypes binding of libnerfool_b200.so (the C ABI declared in include/nerfool_b200.h).
+
+This is the stub a maintainer of the reference would add next to ibrnet/projection.py (see
+INTEGRATION.md).  There is no fallback: if the shared library is missing or a call fails, a RuntimeError
+is raised."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libnerfool_b200.so')
+
+_P = c_void_p
+_I = c_int
+
+# name -> argtypes (all return int status unless listed in _SPECIAL)
+_SIGNATURES = {
+    'nfb_coarse_depths': [_I, _I, c_float, c_float, _I, _P, _P, _P],
+    'nfb_project_gather_fwd': [_I] * 7 + [_P] * 11,
+    'nfb_project_gather_bwd': [_I] * 7 + [_P] * 9,
+    'nfb_ibrnet_view_fwd': [_I] * 4 + [_P] * 3 + [_I] * 4 + [_P] * 10,
+    'nfb_ibrnet_ray_fwd': [_I, _I, _P, _P, _P, _P, _P],
+    'nfb_ibrnet_ray_bwd': [_I, _I, _P, _P, _P, _P, _P, _P],
+    'nfb_ibrnet_view_bwd': [_I] * 4 + [_P] * 3 + [_I] * 4 + [_P] * 14,
+    'nfb_composite_fwd': [_I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P],
+    'nfb_composite_bwd': [_I, _I, _I] + [_P] * 8,
+    'nfb_sample_pdf': [_I, _I, _I, _P, _P, _P, _I, _P, _P, _P],
+    'nfb_fine_depths': [_I, _I, _I, _I, _P, _P, _P, _I, _P, _P],
+}
+EXPORTS = ['nfb_version', 'nfb_last_error_string', 'nfb_ibrnet_param_offset'] + list(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes library handle."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f'{LIB_PATH} is missing: build it with `python -m nerfool_b200.build` '
+            '(nvcc, sm_100a).  nerfool_b200 has no CPU / PyTorch fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.nfb_version.restype = c_int
+    lib.nfb_version.argtypes = []
+    lib.nfb_last_error_string.restype = c_char_p
+    lib.nfb_last_error_string.argtypes = []
+    lib.nfb_ibrnet_param_offset.restype = c_int
+    lib.nfb_ibrnet_param_offset.argtypes = [c_char_p]
+    for name, args in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = c_int
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def call(name, *args):
+    """Invoke an entry point; raise RuntimeError with the library's message on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.nfb_last_error_string().decode('utf-8', 'replace')
+        raise RuntimeError(f'{name} failed ({rc}): {msg}')
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('nerfool_b200 ops need CUDA tensors (no CPU fallback); got a tensor on ' + str(t.device))
+
+
+def f32c(t):
+    """fp32 + contiguous (no copy when already so)."""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

@@ -1,0 +1,95 @@
+"""In-tree build of libnerfool_b200.so (sm_100a only): one nvcc invocation per translation unit, run in
+parallel, then one link.  Usage: ``python -m nerfool_b200.build [--force]``.  The resulting .so sits next
+to this file so it travels with the repo snapshot to the GPU box."""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+OBJ = os.path.join(CSRC, 'build')
+LIB = os.path.join(HERE, 'libnerfool_b200.so')
+
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+              '-Xcompiler', '-fPIC', '-Xptxas', '-v']
+
+# (object name, source, extra defines)
+UNITS = [
+    ('nfb_api', 'nfb_api.cu', []),
+    ('nfb_geom', 'nfb_geom.cu', []),
+    ('nfb_ray_stage', 'nfb_ray_stage.cu', []),
+    ('nfb_view_api', 'nfb_view_api.cu', []),
+    ('nfb_view_inst0', 'nfb_view_inst.cu', ['-DNFB_VIEW_INST=0']),
+    ('nfb_view_inst1', 'nfb_view_inst.cu', ['-DNFB_VIEW_INST=1']),
+    ('nfb_view_inst2', 'nfb_view_inst.cu', ['-DNFB_VIEW_INST=2']),
+    ('nfb_view_inst3', 'nfb_view_inst.cu', ['-DNFB_VIEW_INST=3']),
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get('NVCC'), '/usr/local/cuda/bin/nvcc', 'nvcc'):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError('nvcc not found')
+
+
+def _sources_digest(extra):
+    h = hashlib.sha256()
+    names = sorted(f for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', '.h')))
+    for n in names:
+        with open(os.path.join(CSRC, n), 'rb') as f:
+            h.update(n.encode() + b'\0' + f.read())
+    with open(os.path.join(HERE, '..', 'include', 'nerfool_b200.h'), 'rb') as f:
+        h.update(f.read())
+    h.update(' '.join(NVCC_FLAGS + extra).encode())
+    return h.hexdigest()
+
+
+def _compile(unit):
+    name, src, defs = unit
+    obj = os.path.join(OBJ, name + '.o')
+    stamp = obj + '.sha'
+    digest = _sources_digest(defs)
+    if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return name, 'cached', ''
+    cmd = [_nvcc()] + NVCC_FLAGS + defs + ['-c', os.path.join(CSRC, src), '-o', obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log = r.stdout + r.stderr
+    with open(os.path.join(OBJ, name + '.log'), 'w') as f:
+        f.write(' '.join(cmd) + '\n' + log)
+    if r.returncode != 0:
+        raise RuntimeError(f'nvcc failed for {name}:\n{log[-4000:]}')
+    with open(stamp, 'w') as f:
+        f.write(digest)
+    return name, 'built', log
+
+
+def build(force: bool = False, verbose: bool = True) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJ):
+            if f.endswith('.sha'):
+                os.remove(os.path.join(OBJ, f))
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
+        results = list(ex.map(_compile, UNITS))
+    rebuilt = [n for n, st, _ in results if st == 'built']
+    if verbose:
+        for n, st, _ in results:
+            print(f'[nerfool_b200.build] {n}: {st}')
+    if rebuilt or not os.path.exists(LIB):
+        objs = [os.path.join(OBJ, n + '.o') for n, _, _ in UNITS]
+        cmd = [_nvcc(), '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart']
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('link failed:\n' + r.stdout + r.stderr)
+        if verbose:
+            print('[nerfool_b200.build] linked', LIB)
+    return LIB
+
+
+if __name__ == '__main__':
+    build(force='--force' in sys.argv)

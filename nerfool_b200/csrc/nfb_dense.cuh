@@ -1,0 +1,76 @@
+// Thread-per-row dense layers for the fp32 (CUDA-core) IBRNet kernels.
+// Every thread owns one row of activations in registers; the layer weights sit in shared memory,
+// TRANSPOSED to [K][NP] (NP = N rounded up to 4, padding columns zero) so that one broadcast LDS.128
+// feeds four FMAs in the forward direction and four terms of a dot product in the backward direction.
+#pragma once
+#include "nfb_common.cuh"
+
+// out[0..NP) += x * Wt_row[0..NP)
+template <int NP>
+__device__ __forceinline__ void axpy_row(float (&out)[NP], float x, const float* __restrict__ wrow) {
+#pragma unroll
+  for (int n = 0; n < NP; n += 4) {
+    const float4 w = *reinterpret_cast<const float4*>(wrow + n);
+    out[n + 0] = fmaf(x, w.x, out[n + 0]);
+    out[n + 1] = fmaf(x, w.y, out[n + 1]);
+    out[n + 2] = fmaf(x, w.z, out[n + 2]);
+    out[n + 3] = fmaf(x, w.w, out[n + 3]);
+  }
+}
+
+template <int NP>
+__device__ __forceinline__ void load_bias(float (&out)[NP], const float* __restrict__ b) {
+#pragma unroll
+  for (int n = 0; n < NP; n += 4) {
+    const float4 w = *reinterpret_cast<const float4*>(b + n);
+    out[n + 0] = w.x; out[n + 1] = w.y; out[n + 2] = w.z; out[n + 3] = w.w;
+  }
+}
+
+// out[NP] += in[K] . Wt[K][NP]
+template <int K, int NP>
+__device__ __forceinline__ void dense_acc(const float* __restrict__ Wt, const float (&in)[K], float (&out)[NP]) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) axpy_row<NP>(out, in[k], Wt + k * NP);
+}
+
+// sum_n dy[n] * wrow[n]
+template <int NP>
+__device__ __forceinline__ float dot_row(const float (&dy)[NP], const float* __restrict__ wrow) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int n = 0; n < NP; n += 4) {
+    const float4 w = *reinterpret_cast<const float4*>(wrow + n);
+    a0 = fmaf(dy[n + 0], w.x, a0);
+    a1 = fmaf(dy[n + 1], w.y, a1);
+    a2 = fmaf(dy[n + 2], w.z, a2);
+    a3 = fmaf(dy[n + 3], w.w, a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+// dx[k] = sum_n dy[n] * Wt[k][n]   (transpose product with the same smem layout)
+template <int K, int NP>
+__device__ __forceinline__ void dense_T(const float* __restrict__ Wt, const float (&dy)[NP], float (&dx)[K]) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) dx[k] = dot_row<NP>(dy, Wt + k * NP);
+}
+
+template <int N>
+__device__ __forceinline__ void elu_inplace(float (&a)[N]) {
+#pragma unroll
+  for (int n = 0; n < N; ++n) a[n] = elu_f(a[n]);
+}
+
+// cooperative load of a torch-layout weight [N][K] (global) into transposed smem [K][NP]
+__device__ __forceinline__ void load_wt_transposed(float* __restrict__ dst, const float* __restrict__ src, int N,
+                                                   int K, int NP, int tid, int nthreads) {
+  for (int i = tid; i < K * NP; i += nthreads) {
+    const int k = i / NP, n = i - k * NP;
+    dst[i] = (n < N) ? __ldg(src + n * K + k) : 0.f;
+  }
+}
+__device__ __forceinline__ void load_vec_padded(float* __restrict__ dst, const float* __restrict__ src, int N, int NP,
+                                                int tid, int nthreads) {
+  for (int i = tid; i < NP; i += nthreads) dst[i] = (i < N) ? __ldg(src + i) : 0.f;
+}

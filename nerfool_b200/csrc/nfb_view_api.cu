@@ -1,0 +1,68 @@
+// C-ABI entry points of the IBRNet view stage (argument validation + dispatch to the instantiations).
+#include "nfb_view_stage.cuh"
+using nfbview::ViewArgs;
+
+static int check_view_args(const char* who, int N, int S, int V, const float* rgb_feat, const float* ray_diff,
+                    const float* mask, int H, int W, int fh, int fw, const float* xyz, const float* ray_o,
+                    const float* ray_d, const float* z, const float* cam, const float* imgs, const float* feat,
+                    const float* params) {
+  NFB_REQUIRE(N >= 0 && V >= 1 && params, NFB_EINVAL, "%s: bad arguments (N=%d V=%d)", who, N, V);
+  NFB_REQUIRE(V <= NFB_MAX_VIEWS, NFB_EUNSUPPORTED, "%s: V=%d > %d views", who, V, NFB_MAX_VIEWS);
+  if (rgb_feat) {
+    NFB_REQUIRE(ray_diff && mask, NFB_EINVAL, "%s: tensor mode needs ray_diff and mask", who);
+    NFB_REQUIRE(((uintptr_t)ray_diff % 16) == 0, NFB_EINVAL, "%s: ray_diff must be 16-byte aligned", who);
+  } else {
+    NFB_REQUIRE(H >= 2 && W >= 2 && fh >= 1 && fw >= 1 && cam && imgs && feat, NFB_EINVAL,
+                "%s: fused mode needs image/feature sizes, cam, imgs, feat", who);
+    NFB_REQUIRE(((uintptr_t)feat % 16) == 0, NFB_EINVAL, "%s: feat must be 16-byte aligned", who);
+    if (!xyz)
+      NFB_REQUIRE(ray_o && ray_d && z && S >= 1 && (N % S) == 0, NFB_EINVAL,
+                  "%s: implicit points need ray_o, ray_d, z and S | N", who);
+  }
+  return NFB_OK;
+}
+
+extern "C" int nfb_ibrnet_view_fwd(int N, int S, int V, int anti_alias, const float* rgb_feat, const float* ray_diff,
+                                   const float* mask, int H, int W, int fh, int fw, const float* xyz,
+                                   const float* ray_o, const float* ray_d, const float* z, const float* cam,
+                                   const float* imgs, const float* feat, const float* params, float* ps,
+                                   void* stream) {
+  int rc = check_view_args("nfb_ibrnet_view_fwd", N, S, V, rgb_feat, ray_diff, mask, H, W, fh, fw, xyz, ray_o, ray_d,
+                           z, cam, imgs, feat, params);
+  if (rc) return rc;
+  NFB_REQUIRE(ps, NFB_EINVAL, "nfb_ibrnet_view_fwd: ps is NULL");
+  if (N == 0) return NFB_OK;
+  ViewArgs a{};
+  a.N = N; a.S = S; a.V = V; a.anti_alias = anti_alias;
+  a.rgb_feat = rgb_feat; a.ray_diff = ray_diff; a.mask = mask;
+  a.H = H; a.W = W; a.fh = fh; a.fw = fw;
+  a.pts = PointSrc{xyz, ray_o, ray_d, z, S};
+  a.cam = cam; a.imgs = imgs; a.feat = feat; a.params = params; a.ps = ps;
+  if (rgb_feat) return nfb_launch_view_tensor_fwd(a, (cudaStream_t)stream);
+  return nfb_launch_view_fused_fwd(a, (cudaStream_t)stream);
+}
+
+extern "C" int nfb_ibrnet_view_bwd(int N, int S, int V, int anti_alias, const float* rgb_feat, const float* ray_diff,
+                                   const float* mask, int H, int W, int fh, int fw, const float* xyz,
+                                   const float* ray_o, const float* ray_d, const float* z, const float* cam,
+                                   const float* imgs, const float* feat, const float* params, const float* ps,
+                                   const float* d_ps, float* d_rgb_feat, float* d_feat, float* d_imgs,
+                                   void* stream) {
+  int rc = check_view_args("nfb_ibrnet_view_bwd", N, S, V, rgb_feat, ray_diff, mask, H, W, fh, fw, xyz, ray_o, ray_d,
+                           z, cam, imgs, feat, params);
+  if (rc) return rc;
+  NFB_REQUIRE(ps && d_ps, NFB_EINVAL, "nfb_ibrnet_view_bwd: ps / d_ps is NULL");
+  if (rgb_feat) NFB_REQUIRE(d_rgb_feat, NFB_EINVAL, "nfb_ibrnet_view_bwd: tensor mode needs d_rgb_feat");
+  else NFB_REQUIRE(((uintptr_t)d_feat % 16) == 0, NFB_EINVAL, "nfb_ibrnet_view_bwd: d_feat must be 16-byte aligned");
+  if (N == 0) return NFB_OK;
+  if (!rgb_feat && !d_feat && !d_imgs) return NFB_OK;
+  ViewArgs a{};
+  a.N = N; a.S = S; a.V = V; a.anti_alias = anti_alias;
+  a.rgb_feat = rgb_feat; a.ray_diff = ray_diff; a.mask = mask;
+  a.H = H; a.W = W; a.fh = fh; a.fw = fw;
+  a.pts = PointSrc{xyz, ray_o, ray_d, z, S};
+  a.cam = cam; a.imgs = imgs; a.feat = feat; a.params = params; a.ps = const_cast<float*>(ps);
+  a.d_ps = d_ps; a.d_rgb_feat = d_rgb_feat; a.d_feat = d_feat; a.d_imgs = d_imgs;
+  if (rgb_feat) return nfb_launch_view_tensor_bwd(a, (cudaStream_t)stream);
+  return nfb_launch_view_fused_bwd(a, (cudaStream_t)stream);
+}
