@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the NeRFool / IBRNet per-ray hot path (BASELINE.json: "rays/s fwd and PGD attack iters/s,
+378x504 view ...").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[1] - the view-specific PGD attack on a synthetic
+378x504 LLFF-shaped scene, 4 source views, 64 coarse + 64 importance samples.  One *step* is one attack
+iteration of the hot path over ALL 190,512 rays of the target view: render_rays (coarse + fine) -> masked
+MSE -> backward to the two source feature maps (the cuDNN encoder that turns that gradient into
+delta.grad is out of scope and not timed here) -> sign-step on the feature maps (stand-in for the delta
+update, so consecutive steps depend on each other).  With N > 1 each rank renders its own target view
+(weak scaling, BASELINE configs[2] layout) and ONE NCCL allreduce sums the feature-map gradients.
+
+value       rays/s through forward + backward, inputs resident in HBM, CUDA-event timed, max over ranks
+e2e         the same step through the public API with the step's rays / target colours copied from pinned
+            host memory and the loss read back, inside the timed region
+roofline    the dominant kernel (largest share of the step) against the measured HBM peak, algorithmic
+            gather/scatter bytes (560 B per (sample, view) row gathered, 512 B scattered)
+cpu_baseline / --impl reference : the CPU oracle (oracle/ibrnet_oracle.py, a port of the reference path)
+            on a bounded ray sample with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+import types
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+H, W = 378, 504
+N_SAMPLES, N_IMPORTANCE = 64, 64
+GATHER_B, SCATTER_B = 560, 512          # algorithmic bytes per (sample, view) row, SURVEY.md 8(d)
+
+
+def load_peaks():
+    path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.tmp = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.strip().split(',') for r in open(self.tmp.name) if r.strip()]
+        os.unlink(self.tmp.name)
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for n, val in zip(names, r[5:9]):
+                    if val.strip().lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                continue
+        busy = [x for x in sm if x > 0.5 * max(sm)] if sm else []
+        return {'sm_mhz': statistics.median(busy) if busy else None, 'sm_max_mhz': max(smax) if smax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def build_workload(device, rank, V, seed=0):
+    """Scene + nets, identical on every rank except the target view (rank r renders target r)."""
+    from nerfool_b200.synthetic import make_scene, rays_for_view
+    from nerfool_b200.mlp_network import IBRNet
+    from nerfool_b200.projection import Projector
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    scene = make_scene(H, W, V, seed=seed, kind='llff', n_targets=max(world, 1))
+    ray_o, ray_d = rays_for_view(scene['camera'][rank], H, W)
+    args = types.SimpleNamespace(anti_alias_pooling=1)
+    torch.manual_seed(seed)
+    net_c = IBRNet(args, 32, N_SAMPLES)
+    net_f = IBRNet(args, 32, N_SAMPLES + N_IMPORTANCE)
+    with torch.no_grad():
+        for n in (net_c, net_f):
+            n.out_geometry_fc[2].bias += 0.3       # non-trivial compositing weights
+    model = types.SimpleNamespace(net_coarse=net_c.to(device).eval(), net_fine=net_f.to(device).eval())
+    host = {'ray_o': ray_o.pin_memory(), 'ray_d': ray_d.pin_memory(), 'rgb': scene['rgb'][rank].contiguous().pin_memory()}
+    static = {'depth_range': scene['depth_range'].to(device), 'camera': scene['camera'][rank:rank + 1].to(device),
+              'src_rgbs': scene['src_rgbs'].to(device), 'src_cameras': scene['src_cameras'].to(device)}
+    featmaps = [f.to(device).contiguous() for f in scene['featmaps']]
+    return scene, model, Projector(device), host, static, featmaps
+
+
+def run_ours(a):
+    import torch.distributed as dist
+    from nerfool_b200 import _lib
+    from nerfool_b200.attack import pgd_hot_step
+    from nerfool_b200.render_ray import render_rays
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: nerfool_b200 has no CPU path (use --impl reference for the CPU baseline)')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    group = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+        group = dist.group.WORLD
+    _lib.load()
+    scene, model, projector, host, static, featmaps = build_workload(device, rank, a.views)
+    R = host['ray_o'].shape[0]
+    resident = {k: v.to(device) for k, v in host.items()}
+    eps, alpha = 8.0 / 255.0, 1.0 / 255.0
+    base_fm = [f.clone() for f in featmaps]
+
+    def step(batch):
+        loss, g_c, g_f = pgd_hot_step(model, projector, batch, featmaps, N_SAMPLES, N_IMPORTANCE, inv_uniform=True,
+                                      det=True, max_rays=a.max_rays, group=group)
+        with torch.no_grad():                      # sign-step + projection onto the eps-ball (eval_adv.py:824-839)
+            for f, g, b in zip(featmaps, (g_c, g_f), base_fm):
+                f.add_(alpha * torch.sign(g))
+                torch.minimum(torch.maximum(f, b - eps), b + eps, out=f)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    batch = dict(static)
+    batch.update(resident)
+    for _ in range(a.warmup):
+        step(batch)
+    barrier()
+
+    # ---------------- timed region: K steps, inputs resident ----------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = _lib.LAUNCHES
+    _lib.profile_start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for s, e in ev:
+        s.record()
+        step(batch)
+        e.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    prof = _lib.profile_stop()
+    launches = _lib.LAUNCHES - launches0
+    clocks = sampler.stop() if sampler else None
+    step_ms = [s.elapsed_time(e) for s, e in ev]
+    total_ms = ev[0][0].elapsed_time(ev[-1][1])
+
+    # ---------------- forward-only full-frame pass (rays/s fwd) ----------------
+    fwd_ms = []
+    with torch.no_grad():
+        for i in range(3):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for lo in range(0, R, a.max_rays):
+                chunk = dict(batch)
+                for k in ('ray_o', 'ray_d', 'rgb'):
+                    chunk[k] = batch[k][lo:lo + a.max_rays]
+                render_rays(chunk, model, featmaps, projector, N_SAMPLES, inv_uniform=True, N_importance=N_IMPORTANCE, det=True)
+            e.record()
+            torch.cuda.synchronize()
+            fwd_ms.append(s.elapsed_time(e))
+
+    # ---------------- e2e: host buffers in, loss out, inside the timed region ----------------
+    barrier()
+    e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    for s, e in e2e_ev:
+        s.record()
+        b2 = dict(static)
+        for k, v in host.items():
+            b2[k] = v.to(device, non_blocking=True)
+        loss = step(b2)
+        loss_host = loss.to('cpu', non_blocking=False)      # device -> host read of the step's result
+        e.record()
+    barrier()
+    e2e_total_ms = e2e_ev[0][0].elapsed_time(e2e_ev[-1][1])
+
+    # max over ranks
+    t = torch.tensor([total_ms, e2e_total_ms, statistics.median(fwd_ms)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_total_ms, fwd_med = t.tolist()
+
+    if rank == 0:
+        hbm_peak, peak_src = load_peaks()
+        rows_fwd = {  # (sample, view) rows per launch of each view-stage kernel, per level
+            'coarse': N_SAMPLES * a.views, 'fine': (N_SAMPLES + N_IMPORTANCE) * a.views}
+        # per-kernel totals over the timed region
+        ktot = {k: sum(v) for k, v in prof.items()}
+        kshare = {k: v / sum(ktot.values()) for k, v in ktot.items()}
+        dom = max(ktot, key=ktot.get)
+        n_l = len(prof[dom])
+        avg_ms = ktot[dom] / n_l
+        # algorithmic bytes per launch of the dominant kernel: launches alternate coarse / fine chunks
+        chunks = [min(a.max_rays, R - lo) for lo in range(0, R, a.max_rays)]
+        rows_per_step = sum(chunks) * (rows_fwd['coarse'] + rows_fwd['fine'])
+        per_row = {'nfb_ibrnet_view_fwd': GATHER_B, 'nfb_ibrnet_view_bwd': GATHER_B + SCATTER_B}.get(dom, GATHER_B)
+        launches_per_step = n_l / a.steps
+        alg_bytes = rows_per_step * per_row / launches_per_step
+        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+        ms_per_step = total_ms / a.steps
+        rays_total = R * world
+        out = {
+            'metric': 'rays/s', 'value': rays_total / (ms_per_step * 1e-3), 'unit': 'rays/s',
+            'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms_per_step,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'BASELINE configs[1]: IBRNet view-specific PGD hot-path step (render_rays fwd + masked-MSE + '
+                                   'bwd to source feature maps), 378x504 target view, all 190512 rays per step, '
+                                   f'{a.views} source views, 64 coarse + 64 importance samples, random-init weights',
+                       'rays_per_step_per_gpu': R, 'source_views': a.views, 'max_rays_per_launch': a.max_rays,
+                       'parallelism': f'one target view per GPU x{world}, 1 NCCL allreduce of d(featmaps)/step' if world > 1 else 'single GPU',
+                       'l2': 'per-step working set (per-sample workspaces, several GB) >> 126 MB L2; the 2x6.3 MB feature maps are L2-resident by design'},
+            'pgd_iters_per_s': 1e3 / ms_per_step,
+            'fwd_rays_per_s': rays_total / (fwd_med * 1e-3),
+            'fwd_ms_per_frame': fwd_med,
+            'encoder': 'not timed: the ResUNet stays on cuDNN in the reference and is outside this repo (north_star)',
+            'wall_s_timed_region': t_wall,
+            'step_ms': step_ms,
+            'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+                         'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                         'avg_launch_ms': avg_ms, 'algorithmic_bytes_per_launch': alg_bytes,
+                         'note': 'fp32 CUDA-core MLP: the kernel is FMA-issue bound, not gather bound; see DESIGN.md'},
+            'kernel_share': {k: round(v, 4) for k, v in sorted(kshare.items(), key=lambda kv: -kv[1])},
+            'kernel_ms_per_step': {k: v / a.steps for k, v in ktot.items()},
+            'e2e': {'value': rays_total / (e2e_total_ms / a.steps * 1e-3), 'unit': 'rays/s',
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'ms_per_step': e2e_total_ms / a.steps},
+            'gpu_launches': launches,
+            'clocks': clocks,
+            'loss_last': float(loss_host),
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            out['cpu_baseline'] = cpu_reference(a, sample_rays=a.cpu_rays, steps=1, warmup=1)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference(a, sample_rays, steps, warmup):
+    """The CPU port of the reference path (oracle/) on a bounded sample of the same workload: the same step
+    (render_rays fwd + masked MSE + backward to the feature maps) on `sample_rays` rays of the view."""
+    from oracle import ibrnet_oracle as O
+    from nerfool_b200.synthetic import make_scene, ray_batch_for
+    torch.set_num_threads(os.cpu_count() or 1)
+    scene = make_scene(H, W, a.views, seed=0, kind='llff')
+    ids = np.sort(np.random.RandomState(1).choice(H * W, sample_rays, replace=False))
+    batch = ray_batch_for(scene, ids)
+    pc = O.random_ibrnet_params(N_SAMPLES, 1, sigma_bias=0.3)
+    pf = O.random_ibrnet_params(N_SAMPLES + N_IMPORTANCE, 2, sigma_bias=0.3)
+    times = []
+    for i in range(warmup + steps):
+        fm = tuple(f.clone().requires_grad_(True) for f in scene['featmaps'])
+        t0 = time.perf_counter()
+        out = O.render_rays(batch, pc, pf, fm, N_SAMPLES, inv_uniform=True, n_importance=N_IMPORTANCE, det=True)
+        loss = O.attack_loss(out, batch['rgb'])
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return {'value': sample_rays / sec, 'unit': 'rays/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': f'{sample_rays} random rays of the 378x504 view, same step (fwd + loss + bwd to feature maps), '
+                      f'{warmup} warm-up + mean of {steps}', 'ms_per_step': sec * 1e3}
+
+
+def run_reference(a):
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if rank != 0:
+        return
+    cb = cpu_reference(a, sample_rays=a.cpu_rays, steps=a.steps, warmup=max(1, min(a.warmup, 2)))
+    out = {'impl': 'reference', 'metric': 'rays/s', 'value': cb['value'], 'unit': 'rays/s', 'n_gpus': world,
+           'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': cb['ms_per_step'], 'higher_is_better': True,
+           'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': 'BASELINE configs[1]: IBRNet view-specific PGD hot-path step, 378x504 target view, '
+                                  f'{a.views} source views, 64 + 64 samples; CPU port of the reference path on a bounded sample',
+                      'rays_per_step': a.cpu_rays, 'source_views': a.views},
+           'cpu_baseline': cb,
+           'e2e': {'value': cb['value'], 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--views', type=int, default=4)
+    ap.add_argument('--max-rays', dest='max_rays', type=int, default=65536)
+    ap.add_argument('--cpu-rays', dest='cpu_rays', type=int, default=2048)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == 'ours' else a.warmup
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == '__main__':
+    main()

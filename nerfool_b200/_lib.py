@@ -71,10 +71,39 @@ def stream_ptr(device=None):
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+LAUNCHES = 0          # kernels launched through the C ABI since import (every entry point = one launch)
+_profile = None       # when a dict: entry-point name -> list of (start_event, end_event)
+
+
+def profile_start():
+    """Start recording a CUDA-event pair around every C-ABI call (on the launching stream)."""
+    global _profile
+    _profile = {}
+
+
+def profile_stop():
+    """Stop recording; returns {entry point: [ms per launch, ...]} (synchronises the device)."""
+    global _profile
+    rec, _profile = _profile, None
+    torch.cuda.synchronize()
+    return {k: [a.elapsed_time(b) for a, b in v] for k, v in (rec or {}).items()}
+
+
 def call(name, *args):
     """Invoke an entry point; raise RuntimeError with the library's message on a non-zero status."""
+    global LAUNCHES
     lib = load()
-    rc = getattr(lib, name)(*args)
+    fn = getattr(lib, name)
+    if _profile is not None:
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        _profile.setdefault(name, []).append((a, b))
+    else:
+        rc = fn(*args)
+    LAUNCHES += 1
     if rc != 0:
         msg = lib.nfb_last_error_string().decode('utf-8', 'replace')
         raise RuntimeError(f'{name} failed ({rc}): {msg}')

@@ -1,0 +1,95 @@
+"""Host-side logic of one PGD hot-path step and its multi-GPU form (rays / target views sharded across
+ranks, one allreduce of the feature-map gradient per step).
+
+Mirrors the hot part of ``optimize_adv_perturb`` (/root/reference/eval/ibrnet/eval_adv.py:258-310):
+render_rays on a ray batch -> masked MSE on coarse + fine (criterion.py:23-33, utils.py:48-58) ->
+backward to the source feature maps (from where cuDNN's encoder backward carries it to ``delta``)."""
+from __future__ import annotations
+
+import torch
+
+from .render_ray import render_rays
+
+TINY_NUMBER = 1e-6
+
+
+def img2mse(x, y, mask=None):
+    """utils.py:48-58 (restated: utils.py itself imports matplotlib)."""
+    if mask is None:
+        return torch.mean((x - y) * (x - y))
+    return torch.sum((x - y) * (x - y) * mask.unsqueeze(-1)) / (torch.sum(mask) * x.shape[-1] + TINY_NUMBER)
+
+
+def rgb_loss(ret, gt_rgb):
+    """Criterion(outputs_coarse) + Criterion(outputs_fine) (eval_adv.py:306-310)."""
+    loss = img2mse(ret['outputs_coarse']['rgb'], gt_rgb, ret['outputs_coarse']['mask'].float())
+    if ret['outputs_fine'] is not None:
+        loss = loss + img2mse(ret['outputs_fine']['rgb'], gt_rgb, ret['outputs_fine']['mask'].float())
+    return loss
+
+
+def shard_slice(n_items: int, rank: int, world: int):
+    """Contiguous, balanced shard [lo, hi) of n_items for `rank` (first n_items % world ranks get one more)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pgd_hot_step(model, projector, ray_batch, featmaps, N_samples, N_importance, inv_uniform=True, det=True,
+                 white_bkgd=False, max_rays=65536, group=None, global_norm=False):
+    """One attack step on the rays of `ray_batch` (already this rank's shard).
+    Returns (loss, d_feat_coarse, d_feat_fine); with a process group the gradients are summed over ranks
+    with ONE allreduce (both levels packed in one buffer) and the loss is averaged.
+    Rays are processed in chunks of `max_rays` to bound the size of the per-sample workspaces; the loss of
+    each chunk is normalised by the global mask count so the result equals the un-chunked step."""
+    fm_c = featmaps[0].detach().requires_grad_(True)
+    fm_f = featmaps[1].detach().requires_grad_(True)
+    R = ray_batch['ray_o'].shape[0]
+    n_chunks = max(1, (R + max_rays - 1) // max_rays)
+    dev = ray_batch['ray_o'].device
+    # loss = num_c / (3 den_c + eps) + num_f / (3 den_f + eps) with num/den summed over chunks.  The coarse
+    # term reaches only featmaps[0] and the fine term only featmaps[1] (fine depths are detached,
+    # render_ray.py:219), so each chunk back-propagates its un-normalised numerators and the two gradients
+    # are scaled by their denominators once at the end: identical to the un-chunked step, bounded memory.
+    num = torch.zeros(2, device=dev)
+    den = torch.zeros(2, device=dev)
+    for i in range(n_chunks):
+        lo, hi = i * max_rays, min(R, (i + 1) * max_rays)
+        chunk = dict(ray_batch)
+        for k in ('ray_o', 'ray_d', 'rgb'):
+            chunk[k] = ray_batch[k][lo:hi]
+        ret = render_rays(chunk, model, (fm_c, fm_f), projector, N_samples, inv_uniform=inv_uniform,
+                          N_importance=N_importance, det=det, white_bkgd=white_bkgd)
+        gt = chunk['rgb']
+        part = None
+        for j, lvl in enumerate(('coarse', 'fine')):
+            o = ret['outputs_' + lvl]
+            if o is None:
+                continue
+            m = o['mask'].float()
+            t = torch.sum((o['rgb'] - gt) ** 2 * m.unsqueeze(-1))
+            part = t if part is None else part + t
+            num[j] += t.detach()
+            den[j] += torch.sum(m)
+        part.backward()
+    multi = group is not None and torch.distributed.get_world_size(group) > 1
+    if multi and global_norm:
+        # rays of ONE target view sharded over ranks: img2mse divides by the mask count of the whole batch
+        # (utils.py:58), so the numerators / denominators are summed over ranks first (4 floats)
+        nd = torch.cat([num, den])
+        torch.distributed.all_reduce(nd, op=torch.distributed.ReduceOp.SUM, group=group)
+        num, den = nd[:2], nd[2:]
+    scale = 1.0 / (den * 3 + TINY_NUMBER)
+    g_c = fm_c.grad * scale[0]
+    g_f = fm_f.grad * scale[1] if fm_f.grad is not None else torch.zeros_like(fm_f)
+    loss = (num * scale).sum()
+    if multi:
+        packed = torch.cat([g_c.reshape(-1), g_f.reshape(-1), loss.reshape(1)])
+        torch.distributed.all_reduce(packed, op=torch.distributed.ReduceOp.SUM, group=group)
+        n = g_c.numel()
+        g_c = packed[:n].view_as(g_c)
+        g_f = packed[n:2 * n].view_as(g_f)
+        total = loss if global_norm else packed[-1] / torch.distributed.get_world_size(group)
+    else:
+        total = loss
+    return total, g_c, g_f

@@ -37,9 +37,10 @@ def _nvcc():
     raise RuntimeError('nvcc not found')
 
 
-def _sources_digest(extra):
+def _sources_digest(src, extra):
+    """Digest of one unit's inputs: its own source, every header under csrc/ and the public header."""
     h = hashlib.sha256()
-    names = sorted(f for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', '.h')))
+    names = sorted(f for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h')) or f == src)
     for n in names:
         with open(os.path.join(CSRC, n), 'rb') as f:
             h.update(n.encode() + b'\0' + f.read())
@@ -53,7 +54,7 @@ def _compile(unit):
     name, src, defs = unit
     obj = os.path.join(OBJ, name + '.o')
     stamp = obj + '.sha'
-    digest = _sources_digest(defs)
+    digest = _sources_digest(src, defs)
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == digest:
         return name, 'cached', ''
     cmd = [_nvcc()] + NVCC_FLAGS + defs + ['-c', os.path.join(CSRC, src), '-o', obj]

@@ -38,10 +38,11 @@ __global__ void k_coarse_depths(int R, int S, float near_d, float far_d, int inv
 
 extern "C" int nfb_coarse_depths(int R, int S, float near_depth, float far_depth, int inv_uniform,
                                  const float* t_rand, float* z_out, void* stream) {
-  NFB_REQUIRE(R >= 0 && S >= 2 && z_out, NFB_EINVAL, "nfb_coarse_depths: bad arguments (R=%d S=%d)", R, S);
+  NFB_REQUIRE(R >= 0 && S >= 2, NFB_EINVAL, "nfb_coarse_depths: bad arguments (R=%d S=%d)", R, S);
   NFB_REQUIRE(near_depth > 0 && far_depth > near_depth, NFB_EINVAL,
               "nfb_coarse_depths: need 0 < near < far (render_ray.py:87)");
-  if (R == 0) return NFB_OK;
+  if (R == 0) return NFB_OK;   // empty ray batch: nothing to do, pointers may be NULL
+  NFB_REQUIRE(z_out, NFB_EINVAL, "nfb_coarse_depths: bad arguments (z_out is NULL)");
   const size_t n = (size_t)R * S;
   const int block = 256;
   const int grid = (int)((n + block - 1) / block < (size_t)nfb_num_sms() * 8 ? (n + block - 1) / block
@@ -132,6 +133,7 @@ static int check_geometry_args(const char* who, int N, int S, int V, int H, int 
   NFB_REQUIRE(N >= 0 && V >= 1 && H >= 2 && W >= 2 && fh >= 1 && fw >= 1, NFB_EINVAL,
               "%s: bad sizes N=%d V=%d H=%d W=%d fh=%d fw=%d", who, N, V, H, W, fh, fw);
   NFB_REQUIRE(V <= NFB_MAX_VIEWS, NFB_EUNSUPPORTED, "%s: V=%d > %d views", who, V, NFB_MAX_VIEWS);
+  if (N == 0) return NFB_OK;
   NFB_REQUIRE(cam != nullptr, NFB_EINVAL, "%s: cam is NULL", who);
   if (!xyz) {
     NFB_REQUIRE(ray_o && ray_d && z && S >= 1 && (N % S) == 0, NFB_EINVAL,
@@ -152,6 +154,7 @@ extern "C" int nfb_project_gather_fwd(int N, int S, int V, int H, int W, int fh,
                                       float* rgb_feat, float* ray_diff, float* mask, void* stream) {
   int rc = check_geometry_args("nfb_project_gather_fwd", N, S, V, H, W, fh, fw, xyz, ray_o, ray_d, z, cam);
   if (rc) return rc;
+  if (N == 0) return NFB_OK;
   NFB_REQUIRE(imgs && feat && rgb_feat && ray_diff && mask, NFB_EINVAL, "nfb_project_gather_fwd: NULL buffer");
   NFB_REQUIRE(((uintptr_t)feat % 16) == 0 && ((uintptr_t)ray_diff % 16) == 0, NFB_EINVAL,
               "nfb_project_gather_fwd: feat / ray_diff must be 16-byte aligned");
@@ -169,6 +172,7 @@ extern "C" int nfb_project_gather_bwd(int N, int S, int V, int H, int W, int fh,
                                       void* stream) {
   int rc = check_geometry_args("nfb_project_gather_bwd", N, S, V, H, W, fh, fw, xyz, ray_o, ray_d, z, cam);
   if (rc) return rc;
+  if (N == 0) return NFB_OK;
   NFB_REQUIRE(d_rgb_feat, NFB_EINVAL, "nfb_project_gather_bwd: d_rgb_feat is NULL");
   NFB_REQUIRE(((uintptr_t)d_feat % 16) == 0, NFB_EINVAL, "nfb_project_gather_bwd: d_feat must be 16-byte aligned");
   if (N == 0 || (!d_feat && !d_imgs)) return NFB_OK;
@@ -327,8 +331,9 @@ extern "C" int nfb_composite_fwd(int R, int S, int white_bkgd, const float* raw,
                                  const uint8_t* pixel_mask, const float* n_valid, int n_valid_stride,
                                  float* rgb, float* depth, float* weights, float* alpha, uint8_t* ray_mask,
                                  void* stream) {
-  NFB_REQUIRE(R >= 0 && S >= 1 && raw && z && rgb && depth && weights && alpha && ray_mask, NFB_EINVAL,
-              "nfb_composite_fwd: bad arguments");
+  NFB_REQUIRE(R >= 0 && S >= 1, NFB_EINVAL, "nfb_composite_fwd: bad arguments (R=%d S=%d)", R, S);
+  if (R == 0) return NFB_OK;
+  NFB_REQUIRE(raw && z && rgb && depth && weights && alpha && ray_mask, NFB_EINVAL, "nfb_composite_fwd: NULL buffer");
   NFB_REQUIRE(pixel_mask || n_valid, NFB_EINVAL, "nfb_composite_fwd: need pixel_mask or n_valid");
   NFB_REQUIRE(((uintptr_t)raw % 16) == 0, NFB_EINVAL, "nfb_composite_fwd: raw must be 16-byte aligned");
   if (R == 0) return NFB_OK;
@@ -342,7 +347,9 @@ extern "C" int nfb_composite_fwd(int R, int S, int white_bkgd, const float* raw,
 extern "C" int nfb_composite_bwd(int R, int S, int white_bkgd, const float* raw, const float* z,
                                  const float* d_rgb, const float* d_depth, const float* d_weights,
                                  const float* d_alpha, float* d_raw, void* stream) {
-  NFB_REQUIRE(R >= 0 && S >= 1 && raw && z && d_raw, NFB_EINVAL, "nfb_composite_bwd: bad arguments");
+  NFB_REQUIRE(R >= 0 && S >= 1, NFB_EINVAL, "nfb_composite_bwd: bad arguments (R=%d S=%d)", R, S);
+  if (R == 0) return NFB_OK;
+  NFB_REQUIRE(raw && z && d_raw, NFB_EINVAL, "nfb_composite_bwd: NULL buffer");
   NFB_REQUIRE(((uintptr_t)raw % 16) == 0 && ((uintptr_t)d_raw % 16) == 0, NFB_EINVAL,
               "nfb_composite_bwd: raw / d_raw must be 16-byte aligned");
   NFB_REQUIRE(S <= 4096, NFB_EUNSUPPORTED, "nfb_composite_bwd: S=%d > 4096", S);
@@ -476,7 +483,9 @@ k_fine_depths(int R, int S, int n_imp, int inv_uniform, const float* __restrict_
 
 extern "C" int nfb_sample_pdf(int R, int M, int n, const float* bins, const float* weights, const float* u,
                               int u_rows, float* samples, int64_t* above, void* stream) {
-  NFB_REQUIRE(R >= 0 && M >= 1 && n >= 1 && bins && weights && u && samples, NFB_EINVAL, "nfb_sample_pdf: bad arguments");
+  NFB_REQUIRE(R >= 0 && M >= 1 && n >= 1, NFB_EINVAL, "nfb_sample_pdf: bad arguments (R=%d M=%d n=%d)", R, M, n);
+  if (R == 0) return NFB_OK;
+  NFB_REQUIRE(bins && weights && u && samples, NFB_EINVAL, "nfb_sample_pdf: NULL buffer");
   NFB_REQUIRE(u_rows == 1 || u_rows == R, NFB_EINVAL, "nfb_sample_pdf: u_rows must be 1 or R");
   NFB_REQUIRE(M <= 4096, NFB_EUNSUPPORTED, "nfb_sample_pdf: M=%d > 4096 bins", M);
   if (R == 0) return NFB_OK;
@@ -492,8 +501,9 @@ extern "C" int nfb_sample_pdf(int R, int M, int n, const float* bins, const floa
 extern "C" int nfb_fine_depths(int R, int S, int n_imp, int inv_uniform, const float* z_coarse,
                                const float* weights_coarse, const float* u, int u_rows, float* z_fine,
                                void* stream) {
-  NFB_REQUIRE(R >= 0 && S >= 3 && n_imp >= 1 && z_coarse && weights_coarse && u && z_fine, NFB_EINVAL,
-              "nfb_fine_depths: bad arguments");
+  NFB_REQUIRE(R >= 0 && S >= 3 && n_imp >= 1, NFB_EINVAL, "nfb_fine_depths: bad arguments (R=%d S=%d n_imp=%d)", R, S, n_imp);
+  if (R == 0) return NFB_OK;
+  NFB_REQUIRE(z_coarse && weights_coarse && u && z_fine, NFB_EINVAL, "nfb_fine_depths: NULL buffer");
   NFB_REQUIRE(u_rows == 1 || u_rows == R, NFB_EINVAL, "nfb_fine_depths: u_rows must be 1 or R");
   NFB_REQUIRE(S + n_imp <= 2048, NFB_EUNSUPPORTED, "nfb_fine_depths: S+n_imp=%d > 2048", S + n_imp);
   if (R == 0) return NFB_OK;

@@ -335,8 +335,10 @@ inline int ray_block(int S) { return ((S + 31) / 32) * 32; }
 
 extern "C" int nfb_ibrnet_ray_fwd(int R, int S, const float* ps, const float* params, const float* pos_enc,
                                   float* raw, void* stream) {
-  NFB_REQUIRE(R >= 0 && S >= 1 && ps && params && pos_enc && raw, NFB_EINVAL, "nfb_ibrnet_ray_fwd: bad arguments");
+  NFB_REQUIRE(R >= 0 && S >= 1, NFB_EINVAL, "nfb_ibrnet_ray_fwd: bad arguments (R=%d S=%d)", R, S);
   NFB_REQUIRE(S <= NFB_MAX_SAMPLES, NFB_EUNSUPPORTED, "nfb_ibrnet_ray_fwd: S=%d > %d samples per ray", S, NFB_MAX_SAMPLES);
+  if (R == 0) return NFB_OK;
+  NFB_REQUIRE(ps && params && pos_enc && raw, NFB_EINVAL, "nfb_ibrnet_ray_fwd: NULL buffer");
   NFB_REQUIRE(((uintptr_t)ps % 16) == 0 && ((uintptr_t)raw % 16) == 0, NFB_EINVAL, "nfb_ibrnet_ray_fwd: ps/raw must be 16-byte aligned");
   if (R == 0) return NFB_OK;
   const size_t smem = (size_t)(R_TOTAL + 2 * S * 16) * sizeof(float);
@@ -352,8 +354,10 @@ extern "C" int nfb_ibrnet_ray_fwd(int R, int S, const float* ps, const float* pa
 
 extern "C" int nfb_ibrnet_ray_bwd(int R, int S, const float* ps, const float* params, const float* pos_enc,
                                   const float* d_raw, float* d_ps, void* stream) {
-  NFB_REQUIRE(R >= 0 && S >= 1 && ps && params && pos_enc && d_raw && d_ps, NFB_EINVAL, "nfb_ibrnet_ray_bwd: bad arguments");
+  NFB_REQUIRE(R >= 0 && S >= 1, NFB_EINVAL, "nfb_ibrnet_ray_bwd: bad arguments (R=%d S=%d)", R, S);
   NFB_REQUIRE(S <= NFB_MAX_SAMPLES, NFB_EUNSUPPORTED, "nfb_ibrnet_ray_bwd: S=%d > %d samples per ray", S, NFB_MAX_SAMPLES);
+  if (R == 0) return NFB_OK;
+  NFB_REQUIRE(ps && params && pos_enc && d_raw && d_ps, NFB_EINVAL, "nfb_ibrnet_ray_bwd: NULL buffer");
   NFB_REQUIRE(((uintptr_t)ps % 16) == 0 && ((uintptr_t)d_raw % 16) == 0 && ((uintptr_t)d_ps % 16) == 0, NFB_EINVAL,
               "nfb_ibrnet_ray_bwd: ps/d_raw/d_ps must be 16-byte aligned");
   if (R == 0) return NFB_OK;

@@ -6,8 +6,10 @@ static int check_view_args(const char* who, int N, int S, int V, const float* rg
                     const float* mask, int H, int W, int fh, int fw, const float* xyz, const float* ray_o,
                     const float* ray_d, const float* z, const float* cam, const float* imgs, const float* feat,
                     const float* params) {
-  NFB_REQUIRE(N >= 0 && V >= 1 && params, NFB_EINVAL, "%s: bad arguments (N=%d V=%d)", who, N, V);
+  NFB_REQUIRE(N >= 0 && V >= 1, NFB_EINVAL, "%s: bad arguments (N=%d V=%d)", who, N, V);
   NFB_REQUIRE(V <= NFB_MAX_VIEWS, NFB_EUNSUPPORTED, "%s: V=%d > %d views", who, V, NFB_MAX_VIEWS);
+  if (N == 0) return NFB_OK;
+  NFB_REQUIRE(params, NFB_EINVAL, "%s: params is NULL", who);
   if (rgb_feat) {
     NFB_REQUIRE(ray_diff && mask, NFB_EINVAL, "%s: tensor mode needs ray_diff and mask", who);
     NFB_REQUIRE(((uintptr_t)ray_diff % 16) == 0, NFB_EINVAL, "%s: ray_diff must be 16-byte aligned", who);
@@ -30,8 +32,8 @@ extern "C" int nfb_ibrnet_view_fwd(int N, int S, int V, int anti_alias, const fl
   int rc = check_view_args("nfb_ibrnet_view_fwd", N, S, V, rgb_feat, ray_diff, mask, H, W, fh, fw, xyz, ray_o, ray_d,
                            z, cam, imgs, feat, params);
   if (rc) return rc;
-  NFB_REQUIRE(ps, NFB_EINVAL, "nfb_ibrnet_view_fwd: ps is NULL");
   if (N == 0) return NFB_OK;
+  NFB_REQUIRE(ps, NFB_EINVAL, "nfb_ibrnet_view_fwd: ps is NULL");
   ViewArgs a{};
   a.N = N; a.S = S; a.V = V; a.anti_alias = anti_alias;
   a.rgb_feat = rgb_feat; a.ray_diff = ray_diff; a.mask = mask;
@@ -51,6 +53,7 @@ extern "C" int nfb_ibrnet_view_bwd(int N, int S, int V, int anti_alias, const fl
   int rc = check_view_args("nfb_ibrnet_view_bwd", N, S, V, rgb_feat, ray_diff, mask, H, W, fh, fw, xyz, ray_o, ray_d,
                            z, cam, imgs, feat, params);
   if (rc) return rc;
+  if (N == 0) return NFB_OK;
   NFB_REQUIRE(ps && d_ps, NFB_EINVAL, "nfb_ibrnet_view_bwd: ps / d_ps is NULL");
   if (rgb_feat) NFB_REQUIRE(d_rgb_feat, NFB_EINVAL, "nfb_ibrnet_view_bwd: tensor mode needs d_rgb_feat");
   else NFB_REQUIRE(((uintptr_t)d_feat % 16) == 0, NFB_EINVAL, "nfb_ibrnet_view_bwd: d_feat must be 16-byte aligned");

@@ -1,0 +1,202 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header declares, the
+host-side mirrors keep the reference's interface, argument validation fails loudly, and the multi-rank
+step (gloo, world_size 2) reproduces the single-process gradient."""
+import os
+import re
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, t
+from oracle import ibrnet_oracle as O
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from nerfool_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from nerfool_b200.build import build
+        build(verbose=False)
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(REPO, 'include', 'nerfool_b200.h')).read()
+    declared = set(re.findall(r'\b(nfb_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 14
+    from nerfool_b200 import _lib
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.nfb_version() >= 100
+
+
+def test_param_blob_layout_matches_library(lib):
+    from nerfool_b200.mlp_network import PARAM_ORDER, PARAM_FLOATS, pack_params
+    off = 0
+    for name in PARAM_ORDER:
+        assert lib.nfb_ibrnet_param_offset(name.encode()) == off, name
+        off += int(np.prod(O.IBRNET_PARAM_SHAPES[name])) if O.IBRNET_PARAM_SHAPES[name] else 1
+    assert off == PARAM_FLOATS == 20136
+    assert lib.nfb_ibrnet_param_offset(b'no.such.tensor') == -1
+    p = O.random_ibrnet_params(8, 0)
+    blob = pack_params(p)
+    o = lib.nfb_ibrnet_param_offset(b'vis_fc.2.bias')
+    assert torch.equal(blob[o:o + 33], p['vis_fc.2.bias'])
+
+
+def test_argument_validation_fails_loudly_without_touching_the_gpu(lib):
+    from nerfool_b200 import _lib
+    with pytest.raises(RuntimeError, match='bad arguments'):
+        _lib.call('nfb_coarse_depths', -1, 64, 2.0, 6.0, 0, None, None, None)
+    with pytest.raises(RuntimeError, match='near < far'):
+        _lib.call('nfb_coarse_depths', 4, 64, 6.0, 2.0, 0, None, _lib.c_void_p(16), None)
+    with pytest.raises(RuntimeError, match='> 32 views'):
+        _lib.call('nfb_project_gather_fwd', 10, 1, 33, 8, 8, 2, 2, None, None, None, None, _lib.c_void_p(16),
+                  None, None, None, None, None, None)
+    with pytest.raises(RuntimeError, match='> 256 samples'):
+        _lib.call('nfb_ibrnet_ray_fwd', 1, 257, _lib.c_void_p(16), _lib.c_void_p(16), _lib.c_void_p(16),
+                  _lib.c_void_p(16), None)
+    assert b'samples' in lib.nfb_last_error_string()
+
+
+def test_no_cpu_fallback():
+    from nerfool_b200.projection import Projector
+    from nerfool_b200.mlp_network import IBRNet
+    g = load_golden('render_llff_v3')
+    net = IBRNet(types.SimpleNamespace(anti_alias_pooling=1), 32, int(g['S_c'])).eval()
+    with pytest.raises(RuntimeError, match='CUDA'):
+        net(t(g['rgb_feat_c']), t(g['ray_diff_c']), t(g['mask_c']))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        Projector('cpu').compute(t(g['pts_c']), t(g['camera']), t(g['src_rgbs']), t(g['src_cameras']), t(g['feat_c']))
+    with pytest.raises(NotImplementedError):
+        IBRNet(types.SimpleNamespace(anti_alias_pooling=1), in_feat_ch=16)
+
+
+def test_ibrnet_module_interface_matches_reference_checkpoint_contract():
+    """Parameter / buffer names and shapes of mlp_network.py:153-208 (ckpt contract, model.py:148-160) and the
+    reference's own state_dict from the golden fixture loads strictly."""
+    from nerfool_b200.mlp_network import IBRNet
+    g = load_golden('render_llff_v3')
+    net = IBRNet(types.SimpleNamespace(anti_alias_pooling=1), 32, int(g['S_c']))
+    sd = {k[3:]: t(v) for k, v in g.items() if k.startswith('nc.')}
+    missing, unexpected = net.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    assert sum(p.numel() for p in net.parameters()) == 20136
+    blob = net.param_blob()
+    assert blob.numel() == 20136 and blob is net.param_blob()          # cached until a parameter changes
+    with torch.no_grad():
+        net.s.add_(1.0)
+    assert net.param_blob()[0].item() == pytest.approx(float(g['nc.s']) + 1.0)
+    net.train()
+    with pytest.raises(NotImplementedError):
+        net._check_weight_grad()
+
+
+def test_camera_block_matches_reference_projection_matrices():
+    from nerfool_b200 import ops
+    g = load_golden('render_synth_v5')
+    cams, q = t(g['src_cameras'])[0], t(g['camera'])[0]
+    blk = ops.camera_block(cams, q, 'cpu')
+    V = cams.shape[0]
+    P = O.world_to_pixel_matrices(cams)
+    assert torch.equal(blk[:16 * V].view(V, 16)[:, :12], P[:, :3, :].reshape(V, 12))
+    assert torch.equal(blk[:16 * V].view(V, 16)[:, 12:15], cams[:, 18:].reshape(V, 4, 4)[:, :3, 3])
+    assert torch.equal(blk[16 * V:16 * V + 3], q[18:].reshape(4, 4)[:3, 3])
+    assert ops.camera_block(cams, q, 'cpu') is blk                      # cached on tensor identity + version
+    cams.mul_(1.0)
+    assert ops.camera_block(cams, q, 'cpu') is not blk                  # in-place edit invalidates
+
+
+def test_shard_slice_partitions():
+    from nerfool_b200.attack import shard_slice
+    for n, w in ((190512, 8), (7, 3), (5, 8), (0, 2)):
+        parts = [shard_slice(n, r, w) for r in range(w)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+        sizes = [hi - lo for lo, hi in parts]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_img2mse_matches_oracle():
+    from nerfool_b200.attack import img2mse
+    torch.manual_seed(0)
+    x, y, m = torch.rand(50, 3), torch.rand(50, 3), (torch.rand(50) > 0.3).float()
+    assert torch.equal(img2mse(x, y, m), O.masked_mse(x, y, m))
+    assert torch.equal(img2mse(x, y), O.masked_mse(x, y))
+
+
+# ----------------------------------------------------------------------------------------------------
+# world_size-2 gloo run of the sharded attack step; render_rays is replaced by the CPU oracle so that the
+# HOST logic (chunking, global normalisers, packed allreduce) is what is under test.
+# ----------------------------------------------------------------------------------------------------
+def _oracle_render(g):
+    pc = {k[3:]: t(v) for k, v in g.items() if k.startswith('nc.')}
+    pf = {k[3:]: t(v) for k, v in g.items() if k.startswith('nf.')}
+
+    def render(chunk, model, featmaps, projector, N_samples, inv_uniform=False, N_importance=0, det=False,
+               white_bkgd=False, **kw):
+        return O.render_rays(chunk, pc, pf, featmaps, N_samples, inv_uniform=inv_uniform,
+                             n_importance=N_importance, det=det, white_bkgd=white_bkgd)
+    return render
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(REPO, 'tests'))
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from nerfool_b200 import attack
+    from helpers import load_golden, batch_from_golden
+    g = load_golden('render_llff_v3')
+    attack.render_rays = _oracle_render(g)
+    batch = batch_from_golden(g)
+    lo, hi = attack.shard_slice(batch['ray_o'].shape[0], rank, world)
+    shard = dict(batch)
+    for k in ('ray_o', 'ray_d', 'rgb'):
+        shard[k] = batch[k][lo:hi]
+    loss, gc, gf = attack.pgd_hot_step(None, None, shard, (t(g['feat_c']), t(g['feat_f'])), int(g['S_c']),
+                                       int(g['N_imp']), inv_uniform=bool(g['inv_uniform']), det=True, max_rays=7,
+                                       group=dist.group.WORLD, global_norm=True)
+    q.put((rank, loss.item(), gc.numpy(), gf.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_step_equals_single_process_step_gloo():
+    import torch.multiprocessing as mp
+    from nerfool_b200 import attack
+    from helpers import batch_from_golden
+    g = load_golden('render_llff_v3')
+    batch = batch_from_golden(g)
+    saved = attack.render_rays
+    attack.render_rays = _oracle_render(g)
+    try:
+        loss1, gc1, gf1 = attack.pgd_hot_step(None, None, batch, (t(g['feat_c']), t(g['feat_f'])), int(g['S_c']),
+                                              int(g['N_imp']), inv_uniform=bool(g['inv_uniform']), det=True)
+    finally:
+        attack.render_rays = saved
+    # the un-sharded, un-chunked step equals the reference's loss / gradient (golden)
+    assert abs(loss1.item() - float(g['loss'])) < 1e-5
+    assert ((gc1 - t(g['d_feat_c'])).norm() / t(g['d_feat_c']).norm()) < 1e-5
+
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, loss, gc, gf in res:
+        assert abs(loss - loss1.item()) < 1e-6
+        assert np.abs(gc - gc1.numpy()).max() <= 1e-6 * np.abs(gc1.numpy()).max() + 1e-9
+        assert np.abs(gf - gf1.numpy()).max() <= 1e-5 * np.abs(gf1.numpy()).max() + 1e-9
