@@ -200,3 +200,28 @@ def test_sharded_step_equals_single_process_step_gloo():
         assert abs(loss - loss1.item()) < 1e-6
         assert np.abs(gc - gc1.numpy()).max() <= 1e-6 * np.abs(gc1.numpy()).max() + 1e-9
         assert np.abs(gf - gf1.numpy()).max() <= 1e-5 * np.abs(gf1.numpy()).max() + 1e-9
+
+
+def test_dropin_overlay_resolves_hot_path_modules_and_falls_through(tmp_path, monkeypatch):
+    """The overlay package shadows the three hot-path modules and leaves the rest of ``ibrnet`` to the
+    reference checkout (simulated here with a stub checkout: the real one does not travel to the GPU box)."""
+    import importlib
+    fake = tmp_path / 'ref' / 'ibrnet'
+    fake.mkdir(parents=True)
+    (fake / '__init__.py').write_text('')
+    (fake / 'sample_ray.py').write_text('MARK = "reference sample_ray"\n')
+    (fake / 'projection.py').write_text('MARK = "reference projection (must be shadowed)"\n')
+    monkeypatch.setenv('NERFOOL_REFERENCE_ROOT', str(tmp_path / 'ref'))
+    monkeypatch.syspath_prepend(os.path.join(REPO, 'dropin'))
+    for m in [k for k in sys.modules if k == 'ibrnet' or k.startswith('ibrnet.')]:
+        monkeypatch.delitem(sys.modules, m)
+    ib = importlib.import_module('ibrnet')
+    assert os.path.join(REPO, 'dropin', 'ibrnet') in ib.__path__[0]
+    from nerfool_b200.projection import Projector
+    assert importlib.import_module('ibrnet.projection').Projector is Projector
+    assert importlib.import_module('ibrnet.sample_ray').MARK == 'reference sample_ray'
+    rr = importlib.import_module('ibrnet.render_ray')
+    for name in ('render_rays', 'render_rays_hybrid', 'sample_pdf', 'raw2outputs', 'sample_along_camera_ray'):
+        assert callable(getattr(rr, name))
+    for m in [k for k in sys.modules if k == 'ibrnet' or k.startswith('ibrnet.')]:
+        monkeypatch.delitem(sys.modules, m)
