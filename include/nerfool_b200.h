@@ -44,6 +44,13 @@ typedef enum {
   NFB_ECUDA = -3          /* a CUDA runtime call or launch failed; text carries cudaGetErrorString */
 } NfbStatus;
 
+/* Arithmetic of the dense layers of the IBRNet view stage (`precision` argument):
+ *   NFB_PREC_FP32   fp32 FMA on the CUDA cores (the exactness reference of this library)
+ *   NFB_PREC_BF16X3 tcgen05 tensor cores, operands split hi+lo in bf16, 3 MMA passes, fp32 accumulation:
+ *                   products exact to ~2^-17 -> results inside the reference's fp32 tolerance (default)
+ *   NFB_PREC_BF16   tcgen05 tensor cores, plain bf16 operands, fp32 accumulation (throughput mode)       */
+typedef enum { NFB_PREC_FP32 = 0, NFB_PREC_BF16X3 = 1, NFB_PREC_BF16 = 2 } NfbPrecision;
+
 #define NFB_FEAT_CH 32            /* deep-feature channels per level (config.py:57-58)          */
 #define NFB_ROW_CH 35             /* 3 RGB + 32 features per (sample, view) row                  */
 #define NFB_PS_STRIDE 72          /* floats per sample in the view-stage -> ray-stage buffer     */
@@ -94,7 +101,7 @@ int nfb_ibrnet_view_fwd(int N, int S, int V, int anti_alias,
                         int H, int W, int fh, int fw,
                         const float* xyz, const float* ray_o, const float* ray_d, const float* z,
                         const float* cam, const float* imgs, const float* feat,
-                        const float* params, float* ps, void* stream);
+                        const float* params, float* ps, int precision, void* stream);
 int nfb_ibrnet_ray_fwd(int R, int S, const float* ps, const float* params, const float* pos_enc /*[S][16]*/,
                        float* raw /*[R][S][4]*/, void* stream);
 /* Backward (data gradients): d_raw[R][S][4] -> d_ps[N][72] -> d_rgb_feat[N][V][35] (tensor mode) or a
@@ -107,7 +114,7 @@ int nfb_ibrnet_view_bwd(int N, int S, int V, int anti_alias,
                         const float* xyz, const float* ray_o, const float* ray_d, const float* z,
                         const float* cam, const float* imgs, const float* feat,
                         const float* params, const float* ps, const float* d_ps,
-                        float* d_rgb_feat, float* d_feat, float* d_imgs, void* stream);
+                        float* d_rgb_feat, float* d_feat, float* d_imgs, int precision, void* stream);
 
 /* ---- raw2outputs  (render_ray.py:123-170) ------------------------------------------------------------
  * pixel_mask: uint8 [R][S] (the `mask` argument), or NULL with n_valid (stride n_valid_stride floats per

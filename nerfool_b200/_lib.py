@@ -22,10 +22,10 @@ _SIGNATURES = {
     'nfb_coarse_depths': [_I, _I, c_float, c_float, _I, _P, _P, _P],
     'nfb_project_gather_fwd': [_I] * 7 + [_P] * 11,
     'nfb_project_gather_bwd': [_I] * 7 + [_P] * 9,
-    'nfb_ibrnet_view_fwd': [_I] * 4 + [_P] * 3 + [_I] * 4 + [_P] * 10,
+    'nfb_ibrnet_view_fwd': [_I] * 4 + [_P] * 3 + [_I] * 4 + [_P] * 9 + [_I, _P],
     'nfb_ibrnet_ray_fwd': [_I, _I, _P, _P, _P, _P, _P],
     'nfb_ibrnet_ray_bwd': [_I, _I, _P, _P, _P, _P, _P, _P],
-    'nfb_ibrnet_view_bwd': [_I] * 4 + [_P] * 3 + [_I] * 4 + [_P] * 14,
+    'nfb_ibrnet_view_bwd': [_I] * 4 + [_P] * 3 + [_I] * 4 + [_P] * 13 + [_I, _P],
     'nfb_composite_fwd': [_I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     'nfb_composite_bwd': [_I, _I, _I] + [_P] * 8,
     'nfb_sample_pdf': [_I, _I, _I, _P, _P, _P, _I, _P, _P, _P],
@@ -34,6 +34,26 @@ _SIGNATURES = {
 EXPORTS = ['nfb_version', 'nfb_last_error_string', 'nfb_ibrnet_param_offset'] + list(_SIGNATURES)
 
 _lib = None
+
+# Arithmetic of the view-stage dense layers (include/nerfool_b200.h: NfbPrecision).
+PRECISIONS = {'fp32': 0, 'bf16x3': 1, 'bf16': 2}
+_precision = PRECISIONS[os.environ.get('NFB_PRECISION', 'bf16x3')]
+
+
+def set_precision(name: str) -> None:
+    """'fp32' (CUDA-core FMA), 'bf16x3' (tcgen05, split operands, fp32-equivalent; default) or 'bf16'."""
+    global _precision
+    if name not in PRECISIONS:
+        raise ValueError(f'precision must be one of {sorted(PRECISIONS)}, got {name!r}')
+    _precision = PRECISIONS[name]
+
+
+def get_precision() -> str:
+    return {v: k for k, v in PRECISIONS.items()}[_precision]
+
+
+def precision_code() -> int:
+    return _precision
 
 
 def load():

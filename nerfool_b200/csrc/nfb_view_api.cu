@@ -1,5 +1,6 @@
 // C-ABI entry points of the IBRNet view stage (argument validation + dispatch to the instantiations).
 #include "nfb_view_stage.cuh"
+#include "nfb_view_tc.cuh"
 using nfbview::ViewArgs;
 
 static int check_view_args(const char* who, int N, int S, int V, const float* rgb_feat, const float* ray_diff,
@@ -28,20 +29,24 @@ extern "C" int nfb_ibrnet_view_fwd(int N, int S, int V, int anti_alias, const fl
                                    const float* mask, int H, int W, int fh, int fw, const float* xyz,
                                    const float* ray_o, const float* ray_d, const float* z, const float* cam,
                                    const float* imgs, const float* feat, const float* params, float* ps,
-                                   void* stream) {
+                                   int precision, void* stream) {
   int rc = check_view_args("nfb_ibrnet_view_fwd", N, S, V, rgb_feat, ray_diff, mask, H, W, fh, fw, xyz, ray_o, ray_d,
                            z, cam, imgs, feat, params);
   if (rc) return rc;
   if (N == 0) return NFB_OK;
   NFB_REQUIRE(ps, NFB_EINVAL, "nfb_ibrnet_view_fwd: ps is NULL");
+  NFB_REQUIRE(precision >= NFB_PREC_FP32 && precision <= NFB_PREC_BF16, NFB_EINVAL, "nfb_ibrnet_view_fwd: bad precision %d", precision);
   ViewArgs a{};
   a.N = N; a.S = S; a.V = V; a.anti_alias = anti_alias;
   a.rgb_feat = rgb_feat; a.ray_diff = ray_diff; a.mask = mask;
   a.H = H; a.W = W; a.fh = fh; a.fw = fw;
   a.pts = PointSrc{xyz, ray_o, ray_d, z, S};
   a.cam = cam; a.imgs = imgs; a.feat = feat; a.params = params; a.ps = ps;
-  if (rgb_feat) return nfb_launch_view_tensor_fwd(a, (cudaStream_t)stream);
-  return nfb_launch_view_fused_fwd(a, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == NFB_PREC_BF16X3) return rgb_feat ? nfb_launch_view_tc_fwd_p3_tensor(a, st) : nfb_launch_view_tc_fwd_p3_fused(a, st);
+  if (precision == NFB_PREC_BF16) return rgb_feat ? nfb_launch_view_tc_fwd_p1_tensor(a, st) : nfb_launch_view_tc_fwd_p1_fused(a, st);
+  if (rgb_feat) return nfb_launch_view_tensor_fwd(a, st);
+  return nfb_launch_view_fused_fwd(a, st);
 }
 
 extern "C" int nfb_ibrnet_view_bwd(int N, int S, int V, int anti_alias, const float* rgb_feat, const float* ray_diff,
@@ -49,12 +54,13 @@ extern "C" int nfb_ibrnet_view_bwd(int N, int S, int V, int anti_alias, const fl
                                    const float* ray_o, const float* ray_d, const float* z, const float* cam,
                                    const float* imgs, const float* feat, const float* params, const float* ps,
                                    const float* d_ps, float* d_rgb_feat, float* d_feat, float* d_imgs,
-                                   void* stream) {
+                                   int precision, void* stream) {
   int rc = check_view_args("nfb_ibrnet_view_bwd", N, S, V, rgb_feat, ray_diff, mask, H, W, fh, fw, xyz, ray_o, ray_d,
                            z, cam, imgs, feat, params);
   if (rc) return rc;
   if (N == 0) return NFB_OK;
   NFB_REQUIRE(ps && d_ps, NFB_EINVAL, "nfb_ibrnet_view_bwd: ps / d_ps is NULL");
+  NFB_REQUIRE(precision >= NFB_PREC_FP32 && precision <= NFB_PREC_BF16, NFB_EINVAL, "nfb_ibrnet_view_bwd: bad precision %d", precision);
   if (rgb_feat) NFB_REQUIRE(d_rgb_feat, NFB_EINVAL, "nfb_ibrnet_view_bwd: tensor mode needs d_rgb_feat");
   else NFB_REQUIRE(((uintptr_t)d_feat % 16) == 0, NFB_EINVAL, "nfb_ibrnet_view_bwd: d_feat must be 16-byte aligned");
   if (N == 0) return NFB_OK;

@@ -1,0 +1,564 @@
+// IBRNet view stage on the 5th-generation tensor cores (tcgen05 + TMEM), forward.
+//
+// Same mathematics and row mapping as the fp32 CUDA-core form in nfb_view_stage.cuh -- one thread per
+// (sample, view) row, 128-row groups, cross-view reductions through a per-group exchange buffer -- but every
+// dense layer with >= 16 inputs runs as a 128 x N x K tcgen05.mma tile:
+//   * the thread that owns row i writes the layer input of its row as bf16 into TMEM lane i (tcgen05.st),
+//   * one thread of the group issues the K/16 MMAs against the layer's weight tile resident in shared memory
+//     (canonical no-swizzle K-major layout, nfb_tc.cuh) and commits them to the group's mbarrier,
+//   * every thread reads its own row of the fp32 accumulator back (tcgen05.ld) and applies bias + ELU.
+// NG = 4 groups per CTA (one CTA per SM, 512 TMEM columns = 4 x 128) keep the CUDA cores busy while a group
+// waits for its MMAs.
+//
+// Precision (NPASS): 1 = plain bf16 operands (fp32 accumulate).  3 = "bf16x3": activations and weights are
+// split x = hi + lo (two bf16, ~17 significant bits) and D = hi*hi + lo*hi + hi*lo is accumulated in fp32 --
+// products are exact to ~2^-17, which keeps the whole path inside the reference's fp32 tolerance.
+//
+// TMEM columns of a group (128): D [0,64)  |  1-pass: A [64,120)   3-pass: A_hi [64,96), A_lo [96,128).
+// With 3 passes the 112-wide input of base_fc.0 does not fit in 32+32 columns, so that layer is issued in
+// two rounds (K = 64, then K = 48) accumulating into the same D.
+#pragma once
+#include "nfb_dense.cuh"
+#include "nfb_geom.cuh"
+#include "nfb_tc.cuh"
+#include "nfb_view_stage.cuh"
+
+namespace nfbvtc {
+using namespace nfbtc;
+using nfbview::ViewArgs;
+
+constexpr int GROUP = 128;
+constexpr int NG = 4;
+constexpr int EXS = 37;      // exchange-buffer row stride (floats)
+constexpr int TS_MAX = 64;   // samples per tile cap
+constexpr int MVS = 72;      // per-sample pooled statistics: mean0[35] at 0, var0[35] at 36
+constexpr int GC = 128;      // TMEM columns per group
+constexpr int C_D = 0, C_A = 64, C_ALO = 96;
+
+// ---- weight tiles ---------------------------------------------------------------------------------
+enum : int { L_DIR2 = 0, L_BASE0, L_BASE2, L_VIS0, L_VIS2, L_VISB0, L_RGB0, L_COUNT };
+__host__ __device__ constexpr int layer_n(int l) {
+  return l == L_DIR2 ? 48 : l == L_BASE0 ? 64 : l == L_BASE2 ? 32 : l == L_VIS0 ? 32 : l == L_VIS2 ? 48 : l == L_VISB0 ? 32 : 16;
+}
+__host__ __device__ constexpr int layer_k(int l) {
+  return l == L_DIR2 ? 16 : l == L_BASE0 ? 112 : l == L_BASE2 ? 64 : l == L_VIS0 ? 32 : l == L_VIS2 ? 32 : l == L_VISB0 ? 32 : 48;
+}
+__host__ __device__ constexpr int layer_off(int l) {   // byte offset of the layer's tile inside one (hi or lo) set
+  int o = 0;
+  for (int i = 0; i < l; ++i) o += layer_n(i) * layer_k(i) * 2;
+  return o;
+}
+constexpr int B_SET_BYTES = layer_off(L_COUNT);   // 28672
+static_assert(B_SET_BYTES % 16 == 0, "tile alignment");
+
+// canonical K-major no-swizzle byte offset of element (n, k) in an [N][K] bf16 tile stored K-chunk-major
+__host__ __device__ constexpr uint32_t canon_off(int n, int k, int N) {
+  return (uint32_t)((k >> 3) * (N * 16) + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2);
+}
+
+// ---- fp32 side tables (small layers that stay on the CUDA cores, biases) --------------------------
+enum : int {
+  F_DIR0_W = 0,                 // [4][16]  ray_dir_fc.0 transposed
+  F_DIR0_B = F_DIR0_W + 64,     // 16
+  F_B_DIR2 = F_DIR0_B + 16,     // 48
+  F_B_BASE0 = F_B_DIR2 + 48,    // 64
+  F_B_BASE2 = F_B_BASE0 + 64,   // 32
+  F_B_VIS0 = F_B_BASE2 + 32,    // 32
+  F_B_VIS2 = F_B_VIS0 + 32,     // 48
+  F_B_VISB0 = F_B_VIS2 + 48,    // 32
+  F_W_VISB2 = F_B_VISB0 + 32,   // 32
+  F_B_VISB2 = F_W_VISB2 + 32,   // 4
+  F_B_RGB0 = F_B_VISB2 + 4,     // 16
+  F_W_RGB2 = F_B_RGB0 + 16,     // [16][8] transposed
+  F_B_RGB2 = F_W_RGB2 + 128,    // 8
+  F_W_RGB4 = F_B_RGB2 + 8,      // 8
+  F_B_RGB4 = F_W_RGB4 + 8,      // 4
+  F_S = F_B_RGB4 + 4,           // 4
+  F_TOTAL = F_S + 4
+};
+
+template <int NPASS>
+__host__ __device__ constexpr size_t smem_bytes() {
+  return (size_t)B_SET_BYTES * (NPASS == 3 ? 2 : 1) + sizeof(float) * (F_TOTAL + 16 * NFB_MAX_VIEWS + 4 + NG * GROUP * EXS + NG * TS_MAX * MVS) +
+         NG * 8 + 16;
+}
+
+template <int NPASS>
+static __device__ void load_tile(uint8_t* sB, int layer, const float* __restrict__ w, int n_real, int k_real, int tid, int nt) {
+  const int N = layer_n(layer), K = layer_k(layer);
+  uint8_t* hi = sB + layer_off(layer);
+  uint8_t* lo = hi + B_SET_BYTES;
+  for (int i = tid; i < N * K; i += nt) {
+    const int n = i / K, k = i - n * K;
+    const float v = (n < n_real && k < k_real) ? __ldg(w + n * k_real + k) : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const uint32_t off = canon_off(n, k, N);
+    *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
+    if (NPASS == 3) *reinterpret_cast<__nv_bfloat16*>(lo + off) = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+static __device__ void load_side_tables(float* sf, const float* __restrict__ p, int tid, int nt) {
+  load_wt_transposed(sf + F_DIR0_W, p + P_DIR0_W, 16, 4, 16, tid, nt);
+  load_vec_padded(sf + F_DIR0_B, p + P_DIR0_B, 16, 16, tid, nt);
+  load_vec_padded(sf + F_B_DIR2, p + P_DIR2_B, 35, 48, tid, nt);
+  load_vec_padded(sf + F_B_BASE0, p + P_BASE0_B, 64, 64, tid, nt);
+  load_vec_padded(sf + F_B_BASE2, p + P_BASE2_B, 32, 32, tid, nt);
+  load_vec_padded(sf + F_B_VIS0, p + P_VIS0_B, 32, 32, tid, nt);
+  load_vec_padded(sf + F_B_VIS2, p + P_VIS2_B, 33, 48, tid, nt);
+  load_vec_padded(sf + F_B_VISB0, p + P_VISB0_B, 32, 32, tid, nt);
+  load_vec_padded(sf + F_W_VISB2, p + P_VISB2_W, 32, 32, tid, nt);
+  load_vec_padded(sf + F_B_VISB2, p + P_VISB2_B, 1, 4, tid, nt);
+  load_vec_padded(sf + F_B_RGB0, p + P_RGB0_B, 16, 16, tid, nt);
+  load_wt_transposed(sf + F_W_RGB2, p + P_RGB2_W, 8, 16, 8, tid, nt);
+  load_vec_padded(sf + F_B_RGB2, p + P_RGB2_B, 8, 8, tid, nt);
+  load_vec_padded(sf + F_W_RGB4, p + P_RGB4_W, 8, 8, tid, nt);
+  load_vec_padded(sf + F_B_RGB4, p + P_RGB4_B, 1, 4, tid, nt);
+  if (tid == 0) sf[F_S] = fabsf(__ldg(p + P_S));
+}
+
+// ---- per-thread TMEM helpers ------------------------------------------------------------------------
+// write 16 consecutive layer inputs (K-chunk `kc` of the A operand) of this thread's row
+template <int NPASS>
+__device__ __forceinline__ void a_store16(uint32_t tl, int kc, const float (&v)[16]) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (NPASS == 3) split_bf16(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+    else hi[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+  }
+  tmem_st8(tl + C_A + 8 * kc, hi);
+  if (NPASS == 3) tmem_st8(tl + C_ALO + 8 * kc, lo);
+}
+
+// y[j] = ELU(D[col + j] + bias[j]), 16 outputs
+__device__ __forceinline__ void epi16(uint32_t tl, int col, const float* __restrict__ bias, float (&y)[16]) {
+  tmem_ld16(tl + C_D + col, y);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + j);
+    y[j + 0] = elu_f(y[j + 0] + b.x);
+    y[j + 1] = elu_f(y[j + 1] + b.y);
+    y[j + 2] = elu_f(y[j + 2] + b.z);
+    y[j + 3] = elu_f(y[j + 3] + b.w);
+  }
+}
+
+// MMAs of k-steps [KS0, KS1) of `layer`; the A operand of k-step ks sits in A chunk (ks - KS0).  One thread.
+template <int NPASS, int LAYER, int KS0, int KS1>
+__device__ __forceinline__ void issue_mma(uint32_t tb, uint32_t sB_addr, bool acc0) {
+  constexpr int N = layer_n(LAYER);
+  constexpr uint32_t idesc = idesc_bf16(128, N);
+  const uint32_t bhi = sB_addr + layer_off(LAYER), blo = bhi + B_SET_BYTES;
+#pragma unroll
+  for (int ks = KS0; ks < KS1; ++ks) {
+    const uint64_t dh = smem_desc(bhi + ks * 2 * N * 16, N * 16, 128);
+    const uint32_t ah = tb + C_A + 8 * (ks - KS0);
+    mma_ts(tb + C_D, ah, dh, idesc, acc0 || ks > KS0);
+    if (NPASS == 3) {
+      const uint64_t dl = smem_desc(blo + ks * 2 * N * 16, N * 16, 128);
+      mma_ts(tb + C_D, tb + C_ALO + 8 * (ks - KS0), dh, idesc, true);
+      mma_ts(tb + C_D, ah, dl, idesc, true);
+    }
+  }
+}
+
+// element k of the base_fc.0 input row: mean0[k] (k < 35), var0[k - 35] (k < 70), x0[k - 70] (k < 105), 0 (pad);
+// k is a compile-time constant after unrolling, so the branches fold and x stays in registers
+__device__ __forceinline__ float base0_in(int k, const float* __restrict__ mvs, const float (&x)[NFB_ROW_CH]) {
+  if (k < 35) return mvs[k];
+  if (k < 70) return mvs[36 + (k - 35)];
+  if (k < 105) return x[k - 70];
+  return 0.f;
+}
+
+// all threads of the group: publish the A stores, let thread 0 issue + commit
+#define NFB_TC_ISSUE(LAYER, KS0, KS1, ACC0)                                   \
+  do {                                                                        \
+    tmem_st_wait();                                                           \
+    fence_before_sync();                                                      \
+    named_bar_sync(bar_id, GROUP);                                            \
+    if (tg == 0) {                                                            \
+      fence_after_sync();                                                     \
+      issue_mma<NPASS, LAYER, KS0, KS1>(tb, sB_addr, ACC0);                   \
+      mma_commit(mbar);                                                       \
+    }                                                                         \
+  } while (0)
+#define NFB_TC_WAIT()          \
+  do {                         \
+    mbar_wait(mbar, phase);    \
+    phase ^= 1u;               \
+    fence_after_sync();        \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// forward kernel.  FUSED: rows come from projection + bilinear gather; otherwise from the materialised
+// Projector.compute tensors (rgb_feat / ray_diff / mask).
+// ---------------------------------------------------------------------------------------------------
+template <int NPASS, bool FUSED>
+__global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sB = smem_raw;
+  float* sf = reinterpret_cast<float*>(smem_raw + (size_t)B_SET_BYTES * (NPASS == 3 ? 2 : 1));
+  float* s_cam = sf + F_TOTAL;
+  float* ex_all = s_cam + (16 * NFB_MAX_VIEWS + 4);
+  float* mv_all = ex_all + NG * GROUP * EXS;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(mv_all + NG * TS_MAX * MVS);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + NG);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int grp = tid / GROUP, tg = tid % GROUP;
+  float* ex = ex_all + (size_t)grp * GROUP * EXS;
+  float* mv = mv_all + (size_t)grp * TS_MAX * MVS;
+  const int bar_id = 1 + grp;
+  uint64_t* mbar = s_bar + grp;
+
+  if (warp == 0) tmem_alloc(s_tmem, NG * GC);
+  if (tid == 0) {
+    for (int g = 0; g < NG; ++g) mbar_init(s_bar + g, 1);
+    mbar_init_fence();
+  }
+  {
+    const float* p = a.params;
+    load_tile<NPASS>(sB, L_DIR2, p + P_DIR2_W, 35, 16, tid, blockDim.x);
+    load_tile<NPASS>(sB, L_BASE0, p + P_BASE0_W, 64, 105, tid, blockDim.x);
+    load_tile<NPASS>(sB, L_BASE2, p + P_BASE2_W, 32, 64, tid, blockDim.x);
+    load_tile<NPASS>(sB, L_VIS0, p + P_VIS0_W, 32, 32, tid, blockDim.x);
+    load_tile<NPASS>(sB, L_VIS2, p + P_VIS2_W, 33, 32, tid, blockDim.x);
+    load_tile<NPASS>(sB, L_VISB0, p + P_VISB0_W, 32, 32, tid, blockDim.x);
+    load_tile<NPASS>(sB, L_RGB0, p + P_RGB0_W, 16, 37, tid, blockDim.x);
+    load_side_tables(sf, p, tid, blockDim.x);
+    if (FUSED)
+      for (int i = tid; i < 16 * a.V + 3; i += blockDim.x) s_cam[i] = __ldg(a.cam + i);
+  }
+  fence_proxy_async_smem();     // weight tiles were written through the generic proxy, tcgen05.mma reads them through the async proxy
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+
+  const uint32_t tb = *s_tmem + (uint32_t)(grp * GC);                 // group's column base (lane field 0)
+  const uint32_t tl = tb + ((uint32_t)((warp & 3) * 32) << 16);       // + this warp's lane quarter
+  const uint32_t sB_addr = smem_u32(sB);
+  uint32_t phase = 0;
+
+  const int V = a.V;
+  const int TS = (GROUP / V < TS_MAX) ? GROUP / V : TS_MAX;
+  const int sl = tg / V, v = tg - sl * V;
+  const int ntiles = (a.N + TS - 1) / TS;
+  const float Wm1 = (float)a.W - 1.f, Hm1 = (float)a.H - 1.f;
+  const float s_abs = sf[F_S];
+
+  for (int tile = blockIdx.x * NG + grp; tile < ntiles; tile += gridDim.x * NG) {
+    const int p = tile * TS + sl;
+    const bool active = (sl < TS) && (p < a.N);
+    const int base = active ? sl * V : 0;
+    float* mvs = mv + (active ? sl : 0) * MVS;
+
+    // ---------------- projection, ray_diff, bilinear gather ----------------
+    float x[NFB_ROW_CH];
+    float rd[4];
+    float mk = 0.f;
+    if (FUSED) {
+      if (active) {
+        float X, Y, Z;
+        load_point(a.pts, p, X, Y, Z);
+        const ViewGeom g = view_geometry(X, Y, Z, s_cam + 16 * v, s_cam + 16 * V, Wm1, Hm1);
+        gather_row(g, v, a.H, a.W, a.fh, a.fw, a.imgs, a.feat, x);
+        rd[0] = g.rd[0]; rd[1] = g.rd[1]; rd[2] = g.rd[2]; rd[3] = g.rd[3];
+        mk = g.mask;
+      } else {
+#pragma unroll
+        for (int c = 0; c < NFB_ROW_CH; ++c) x[c] = 0.f;
+        rd[0] = rd[1] = rd[2] = rd[3] = 0.f;
+      }
+    } else {
+      // the tile's rows are contiguous in rgb_feat: coalesced copy through the exchange buffer
+      const size_t row0 = (size_t)tile * TS * V;
+      const size_t total = (size_t)a.N * V;
+      const int rows_here = (int)((total - row0 < (size_t)(TS * V)) ? (total - row0) : (size_t)(TS * V));
+      const float* src = a.rgb_feat + row0 * NFB_ROW_CH;
+      for (int i = tg; i < rows_here * NFB_ROW_CH; i += GROUP) {
+        const int rr = i / NFB_ROW_CH, cc = i - rr * NFB_ROW_CH;
+        ex[rr * EXS + cc] = __ldg(src + i);
+      }
+      named_bar_sync(bar_id, GROUP);
+#pragma unroll
+      for (int c = 0; c < NFB_ROW_CH; ++c) x[c] = active ? ex[tg * EXS + c] : 0.f;
+      if (active) {
+        const size_t row = (size_t)p * V + v;
+        const float4 q = __ldg(reinterpret_cast<const float4*>(a.ray_diff) + row);
+        rd[0] = q.x; rd[1] = q.y; rd[2] = q.z; rd[3] = q.w;
+        mk = __ldg(a.mask + row);
+      } else {
+        rd[0] = rd[1] = rd[2] = rd[3] = 0.f;
+      }
+      named_bar_sync(bar_id, GROUP);
+    }
+    const float rgb_in0 = x[0], rgb_in1 = x[1], rgb_in2 = x[2];
+
+    // ---------------- ray_dir_fc.0 on the CUDA cores (K = 4), ray_dir_fc.2 as MMA ----------------
+    {
+      float a1[16];
+      load_bias<16>(a1, sf + F_DIR0_B);
+      dense_acc<4, 16>(sf + F_DIR0_W, rd, a1);
+      elu_inplace<16>(a1);
+      a_store16<NPASS>(tl, 0, a1);
+    }
+    NFB_TC_ISSUE(L_DIR2, 0, 1, false);
+
+    // ---------------- pooling weights (overlaps the MMA) ----------------
+    float w, n_valid;
+    {
+      const float e = a.anti_alias ? (float)exp((double)__fmul_rn(s_abs, __fsub_rn(rd[3], 1.f))) : 1.f;
+      ex[tg * EXS + 35] = e;
+      ex[tg * EXS + 36] = mk;
+      named_bar_sync(bar_id, GROUP);
+      float mn = 3.4e38f, nv = 0.f;
+      for (int u = 0; u < V; ++u) {
+        mn = fminf(mn, ex[(base + u) * EXS + 35]);
+        nv += ex[(base + u) * EXS + 36];
+      }
+      if (!a.anti_alias) mn = 0.f;
+      float sum = 0.f;
+      for (int u = 0; u < V; ++u) sum += (ex[(base + u) * EXS + 35] - mn) * ex[(base + u) * EXS + 36];
+      w = (e - mn) * mk / (sum + 1e-8f);
+      n_valid = nv;
+      named_bar_sync(bar_id, GROUP);
+    }
+
+    // ---------------- x0 = rgb_feat + direction_feat ----------------
+    NFB_TC_WAIT();
+#pragma unroll
+    for (int c0 = 0; c0 < 48; c0 += 16) {
+      float df[16];
+      epi16(tl, c0, sf + F_B_DIR2 + c0, df);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (c0 + j < NFB_ROW_CH) x[c0 + j] += df[j];
+    }
+
+    // ---------------- first pooling: weighted mean / variance over views ----------------
+#pragma unroll
+    for (int c = 0; c < NFB_ROW_CH; ++c) ex[tg * EXS + c] = x[c];
+    ex[tg * EXS + 35] = w;
+    named_bar_sync(bar_id, GROUP);
+    if (active) {
+      for (int c = v; c < NFB_ROW_CH; c += V) {
+        float m = 0.f;
+        for (int u = 0; u < V; ++u) m = fmaf(ex[(base + u) * EXS + c], ex[(base + u) * EXS + 35], m);
+        float vr = 0.f;
+        for (int u = 0; u < V; ++u) {
+          const float d = ex[(base + u) * EXS + c] - m;
+          vr = fmaf(ex[(base + u) * EXS + 35] * d, d, vr);
+        }
+        mvs[c] = m;
+        mvs[36 + c] = vr;
+      }
+    }
+    named_bar_sync(bar_id, GROUP);
+
+    // ---------------- base_fc.0 : [mean | var | x0] (105 -> 64) ----------------
+    if (NPASS == 1) {
+#pragma unroll
+      for (int kc = 0; kc < 7; ++kc) {
+        float t[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) t[j] = base0_in(16 * kc + j, mvs, x);
+        a_store16<NPASS>(tl, kc, t);
+      }
+      NFB_TC_ISSUE(L_BASE0, 0, 7, false);
+      NFB_TC_WAIT();
+    } else {
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        float t[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) t[j] = base0_in(16 * kc + j, mvs, x);
+        a_store16<NPASS>(tl, kc, t);
+      }
+      NFB_TC_ISSUE(L_BASE0, 0, 4, false);
+      NFB_TC_WAIT();
+#pragma unroll
+      for (int kc = 4; kc < 7; ++kc) {
+        float t[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) t[j] = base0_in(16 * kc + j, mvs, x);
+        a_store16<NPASS>(tl, kc - 4, t);
+      }
+      NFB_TC_ISSUE(L_BASE0, 4, 7, true);
+      NFB_TC_WAIT();
+    }
+
+    // ---------------- base_fc.2 (64 -> 32) ----------------
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+      float h[16];
+      epi16(tl, 16 * kc, sf + F_B_BASE0 + 16 * kc, h);
+      a_store16<NPASS>(tl, kc, h);
+    }
+    NFB_TC_ISSUE(L_BASE2, 0, 4, false);
+    NFB_TC_WAIT();
+
+    // ---------------- vis_fc (32 -> 32 -> 33) on x1 * w ----------------
+    float x1[32];
+#pragma unroll
+    for (int kc = 0; kc < 2; ++kc) {
+      float h[16];
+      epi16(tl, 16 * kc, sf + F_B_BASE2 + 16 * kc, h);
+      float t[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        x1[16 * kc + j] = h[j];
+        t[j] = h[j] * w;
+      }
+      a_store16<NPASS>(tl, kc, t);
+    }
+    NFB_TC_ISSUE(L_VIS0, 0, 2, false);
+    NFB_TC_WAIT();
+#pragma unroll
+    for (int kc = 0; kc < 2; ++kc) {
+      float h[16];
+      epi16(tl, 16 * kc, sf + F_B_VIS0 + 16 * kc, h);
+      a_store16<NPASS>(tl, kc, h);
+    }
+    NFB_TC_ISSUE(L_VIS2, 0, 2, false);
+    NFB_TC_WAIT();
+
+    // x2 = x1 + x_res ; vis1 = sigmoid(xv[32]) * mask ; vis_fc2 on x2 * vis1
+    float vis1;
+    {
+      float h[16];
+      epi16(tl, 32, sf + F_B_VIS2 + 32, h);
+      vis1 = sigmoid_f(h[0]) * mk;
+    }
+#pragma unroll
+    for (int kc = 0; kc < 2; ++kc) {
+      float h[16];
+      epi16(tl, 16 * kc, sf + F_B_VIS2 + 16 * kc, h);
+      float t[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        x1[16 * kc + j] += h[j];            // x1 now holds x2
+        t[j] = x1[16 * kc + j] * vis1;
+      }
+      a_store16<NPASS>(tl, kc, t);
+    }
+    NFB_TC_ISSUE(L_VISB0, 0, 2, false);
+    NFB_TC_WAIT();
+    float vis2;
+    {
+      float z = sf[F_B_VISB2];
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc) {
+        float h[16];
+        epi16(tl, 16 * kc, sf + F_B_VISB0 + 16 * kc, h);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z = fmaf(h[j], sf[F_W_VISB2 + 16 * kc + j], z);
+      }
+      vis2 = sigmoid_f(z) * mk;
+    }
+
+    // ---------------- rgb_fc on [x2, vis2, ray_diff] (37 -> 16 -> 8 -> 1) ----------------
+    {
+      float t[16];
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) t[j] = x1[16 * kc + j];
+        a_store16<NPASS>(tl, kc, t);
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t[j] = 0.f;
+      t[0] = vis2; t[1] = rd[0]; t[2] = rd[1]; t[3] = rd[2]; t[4] = rd[3];
+      a_store16<NPASS>(tl, 2, t);
+    }
+    NFB_TC_ISSUE(L_RGB0, 0, 3, false);
+    NFB_TC_WAIT();
+    float logit;
+    {
+      float g1[16];
+      epi16(tl, 0, sf + F_B_RGB0, g1);
+      float g2[8];
+      load_bias<8>(g2, sf + F_B_RGB2);
+      dense_acc<16, 8>(sf + F_W_RGB2, g1, g2);
+      elu_inplace<8>(g2);
+      logit = dot_row<8>(g2, sf + F_W_RGB4) + sf[F_B_RGB4];
+      if (mk == 0.f) logit = -1e9f;
+    }
+
+    // ---------------- second pooling, blending, output ----------------
+#pragma unroll
+    for (int c = 0; c < 32; ++c) ex[tg * EXS + c] = x1[c];
+    ex[tg * EXS + 32] = vis2;
+    ex[tg * EXS + 33] = logit;
+    ex[tg * EXS + 34] = rgb_in0;
+    ex[tg * EXS + 35] = rgb_in1;
+    ex[tg * EXS + 36] = rgb_in2;
+    named_bar_sync(bar_id, GROUP);
+    if (active) {
+      float D = 1e-8f;
+      for (int u = 0; u < V; ++u) D += ex[(base + u) * EXS + 32];
+      float* out = a.ps + (size_t)p * NFB_PS_STRIDE;
+      for (int c = v; c < 32; c += V) {
+        float m = 0.f;
+        for (int u = 0; u < V; ++u) m = fmaf(ex[(base + u) * EXS + c], ex[(base + u) * EXS + 32] / D, m);
+        float vr = 0.f;
+        for (int u = 0; u < V; ++u) {
+          const float d = ex[(base + u) * EXS + c] - m;
+          vr = fmaf((ex[(base + u) * EXS + 32] / D) * d, d, vr);
+        }
+        out[PS_MEAN + c] = m;
+        out[PS_VAR + c] = vr;
+      }
+      if (v == 0) {
+        float mx = -3.4e38f;
+        for (int u = 0; u < V; ++u) mx = fmaxf(mx, ex[(base + u) * EXS + 33]);
+        float se = 0.f;
+        for (int u = 0; u < V; ++u) se += __expf(ex[(base + u) * EXS + 33] - mx);
+        const float inv_se = 1.f / se;
+        float wsum = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
+        for (int u = 0; u < V; ++u) {
+          wsum += ex[(base + u) * EXS + 32] / D;
+          const float b = __expf(ex[(base + u) * EXS + 33] - mx) * inv_se;
+          r0 = fmaf(b, ex[(base + u) * EXS + 34], r0);
+          r1 = fmaf(b, ex[(base + u) * EXS + 35], r1);
+          r2 = fmaf(b, ex[(base + u) * EXS + 36], r2);
+        }
+        out[PS_WMEAN] = wsum / (float)V;
+        out[PS_RGB + 0] = r0; out[PS_RGB + 1] = r1; out[PS_RGB + 2] = r2;
+        out[PS_NVALID] = n_valid;
+        out[69] = 0.f; out[70] = 0.f; out[71] = 0.f;
+      }
+    }
+    named_bar_sync(bar_id, GROUP);            // exchange buffer is reused by the next tile
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(*s_tmem, NG * GC);
+}
+
+template <int NPASS, bool FUSED>
+int launch_view_tc_fwd(const ViewArgs& a, cudaStream_t st) {
+  constexpr size_t smem = smem_bytes<NPASS>();
+  cudaError_t e = cudaFuncSetAttribute(k_view_tc_fwd<NPASS, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return nfb_set_error(NFB_ECUDA, "k_view_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  const int TS = (GROUP / a.V < TS_MAX) ? GROUP / a.V : TS_MAX;
+  const int ntiles = (a.N + TS - 1) / TS;
+  int grid = (ntiles + NG - 1) / NG;
+  const int cap = nfb_num_sms();
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  k_view_tc_fwd<NPASS, FUSED><<<grid, GROUP * NG, smem, st>>>(a);
+  NFB_CHECK_LAUNCH("k_view_tc_fwd");
+  return NFB_OK;
+}
+
+}  // namespace nfbvtc
+
+// defined in nfb_view_tc_inst.cu (one instantiation per translation unit)
+int nfb_launch_view_tc_fwd_p1_fused(const nfbview::ViewArgs& a, cudaStream_t st);
+int nfb_launch_view_tc_fwd_p3_fused(const nfbview::ViewArgs& a, cudaStream_t st);
+int nfb_launch_view_tc_fwd_p1_tensor(const nfbview::ViewArgs& a, cudaStream_t st);
+int nfb_launch_view_tc_fwd_p3_tensor(const nfbview::ViewArgs& a, cudaStream_t st);

@@ -154,10 +154,11 @@ class IBRNetAggregate(torch.autograd.Function):
         with torch.cuda.device(dev):
             st = stream_ptr(dev)
             call('nfb_ibrnet_view_fwd', N, S, V, int(anti_alias), ptr(rf), ptr(rd), ptr(mk), 0, 0, 0, 0,
-                 None, None, None, None, None, None, None, ptr(params), ptr(ps), st)
+                 None, None, None, None, None, None, None, ptr(params), ptr(ps), _lib.precision_code(), st)
             call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), st)
         ctx.save_for_backward(rf, rd, mk, params, pos_enc, ps)
         ctx.dims = (R, S, V, int(anti_alias))
+        ctx.precision = _lib.precision_code()
         return raw
 
     @staticmethod
@@ -176,7 +177,7 @@ class IBRNetAggregate(torch.autograd.Function):
                 call('nfb_ibrnet_ray_bwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(g), ptr(d_ps), st)
                 call('nfb_ibrnet_view_bwd', N, S, V, aa, ptr(rf), ptr(rd), ptr(mk), 0, 0, 0, 0,
                      None, None, None, None, None, None, None, ptr(params), ptr(ps), ptr(d_ps),
-                     ptr(d_rf), None, None, st)
+                     ptr(d_rf), None, None, ctx.precision, st)
         return d_rf, None, None, None, None, None
 
 
@@ -286,7 +287,8 @@ class RenderLevel(torch.autograd.Function):
         with torch.cuda.device(dev):
             st = stream_ptr(dev)
             call('nfb_ibrnet_view_fwd', N, S, V, int(anti_alias), None, None, None, H, W, fh, fw,
-                 None, ptr(o_c), ptr(d_c), ptr(z_c), ptr(cam), ptr(imgs_c), ptr(feat), ptr(params), ptr(ps), st)
+                 None, ptr(o_c), ptr(d_c), ptr(z_c), ptr(cam), ptr(imgs_c), ptr(feat), ptr(params), ptr(ps),
+                 _lib.precision_code(), st)
             call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), st)
             call('nfb_composite_fwd', R, S, int(white_bkgd), ptr(raw), ptr(z_c), None, ptr(ps[:, 68:]), PS_STRIDE,
                  ptr(rgb), ptr(depth), ptr(weights), ptr(alpha), ptr(ray_mask), st)
@@ -294,6 +296,7 @@ class RenderLevel(torch.autograd.Function):
         if need:
             ctx.save_for_backward(feat, imgs_c, o_c, d_c, z_c, cam, params, pos_enc, ps, raw)
         ctx.dims = (R, S, V, H, W, fh, fw, int(anti_alias), int(white_bkgd))
+        ctx.precision = _lib.precision_code()
         ctx.imgs_shape = imgs.shape
         ctx.set_materialize_grads(False)
         ray_mask = ray_mask.view(torch.bool)
@@ -318,6 +321,6 @@ class RenderLevel(torch.autograd.Function):
             call('nfb_ibrnet_ray_bwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(d_raw), ptr(d_ps), st)
             call('nfb_ibrnet_view_bwd', N, S, V, aa, None, None, None, H, W, fh, fw,
                  None, ptr(o_c), ptr(d_c), ptr(z_c), ptr(cam), ptr(imgs_c), ptr(feat), ptr(params), ptr(ps),
-                 ptr(d_ps), None, ptr(d_feat), ptr(d_imgs), st)
+                 ptr(d_ps), None, ptr(d_feat), ptr(d_imgs), ctx.precision, st)
         return (d_feat.permute(0, 3, 1, 2) if need_feat else None, d_imgs,
                 None, None, None, None, None, None, None, None, None, None)
