@@ -41,15 +41,33 @@ def _nvcc():
     raise RuntimeError('nvcc not found')
 
 
+_INC_RE = None
+
+
+def _deps(path, seen):
+    """Transitive closure of the quoted #includes of one source file (paths relative to the includer)."""
+    global _INC_RE
+    import re
+    if _INC_RE is None:
+        _INC_RE = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return
+    seen.add(path)
+    with open(path) as f:
+        text = f.read()
+    for inc in _INC_RE.findall(text):
+        _deps(os.path.join(os.path.dirname(path), inc), seen)
+
+
 def _sources_digest(src, extra):
-    """Digest of one unit's inputs: its own source, every header under csrc/ and the public header."""
+    """Digest of one unit's inputs: its source and the headers it (transitively) includes."""
+    seen = set()
+    _deps(os.path.join(CSRC, src), seen)
     h = hashlib.sha256()
-    names = sorted(f for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h')) or f == src)
-    for n in names:
-        with open(os.path.join(CSRC, n), 'rb') as f:
-            h.update(n.encode() + b'\0' + f.read())
-    with open(os.path.join(HERE, '..', 'include', 'nerfool_b200.h'), 'rb') as f:
-        h.update(f.read())
+    for n in sorted(seen):
+        with open(n, 'rb') as f:
+            h.update(os.path.basename(n).encode() + b'\0' + f.read())
     h.update(' '.join(NVCC_FLAGS + extra).encode())
     return h.hexdigest()
 

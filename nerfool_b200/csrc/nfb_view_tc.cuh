@@ -30,8 +30,10 @@ using nfbview::ViewArgs;
 constexpr int GROUP = 128;
 constexpr int NG = 4;
 constexpr int EXS = 37;      // exchange-buffer row stride (floats)
-constexpr int TS_MAX = 64;   // samples per tile cap
+constexpr int TS_MAX = 32;   // samples per tile cap (V < 4 leaves part of a 128-row tile idle)
 constexpr int MVS = 72;      // per-sample pooled statistics: mean0[35] at 0, var0[35] at 36
+constexpr int MVP = 72;      // 32-bit words per sample of the packed copy: bf16 hi halves of [mean | var] (70 values =
+                             // 35 words) at 0, lo halves at 36 -- already in base_fc.0 operand order
 constexpr int GC = 128;      // TMEM columns per group
 constexpr int C_D = 0, C_A = 64, C_ALO = 96;
 
@@ -79,8 +81,8 @@ enum : int {
 
 template <int NPASS>
 __host__ __device__ constexpr size_t smem_bytes() {
-  return (size_t)B_SET_BYTES * (NPASS == 3 ? 2 : 1) + sizeof(float) * (F_TOTAL + 16 * NFB_MAX_VIEWS + 4 + NG * GROUP * EXS + NG * TS_MAX * MVS) +
-         NG * 8 + 16;
+  return (size_t)B_SET_BYTES * (NPASS == 3 ? 2 : 1) +
+         sizeof(float) * (F_TOTAL + 16 * NFB_MAX_VIEWS + 4 + NG * GROUP * EXS + NG * TS_MAX * (MVS + MVP)) + NG * 8 + 16;
 }
 
 template <int NPASS>
@@ -131,6 +133,18 @@ __device__ __forceinline__ void a_store16(uint32_t tl, int kc, const float (&v)[
   if (NPASS == 3) tmem_st8(tl + C_ALO + 8 * kc, lo);
 }
 
+// same, from 8 already packed words (hi) and their lo twins
+template <int NPASS>
+__device__ __forceinline__ void a_store_words(uint32_t tl, int kc, const uint32_t (&hi)[8], const uint32_t (&lo)[8]) {
+  tmem_st8(tl + C_A + 8 * kc, hi);
+  if (NPASS == 3) tmem_st8(tl + C_ALO + 8 * kc, lo);
+}
+template <int NPASS>
+__device__ __forceinline__ void pack_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  if (NPASS == 3) split_bf16(a, b, hi, lo);
+  else { hi = pack_bf16(a, b); lo = 0u; }
+}
+
 // y[j] = ELU(D[col + j] + bias[j]), 16 outputs
 __device__ __forceinline__ void epi16(uint32_t tl, int col, const float* __restrict__ bias, float (&y)[16]) {
   tmem_ld16(tl + C_D + col, y);
@@ -138,10 +152,10 @@ __device__ __forceinline__ void epi16(uint32_t tl, int col, const float* __restr
 #pragma unroll
   for (int j = 0; j < 16; j += 4) {
     const float4 b = *reinterpret_cast<const float4*>(bias + j);
-    y[j + 0] = elu_f(y[j + 0] + b.x);
-    y[j + 1] = elu_f(y[j + 1] + b.y);
-    y[j + 2] = elu_f(y[j + 2] + b.z);
-    y[j + 3] = elu_f(y[j + 3] + b.w);
+    y[j + 0] = elu_fast(y[j + 0] + b.x);
+    y[j + 1] = elu_fast(y[j + 1] + b.y);
+    y[j + 2] = elu_fast(y[j + 2] + b.z);
+    y[j + 3] = elu_fast(y[j + 3] + b.w);
   }
 }
 
@@ -204,13 +218,15 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
   float* s_cam = sf + F_TOTAL;
   float* ex_all = s_cam + (16 * NFB_MAX_VIEWS + 4);
   float* mv_all = ex_all + NG * GROUP * EXS;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(mv_all + NG * TS_MAX * MVS);
+  uint32_t* mvp_all = reinterpret_cast<uint32_t*>(mv_all + NG * TS_MAX * MVS);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(mvp_all + NG * TS_MAX * MVP);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + NG);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int grp = tid / GROUP, tg = tid % GROUP;
   float* ex = ex_all + (size_t)grp * GROUP * EXS;
   float* mv = mv_all + (size_t)grp * TS_MAX * MVS;
+  uint32_t* mvp = mvp_all + (size_t)grp * TS_MAX * MVP;
   const int bar_id = 1 + grp;
   uint64_t* mbar = s_bar + grp;
 
@@ -254,6 +270,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
     const bool active = (sl < TS) && (p < a.N);
     const int base = active ? sl * V : 0;
     float* mvs = mv + (active ? sl : 0) * MVS;
+    uint32_t* mvps = mvp + (active ? sl : 0) * MVP;
 
     // ---------------- projection, ray_diff, bilinear gather ----------------
     float x[NFB_ROW_CH];
@@ -302,7 +319,8 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       float a1[16];
       load_bias<16>(a1, sf + F_DIR0_B);
       dense_acc<4, 16>(sf + F_DIR0_W, rd, a1);
-      elu_inplace<16>(a1);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a1[j] = elu_fast(a1[j]);
       a_store16<NPASS>(tl, 0, a1);
     }
     NFB_TC_ISSUE(L_DIR2, 0, 1, false);
@@ -354,39 +372,59 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
         }
         mvs[c] = m;
         mvs[36 + c] = vr;
+        // the operand halves of this statistic, split once per sample instead of once per row
+        __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(mvps);
+        __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(mvps + 36);
+        const __nv_bfloat16 mh = __float2bfloat16_rn(m), vh = __float2bfloat16_rn(vr);
+        ph[c] = mh;
+        ph[35 + c] = vh;
+        if (NPASS == 3) {
+          pl[c] = __float2bfloat16_rn(m - __bfloat162float(mh));
+          pl[35 + c] = __float2bfloat16_rn(vr - __bfloat162float(vh));
+        }
       }
     }
     named_bar_sync(bar_id, GROUP);
 
     // ---------------- base_fc.0 : [mean | var | x0] (105 -> 64) ----------------
-    if (NPASS == 1) {
-#pragma unroll
-      for (int kc = 0; kc < 7; ++kc) {
-        float t[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) t[j] = base0_in(16 * kc + j, mvs, x);
-        a_store16<NPASS>(tl, kc, t);
-      }
-      NFB_TC_ISSUE(L_BASE0, 0, 7, false);
-      NFB_TC_WAIT();
-    } else {
+    // operand words 0..34 = packed [mean | var] of the sample (shared memory), words 35..52 = x0 pairs, 53..55 = 0
+    {
+      // K chunks 0..3 (k < 64): statistics only
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
-        float t[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) t[j] = base0_in(16 * kc + j, mvs, x);
-        a_store16<NPASS>(tl, kc, t);
+        uint32_t hi[8], lo[8];
+        const uint4 h0 = *reinterpret_cast<const uint4*>(mvps + 8 * kc), h1 = *reinterpret_cast<const uint4*>(mvps + 8 * kc + 4);
+        hi[0] = h0.x; hi[1] = h0.y; hi[2] = h0.z; hi[3] = h0.w; hi[4] = h1.x; hi[5] = h1.y; hi[6] = h1.z; hi[7] = h1.w;
+        if (NPASS == 3) {
+          const uint4 l0 = *reinterpret_cast<const uint4*>(mvps + 36 + 8 * kc), l1 = *reinterpret_cast<const uint4*>(mvps + 36 + 8 * kc + 4);
+          lo[0] = l0.x; lo[1] = l0.y; lo[2] = l0.z; lo[3] = l0.w; lo[4] = l1.x; lo[5] = l1.y; lo[6] = l1.z; lo[7] = l1.w;
+        }
+        a_store_words<NPASS>(tl, kc, hi, lo);
       }
-      NFB_TC_ISSUE(L_BASE0, 0, 4, false);
-      NFB_TC_WAIT();
-#pragma unroll
-      for (int kc = 4; kc < 7; ++kc) {
-        float t[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) t[j] = base0_in(16 * kc + j, mvs, x);
-        a_store16<NPASS>(tl, kc - 4, t);
+      if (NPASS == 3) {               // A region holds K = 64 per round: issue the first round now
+        NFB_TC_ISSUE(L_BASE0, 0, 4, false);
+        NFB_TC_WAIT();
       }
-      NFB_TC_ISSUE(L_BASE0, 4, 7, true);
+      constexpr int KC0 = (NPASS == 3) ? 4 : 0;   // chunk index offset of the second round
+      {
+        uint32_t hi[8], lo[8];
+        hi[0] = mvps[32]; hi[1] = mvps[33]; hi[2] = mvps[34];
+        if (NPASS == 3) { lo[0] = mvps[36 + 32]; lo[1] = mvps[36 + 33]; lo[2] = mvps[36 + 34]; }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) pack_pair<NPASS>(x[2 * j], x[2 * j + 1], hi[3 + j], lo[3 + j]);
+        a_store_words<NPASS>(tl, 4 - KC0, hi, lo);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pack_pair<NPASS>(x[10 + 2 * j], x[11 + 2 * j], hi[j], lo[j]);
+        a_store_words<NPASS>(tl, 5 - KC0, hi, lo);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pack_pair<NPASS>(x[26 + 2 * j], x[27 + 2 * j], hi[j], lo[j]);
+        pack_pair<NPASS>(x[34], 0.f, hi[4], lo[4]);
+        hi[5] = hi[6] = hi[7] = 0u;
+        lo[5] = lo[6] = lo[7] = 0u;
+        a_store_words<NPASS>(tl, 6 - KC0, hi, lo);
+      }
+      if (NPASS == 3) NFB_TC_ISSUE(L_BASE0, 4, 7, true);
+      else NFB_TC_ISSUE(L_BASE0, 0, 7, false);
       NFB_TC_WAIT();
     }
 
@@ -482,7 +520,8 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       float g2[8];
       load_bias<8>(g2, sf + F_B_RGB2);
       dense_acc<16, 8>(sf + F_W_RGB2, g1, g2);
-      elu_inplace<8>(g2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g2[j] = elu_fast(g2[j]);
       logit = dot_row<8>(g2, sf + F_W_RGB4) + sf[F_B_RGB4];
       if (mk == 0.f) logit = -1e9f;
     }
@@ -499,14 +538,15 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
     if (active) {
       float D = 1e-8f;
       for (int u = 0; u < V; ++u) D += ex[(base + u) * EXS + 32];
+      const float invD = 1.f / D;
       float* out = a.ps + (size_t)p * NFB_PS_STRIDE;
       for (int c = v; c < 32; c += V) {
         float m = 0.f;
-        for (int u = 0; u < V; ++u) m = fmaf(ex[(base + u) * EXS + c], ex[(base + u) * EXS + 32] / D, m);
+        for (int u = 0; u < V; ++u) m = fmaf(ex[(base + u) * EXS + c], ex[(base + u) * EXS + 32] * invD, m);
         float vr = 0.f;
         for (int u = 0; u < V; ++u) {
           const float d = ex[(base + u) * EXS + c] - m;
-          vr = fmaf((ex[(base + u) * EXS + 32] / D) * d, d, vr);
+          vr = fmaf((ex[(base + u) * EXS + 32] * invD) * d, d, vr);
         }
         out[PS_MEAN + c] = m;
         out[PS_VAR + c] = vr;
@@ -519,7 +559,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
         const float inv_se = 1.f / se;
         float wsum = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
         for (int u = 0; u < V; ++u) {
-          wsum += ex[(base + u) * EXS + 32] / D;
+          wsum += ex[(base + u) * EXS + 32] * invD;
           const float b = __expf(ex[(base + u) * EXS + 33] - mx) * inv_se;
           r0 = fmaf(b, ex[(base + u) * EXS + 34], r0);
           r1 = fmaf(b, ex[(base + u) * EXS + 35], r1);

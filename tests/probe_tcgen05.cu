@@ -19,6 +19,7 @@ struct Cfg {
   int passes;      // 1: hi only   3: hi*hi + lo*hi + hi*lo
   int ones_bias;   // 1: bias through a persistent "ones" K-block
   int groups;      // row groups (128 threads each) running concurrently in the CTA
+  int b_mn;        // 0: B stored K-major.  1/2: B' = W^T read MN-major from the K-major tile of W[K][N] (1: LBO=128,SBO=K*16  2: exchanged)
 };
 
 // canonical K-major no-swizzle offset (bytes) of element (r, k) of an [R][K] bf16 tile stored K-chunk-major
@@ -58,6 +59,7 @@ k_probe(Cfg c, const float* __restrict__ A, const float* __restrict__ B, const f
     const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
     uint32_t off = c.swap_lbo == 1 ? (uint32_t)((k >> 3) * 128 + (n >> 3) * (KB * 16) + (n & 7) * 16 + (k & 7) * 2)
                               : canon_off(n, k, N);
+    if (c.b_mn) off = canon_off(k, n, KB);          // physical tile = W[k][n] (rows k, KB of them), K-major canonical
     *reinterpret_cast<__nv_bfloat16*>(sBhi + off) = h;
     *reinterpret_cast<__nv_bfloat16*>(sBlo + off) = l;
   }
@@ -71,7 +73,7 @@ k_probe(Cfg c, const float* __restrict__ A, const float* __restrict__ B, const f
     const uint32_t gcol = (uint32_t)grp * (uint32_t)(512 / c.groups);
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t d_col = tbase + gcol;
-    const uint32_t ahi_col = d_col + 64, alo_col = ahi_col + K / 2;
+    const uint32_t ahi_col = d_col + (N > 64 ? 128 : 64), alo_col = ahi_col + K / 2;
     const uint32_t ones_col = (c.passes == 3) ? alo_col + K / 2 : alo_col;
 
     // ---- A operand: this thread's row ----
@@ -109,17 +111,22 @@ k_probe(Cfg c, const float* __restrict__ A, const float* __restrict__ B, const f
 
     if (tg == 0) {
       fence_after_sync();
-      const uint32_t idesc = idesc_bf16(128, N);
+      const uint32_t idesc = idesc_bf16(128, N) | (c.b_mn ? (1u << 16) : 0u);
       uint32_t b_lbo = c.swap_lbo == 1 ? 128u : (uint32_t)N * 16u, b_sbo = c.swap_lbo == 1 ? (uint32_t)KB * 16u : 128u;
       uint32_t a_lbo = c.swap_lbo == 1 ? 128u : 128u * 16u, a_sbo = c.swap_lbo == 1 ? (uint32_t)K * 16u : 128u;
       const uint32_t b_kstep = c.swap_lbo == 1 ? 256u : 2u * (uint32_t)N * 16u;   // bytes per K=16
       const uint32_t a_kstep = c.swap_lbo == 1 ? 256u : 2u * 128u * 16u;
       if (c.swap_lbo == 2) { uint32_t t = b_lbo; b_lbo = b_sbo; b_sbo = t; t = a_lbo; a_lbo = a_sbo; a_sbo = t; }
+      uint32_t b_kstep_eff = b_kstep;
+      if (c.b_mn) {
+        b_lbo = 128u; b_sbo = (uint32_t)KB * 16u; b_kstep_eff = 256u;
+        if (c.b_mn == 2) { b_lbo = (uint32_t)KB * 16u; b_sbo = 128u; }
+      }
       bool acc = false;
       for (int pass = 0; pass < c.passes; ++pass) {
         const uint8_t* bsel = (pass == 2) ? sBlo : sBhi;        // pass 0: hi*hi, 1: lo*hi, 2: hi*lo
         for (int ks = 0; ks < K / 16; ++ks) {
-          const uint64_t bd = smem_desc(smem_u32(bsel) + ks * b_kstep, b_lbo, b_sbo);
+          const uint64_t bd = smem_desc(smem_u32(bsel) + ks * b_kstep_eff, b_lbo, b_sbo);
           if (c.a_in_tmem) {
             const uint32_t acol = ((pass == 1) ? alo_col : ahi_col) + ks * 8;
             mma_ts(d_col, acol, bd, idesc, acc);
@@ -133,8 +140,8 @@ k_probe(Cfg c, const float* __restrict__ A, const float* __restrict__ B, const f
       }
       if (c.ones_bias && c.a_in_tmem) {
         const int ks = K / 16;
-        mma_ts(d_col, ones_col, smem_desc(smem_u32(sBhi) + ks * b_kstep, b_lbo, b_sbo), idesc, true);
-        if (c.passes == 3) mma_ts(d_col, ones_col, smem_desc(smem_u32(sBlo) + ks * b_kstep, b_lbo, b_sbo), idesc, true);
+        mma_ts(d_col, ones_col, smem_desc(smem_u32(sBhi) + ks * b_kstep_eff, b_lbo, b_sbo), idesc, true);
+        if (c.passes == 3) mma_ts(d_col, ones_col, smem_desc(smem_u32(sBlo) + ks * b_kstep_eff, b_lbo, b_sbo), idesc, true);
       }
       mma_commit(&s_bar[grp]);
     }
@@ -163,19 +170,23 @@ int main(int argc, char** argv) {
   const int variant = argc > 1 ? atoi(argv[1]) : 0;
   // N, K, a_in_tmem, swap_lbo, swap_pack, passes, ones_bias, groups
   const Cfg table[] = {
-      {48, 32, 1, 0, 0, 1, 0, 1},    // 0: ts, canonical
-      {48, 32, 1, 1, 0, 1, 0, 1},    // 1: ts, LBO/SBO swapped
-      {48, 32, 1, 0, 1, 1, 0, 1},    // 2: ts, A packing swapped
-      {48, 32, 0, 0, 0, 1, 0, 1},    // 3: ss, canonical
-      {48, 32, 0, 1, 0, 1, 0, 1},    // 4: ss, swapped
-      {64, 112, 1, 0, 0, 1, 1, 4},   // 5: ts, base_fc.0 shape, bias block, 4 groups
-      {64, 112, 1, 0, 0, 3, 1, 2},   // 6: ts, 3-pass, 2 groups
-      {16, 48, 1, 0, 0, 3, 1, 2},    // 7: ts, rgb_fc.0 shape
-      {32, 64, 1, 0, 0, 1, 1, 4},    // 8: ts, base_fc.2 shape
-      {64, 112, 0, 0, 0, 3, 0, 1},   // 9: ss 3-pass
-      {48, 32, 1, 2, 0, 1, 0, 1},    // 10: ts, descriptor fields exchanged
-      {48, 32, 0, 2, 0, 1, 0, 1},    // 11: ss, descriptor fields exchanged
-      {48, 48, 1, 0, 0, 1, 1, 4},    // 12: ts, vis_fc.2-like with 4 groups
+      {48, 32, 1, 0, 0, 1, 0, 1, 0},    // 0: ts, canonical
+      {48, 32, 1, 1, 0, 1, 0, 1, 0},    // 1: ts, LBO/SBO swapped
+      {48, 32, 1, 0, 1, 1, 0, 1, 0},    // 2: ts, A packing swapped
+      {48, 32, 0, 0, 0, 1, 0, 1, 0},    // 3: ss, canonical
+      {48, 32, 0, 1, 0, 1, 0, 1, 0},    // 4: ss, swapped
+      {64, 112, 1, 0, 0, 1, 1, 4, 0},   // 5: ts, base_fc.0 shape, bias block, 4 groups
+      {64, 112, 1, 0, 0, 3, 1, 2, 0},   // 6: ts, 3-pass, 2 groups
+      {16, 48, 1, 0, 0, 3, 1, 2, 0},    // 7: ts, rgb_fc.0 shape
+      {32, 64, 1, 0, 0, 1, 1, 4, 0},    // 8: ts, base_fc.2 shape
+      {64, 112, 0, 0, 0, 3, 0, 1, 0},   // 9: ss 3-pass
+      {48, 32, 1, 2, 0, 1, 0, 1, 0},    // 10: ts, descriptor fields exchanged
+      {48, 32, 0, 2, 0, 1, 0, 1, 0},    // 11: ss, descriptor fields exchanged
+      {48, 48, 1, 0, 0, 1, 1, 4, 0},    // 12: ts, vis_fc.2-like with 4 groups
+      {48, 32, 1, 0, 0, 1, 0, 1, 1},    // 13: ts, B' = W^T MN-major (LBO=128, SBO=K*16)
+      {48, 32, 1, 0, 0, 1, 0, 1, 2},    // 14: ts, B' MN-major, fields exchanged
+      {64, 64, 1, 0, 0, 3, 0, 2, 1},    // 15: ts, 3-pass, MN-major, base_fc.0^T-like (first N half)
+      {112, 64, 1, 0, 0, 3, 0, 2, 1},   // 16: ts, N = 112
   };
   const int nvar = sizeof(table) / sizeof(table[0]);
   if (variant < 0 || variant >= nvar) { printf("variant out of range\n"); return 2; }
@@ -220,9 +231,9 @@ int main(int argc, char** argv) {
       err_bf = fmax(err_bf, fabs(d - sb));
       mag = fmax(mag, fabs(se));
     }
-  printf("variant %d: N=%d K=%d %s swap_lbo=%d swap_pack=%d passes=%d bias=%d groups=%d | cuda=%s timeout=%d | "
+  printf("variant %d: bmn=%d N=%d K=%d %s swap_lbo=%d swap_pack=%d passes=%d bias=%d groups=%d | cuda=%s timeout=%d | "
          "max|D-exact|=%.3e max|D-bf16ref|=%.3e (max|D|=%.3f) => %s\n",
-         variant, c.N, c.K, c.a_in_tmem ? "ts" : "ss", c.swap_lbo, c.swap_pack, c.passes, c.ones_bias, c.groups,
+         variant, c.b_mn, c.N, c.K, c.a_in_tmem ? "ts" : "ss", c.swap_lbo, c.swap_pack, c.passes, c.ones_bias, c.groups,
          cudaGetErrorString(e), st, err_exact, err_bf, mag,
          (e == cudaSuccess && !st && ((c.passes == 1 && err_bf < 1e-4) || (c.passes == 3 && err_exact < 1e-4))) ? "PASS" : "FAIL");
   return 0;
