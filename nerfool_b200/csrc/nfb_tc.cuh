@@ -136,6 +136,54 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                : "memory");
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+// raw 32-bit words
+__device__ __forceinline__ void tmem_ld16u(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8u(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld4u(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+
+// ELU-derivative stash.  For y = ELU(x): ELU'(x) = 1 (y > 0) or y + 1 (y <= 0), i.e. ELU' = 2 - t with
+// t = 1 - min(y, 0) in [1, 2].  t is clamped just below 2 and bits [23:8] of its fp32 pattern (15 mantissa bits,
+// truncation error < 2^-15) are kept, two values per 32-bit word, so that encode and decode are one PRMT each.
+__device__ __forceinline__ uint32_t elu_stash_pack(float y0, float y1) {
+  const float t0 = fminf(1.f - fminf(y0, 0.f), 1.9999999f);
+  const float t1 = fminf(1.f - fminf(y1, 0.f), 1.9999999f);
+  return __byte_perm(__float_as_uint(t0), __float_as_uint(t1), 0x6521);   // {t0.b1, t0.b2, t1.b1, t1.b2}
+}
+__device__ __forceinline__ float elu_stash_lo(uint32_t w) {   // ELU' of the first value of the pair
+  return 2.f - __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7104));      // {0, w.b0, w.b1, 0x3F}
+}
+__device__ __forceinline__ float elu_stash_hi(uint32_t w) {
+  return 2.f - __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7324));      // {0, w.b2, w.b3, 0x3F}
+}
+
 // ELU with one MUFU and no branch: elu(x) = max(x, min(exp(x) - 1, 0))
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

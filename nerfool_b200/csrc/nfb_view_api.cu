@@ -1,6 +1,7 @@
 // C-ABI entry points of the IBRNet view stage (argument validation + dispatch to the instantiations).
 #include "nfb_view_stage.cuh"
 #include "nfb_view_tc.cuh"
+#include "nfb_view_tc_bwd.cuh"
 using nfbview::ViewArgs;
 
 static int check_view_args(const char* who, int N, int S, int V, const float* rgb_feat, const float* ray_diff,
@@ -72,6 +73,10 @@ extern "C" int nfb_ibrnet_view_bwd(int N, int S, int V, int anti_alias, const fl
   a.pts = PointSrc{xyz, ray_o, ray_d, z, S};
   a.cam = cam; a.imgs = imgs; a.feat = feat; a.params = params; a.ps = const_cast<float*>(ps);
   a.d_ps = d_ps; a.d_rgb_feat = d_rgb_feat; a.d_feat = d_feat; a.d_imgs = d_imgs;
-  if (rgb_feat) return nfb_launch_view_tensor_bwd(a, (cudaStream_t)stream);
-  return nfb_launch_view_fused_bwd(a, (cudaStream_t)stream);
+  NFB_REQUIRE(((uintptr_t)ps % 16) == 0 && ((uintptr_t)d_ps % 16) == 0, NFB_EINVAL, "nfb_ibrnet_view_bwd: ps / d_ps must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == NFB_PREC_BF16X3) return rgb_feat ? nfb_launch_view_tc_bwd_p3_tensor(a, st) : nfb_launch_view_tc_bwd_p3_fused(a, st);
+  if (precision == NFB_PREC_BF16) return rgb_feat ? nfb_launch_view_tc_bwd_p1_tensor(a, st) : nfb_launch_view_tc_bwd_p1_fused(a, st);
+  if (rgb_feat) return nfb_launch_view_tensor_bwd(a, st);
+  return nfb_launch_view_fused_bwd(a, st);
 }
