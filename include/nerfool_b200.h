@@ -44,7 +44,8 @@ typedef enum {
   NFB_ECUDA = -3          /* a CUDA runtime call or launch failed; text carries cudaGetErrorString */
 } NfbStatus;
 
-/* Arithmetic of the dense layers of the IBRNet view stage (`precision` argument):
+/* Arithmetic of the dense layers of the IBRNet view and ray stages (`precision` argument; the ray stage takes its
+ * tensor-core form for S <= 128 samples per ray and the fp32 form beyond):
  *   NFB_PREC_FP32   fp32 FMA on the CUDA cores (the exactness reference of this library)
  *   NFB_PREC_BF16X3 tcgen05 tensor cores, operands split hi+lo in bf16, 3 MMA passes, fp32 accumulation:
  *                   products exact to ~2^-17 -> results inside the reference's fp32 tolerance (default)
@@ -103,11 +104,11 @@ int nfb_ibrnet_view_fwd(int N, int S, int V, int anti_alias,
                         const float* cam, const float* imgs, const float* feat,
                         const float* params, float* ps, int precision, void* stream);
 int nfb_ibrnet_ray_fwd(int R, int S, const float* ps, const float* params, const float* pos_enc /*[S][16]*/,
-                       float* raw /*[R][S][4]*/, void* stream);
+                       float* raw /*[R][S][4]*/, int precision, void* stream);
 /* Backward (data gradients): d_raw[R][S][4] -> d_ps[N][72] -> d_rgb_feat[N][V][35] (tensor mode) or a
  * scatter into d_feat / d_imgs (fused mode, rgb_feat == NULL).                                         */
 int nfb_ibrnet_ray_bwd(int R, int S, const float* ps, const float* params, const float* pos_enc,
-                       const float* d_raw, float* d_ps, void* stream);
+                       const float* d_raw, float* d_ps, int precision, void* stream);
 int nfb_ibrnet_view_bwd(int N, int S, int V, int anti_alias,
                         const float* rgb_feat, const float* ray_diff, const float* mask,
                         int H, int W, int fh, int fw,

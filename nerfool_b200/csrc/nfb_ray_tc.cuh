@@ -1,0 +1,598 @@
+// IBRNet ray stage on the 5th-generation tensor cores (tcgen05 + TMEM), forward and data-gradient:
+// geometry_fc, + pos_encoding, 4-head d_k = 4 self-attention over the samples of a ray (row-masked), fc + residual +
+// LayerNorm(eps 1e-6), sigma head (mlp_network.py:259-265, 69-119, 23-43).
+//
+// Mapping: one thread per sample; a 128-thread group owns floor(128 / S) whole rays per tile (S <= 128; longer rays
+// take the fp32 kernels in nfb_ray_stage.cu).  Dense layers run as 128 x N x K tcgen05.mma tiles exactly like the view
+// stage (A operand = the rows' activations written to TMEM by their threads, B = weight tiles resident in shared
+// memory, D read back with tcgen05.ld); the backward products dX = dY W read the same tiles MN-major.  The attention
+// itself (d_k = 4 per head: too thin for an MMA) stays on the CUDA cores with K / V (backward: Q, dO, softmax
+// statistics) of the group's rays in shared memory.
+//
+// TMEM columns of a group: D [0,64) | A hi [64,96) | A lo [96,128) | backward only: ELU'(h64) codes [128,160).
+#pragma once
+#include "nfb_dense.cuh"
+#include "nfb_tc.cuh"
+
+namespace nfbrtc {
+using namespace nfbtc;
+
+constexpr int GROUP = 128;
+constexpr int RC_D = 0, RC_A = 64, RC_ALO = 96, RC_HQ = 128;
+
+enum : int { RL_GEO0 = 0, RL_GEO2, RL_QKV, RL_FC, RL_OG0, RL_COUNT };
+__host__ __device__ constexpr int rl_n(int l) { return l == RL_GEO0 ? 64 : l == RL_QKV ? 48 : 16; }
+__host__ __device__ constexpr int rl_k(int l) { return (l == RL_GEO0 || l == RL_GEO2) ? 64 : 16; }
+__host__ __device__ constexpr int rl_off(int l) {
+  int o = 0;
+  for (int i = 0; i < l; ++i) o += rl_n(i) * rl_k(i) * 2;
+  return o;
+}
+constexpr int R_SET_BYTES = rl_off(RL_COUNT);   // 12800
+static_assert(R_SET_BYTES % 16 == 0, "tile alignment");
+
+enum : int {
+  RF_B_GEO0 = 0,               // 64
+  RF_WCOL = RF_B_GEO0 + 64,    // 64: geometry_fc.0.weight[:, 64] (the mean-weight input, handled on the CUDA cores)
+  RF_B_GEO2 = RF_WCOL + 64,    // 16
+  RF_LNW = RF_B_GEO2 + 16,     // 16
+  RF_LNB = RF_LNW + 16,        // 16
+  RF_B_OG0 = RF_LNB + 16,      // 16
+  RF_W_OG2 = RF_B_OG0 + 16,    // 16
+  RF_B_OG2 = RF_W_OG2 + 16,    // 4
+  RF_TOTAL = RF_B_OG2 + 4
+};
+
+constexpr float INV_TEMP = 0.5f;     // 1 / sqrt(d_k), d_k = 4 (mlp_network.py:84)
+constexpr float LN_EPS = 1e-6f;      // mlp_network.py:87
+constexpr float LOG2E = 1.4426950408889634f;
+
+template <int NPASS, bool BWD>
+struct Cfg {
+  static constexpr int NG = BWD ? 2 : 4;
+  static constexpr int GC = BWD ? 256 : 128;
+  // per-group shared memory (floats): K, V [128][16]; backward: Q, dO [128][16] and statistics [128][4] float4
+  static constexpr int GROUP_FLOATS = BWD ? (4 * GROUP * 16 + GROUP * 16) : (2 * GROUP * 16);
+  static size_t smem(int S) {
+    return (size_t)R_SET_BYTES * (NPASS == 3 ? 2 : 1) + sizeof(float) * (RF_TOTAL + (size_t)S * 16 + (size_t)NG * GROUP_FLOATS) +
+           NG * 8 + 16;
+  }
+};
+
+template <int NPASS>
+static __device__ void load_rtile(uint8_t* sB, int layer, const float* __restrict__ w, int n_real, int row_stride, int tid, int nt) {
+  const int N = rl_n(layer), K = rl_k(layer);
+  uint8_t* hi = sB + rl_off(layer);
+  uint8_t* lo = hi + R_SET_BYTES;
+  for (int i = tid; i < N * K; i += nt) {
+    const int n = i / K, k = i - n * K;
+    const float v = (n < n_real) ? __ldg(w + n * row_stride + k) : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const uint32_t off = (uint32_t)((k >> 3) * (N * 16) + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2);
+    *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
+    if (NPASS == 3) *reinterpret_cast<__nv_bfloat16*>(lo + off) = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+template <int NPASS>
+__device__ __forceinline__ void r_put16(uint32_t tl, int kc, const float (&v)[16]) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (NPASS == 3) split_bf16(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+    else hi[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+  }
+  tmem_st8(tl + RC_A + 8 * kc, hi);
+  if (NPASS == 3) tmem_st8(tl + RC_ALO + 8 * kc, lo);
+}
+__device__ __forceinline__ void r_ld16(uint32_t tl, int col, float (&y)[16]) {
+  tmem_ld16(tl + RC_D + col, y);
+  tmem_ld_wait();
+}
+
+// forward: D[128][N] = A[128][K] W^T ; backward: D[128][K] = A[128][N] W (MN-major read of the same tile)
+template <int NPASS, int LAYER>
+__device__ __forceinline__ void r_issue_fwd(uint32_t tb, uint32_t sB_addr) {
+  constexpr int N = rl_n(LAYER), K = rl_k(LAYER);
+  constexpr uint32_t idesc = idesc_bf16(128, N);
+  const uint32_t bhi = sB_addr + rl_off(LAYER), blo = bhi + R_SET_BYTES;
+#pragma unroll
+  for (int ks = 0; ks < K / 16; ++ks) {
+    const uint64_t dh = smem_desc(bhi + ks * 2 * N * 16, N * 16, 128);
+    const uint32_t ah = tb + RC_A + 8 * ks;
+    mma_ts(tb + RC_D, ah, dh, idesc, ks > 0);
+    if (NPASS == 3) {
+      const uint64_t dl = smem_desc(blo + ks * 2 * N * 16, N * 16, 128);
+      mma_ts(tb + RC_D, tb + RC_ALO + 8 * ks, dh, idesc, true);
+      mma_ts(tb + RC_D, ah, dl, idesc, true);
+    }
+  }
+}
+template <int NPASS, int LAYER>
+__device__ __forceinline__ void r_issue_bwd(uint32_t tb, uint32_t sB_addr) {
+  constexpr int NO = rl_n(LAYER), KI = rl_k(LAYER);
+  constexpr uint32_t idesc = idesc_bf16(128, KI) | (1u << 16);
+  const uint32_t bhi = sB_addr + rl_off(LAYER), blo = bhi + R_SET_BYTES;
+#pragma unroll
+  for (int ks = 0; ks < NO / 16; ++ks) {
+    const uint64_t dh = smem_desc(bhi + ks * 256, 128, NO * 16);
+    const uint32_t ah = tb + RC_A + 8 * ks;
+    mma_ts(tb + RC_D, ah, dh, idesc, ks > 0);
+    if (NPASS == 3) {
+      const uint64_t dl = smem_desc(blo + ks * 256, 128, NO * 16);
+      mma_ts(tb + RC_D, tb + RC_ALO + 8 * ks, dh, idesc, true);
+      mma_ts(tb + RC_D, ah, dl, idesc, true);
+    }
+  }
+}
+
+#define NFB_RTC_SYNC_ISSUE(STMT)                                              \
+  do {                                                                        \
+    tmem_st_wait();                                                           \
+    fence_before_sync();                                                      \
+    named_bar_sync(bar_id, GROUP);                                            \
+    if (tg == 0) {                                                            \
+      fence_after_sync();                                                     \
+      STMT;                                                                   \
+      mma_commit(mbar);                                                       \
+    }                                                                         \
+  } while (0)
+#define NFB_RTC_FWD(LAYER) NFB_RTC_SYNC_ISSUE((r_issue_fwd<NPASS, LAYER>(tb, sB_addr)))
+#define NFB_RTC_BWD(LAYER) NFB_RTC_SYNC_ISSUE((r_issue_bwd<NPASS, LAYER>(tb, sB_addr)))
+#define NFB_RTC_WAIT()         \
+  do {                         \
+    mbar_wait(mbar, phase);    \
+    phase ^= 1u;               \
+    fence_after_sync();        \
+  } while (0)
+
+struct RayArgs {
+  int R, S;
+  const float* ps;
+  const float* params;
+  const float* pos_enc;
+  float* raw;           // forward output
+  const float* d_raw;   // backward input
+  float* d_ps;          // backward output
+};
+
+template <int NPASS, bool BWD>
+__global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayArgs a) {
+  using C = Cfg<NPASS, BWD>;
+  constexpr int NG = C::NG;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sB = smem_raw;
+  float* sf = reinterpret_cast<float*>(smem_raw + (size_t)R_SET_BYTES * (NPASS == 3 ? 2 : 1));
+  float* s_pos = sf + RF_TOTAL;
+  float* s_grp = s_pos + (size_t)a.S * 16;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_grp + (size_t)NG * C::GROUP_FLOATS);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + NG);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int grp = tid / GROUP, tg = tid % GROUP;
+  float* sk = s_grp + (size_t)grp * C::GROUP_FLOATS;   // [128][16]
+  float* sv = sk + GROUP * 16;
+  float* sq = sv + GROUP * 16;                          // backward only
+  float* sdo = sq + GROUP * 16;
+  float* sst = sdo + GROUP * 16;                        // [128][4] float4 {m2, 1/l, D, valid}
+  const int bar_id = 1 + grp;
+  uint64_t* mbar = s_bar + grp;
+
+  if (warp == 0) tmem_alloc(s_tmem, NG * C::GC);
+  if (tid == 0) {
+    for (int g = 0; g < NG; ++g) mbar_init(s_bar + g, 1);
+    mbar_init_fence();
+  }
+  {
+    const float* p = a.params;
+    load_rtile<NPASS>(sB, RL_GEO0, p + P_GEO0_W, 64, 65, tid, blockDim.x);
+    load_rtile<NPASS>(sB, RL_GEO2, p + P_GEO2_W, 16, 64, tid, blockDim.x);
+    load_rtile<NPASS>(sB, RL_QKV, p + P_ATT_Q, 48, 16, tid, blockDim.x);
+    load_rtile<NPASS>(sB, RL_FC, p + P_ATT_FC, 16, 16, tid, blockDim.x);
+    load_rtile<NPASS>(sB, RL_OG0, p + P_OG0_W, 16, 16, tid, blockDim.x);
+    for (int i = tid; i < 64; i += blockDim.x) {
+      sf[RF_B_GEO0 + i] = __ldg(p + P_GEO0_B + i);
+      sf[RF_WCOL + i] = __ldg(p + P_GEO0_W + i * 65 + 64);
+    }
+    for (int i = tid; i < 16; i += blockDim.x) {
+      sf[RF_B_GEO2 + i] = __ldg(p + P_GEO2_B + i);
+      sf[RF_LNW + i] = __ldg(p + P_LN_W + i);
+      sf[RF_LNB + i] = __ldg(p + P_LN_B + i);
+      sf[RF_B_OG0 + i] = __ldg(p + P_OG0_B + i);
+      sf[RF_W_OG2 + i] = __ldg(p + P_OG2_W + i);
+    }
+    if (tid == 0) sf[RF_B_OG2] = __ldg(p + P_OG2_B);
+    for (int i = tid; i < a.S * 16; i += blockDim.x) s_pos[i] = __ldg(a.pos_enc + i);
+  }
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+
+  const uint32_t tb = *s_tmem + (uint32_t)(grp * C::GC);
+  const uint32_t tl = tb + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t sB_addr = smem_u32(sB);
+  uint32_t phase = 0;
+
+  const int S = a.S;
+  const int RPG = GROUP / S;                       // whole rays per group tile (>= 1)
+  const int rl = tg / S, s = tg - rl * S;          // ray within the tile, sample within the ray
+  const int kb = (rl < RPG ? rl : 0) * S;          // first K / V row of this thread's ray
+  const int ntiles = (a.R + RPG - 1) / RPG;
+
+  for (int tile = blockIdx.x * NG + grp; tile < ntiles; tile += gridDim.x * NG) {
+    const int ray = tile * RPG + rl;
+    const bool act = (rl < RPG) && (ray < a.R);
+    const size_t smp = act ? ((size_t)ray * S + s) : 0;
+    const float* psrow = a.ps + smp * NFB_PS_STRIDE;
+
+    // ---------------- geometry_fc.0 : 64 pooled statistics on the tensor cores, the mean weight on the CUDA cores ----
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+      float t[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 q4 = __ldg(reinterpret_cast<const float4*>(psrow) + 4 * kc + j);
+        t[4 * j] = q4.x; t[4 * j + 1] = q4.y; t[4 * j + 2] = q4.z; t[4 * j + 3] = q4.w;
+      }
+      r_put16<NPASS>(tl, kc, t);
+    }
+    const float4 tail = __ldg(reinterpret_cast<const float4*>(psrow) + 16);   // {mean weight, rgb}
+    const float nvalid = __ldg(psrow + PS_NVALID);
+    const bool row_valid = nvalid > 1.f;
+    NFB_RTC_FWD(RL_GEO0);
+    NFB_RTC_WAIT();
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+      float h[16];
+      r_ld16(tl, 16 * kc, h);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        h[j] = elu_fast(h[j] + fmaf(tail.x, sf[RF_WCOL + 16 * kc + j], sf[RF_B_GEO0 + 16 * kc + j]));
+      if (BWD) {
+        uint32_t q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[j] = elu_stash_pack(h[2 * j], h[2 * j + 1]);
+        tmem_st8(tl + RC_HQ + 8 * kc, q);
+      }
+      r_put16<NPASS>(tl, kc, h);
+    }
+    NFB_RTC_FWD(RL_GEO2);
+    NFB_RTC_WAIT();
+    float xin[16];
+    uint32_t gq[8];
+    {
+      r_ld16(tl, 0, xin);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) xin[j] = elu_fast(xin[j] + sf[RF_B_GEO2 + j]);
+      if (BWD) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gq[j] = elu_stash_pack(xin[2 * j], xin[2 * j + 1]);
+      }
+      const float* pe = s_pos + (act ? s : 0) * 16;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) xin[j] += pe[j];
+      r_put16<NPASS>(tl, 0, xin);
+    }
+    NFB_RTC_FWD(RL_QKV);
+    NFB_RTC_WAIT();
+
+    // ---------------- attention ----------------
+    float q[16];
+    {
+      float kk[16], vv[16];
+      r_ld16(tl, 0, q);
+      r_ld16(tl, 16, kk);
+      r_ld16(tl, 32, vv);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) q[c] *= INV_TEMP * LOG2E;       // scores in the log2 domain
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+        *reinterpret_cast<float4*>(sk + tg * 16 + c) = make_float4(kk[c], kk[c + 1], kk[c + 2], kk[c + 3]);
+        *reinterpret_cast<float4*>(sv + tg * 16 + c) = make_float4(vv[c], vv[c + 1], vv[c + 2], vv[c + 3]);
+      }
+    }
+    named_bar_sync(bar_id, GROUP);
+    float o[16], m2[4], il[4];
+    {
+      const float* kr = sk + kb * 16;
+      const float* vr = sv + kb * 16;
+      if (row_valid) {
+        float mx0 = -3.4e38f, mx1 = -3.4e38f, mx2 = -3.4e38f, mx3 = -3.4e38f;
+        for (int j = 0; j < S; ++j) {
+          const float4 k0 = *reinterpret_cast<const float4*>(kr + j * 16);
+          const float4 k1 = *reinterpret_cast<const float4*>(kr + j * 16 + 4);
+          const float4 k2 = *reinterpret_cast<const float4*>(kr + j * 16 + 8);
+          const float4 k3 = *reinterpret_cast<const float4*>(kr + j * 16 + 12);
+          mx0 = fmaxf(mx0, q[0] * k0.x + q[1] * k0.y + q[2] * k0.z + q[3] * k0.w);
+          mx1 = fmaxf(mx1, q[4] * k1.x + q[5] * k1.y + q[6] * k1.z + q[7] * k1.w);
+          mx2 = fmaxf(mx2, q[8] * k2.x + q[9] * k2.y + q[10] * k2.z + q[11] * k2.w);
+          mx3 = fmaxf(mx3, q[12] * k3.x + q[13] * k3.y + q[14] * k3.z + q[15] * k3.w);
+        }
+        m2[0] = mx0; m2[1] = mx1; m2[2] = mx2; m2[3] = mx3;
+      } else {
+        m2[0] = m2[1] = m2[2] = m2[3] = 0.f;
+      }
+      float l[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 16; ++c) o[c] = 0.f;
+      for (int j = 0; j < S; ++j) {
+        float p[4] = {1.f, 1.f, 1.f, 1.f};     // masked_fill(mask == 0, -1e9) on a whole query row = uniform attention
+        if (row_valid) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const float4 k = *reinterpret_cast<const float4*>(kr + j * 16 + 4 * h);
+            const float sc = q[4 * h] * k.x + q[4 * h + 1] * k.y + q[4 * h + 2] * k.z + q[4 * h + 3] * k.w;
+            p[h] = ex2_approx(sc - m2[h]);
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float4 vj = *reinterpret_cast<const float4*>(vr + j * 16 + 4 * h);
+          l[h] += p[h];
+          o[4 * h] = fmaf(p[h], vj.x, o[4 * h]);
+          o[4 * h + 1] = fmaf(p[h], vj.y, o[4 * h + 1]);
+          o[4 * h + 2] = fmaf(p[h], vj.z, o[4 * h + 2]);
+          o[4 * h + 3] = fmaf(p[h], vj.w, o[4 * h + 3]);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        il[h] = 1.f / l[h];
+        o[4 * h] *= il[h]; o[4 * h + 1] *= il[h]; o[4 * h + 2] *= il[h]; o[4 * h + 3] *= il[h];
+      }
+    }
+
+    // ---------------- fc + residual + LayerNorm + sigma head ----------------
+    r_put16<NPASS>(tl, 0, o);
+    NFB_RTC_FWD(RL_FC);
+    NFB_RTC_WAIT();
+    float xhat[16];
+    float rstd;
+    {
+      float y[16];
+      r_ld16(tl, 0, y);
+      float mu = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        y[c] += xin[c];
+        mu += y[c];
+      }
+      mu *= (1.f / 16.f);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) var = fmaf(y[c] - mu, y[c] - mu, var);
+      var *= (1.f / 16.f);
+      rstd = rsqrtf(var + LN_EPS);
+      float ln[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        xhat[c] = (y[c] - mu) * rstd;
+        ln[c] = fmaf(xhat[c], sf[RF_LNW + c], sf[RF_LNB + c]);
+      }
+      r_put16<NPASS>(tl, 0, ln);
+    }
+    NFB_RTC_FWD(RL_OG0);
+    NFB_RTC_WAIT();
+    float hh[16];
+    float z2 = sf[RF_B_OG2];
+    r_ld16(tl, 0, hh);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      hh[c] = elu_fast(hh[c] + sf[RF_B_OG0 + c]);
+      z2 = fmaf(hh[c], sf[RF_W_OG2 + c], z2);
+    }
+
+    if (!BWD) {
+      float sigma = fmaxf(z2, 0.f);
+      if (nvalid < 1.f) sigma = 0.f;                     // mlp_network.py:265
+      if (act) reinterpret_cast<float4*>(a.raw)[smp] = make_float4(tail.y, tail.z, tail.w, sigma);
+      named_bar_sync(bar_id, GROUP);                     // K / V rows are rewritten by the next tile
+      continue;
+    }
+
+    // =================================== backward ===================================
+    if (BWD) {
+      float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (act) dr = __ldg(reinterpret_cast<const float4*>(a.d_raw) + smp);
+      const float dz2 = (z2 > 0.f && !(nvalid < 1.f)) ? dr.w : 0.f;
+      // sigma head
+      {
+        float dh[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) dh[k] = dz2 * sf[RF_W_OG2 + k] * elu_grad_from_out(hh[k]);
+        r_put16<NPASS>(tl, 0, dh);
+      }
+      NFB_RTC_BWD(RL_OG0);
+      NFB_RTC_WAIT();
+      // LayerNorm backward: dy = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dln * gamma
+      float dy[16];
+      {
+        r_ld16(tl, 0, dy);
+        float gsum = 0.f, gx = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          dy[c] *= sf[RF_LNW + c];
+          gsum += dy[c];
+          gx = fmaf(dy[c], xhat[c], gx);
+        }
+        gsum *= (1.f / 16.f); gx *= (1.f / 16.f);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) dy[c] = rstd * (dy[c] - gsum - xhat[c] * gx);
+        r_put16<NPASS>(tl, 0, dy);
+      }
+      NFB_RTC_BWD(RL_FC);
+      NFB_RTC_WAIT();
+      float dO[16];
+      r_ld16(tl, 0, dO);
+      float Dh[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h)
+        Dh[h] = dO[4 * h] * o[4 * h] + dO[4 * h + 1] * o[4 * h + 1] + dO[4 * h + 2] * o[4 * h + 2] + dO[4 * h + 3] * o[4 * h + 3];
+      // publish per-query quantities for the key-side pass
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+        *reinterpret_cast<float4*>(sq + tg * 16 + c) = make_float4(q[c], q[c + 1], q[c + 2], q[c + 3]);
+        *reinterpret_cast<float4*>(sdo + tg * 16 + c) = make_float4(dO[c], dO[c + 1], dO[c + 2], dO[c + 3]);
+      }
+#pragma unroll
+      for (int h = 0; h < 4; ++h)
+        *reinterpret_cast<float4*>(sst + (tg * 4 + h) * 4) = make_float4(m2[h], il[h], Dh[h], row_valid ? 1.f : 0.f);
+      named_bar_sync(bar_id, GROUP);
+
+      float dqkv[48];
+#pragma unroll
+      for (int c = 0; c < 48; ++c) dqkv[c] = 0.f;
+      // query side: dq_i = sum_j dS_ij k_j  (zero for masked rows: masked_fill blocks the gradient)
+      if (row_valid) {
+        const float* kr = sk + kb * 16;
+        const float* vr = sv + kb * 16;
+        for (int j = 0; j < S; ++j) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const float4 k = *reinterpret_cast<const float4*>(kr + j * 16 + 4 * h);
+            const float4 vj = *reinterpret_cast<const float4*>(vr + j * 16 + 4 * h);
+            const float sc = q[4 * h] * k.x + q[4 * h + 1] * k.y + q[4 * h + 2] * k.z + q[4 * h + 3] * k.w;
+            const float pj = ex2_approx(sc - m2[h]) * il[h];
+            const float dP = dO[4 * h] * vj.x + dO[4 * h + 1] * vj.y + dO[4 * h + 2] * vj.z + dO[4 * h + 3] * vj.w;
+            const float dS = pj * (dP - Dh[h]);
+            dqkv[4 * h] = fmaf(dS, k.x, dqkv[4 * h]);
+            dqkv[4 * h + 1] = fmaf(dS, k.y, dqkv[4 * h + 1]);
+            dqkv[4 * h + 2] = fmaf(dS, k.z, dqkv[4 * h + 2]);
+            dqkv[4 * h + 3] = fmaf(dS, k.w, dqkv[4 * h + 3]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) dqkv[c] *= INV_TEMP;
+      }
+      // key side: dk_j = sum_i dS_ij q_i ; dv_j = sum_i p_ij dO_i   (this thread is key j)
+      {
+        const float invS = 1.f / (float)S;
+        float kk[16], vv[16];
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) {
+          const float4 k4 = *reinterpret_cast<const float4*>(sk + tg * 16 + c);
+          const float4 v4 = *reinterpret_cast<const float4*>(sv + tg * 16 + c);
+          kk[c] = k4.x; kk[c + 1] = k4.y; kk[c + 2] = k4.z; kk[c + 3] = k4.w;
+          vv[c] = v4.x; vv[c + 1] = v4.y; vv[c + 2] = v4.z; vv[c + 3] = v4.w;
+        }
+        const float* qr = sq + kb * 16;
+        const float* dr_ = sdo + kb * 16;
+        const float* st = sst + kb * 16;
+        for (int i = 0; i < S; ++i) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const float4 qi = *reinterpret_cast<const float4*>(qr + i * 16 + 4 * h);
+            const float4 di = *reinterpret_cast<const float4*>(dr_ + i * 16 + 4 * h);
+            const float4 sti = *reinterpret_cast<const float4*>(st + (i * 4 + h) * 4);
+            float pij = invS, dS = 0.f;
+            if (sti.w != 0.f) {
+              const float sc = qi.x * kk[4 * h] + qi.y * kk[4 * h + 1] + qi.z * kk[4 * h + 2] + qi.w * kk[4 * h + 3];
+              pij = ex2_approx(sc - sti.x) * sti.y;
+              const float dP = di.x * vv[4 * h] + di.y * vv[4 * h + 1] + di.z * vv[4 * h + 2] + di.w * vv[4 * h + 3];
+              dS = pij * (dP - sti.z);
+            }
+            // q in shared memory carries the 0.5 * log2(e) score scale; d k = sum dS * q_scaled / log2(e)
+            dqkv[16 + 4 * h] = fmaf(dS, qi.x, dqkv[16 + 4 * h]);
+            dqkv[16 + 4 * h + 1] = fmaf(dS, qi.y, dqkv[16 + 4 * h + 1]);
+            dqkv[16 + 4 * h + 2] = fmaf(dS, qi.z, dqkv[16 + 4 * h + 2]);
+            dqkv[16 + 4 * h + 3] = fmaf(dS, qi.w, dqkv[16 + 4 * h + 3]);
+            dqkv[32 + 4 * h] = fmaf(pij, di.x, dqkv[32 + 4 * h]);
+            dqkv[32 + 4 * h + 1] = fmaf(pij, di.y, dqkv[32 + 4 * h + 1]);
+            dqkv[32 + 4 * h + 2] = fmaf(pij, di.z, dqkv[32 + 4 * h + 2]);
+            dqkv[32 + 4 * h + 3] = fmaf(pij, di.w, dqkv[32 + 4 * h + 3]);
+          }
+        }
+#pragma unroll
+        for (int c = 16; c < 32; ++c) dqkv[c] *= (1.f / LOG2E);
+      }
+      // d xin = dy (residual) + [dq | dk | dv] Wqkv ; pos_encoding is a constant
+#pragma unroll
+      for (int kc = 0; kc < 3; ++kc) {
+        float t[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) t[j] = dqkv[16 * kc + j];
+        r_put16<NPASS>(tl, kc, t);
+      }
+      NFB_RTC_BWD(RL_QKV);
+      NFB_RTC_WAIT();
+      {
+        float dx[16];
+        r_ld16(tl, 0, dx);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dx[2 * j] = (dx[2 * j] + dy[2 * j]) * elu_stash_lo(gq[j]);
+          dx[2 * j + 1] = (dx[2 * j + 1] + dy[2 * j + 1]) * elu_stash_hi(gq[j]);
+        }
+        r_put16<NPASS>(tl, 0, dx);
+      }
+      NFB_RTC_BWD(RL_GEO2);
+      NFB_RTC_WAIT();
+      float dwm = 0.f;
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        float dh[16];
+        r_ld16(tl, 16 * kc, dh);
+        uint32_t qc[8];
+        tmem_ld8u(tl + RC_HQ + 8 * kc, qc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dh[2 * j] *= elu_stash_lo(qc[j]);
+          dh[2 * j + 1] *= elu_stash_hi(qc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dwm = fmaf(dh[j], sf[RF_WCOL + 16 * kc + j], dwm);
+        r_put16<NPASS>(tl, kc, dh);
+      }
+      NFB_RTC_BWD(RL_GEO0);
+      NFB_RTC_WAIT();
+      {
+        float4* out = reinterpret_cast<float4*>(a.d_ps + smp * NFB_PS_STRIDE);
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+          float t[16];
+          r_ld16(tl, 16 * kc, t);
+          if (act) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[4 * kc + j] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
+          }
+        }
+        if (act) {
+          out[16] = make_float4(dwm, dr.x, dr.y, dr.z);
+          out[17] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      named_bar_sync(bar_id, GROUP);                     // K / V / Q / dO rows are rewritten by the next tile
+    }
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(*s_tmem, NG * C::GC);
+}
+
+template <int NPASS, bool BWD>
+int launch_ray_tc(const RayArgs& a, cudaStream_t st) {
+  using C = Cfg<NPASS, BWD>;
+  const size_t smem = C::smem(a.S);
+  cudaError_t e = cudaFuncSetAttribute(k_ray_tc<NPASS, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return nfb_set_error(NFB_ECUDA, "k_ray_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  const int RPG = GROUP / a.S;
+  const int ntiles = (a.R + RPG - 1) / RPG;
+  int grid = (ntiles + C::NG - 1) / C::NG;
+  const int cap = nfb_num_sms();
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  k_ray_tc<NPASS, BWD><<<grid, GROUP * C::NG, smem, st>>>(a);
+  NFB_CHECK_LAUNCH("k_ray_tc");
+  return NFB_OK;
+}
+
+}  // namespace nfbrtc
+
+// defined in nfb_ray_tc_inst.cu (one instantiation per translation unit)
+int nfb_launch_ray_tc_fwd_p1(const nfbrtc::RayArgs& a, cudaStream_t st);
+int nfb_launch_ray_tc_fwd_p3(const nfbrtc::RayArgs& a, cudaStream_t st);
+int nfb_launch_ray_tc_bwd_p1(const nfbrtc::RayArgs& a, cudaStream_t st);
+int nfb_launch_ray_tc_bwd_p3(const nfbrtc::RayArgs& a, cudaStream_t st);

@@ -155,7 +155,7 @@ class IBRNetAggregate(torch.autograd.Function):
             st = stream_ptr(dev)
             call('nfb_ibrnet_view_fwd', N, S, V, int(anti_alias), ptr(rf), ptr(rd), ptr(mk), 0, 0, 0, 0,
                  None, None, None, None, None, None, None, ptr(params), ptr(ps), _lib.precision_code(), st)
-            call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), st)
+            call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), _lib.precision_code(), st)
         ctx.save_for_backward(rf, rd, mk, params, pos_enc, ps)
         ctx.dims = (R, S, V, int(anti_alias))
         ctx.precision = _lib.precision_code()
@@ -174,7 +174,7 @@ class IBRNetAggregate(torch.autograd.Function):
             d_rf = torch.empty_like(rf)
             with torch.cuda.device(dev):
                 st = stream_ptr(dev)
-                call('nfb_ibrnet_ray_bwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(g), ptr(d_ps), st)
+                call('nfb_ibrnet_ray_bwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(g), ptr(d_ps), ctx.precision, st)
                 call('nfb_ibrnet_view_bwd', N, S, V, aa, ptr(rf), ptr(rd), ptr(mk), 0, 0, 0, 0,
                      None, None, None, None, None, None, None, ptr(params), ptr(ps), ptr(d_ps),
                      ptr(d_rf), None, None, ctx.precision, st)
@@ -289,7 +289,7 @@ class RenderLevel(torch.autograd.Function):
             call('nfb_ibrnet_view_fwd', N, S, V, int(anti_alias), None, None, None, H, W, fh, fw,
                  None, ptr(o_c), ptr(d_c), ptr(z_c), ptr(cam), ptr(imgs_c), ptr(feat), ptr(params), ptr(ps),
                  _lib.precision_code(), st)
-            call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), st)
+            call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), _lib.precision_code(), st)
             call('nfb_composite_fwd', R, S, int(white_bkgd), ptr(raw), ptr(z_c), None, ptr(ps[:, 68:]), PS_STRIDE,
                  ptr(rgb), ptr(depth), ptr(weights), ptr(alpha), ptr(ray_mask), st)
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
@@ -318,7 +318,7 @@ class RenderLevel(torch.autograd.Function):
             st = stream_ptr(dev)
             call('nfb_composite_bwd', R, S, white, ptr(raw), ptr(z_c), ptr(f32c(d_rgb)), ptr(f32c(d_depth)),
                  ptr(f32c(d_weights)), ptr(f32c(d_alpha)), ptr(d_raw), st)
-            call('nfb_ibrnet_ray_bwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(d_raw), ptr(d_ps), st)
+            call('nfb_ibrnet_ray_bwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(d_raw), ptr(d_ps), ctx.precision, st)
             call('nfb_ibrnet_view_bwd', N, S, V, aa, None, None, None, H, W, fh, fw,
                  None, ptr(o_c), ptr(d_c), ptr(z_c), ptr(cam), ptr(imgs_c), ptr(feat), ptr(params), ptr(ps),
                  ptr(d_ps), None, ptr(d_feat), ptr(d_imgs), ctx.precision, st)

@@ -169,7 +169,10 @@ def test_ibrnet_golden_and_no_anti_alias(dev):
     net.anti_alias_pooling = 0
     raw0 = net(t(g['rgb_feat_c']).to(dev), t(g['ray_diff_c']).to(dev), t(g['mask_c']).to(dev))
     ref0 = O.ibrnet_forward(p, p['pos_encoding'], t(g['rgb_feat_c']), t(g['ray_diff_c']), t(g['mask_c']), anti_alias_pooling=False)
-    assert maxabs(raw0.cpu(), ref0) < 2e-5
+    ref0_64 = O.ibrnet_forward(_dbl(p), p['pos_encoding'].double(), t(g['rgb_feat_c']).double(), t(g['ray_diff_c']).double(),
+                               t(g['mask_c']).double(), anti_alias_pooling=False)
+    # bf16x3 tensor-core layers + ex2.approx activations: a few 1e-5 on O(1) sigma, well inside the 1e-4 north-star bound
+    _within_truth(raw0, ref0, ref0_64, 5e-5, 'raw (mean pooling)')
 
 
 def test_ibrnet_all_views_masked_and_single_valid(dev):
