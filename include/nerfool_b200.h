@@ -97,12 +97,18 @@ int nfb_project_gather_bwd(int N, int S, int V, int H, int W, int fh, int fw,
  * View-stage input is EITHER the materialised tensors (rgb_feat/ray_diff/mask as Projector.compute
  * returns them) OR, in fused mode (rgb_feat == NULL), the geometry arguments of nfb_project_gather_fwd:
  * the kernel then projects and gathers on the fly and [N][V][35] is never written.                     */
+/* Activation stash (optional, fused tensor-core forms only): when `stash` is non-NULL the forward also writes what the
+ * data-gradient needs per (sample, view) row -- x0, x2, a few scalars and 16-bit ELU-derivative codes, 768 B per
+ * row -- and nfb_ibrnet_view_bwd given the same buffer runs as a pure backward instead of recomputing the forward
+ * (on a B200 the 2 x 768 B/row of HBM traffic is several times cheaper than the recompute).  The caller allocates
+ * nfb_view_stash_bytes(N, V) bytes (16-byte aligned) and keeps them until the backward has run. */
+size_t nfb_view_stash_bytes(int N, int V);
 int nfb_ibrnet_view_fwd(int N, int S, int V, int anti_alias,
                         const float* rgb_feat, const float* ray_diff, const float* mask,
                         int H, int W, int fh, int fw,
                         const float* xyz, const float* ray_o, const float* ray_d, const float* z,
                         const float* cam, const float* imgs, const float* feat,
-                        const float* params, float* ps, int precision, void* stream);
+                        const float* params, float* ps, float* stash, int precision, void* stream);
 int nfb_ibrnet_ray_fwd(int R, int S, const float* ps, const float* params, const float* pos_enc /*[S][16]*/,
                        float* raw /*[R][S][4]*/, int precision, void* stream);
 /* Backward (data gradients): d_raw[R][S][4] -> d_ps[N][72] -> d_rgb_feat[N][V][35] (tensor mode) or a
@@ -115,7 +121,8 @@ int nfb_ibrnet_view_bwd(int N, int S, int V, int anti_alias,
                         const float* xyz, const float* ray_o, const float* ray_d, const float* z,
                         const float* cam, const float* imgs, const float* feat,
                         const float* params, const float* ps, const float* d_ps,
-                        float* d_rgb_feat, float* d_feat, float* d_imgs, int precision, void* stream);
+                        float* d_rgb_feat, float* d_feat, float* d_imgs, const float* stash, int precision,
+                        void* stream);
 
 /* ---- raw2outputs  (render_ray.py:123-170) ------------------------------------------------------------
  * pixel_mask: uint8 [R][S] (the `mask` argument), or NULL with n_valid (stride n_valid_stride floats per

@@ -22,16 +22,16 @@ _SIGNATURES = {
     'nfb_coarse_depths': [_I, _I, c_float, c_float, _I, _P, _P, _P],
     'nfb_project_gather_fwd': [_I] * 7 + [_P] * 11,
     'nfb_project_gather_bwd': [_I] * 7 + [_P] * 9,
-    'nfb_ibrnet_view_fwd': [_I] * 4 + [_P] * 3 + [_I] * 4 + [_P] * 9 + [_I, _P],
+    'nfb_ibrnet_view_fwd': [_I] * 4 + [_P] * 3 + [_I] * 4 + [_P] * 10 + [_I, _P],
     'nfb_ibrnet_ray_fwd': [_I, _I, _P, _P, _P, _P, _I, _P],
     'nfb_ibrnet_ray_bwd': [_I, _I, _P, _P, _P, _P, _P, _I, _P],
-    'nfb_ibrnet_view_bwd': [_I] * 4 + [_P] * 3 + [_I] * 4 + [_P] * 13 + [_I, _P],
+    'nfb_ibrnet_view_bwd': [_I] * 4 + [_P] * 3 + [_I] * 4 + [_P] * 14 + [_I, _P],
     'nfb_composite_fwd': [_I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     'nfb_composite_bwd': [_I, _I, _I] + [_P] * 8,
     'nfb_sample_pdf': [_I, _I, _I, _P, _P, _P, _I, _P, _P, _P],
     'nfb_fine_depths': [_I, _I, _I, _I, _P, _P, _P, _I, _P, _P],
 }
-EXPORTS = ['nfb_version', 'nfb_last_error_string', 'nfb_ibrnet_param_offset'] + list(_SIGNATURES)
+EXPORTS = ['nfb_version', 'nfb_last_error_string', 'nfb_ibrnet_param_offset', 'nfb_view_stash_bytes'] + list(_SIGNATURES)
 
 _lib = None
 
@@ -56,6 +56,19 @@ def precision_code() -> int:
     return _precision
 
 
+# Largest activation stash (GiB, per render level) the fused backward may allocate; beyond it the backward recomputes
+# the forward instead (include/nerfool_b200.h: nfb_view_stash_bytes).  0 disables the stash.
+STASH_MAX_GIB = float(os.environ.get('NFB_STASH_MAX_GIB', '48'))
+
+
+def stash_bytes(N: int, V: int) -> int:
+    """Size of the activation stash for N samples x V views, or 0 when it is disabled / too large / fp32 mode."""
+    if _precision == PRECISIONS['fp32'] or STASH_MAX_GIB <= 0:
+        return 0
+    n = int(load().nfb_view_stash_bytes(int(N), int(V)))
+    return n if n <= STASH_MAX_GIB * 2 ** 30 else 0
+
+
 def load():
     """Load (once) and return the ctypes library handle."""
     global _lib
@@ -72,6 +85,8 @@ def load():
     lib.nfb_last_error_string.argtypes = []
     lib.nfb_ibrnet_param_offset.restype = c_int
     lib.nfb_ibrnet_param_offset.argtypes = [c_char_p]
+    lib.nfb_view_stash_bytes.restype = ctypes.c_size_t
+    lib.nfb_view_stash_bytes.argtypes = [c_int, c_int]
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int

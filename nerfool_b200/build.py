@@ -35,6 +35,10 @@ UNITS = [
     ('nfb_view_tc_bwd_inst1', 'nfb_view_tc_bwd_inst.cu', ['-DNFB_VTCB_INST=1']),
     ('nfb_view_tc_bwd_inst2', 'nfb_view_tc_bwd_inst.cu', ['-DNFB_VTCB_INST=2']),
     ('nfb_view_tc_bwd_inst3', 'nfb_view_tc_bwd_inst.cu', ['-DNFB_VTCB_INST=3']),
+    ('nfb_view_tc_bwd2_inst0', 'nfb_view_tc_bwd2_inst.cu', ['-DNFB_VTCS_INST=0']),
+    ('nfb_view_tc_bwd2_inst1', 'nfb_view_tc_bwd2_inst.cu', ['-DNFB_VTCS_INST=1']),
+    ('nfb_view_tc_bwd2_inst2', 'nfb_view_tc_bwd2_inst.cu', ['-DNFB_VTCS_INST=2']),
+    ('nfb_view_tc_bwd2_inst3', 'nfb_view_tc_bwd2_inst.cu', ['-DNFB_VTCS_INST=3']),
     ('nfb_ray_tc_inst0', 'nfb_ray_tc_inst.cu', ['-DNFB_RTC_INST=0']),
     ('nfb_ray_tc_inst1', 'nfb_ray_tc_inst.cu', ['-DNFB_RTC_INST=1']),
     ('nfb_ray_tc_inst2', 'nfb_ray_tc_inst.cu', ['-DNFB_RTC_INST=2']),

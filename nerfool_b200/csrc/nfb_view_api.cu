@@ -2,6 +2,7 @@
 #include "nfb_view_stage.cuh"
 #include "nfb_view_tc.cuh"
 #include "nfb_view_tc_bwd.cuh"
+#include "nfb_view_tc_bwd2.cuh"
 using nfbview::ViewArgs;
 
 static int check_view_args(const char* who, int N, int S, int V, const float* rgb_feat, const float* ray_diff,
@@ -26,11 +27,17 @@ static int check_view_args(const char* who, int N, int S, int V, const float* rg
   return NFB_OK;
 }
 
+extern "C" size_t nfb_view_stash_bytes(int N, int V) {
+  if (N <= 0 || V < 1 || V > NFB_MAX_VIEWS) return 0;
+  const int TS = (nfbvtc::GROUP / V < nfbvtc::TS_MAX) ? nfbvtc::GROUP / V : nfbvtc::TS_MAX;
+  return (size_t)((N + TS - 1) / TS) * nfbvtc::ST_TILE_BYTES;
+}
+
 extern "C" int nfb_ibrnet_view_fwd(int N, int S, int V, int anti_alias, const float* rgb_feat, const float* ray_diff,
                                    const float* mask, int H, int W, int fh, int fw, const float* xyz,
                                    const float* ray_o, const float* ray_d, const float* z, const float* cam,
                                    const float* imgs, const float* feat, const float* params, float* ps,
-                                   int precision, void* stream) {
+                                   float* stash, int precision, void* stream) {
   int rc = check_view_args("nfb_ibrnet_view_fwd", N, S, V, rgb_feat, ray_diff, mask, H, W, fh, fw, xyz, ray_o, ray_d,
                            z, cam, imgs, feat, params);
   if (rc) return rc;
@@ -44,6 +51,13 @@ extern "C" int nfb_ibrnet_view_fwd(int N, int S, int V, int anti_alias, const fl
   a.pts = PointSrc{xyz, ray_o, ray_d, z, S};
   a.cam = cam; a.imgs = imgs; a.feat = feat; a.params = params; a.ps = ps;
   cudaStream_t st = (cudaStream_t)stream;
+  if (stash) {
+    NFB_REQUIRE(!rgb_feat && precision != NFB_PREC_FP32, NFB_EUNSUPPORTED,
+                "nfb_ibrnet_view_fwd: the activation stash exists for the fused tensor-core forms only");
+    NFB_REQUIRE(((uintptr_t)stash % 16) == 0, NFB_EINVAL, "nfb_ibrnet_view_fwd: stash must be 16-byte aligned");
+    a.stash = stash;
+    return precision == NFB_PREC_BF16 ? nfb_launch_view_tc_fwd_p1_fused_save(a, st) : nfb_launch_view_tc_fwd_p3_fused_save(a, st);
+  }
   if (precision == NFB_PREC_BF16X3) return rgb_feat ? nfb_launch_view_tc_fwd_p3_tensor(a, st) : nfb_launch_view_tc_fwd_p3_fused(a, st);
   if (precision == NFB_PREC_BF16) return rgb_feat ? nfb_launch_view_tc_fwd_p1_tensor(a, st) : nfb_launch_view_tc_fwd_p1_fused(a, st);
   if (rgb_feat) return nfb_launch_view_tensor_fwd(a, st);
@@ -55,7 +69,7 @@ extern "C" int nfb_ibrnet_view_bwd(int N, int S, int V, int anti_alias, const fl
                                    const float* ray_o, const float* ray_d, const float* z, const float* cam,
                                    const float* imgs, const float* feat, const float* params, const float* ps,
                                    const float* d_ps, float* d_rgb_feat, float* d_feat, float* d_imgs,
-                                   int precision, void* stream) {
+                                   const float* stash, int precision, void* stream) {
   int rc = check_view_args("nfb_ibrnet_view_bwd", N, S, V, rgb_feat, ray_diff, mask, H, W, fh, fw, xyz, ray_o, ray_d,
                            z, cam, imgs, feat, params);
   if (rc) return rc;
@@ -75,6 +89,13 @@ extern "C" int nfb_ibrnet_view_bwd(int N, int S, int V, int anti_alias, const fl
   a.d_ps = d_ps; a.d_rgb_feat = d_rgb_feat; a.d_feat = d_feat; a.d_imgs = d_imgs;
   NFB_REQUIRE(((uintptr_t)ps % 16) == 0 && ((uintptr_t)d_ps % 16) == 0, NFB_EINVAL, "nfb_ibrnet_view_bwd: ps / d_ps must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  if (stash) {
+    NFB_REQUIRE(!rgb_feat && precision != NFB_PREC_FP32, NFB_EUNSUPPORTED,
+                "nfb_ibrnet_view_bwd: the activation stash exists for the fused tensor-core forms only");
+    NFB_REQUIRE(((uintptr_t)stash % 16) == 0, NFB_EINVAL, "nfb_ibrnet_view_bwd: stash must be 16-byte aligned");
+    a.stash = const_cast<float*>(stash);
+    return precision == NFB_PREC_BF16 ? nfb_launch_view_tc_bwd_stash_p1(a, st) : nfb_launch_view_tc_bwd_stash_p3(a, st);
+  }
   if (precision == NFB_PREC_BF16X3) return rgb_feat ? nfb_launch_view_tc_bwd_p3_tensor(a, st) : nfb_launch_view_tc_bwd_p3_fused(a, st);
   if (precision == NFB_PREC_BF16) return rgb_feat ? nfb_launch_view_tc_bwd_p1_tensor(a, st) : nfb_launch_view_tc_bwd_p1_fused(a, st);
   if (rgb_feat) return nfb_launch_view_tensor_bwd(a, st);

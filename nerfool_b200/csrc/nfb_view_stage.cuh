@@ -86,6 +86,8 @@ struct ViewArgs {
   // backward only
   const float* d_ps;
   float* d_rgb_feat; float* d_feat; float* d_imgs;
+  // tensor-core fused mode: activation stash written by the forward, read by the backward (nfb_view_tc.cuh)
+  float* stash;
 };
 
 // ---------------------------------------------------------------------------------------------------

@@ -187,6 +187,60 @@ __device__ __forceinline__ float base0_in(int k, const float* __restrict__ mvs, 
   return 0.f;
 }
 
+// ---- activation stash (forward with SAVE -> nfb_view_tc_bwd2.cuh) ----------------------------------------
+// What the data-gradient needs from the forward, written once instead of recomputed: per 128-row tile
+// ST_PLANES planes of [128 rows][4 words] (a thread's 16-byte vector sits next to its neighbours': coalesced).
+//   planes  0..8   x0 = rgb_feat + direction_feat (35 fp32, 1 pad)
+//   planes  9..16  x2 (32 fp32)
+//   plane   17     w, mask, sigmoid(vis_fc.2[32]), sigmoid(vis_fc2)
+//   plane   18     blending logit, grid x, grid y, rgb_in[0]
+//   plane   19     rgb_in[1], rgb_in[2], ELU' code of vis_fc.2[32], pad
+//   planes 20..27  ELU' codes of h1 (base_fc.0 out, 64)      28..31 x1 (base_fc.2 out, 32)
+//   planes 32..35  hv (vis_fc.0 out, 32)   36..39 xv[0..32) (vis_fc.2 out)   40..43 hv2 (vis_fc2.0 out, 32)
+//   planes 44..45  g1 (rgb_fc.0 out, 16)   46 g2 (rgb_fc.2 out, 8)   47 spare
+enum : int { SP_X0 = 0, SP_X2 = 9, SP_SA = 17, SP_SB = 18, SP_SC = 19, SP_H1 = 20, SP_X1 = 28, SP_HV = 32, SP_XV = 36,
+             SP_HV2 = 40, SP_G1 = 44, SP_G2 = 46, ST_PLANES = 48 };
+constexpr size_t ST_TILE_BYTES = (size_t)ST_PLANES * GROUP * 16;   // 98304
+
+// ELU and the 16-bit code of its derivative from one exponential: y = max(x, min(e - 1, 0)), ELU' = min(e, 1) = 2 - t
+// with t = max(1.9999999 - e, 1) in [1, 2) (nfb_tc.cuh: elu_stash_*)
+__device__ __forceinline__ void elu_with_t(float x, float& y, float& t) {
+  const float e = ex2_approx(x * 1.4426950408889634f);
+  y = fmaxf(x, fminf(e - 1.f, 0.f));
+  t = fmaxf(1.9999999f - e, 1.f);
+}
+__device__ __forceinline__ uint32_t pack_t(float t0, float t1) {
+  return __byte_perm(__float_as_uint(t0), __float_as_uint(t1), 0x6521);
+}
+// y[j] = ELU(D[col + j] + bias[j]) and the derivative codes of the 16 outputs
+__device__ __forceinline__ void epi16_code(uint32_t tl, int col, const float* __restrict__ bias, float (&y)[16], uint32_t (&q)[8]) {
+  tmem_ld16(tl + C_D + col, y);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + j);
+    float t0, t1, t2, t3;
+    elu_with_t(y[j + 0] + b.x, y[j + 0], t0);
+    elu_with_t(y[j + 1] + b.y, y[j + 1], t1);
+    elu_with_t(y[j + 2] + b.z, y[j + 2], t2);
+    elu_with_t(y[j + 3] + b.w, y[j + 3], t3);
+    q[j / 2] = pack_t(t0, t1);
+    q[j / 2 + 1] = pack_t(t2, t3);
+  }
+}
+template <bool SAVE>
+__device__ __forceinline__ void epi16_s(uint32_t tl, int col, const float* __restrict__ bias, float (&y)[16], uint32_t (&q)[8]) {
+  if (SAVE) epi16_code(tl, col, bias, y, q);
+  else epi16(tl, col, bias, y);
+}
+__device__ __forceinline__ void st_plane(float4* sp, int plane, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  sp[plane * GROUP] = make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d));
+}
+__device__ __forceinline__ void st_codes8(float4* sp, int plane, const uint32_t (&q)[8]) {
+  st_plane(sp, plane, q[0], q[1], q[2], q[3]);
+  st_plane(sp, plane + 1, q[4], q[5], q[6], q[7]);
+}
+
 // all threads of the group: publish the A stores, let thread 0 issue + commit
 #define NFB_TC_ISSUE(LAYER, KS0, KS1, ACC0)                                   \
   do {                                                                        \
@@ -210,7 +264,7 @@ __device__ __forceinline__ float base0_in(int k, const float* __restrict__ mvs, 
 // forward kernel.  FUSED: rows come from projection + bilinear gather; otherwise from the materialised
 // Projector.compute tensors (rgb_feat / ray_diff / mask).
 // ---------------------------------------------------------------------------------------------------
-template <int NPASS, bool FUSED>
+template <int NPASS, bool FUSED, bool SAVE>
 __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sB = smem_raw;
@@ -271,11 +325,14 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
     const int base = active ? sl * V : 0;
     float* mvs = mv + (active ? sl : 0) * MVS;
     uint32_t* mvps = mvp + (active ? sl : 0) * MVP;
+    float4* sp = reinterpret_cast<float4*>(a.stash) + (size_t)tile * (ST_PLANES * GROUP) + tg;
+    const bool save = SAVE && active;
 
     // ---------------- projection, ray_diff, bilinear gather ----------------
     float x[NFB_ROW_CH];
     float rd[4];
     float mk = 0.f;
+    float ggx = 0.f, ggy = 0.f;
     if (FUSED) {
       if (active) {
         float X, Y, Z;
@@ -283,7 +340,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
         const ViewGeom g = view_geometry(X, Y, Z, s_cam + 16 * v, s_cam + 16 * V, Wm1, Hm1);
         gather_row(g, v, a.H, a.W, a.fh, a.fw, a.imgs, a.feat, x);
         rd[0] = g.rd[0]; rd[1] = g.rd[1]; rd[2] = g.rd[2]; rd[3] = g.rd[3];
-        mk = g.mask;
+        mk = g.mask; ggx = g.gx; ggy = g.gy;
       } else {
 #pragma unroll
         for (int c = 0; c < NFB_ROW_CH; ++c) x[c] = 0.f;
@@ -356,6 +413,11 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
         if (c0 + j < NFB_ROW_CH) x[c0 + j] += df[j];
     }
 
+    if (save) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sp[(SP_X0 + j) * GROUP] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+      sp[(SP_X0 + 8) * GROUP] = make_float4(x[32], x[33], x[34], 0.f);
+    }
     // ---------------- first pooling: weighted mean / variance over views ----------------
 #pragma unroll
     for (int c = 0; c < NFB_ROW_CH; ++c) ex[tg * EXS + c] = x[c];
@@ -432,7 +494,9 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
 #pragma unroll
     for (int kc = 0; kc < 4; ++kc) {
       float h[16];
-      epi16(tl, 16 * kc, sf + F_B_BASE0 + 16 * kc, h);
+      uint32_t q[8];
+      epi16_s<SAVE>(tl, 16 * kc, sf + F_B_BASE0 + 16 * kc, h, q);
+      if (save) st_codes8(sp, SP_H1 + 2 * kc, q);
       a_store16<NPASS>(tl, kc, h);
     }
     NFB_TC_ISSUE(L_BASE2, 0, 4, false);
@@ -443,7 +507,9 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
 #pragma unroll
     for (int kc = 0; kc < 2; ++kc) {
       float h[16];
-      epi16(tl, 16 * kc, sf + F_B_BASE2 + 16 * kc, h);
+      uint32_t q[8];
+      epi16_s<SAVE>(tl, 16 * kc, sf + F_B_BASE2 + 16 * kc, h, q);
+      if (save) st_codes8(sp, SP_X1 + 2 * kc, q);
       float t[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -457,44 +523,60 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
 #pragma unroll
     for (int kc = 0; kc < 2; ++kc) {
       float h[16];
-      epi16(tl, 16 * kc, sf + F_B_VIS0 + 16 * kc, h);
+      uint32_t q[8];
+      epi16_s<SAVE>(tl, 16 * kc, sf + F_B_VIS0 + 16 * kc, h, q);
+      if (save) st_codes8(sp, SP_HV + 2 * kc, q);
       a_store16<NPASS>(tl, kc, h);
     }
     NFB_TC_ISSUE(L_VIS2, 0, 2, false);
     NFB_TC_WAIT();
 
     // x2 = x1 + x_res ; vis1 = sigmoid(xv[32]) * mask ; vis_fc2 on x2 * vis1
-    float vis1;
+    float vis1, sg1;
+    uint32_t xvq16 = 0u;
     {
       float h[16];
-      epi16(tl, 32, sf + F_B_VIS2 + 32, h);
-      vis1 = sigmoid_f(h[0]) * mk;
+      uint32_t q[8];
+      epi16_s<SAVE>(tl, 32, sf + F_B_VIS2 + 32, h, q);
+      if (SAVE) xvq16 = q[0];
+      sg1 = sigmoid_f(h[0]);
+      vis1 = sg1 * mk;
     }
 #pragma unroll
     for (int kc = 0; kc < 2; ++kc) {
       float h[16];
-      epi16(tl, 16 * kc, sf + F_B_VIS2 + 16 * kc, h);
+      uint32_t q[8];
+      epi16_s<SAVE>(tl, 16 * kc, sf + F_B_VIS2 + 16 * kc, h, q);
+      if (save) st_codes8(sp, SP_XV + 2 * kc, q);
       float t[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         x1[16 * kc + j] += h[j];            // x1 now holds x2
         t[j] = x1[16 * kc + j] * vis1;
       }
+      if (save) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sp[(SP_X2 + 4 * kc + j) * GROUP] = make_float4(x1[16 * kc + 4 * j], x1[16 * kc + 4 * j + 1], x1[16 * kc + 4 * j + 2], x1[16 * kc + 4 * j + 3]);
+      }
       a_store16<NPASS>(tl, kc, t);
     }
     NFB_TC_ISSUE(L_VISB0, 0, 2, false);
     NFB_TC_WAIT();
-    float vis2;
+    float vis2, sg2;
     {
       float z = sf[F_B_VISB2];
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
         float h[16];
-        epi16(tl, 16 * kc, sf + F_B_VISB0 + 16 * kc, h);
+        uint32_t q[8];
+        epi16_s<SAVE>(tl, 16 * kc, sf + F_B_VISB0 + 16 * kc, h, q);
+        if (save) st_codes8(sp, SP_HV2 + 2 * kc, q);
 #pragma unroll
         for (int j = 0; j < 16; ++j) z = fmaf(h[j], sf[F_W_VISB2 + 16 * kc + j], z);
       }
-      vis2 = sigmoid_f(z) * mk;
+      sg2 = sigmoid_f(z);
+      vis2 = sg2 * mk;
     }
 
     // ---------------- rgb_fc on [x2, vis2, ray_diff] (37 -> 16 -> 8 -> 1) ----------------
@@ -516,14 +598,30 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
     float logit;
     {
       float g1[16];
-      epi16(tl, 0, sf + F_B_RGB0, g1);
+      uint32_t q1[8];
+      epi16_s<SAVE>(tl, 0, sf + F_B_RGB0, g1, q1);
       float g2[8];
       load_bias<8>(g2, sf + F_B_RGB2);
       dense_acc<16, 8>(sf + F_W_RGB2, g1, g2);
+      if (SAVE) {
+        float t[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g2[j] = elu_fast(g2[j]);
+        for (int j = 0; j < 8; ++j) elu_with_t(g2[j], g2[j], t[j]);
+        if (save) {
+          st_codes8(sp, SP_G1, q1);
+          st_plane(sp, SP_G2, pack_t(t[0], t[1]), pack_t(t[2], t[3]), pack_t(t[4], t[5]), pack_t(t[6], t[7]));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g2[j] = elu_fast(g2[j]);
+      }
       logit = dot_row<8>(g2, sf + F_W_RGB4) + sf[F_B_RGB4];
       if (mk == 0.f) logit = -1e9f;
+      if (save) {
+        sp[SP_SA * GROUP] = make_float4(w, mk, sg1, sg2);
+        sp[SP_SB * GROUP] = make_float4(logit, ggx, ggy, rgb_in0);
+        st_plane(sp, SP_SC, __float_as_uint(rgb_in1), __float_as_uint(rgb_in2), xvq16, 0u);
+      }
     }
 
     // ---------------- second pooling, blending, output ----------------
@@ -579,10 +677,10 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
   if (warp == 0) tmem_dealloc(*s_tmem, NG * GC);
 }
 
-template <int NPASS, bool FUSED>
+template <int NPASS, bool FUSED, bool SAVE = false>
 int launch_view_tc_fwd(const ViewArgs& a, cudaStream_t st) {
   constexpr size_t smem = smem_bytes<NPASS>();
-  cudaError_t e = cudaFuncSetAttribute(k_view_tc_fwd<NPASS, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_view_tc_fwd<NPASS, FUSED, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nfb_set_error(NFB_ECUDA, "k_view_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int TS = (GROUP / a.V < TS_MAX) ? GROUP / a.V : TS_MAX;
   const int ntiles = (a.N + TS - 1) / TS;
@@ -590,7 +688,7 @@ int launch_view_tc_fwd(const ViewArgs& a, cudaStream_t st) {
   const int cap = nfb_num_sms();
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  k_view_tc_fwd<NPASS, FUSED><<<grid, GROUP * NG, smem, st>>>(a);
+  k_view_tc_fwd<NPASS, FUSED, SAVE><<<grid, GROUP * NG, smem, st>>>(a);
   NFB_CHECK_LAUNCH("k_view_tc_fwd");
   return NFB_OK;
 }
@@ -602,3 +700,5 @@ int nfb_launch_view_tc_fwd_p1_fused(const nfbview::ViewArgs& a, cudaStream_t st)
 int nfb_launch_view_tc_fwd_p3_fused(const nfbview::ViewArgs& a, cudaStream_t st);
 int nfb_launch_view_tc_fwd_p1_tensor(const nfbview::ViewArgs& a, cudaStream_t st);
 int nfb_launch_view_tc_fwd_p3_tensor(const nfbview::ViewArgs& a, cudaStream_t st);
+int nfb_launch_view_tc_fwd_p1_fused_save(const nfbview::ViewArgs& a, cudaStream_t st);
+int nfb_launch_view_tc_fwd_p3_fused_save(const nfbview::ViewArgs& a, cudaStream_t st);

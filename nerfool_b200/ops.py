@@ -154,7 +154,7 @@ class IBRNetAggregate(torch.autograd.Function):
         with torch.cuda.device(dev):
             st = stream_ptr(dev)
             call('nfb_ibrnet_view_fwd', N, S, V, int(anti_alias), ptr(rf), ptr(rd), ptr(mk), 0, 0, 0, 0,
-                 None, None, None, None, None, None, None, ptr(params), ptr(ps), _lib.precision_code(), st)
+                 None, None, None, None, None, None, None, ptr(params), ptr(ps), None, _lib.precision_code(), st)
             call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), _lib.precision_code(), st)
         ctx.save_for_backward(rf, rd, mk, params, pos_enc, ps)
         ctx.dims = (R, S, V, int(anti_alias))
@@ -177,7 +177,7 @@ class IBRNetAggregate(torch.autograd.Function):
                 call('nfb_ibrnet_ray_bwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(g), ptr(d_ps), ctx.precision, st)
                 call('nfb_ibrnet_view_bwd', N, S, V, aa, ptr(rf), ptr(rd), ptr(mk), 0, 0, 0, 0,
                      None, None, None, None, None, None, None, ptr(params), ptr(ps), ptr(d_ps),
-                     ptr(d_rf), None, None, ctx.precision, st)
+                     ptr(d_rf), None, None, None, ctx.precision, st)
         return d_rf, None, None, None, None, None
 
 
@@ -284,15 +284,19 @@ class RenderLevel(torch.autograd.Function):
         weights = torch.empty(R, S, device=dev, dtype=torch.float32)
         alpha = torch.empty(R, S, device=dev, dtype=torch.float32)
         ray_mask = torch.empty(R, device=dev, dtype=torch.uint8)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        # activation stash for the backward (768 B per (sample, view) row): written only when a gradient is wanted
+        n_stash = _lib.stash_bytes(N, V) if need else 0
+        stash = torch.empty(n_stash, device=dev, dtype=torch.uint8) if n_stash else None
         with torch.cuda.device(dev):
             st = stream_ptr(dev)
             call('nfb_ibrnet_view_fwd', N, S, V, int(anti_alias), None, None, None, H, W, fh, fw,
                  None, ptr(o_c), ptr(d_c), ptr(z_c), ptr(cam), ptr(imgs_c), ptr(feat), ptr(params), ptr(ps),
-                 _lib.precision_code(), st)
+                 ptr(stash), _lib.precision_code(), st)
             call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), _lib.precision_code(), st)
             call('nfb_composite_fwd', R, S, int(white_bkgd), ptr(raw), ptr(z_c), None, ptr(ps[:, 68:]), PS_STRIDE,
                  ptr(rgb), ptr(depth), ptr(weights), ptr(alpha), ptr(ray_mask), st)
-        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        ctx.stash = stash
         if need:
             ctx.save_for_backward(feat, imgs_c, o_c, d_c, z_c, cam, params, pos_enc, ps, raw)
         ctx.dims = (R, S, V, H, W, fh, fw, int(anti_alias), int(white_bkgd))
@@ -321,6 +325,7 @@ class RenderLevel(torch.autograd.Function):
             call('nfb_ibrnet_ray_bwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(d_raw), ptr(d_ps), ctx.precision, st)
             call('nfb_ibrnet_view_bwd', N, S, V, aa, None, None, None, H, W, fh, fw,
                  None, ptr(o_c), ptr(d_c), ptr(z_c), ptr(cam), ptr(imgs_c), ptr(feat), ptr(params), ptr(ps),
-                 ptr(d_ps), None, ptr(d_feat), ptr(d_imgs), ctx.precision, st)
+                 ptr(d_ps), None, ptr(d_feat), ptr(d_imgs), ptr(ctx.stash), ctx.precision, st)
+        ctx.stash = None
         return (d_feat.permute(0, 3, 1, 2) if need_feat else None, d_imgs,
                 None, None, None, None, None, None, None, None, None, None)

@@ -1,56 +1,71 @@
-"""Join an ncu SASS source-page CSV (per-instruction executed counts / stall samples) with nvdisasm line info
-of the same kernel, and aggregate by CUDA source line.
-usage: python profiles/sass_lines.py <ncu_source.csv> <object.o> <kernel-name-substring> [top]"""
+"""Join an ncu SASS source-page CSV (`ncu -i x.ncu-rep --page source --csv --print-source sass`, one block per
+captured launch) with the nvdisasm line info of the same kernel, and aggregate instruction counts, stall samples and
+stall reasons by CUDA source line.
+usage: python profiles/sass_lines.py <ncu_source.csv> <object.o> <kernel-name-substring> [occurrence=0] [top=50]"""
 import collections
 import csv
+import glob
+import os
 import re
 import subprocess
 import sys
+import tempfile
 
 src_csv, obj, kname = sys.argv[1:4]
-top = int(sys.argv[4]) if len(sys.argv) > 4 else 60
+occ = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+top = int(sys.argv[5]) if len(sys.argv) > 5 else 50
 
-import glob, os, tempfile
 tmp = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(obj)], cwd=tmp, capture_output=True)
 cubin = glob.glob(os.path.join(tmp, '*.cubin'))[0]
 dis = subprocess.run(['nvdisasm', '-g', '-c', cubin], capture_output=True, text=True).stdout.splitlines()
-# locate the function
 start = None
 for i, l in enumerate(dis):
-    if l.startswith('.text.') and kname in l:
-        start = i
-        break
-    if re.match(r'\s*\.section\s+\.text\.\S*' + re.escape(kname), l):
+    if re.match(r'\s*\.section\s+\.text\.\S*' + re.escape(kname), l) or (l.startswith('.text.') and kname in l):
         start = i
         break
 assert start is not None, 'kernel not found in disassembly'
-lines = []          # (file:line) per instruction, in order
+lines = []          # innermost "file:line" per instruction, in order
 cur = '?'
 for l in dis[start + 1:]:
-    if l.startswith('.section') or re.match(r'\s*\.section', l):
-        if lines:
-            break
+    if re.match(r'\s*\.section', l) and lines:
+        break
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m:
         cur = f'{m.group(1).split("/")[-1]}:{m.group(2)}'
-        # inlined-at chains: keep the outermost user line too
         continue
     if re.match(r'\s+/\*[0-9a-f]{4,}\*/', l):
         lines.append(cur)
 
+csv.field_size_limit(1 << 30)
 rows = list(csv.reader(open(src_csv)))
-h = [i for i, r in enumerate(rows) if r and r[0] == 'Address'][0]
-hdr = rows[h]
+blocks = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name' and kname in r[1]]
+b = blocks[occ]
+hdr = rows[b + 1]
+end = next((i for i in range(b + 2, len(rows)) if rows[i] and rows[i][0] == 'Kernel Name'), len(rows))
+data = [r for r in rows[b + 2:end] if len(r) == len(hdr)]
 ii, si = hdr.index('Instructions Executed'), hdr.index('# Samples')
-data = rows[h + 1:]
-print(f'{len(lines)} SASS instructions with line info, {len(data)} in the ncu page')
+stall_cols = [(i, n) for i, n in enumerate(hdr) if n.startswith('stall_') and 'Not Issued' not in n]
+print(f'{rows[b][1]}: {len(lines)} SASS instructions with line info, {len(data)} in the ncu page')
 agg_i, agg_s = collections.Counter(), collections.Counter()
+reasons = collections.Counter()
+line_reason = collections.defaultdict(collections.Counter)
+ops = collections.Counter()
 for k, r in enumerate(data):
     key = lines[k] if k < len(lines) else '?'
-    agg_i[key] += int(r[ii])
+    n = int(r[ii])
+    agg_i[key] += n
     agg_s[key] += int(r[si])
+    ops[r[1].split()[0] if not r[1].strip().startswith('@') else r[1].split()[1]] += n
+    for i, name in stall_cols:
+        v = int(r[i])
+        if v:
+            reasons[name] += v
+            line_reason[key][name] += v
 ti, ts = sum(agg_i.values()), sum(agg_s.values())
 print(f'total warp instructions {ti}, samples {ts}')
-for key, n in agg_i.most_common(top):
-    print(f'{100 * n / ti:6.2f}% inst  {100 * agg_s[key] / max(ts, 1):6.2f}% samples   {key}')
+print('stall reasons:', ', '.join(f'{k[6:]} {100 * v / max(ts, 1):.1f}%' for k, v in reasons.most_common(10)))
+print('top opcodes:', ', '.join(f'{k} {100 * v / ti:.1f}%' for k, v in ops.most_common(24)))
+for key, n in sorted(agg_s.items(), key=lambda kv: -kv[1])[:top]:
+    why = ', '.join(f'{k[6:]} {v}' for k, v in line_reason[key].most_common(3))
+    print(f'{100 * n / max(ts, 1):6.2f}% samples {100 * agg_i[key] / ti:6.2f}% inst   {key:28s} {why}')

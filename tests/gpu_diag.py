@@ -103,7 +103,7 @@ def run(V, R, S_c, n_imp, H=378, W=504, kind='llff', inv_uniform=True, seed=0, t
     ps = torch.zeros(N, 72, device=dev)
     st = _lib.stream_ptr(dev)
     _lib.call('nfb_ibrnet_view_fwd', N, S_c, V, 1, _lib.ptr(rf_in), _lib.ptr(rd_in), _lib.ptr(mk_in), 0, 0, 0, 0,
-              None, None, None, None, None, None, None, _lib.ptr(blob), _lib.ptr(ps), st)
+              None, None, None, None, None, None, None, _lib.ptr(blob), _lib.ptr(ps), None, _lib.precision_code(), st)
     torch.cuda.synchronize()
     ps_c = ps.cpu().view(R, S_c, 72)
     rec(f'{tag}/view.mean2', ps_c[..., 0:32], want['gf_in'][..., 0:32])
