@@ -77,6 +77,20 @@ __device__ __forceinline__ void ld_codes8(const float4* sp, int plane, uint32_t 
   q[4] = __float_as_uint(b.x); q[5] = __float_as_uint(b.y); q[6] = __float_as_uint(b.z); q[7] = __float_as_uint(b.w);
 }
 
+__device__ __forceinline__ void ld_codes16(const float4* sp, int plane, uint32_t (&q)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 a = __ldcs(sp + (plane + i) * GROUP);
+    q[4 * i] = __float_as_uint(a.x); q[4 * i + 1] = __float_as_uint(a.y);
+    q[4 * i + 2] = __float_as_uint(a.z); q[4 * i + 3] = __float_as_uint(a.w);
+  }
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <int NPASS>
 __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -135,15 +149,32 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
     const float* dp = dpb + (active ? sl : 0) * DPS;
     const float4* sp = reinterpret_cast<const float4*>(a.stash) + (size_t)tile * (ST_PLANES * GROUP) + tg;
 
-    // ---------------- stage the cotangents / forward means of the tile's samples ----------------
+    // ---------------- stage the cotangents / forward means of the tile's samples (asynchronous copies) ----------------
     {
       const int p0 = tile * TS;
       const int ns = (a.N - p0 < TS) ? (a.N - p0) : TS;
       for (int i = tg; i < ns * 25; i += GROUP) {        // 17 float4 of d_ps (68 floats) + 8 float4 of ps (mean)
         const int s = i / 25, j = i - s * 25;
-        const float4 q = (j < 17) ? __ldg(reinterpret_cast<const float4*>(a.d_ps + (size_t)(p0 + s) * NFB_PS_STRIDE) + j)
-                                  : __ldg(reinterpret_cast<const float4*>(a.ps + (size_t)(p0 + s) * NFB_PS_STRIDE) + (j - 17));
-        *reinterpret_cast<float4*>(dpb + s * DPS + 4 * j) = q;
+        const float4* src = (j < 17) ? reinterpret_cast<const float4*>(a.d_ps + (size_t)(p0 + s) * NFB_PS_STRIDE) + j
+                                     : reinterpret_cast<const float4*>(a.ps + (size_t)(p0 + s) * NFB_PS_STRIDE) + (j - 17);
+        cp_async16(dpb + s * DPS + 4 * j, src);
+      }
+      // pull the NEXT tile of this group towards L2 while this one is processed: its stash planes (one line per 8 rows)
+      // and its cotangent rows
+      const int nt = tile + gridDim.x * NG;
+      if (nt < ntiles) {
+        if ((tg & 7) == 0) {
+          const float4* np = reinterpret_cast<const float4*>(a.stash) + (size_t)nt * (ST_PLANES * GROUP) + tg;
+#pragma unroll 8
+          for (int pl = 0; pl < ST_PLANES - 1; ++pl) prefetch_l2(np + pl * GROUP);
+        }
+        const int q0 = nt * TS;
+        const int nn = (a.N - q0 < TS) ? (a.N - q0) : TS;
+        for (int i = tg; i < nn * 5; i += GROUP) {       // 288-byte rows: 3 lines of d_ps, 2 of ps (first 128 B = means)
+          const int s = i / 5, j = i - s * 5;
+          prefetch_l2(j < 3 ? reinterpret_cast<const char*>(a.d_ps + (size_t)(q0 + s) * NFB_PS_STRIDE) + 128 * j
+                            : reinterpret_cast<const char*>(a.ps + (size_t)(q0 + s) * NFB_PS_STRIDE) + 128 * (j - 3));
+        }
       }
     }
 
@@ -190,6 +221,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
     ex[tg * EXS + 34] = rgb_in0;
     ex[tg * EXS + 35] = rgb_in1;
     ex[tg * EXS + 36] = rgb_in2;
+    cp_async_wait_all();                    // the staged cotangent rows are read after this barrier
     named_bar_sync(bar_id, GROUP);
     float Dsum = 1e-8f;
     for (int u = 0; u < V; ++u) Dsum += ex[(base + u) * EXS + 32];
@@ -271,6 +303,8 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       for (int u = 0; u < V; ++u) sdv += ex[(base + u) * EXS + 33];
       d_vis2 = d_w2 * invD - sdv * invD * invD;
     }
+    uint32_t cq[16];                        // ELU' codes of the next layer, loaded ahead of the MMA wait
+    ld_codes16(sp, SP_HV2, cq);
     NFB_TCS_WAIT();
 #pragma unroll
     for (int kc = 0; kc < 2; ++kc) {
@@ -291,17 +325,16 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       const float dz = d_vis2 * mk * sg2 * (1.f - sg2);
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
-        uint32_t q[8];
-        ld_codes8(sp, SP_HV2 + 2 * kc, q);
         float dh[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          dh[2 * j] = dz * sf[F_W_VISB2 + 16 * kc + 2 * j] * elu_stash_lo(q[j]);
-          dh[2 * j + 1] = dz * sf[F_W_VISB2 + 16 * kc + 2 * j + 1] * elu_stash_hi(q[j]);
+          dh[2 * j] = dz * sf[F_W_VISB2 + 16 * kc + 2 * j] * elu_stash_lo(cq[8 * kc + j]);
+          dh[2 * j + 1] = dz * sf[F_W_VISB2 + 16 * kc + 2 * j + 1] * elu_stash_hi(cq[8 * kc + j]);
         }
         a_store16<NPASS>(tl, kc, dh);
       }
       NFB_TCS_BWD(L_VISB0, 0, 32);
+      ld_codes16(sp, SP_XV, cq);
       NFB_TCS_WAIT();
       d_vis1 = 0.f;
 #pragma unroll
@@ -320,13 +353,11 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
     {
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
-        uint32_t q[8];
-        ld_codes8(sp, SP_XV + 2 * kc, q);
         float dxv[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          dxv[2 * j] = d_x2[16 * kc + 2 * j] * elu_stash_lo(q[j]);
-          dxv[2 * j + 1] = d_x2[16 * kc + 2 * j + 1] * elu_stash_hi(q[j]);
+          dxv[2 * j] = d_x2[16 * kc + 2 * j] * elu_stash_lo(cq[8 * kc + j]);
+          dxv[2 * j + 1] = d_x2[16 * kc + 2 * j + 1] * elu_stash_hi(cq[8 * kc + j]);
         }
         a_store16<NPASS>(tl, kc, dxv);
       }
@@ -337,49 +368,53 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       a_store16<NPASS>(tl, 2, dxv);
     }
     NFB_TCS_BWD(L_VIS2, 0, 32);
+    ld_codes16(sp, SP_HV, cq);
     NFB_TCS_WAIT();
 #pragma unroll
     for (int kc = 0; kc < 2; ++kc) {
-      uint32_t q[8];
-      ld_codes8(sp, SP_HV + 2 * kc, q);
       float dh[16];
       d_raw16(tl, 16 * kc, dh);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        dh[2 * j] *= elu_stash_lo(q[j]);
-        dh[2 * j + 1] *= elu_stash_hi(q[j]);
+        dh[2 * j] *= elu_stash_lo(cq[8 * kc + j]);
+        dh[2 * j + 1] *= elu_stash_hi(cq[8 * kc + j]);
       }
       a_store16<NPASS>(tl, kc, dh);
     }
     NFB_TCS_BWD(L_VIS0, 0, 32);
+    ld_codes16(sp, SP_X1, cq);
     NFB_TCS_WAIT();
 
     // (6) base_fc backward
 #pragma unroll
     for (int kc = 0; kc < 2; ++kc) {
-      uint32_t q[8];
-      ld_codes8(sp, SP_X1 + 2 * kc, q);
       float dt[16];
       d_raw16(tl, 16 * kc, dt);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        dt[2 * j] = fmaf(dt[2 * j], w, d_x2[16 * kc + 2 * j]) * elu_stash_lo(q[j]);
-        dt[2 * j + 1] = fmaf(dt[2 * j + 1], w, d_x2[16 * kc + 2 * j + 1]) * elu_stash_hi(q[j]);
+        dt[2 * j] = fmaf(dt[2 * j], w, d_x2[16 * kc + 2 * j]) * elu_stash_lo(cq[8 * kc + j]);
+        dt[2 * j + 1] = fmaf(dt[2 * j + 1], w, d_x2[16 * kc + 2 * j + 1]) * elu_stash_hi(cq[8 * kc + j]);
       }
       a_store16<NPASS>(tl, kc, dt);
     }
     NFB_TCS_BWD(L_BASE2, 0, 64);
+    uint32_t hq[32];
+    ld_codes16(sp, SP_H1, cq);
+    {
+      uint32_t t16[16];
+      ld_codes16(sp, SP_H1 + 4, t16);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { hq[j] = cq[j]; hq[16 + j] = t16[j]; }
+    }
     NFB_TCS_WAIT();
 #pragma unroll
     for (int kc = 0; kc < 4; ++kc) {
-      uint32_t q[8];
-      ld_codes8(sp, SP_H1 + 2 * kc, q);
       float dh[16];
       d_raw16(tl, 16 * kc, dh);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        dh[2 * j] *= elu_stash_lo(q[j]);
-        dh[2 * j + 1] *= elu_stash_hi(q[j]);
+        dh[2 * j] *= elu_stash_lo(hq[8 * kc + j]);
+        dh[2 * j + 1] *= elu_stash_hi(hq[8 * kc + j]);
       }
       a_store16<NPASS>(tl, kc, dh);
     }
@@ -415,6 +450,12 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       }
     }
     named_bar_sync(bar_id, GROUP);
+    float x0[36];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const float4 q = active ? __ldcs(sp + (SP_X0 + j) * GROUP) : make_float4(0.f, 0.f, 0.f, 0.f);
+      x0[4 * j] = q.x; x0[4 * j + 1] = q.y; x0[4 * j + 2] = q.z; x0[4 * j + 3] = q.w;
+    }
     NFB_TCS_WAIT();
     float d_row[NFB_ROW_CH];
     {
@@ -447,13 +488,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
     named_bar_sync(bar_id, GROUP);
     if (active) {
 #pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        const float4 q = __ldcs(sp + (SP_X0 + j) * GROUP);
-        d_row[4 * j] += w * (mvs[4 * j] + q.x * mvs[36 + 4 * j]);
-        d_row[4 * j + 1] += w * (mvs[4 * j + 1] + q.y * mvs[36 + 4 * j + 1]);
-        d_row[4 * j + 2] += w * (mvs[4 * j + 2] + q.z * mvs[36 + 4 * j + 2]);
-        if (j < 8) d_row[4 * j + 3] += w * (mvs[4 * j + 3] + q.w * mvs[36 + 4 * j + 3]);
-      }
+      for (int c = 0; c < NFB_ROW_CH; ++c) d_row[c] += w * (mvs[c] + x0[c] * mvs[36 + c]);
       d_row[0] = fmaf(blend, d_r0, d_row[0]);
       d_row[1] = fmaf(blend, d_r1, d_row[1]);
       d_row[2] = fmaf(blend, d_r2, d_row[2]);

@@ -392,6 +392,71 @@ def test_render_rays_stochastic_sampling_runs_and_is_sorted(dev):
     assert float(z.min()) >= 2.0 - 1e-4 and float(z.max()) <= 12.0 + 1e-4
 
 
+def _small_attack_case(dev, V=4, R=192, S=64, NI=64):
+    scene, batch = _scene(V, R, 378, 504, 'llff', seed=21)
+    gb = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    model = types.SimpleNamespace(net_coarse=_net(_params(S, 7), S, dev), net_fine=_net(_params(S + NI, 8), S + NI, dev))
+    return scene, gb, model, S, NI
+
+
+def _attack_grads(dev, scene, gb, model, S, NI):
+    from nerfool_b200.projection import Projector
+    from nerfool_b200.render_ray import render_rays
+    from nerfool_b200.attack import rgb_loss
+    fm = tuple(f.to(dev).requires_grad_(True) for f in scene['featmaps'])
+    out = render_rays(gb, model, fm, Projector(dev), S, inv_uniform=True, N_importance=NI, det=True)
+    rgb_loss(out, gb['rgb']).backward()
+    return out, fm
+
+
+def test_precision_modes(dev):
+    """NfbPrecision: bf16x3 (default) is fp32-equivalent; plain bf16 stays within 0.05 dB PSNR of the fp32 render
+    (north star) and its PGD gradient points the same way."""
+    from nerfool_b200 import _lib
+    scene, gb, model, S, NI = _small_attack_case(dev)
+    saved = _lib.get_precision()
+    res = {}
+    try:
+        for mode in ('fp32', 'bf16x3', 'bf16'):
+            _lib.set_precision(mode)
+            res[mode] = _attack_grads(dev, scene, gb, model, S, NI)
+    finally:
+        _lib.set_precision(saved)
+    ref_out, ref_fm = res['fp32']
+    gt = gb['rgb']
+
+    def psnr(o):
+        return float(-10.0 * torch.log10(torch.mean((o['outputs_coarse']['rgb'] - gt) ** 2)))
+
+    o3, f3 = res['bf16x3']
+    assert maxabs(o3['outputs_coarse']['rgb'].cpu(), ref_out['outputs_coarse']['rgb'].cpu()) < 1e-4
+    assert maxabs(o3['outputs_coarse']['depth'].cpu(), ref_out['outputs_coarse']['depth'].cpu()) < 1e-4
+    assert relerr(f3[0].grad.cpu(), ref_fm[0].grad.cpu()) < 1e-3
+    o1, f1 = res['bf16']
+    assert torch.equal(o1['outputs_coarse']['mask'], ref_out['outputs_coarse']['mask'])
+    assert abs(psnr(o1) - psnr(ref_out)) < 0.05
+    g1, g0 = f1[0].grad.flatten().double(), ref_fm[0].grad.flatten().double()
+    assert float(torch.dot(g1, g0) / (g1.norm() * g0.norm())) > 0.995
+
+
+def test_stash_backward_equals_recompute_backward(dev):
+    """The two fused tensor-core backward forms (activation stash vs forward recompute) give the same gradient."""
+    from nerfool_b200 import _lib
+    scene, gb, model, S, NI = _small_attack_case(dev, V=5, R=77)
+    saved = _lib.STASH_MAX_GIB
+    try:
+        _lib.STASH_MAX_GIB = 48.0
+        assert _lib.stash_bytes(77 * S, 5) > 0
+        _, fm_s = _attack_grads(dev, scene, gb, model, S, NI)
+        _lib.STASH_MAX_GIB = 0.0
+        assert _lib.stash_bytes(77 * S, 5) == 0
+        _, fm_r = _attack_grads(dev, scene, gb, model, S, NI)
+    finally:
+        _lib.STASH_MAX_GIB = saved
+    for a, b in zip(fm_s, fm_r):
+        assert relerr(a.grad.cpu(), b.grad.cpu()) < 2e-4
+
+
 def test_full_size_properties(dev):
     """BASELINE-size chunk (4096 rays, V=4, 64+64): size-independent properties instead of an oracle run:
     weights in [0,1] and sum <= 1, rgb in the convex hull of source colours, determinism, linearity of the

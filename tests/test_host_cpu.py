@@ -65,6 +65,13 @@ def test_argument_validation_fails_loudly_without_touching_the_gpu(lib):
     assert b'samples' in lib.nfb_last_error_string()
 
 
+def test_stash_size_query(lib):
+    """nfb_view_stash_bytes: one 96 KiB tile (48 planes x 128 rows x 16 B) per floor(128 / V) samples."""
+    assert lib.nfb_view_stash_bytes(6400, 4) == (6400 // 32) * 48 * 128 * 16
+    assert lib.nfb_view_stash_bytes(100, 10) == -(-100 // 12) * 48 * 128 * 16
+    assert lib.nfb_view_stash_bytes(0, 4) == 0 and lib.nfb_view_stash_bytes(10, 33) == 0
+
+
 def test_no_cpu_fallback():
     from nerfool_b200.projection import Projector
     from nerfool_b200.mlp_network import IBRNet
