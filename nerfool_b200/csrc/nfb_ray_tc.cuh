@@ -146,6 +146,20 @@ __device__ __forceinline__ void r_issue_bwd(uint32_t tb, uint32_t sB_addr) {
     fence_after_sync();        \
   } while (0)
 
+// log2-domain scores of one key row against a query: k4[d] = dimension d of the four heads; (head 0, head 1) in s01
+__device__ __forceinline__ void attn_scores(const float4* __restrict__ k4, const float2 (&q01)[4], const float2 (&q23)[4],
+                                            float2& s01, float2& s23) {
+  const float4 a = k4[0], b = k4[1], c = k4[2], d = k4[3];
+  s01 = __fmul2_rn(q01[0], make_float2(a.x, a.y));
+  s23 = __fmul2_rn(q23[0], make_float2(a.z, a.w));
+  s01 = __ffma2_rn(q01[1], make_float2(b.x, b.y), s01);
+  s23 = __ffma2_rn(q23[1], make_float2(b.z, b.w), s23);
+  s01 = __ffma2_rn(q01[2], make_float2(c.x, c.y), s01);
+  s23 = __ffma2_rn(q23[2], make_float2(c.z, c.w), s23);
+  s01 = __ffma2_rn(q01[3], make_float2(d.x, d.y), s01);
+  s23 = __ffma2_rn(q23[3], make_float2(d.z, d.w), s23);
+}
+
 struct RayArgs {
   int R, S;
   const float* ps;
@@ -278,68 +292,67 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
     NFB_RTC_WAIT();
 
     // ---------------- attention ----------------
-    float q[16];
+    // K / V / Q rows live in shared memory DIMENSION-major ([d][head]): one LDS.128 brings dimension d of all four
+    // heads, and the (head 0, head 1) / (head 2, head 3) pairs feed the packed FFMA2 / FADD2 / FMUL2 pipes (on sm_100
+    // the scalar fp32 instructions issue at half the packed rate).  Masked query rows (<= 1 valid view:
+    // masked_fill(mask == 0, -1e9) on the whole row = uniform attention) carry q = 0, so their scores, maxima and
+    // probabilities come out as 0, 0 and 1 without a branch.
+    float2 q01[4], q23[4];
     {
-      float kk[16], vv[16];
-      r_ld16(tl, 0, q);
+      float qq[16], kk[16], vv[16];
+      r_ld16(tl, 0, qq);
       r_ld16(tl, 16, kk);
       r_ld16(tl, 32, vv);
+      const float qs = row_valid ? INV_TEMP * LOG2E : 0.f;          // scores in the log2 domain
 #pragma unroll
-      for (int c = 0; c < 16; ++c) q[c] *= INV_TEMP * LOG2E;       // scores in the log2 domain
-#pragma unroll
-      for (int c = 0; c < 16; c += 4) {
-        *reinterpret_cast<float4*>(sk + tg * 16 + c) = make_float4(kk[c], kk[c + 1], kk[c + 2], kk[c + 3]);
-        *reinterpret_cast<float4*>(sv + tg * 16 + c) = make_float4(vv[c], vv[c + 1], vv[c + 2], vv[c + 3]);
+      for (int d = 0; d < 4; ++d) {
+        q01[d] = make_float2(qq[d] * qs, qq[4 + d] * qs);
+        q23[d] = make_float2(qq[8 + d] * qs, qq[12 + d] * qs);
+        *reinterpret_cast<float4*>(sk + tg * 16 + 4 * d) = make_float4(kk[d], kk[4 + d], kk[8 + d], kk[12 + d]);
+        *reinterpret_cast<float4*>(sv + tg * 16 + 4 * d) = make_float4(vv[d], vv[4 + d], vv[8 + d], vv[12 + d]);
       }
     }
     named_bar_sync(bar_id, GROUP);
     float o[16], m2[4], il[4];
     {
-      const float* kr = sk + kb * 16;
-      const float* vr = sv + kb * 16;
-      if (row_valid) {
-        float mx0 = -3.4e38f, mx1 = -3.4e38f, mx2 = -3.4e38f, mx3 = -3.4e38f;
-        for (int j = 0; j < S; ++j) {
-          const float4 k0 = *reinterpret_cast<const float4*>(kr + j * 16);
-          const float4 k1 = *reinterpret_cast<const float4*>(kr + j * 16 + 4);
-          const float4 k2 = *reinterpret_cast<const float4*>(kr + j * 16 + 8);
-          const float4 k3 = *reinterpret_cast<const float4*>(kr + j * 16 + 12);
-          mx0 = fmaxf(mx0, q[0] * k0.x + q[1] * k0.y + q[2] * k0.z + q[3] * k0.w);
-          mx1 = fmaxf(mx1, q[4] * k1.x + q[5] * k1.y + q[6] * k1.z + q[7] * k1.w);
-          mx2 = fmaxf(mx2, q[8] * k2.x + q[9] * k2.y + q[10] * k2.z + q[11] * k2.w);
-          mx3 = fmaxf(mx3, q[12] * k3.x + q[13] * k3.y + q[14] * k3.z + q[15] * k3.w);
-        }
-        m2[0] = mx0; m2[1] = mx1; m2[2] = mx2; m2[3] = mx3;
-      } else {
-        m2[0] = m2[1] = m2[2] = m2[3] = 0.f;
-      }
-      float l[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < 16; ++c) o[c] = 0.f;
+      const float4* kr = reinterpret_cast<const float4*>(sk + kb * 16);
+      const float4* vr = reinterpret_cast<const float4*>(sv + kb * 16);
+      float2 mx01 = make_float2(-3.4e38f, -3.4e38f), mx23 = mx01;
       for (int j = 0; j < S; ++j) {
-        float p[4] = {1.f, 1.f, 1.f, 1.f};     // masked_fill(mask == 0, -1e9) on a whole query row = uniform attention
-        if (row_valid) {
+        float2 s01, s23;
+        attn_scores(kr + 4 * j, q01, q23, s01, s23);
+        mx01.x = fmaxf(mx01.x, s01.x); mx01.y = fmaxf(mx01.y, s01.y);
+        mx23.x = fmaxf(mx23.x, s23.x); mx23.y = fmaxf(mx23.y, s23.y);
+      }
+      m2[0] = mx01.x; m2[1] = mx01.y; m2[2] = mx23.x; m2[3] = mx23.y;
+      const float2 nm01 = make_float2(-mx01.x, -mx01.y), nm23 = make_float2(-mx23.x, -mx23.y);
+      float2 l01 = make_float2(0.f, 0.f), l23 = l01;
+      float2 o01[4], o23[4];
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const float4 k = *reinterpret_cast<const float4*>(kr + j * 16 + 4 * h);
-            const float sc = q[4 * h] * k.x + q[4 * h + 1] * k.y + q[4 * h + 2] * k.z + q[4 * h + 3] * k.w;
-            p[h] = ex2_approx(sc - m2[h]);
-          }
-        }
+      for (int d = 0; d < 4; ++d) o01[d] = o23[d] = make_float2(0.f, 0.f);
+      for (int j = 0; j < S; ++j) {
+        float2 s01, s23;
+        attn_scores(kr + 4 * j, q01, q23, s01, s23);
+        s01 = __fadd2_rn(s01, nm01);
+        s23 = __fadd2_rn(s23, nm23);
+        const float2 p01 = make_float2(ex2_approx(s01.x), ex2_approx(s01.y));
+        const float2 p23 = make_float2(ex2_approx(s23.x), ex2_approx(s23.y));
+        l01 = __fadd2_rn(l01, p01);
+        l23 = __fadd2_rn(l23, p23);
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const float4 vj = *reinterpret_cast<const float4*>(vr + j * 16 + 4 * h);
-          l[h] += p[h];
-          o[4 * h] = fmaf(p[h], vj.x, o[4 * h]);
-          o[4 * h + 1] = fmaf(p[h], vj.y, o[4 * h + 1]);
-          o[4 * h + 2] = fmaf(p[h], vj.z, o[4 * h + 2]);
-          o[4 * h + 3] = fmaf(p[h], vj.w, o[4 * h + 3]);
+        for (int d = 0; d < 4; ++d) {
+          const float4 vj = vr[4 * j + d];
+          o01[d] = __ffma2_rn(p01, make_float2(vj.x, vj.y), o01[d]);
+          o23[d] = __ffma2_rn(p23, make_float2(vj.z, vj.w), o23[d]);
         }
       }
+      il[0] = 1.f / l01.x; il[1] = 1.f / l01.y; il[2] = 1.f / l23.x; il[3] = 1.f / l23.y;
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        il[h] = 1.f / l[h];
-        o[4 * h] *= il[h]; o[4 * h + 1] *= il[h]; o[4 * h + 2] *= il[h]; o[4 * h + 3] *= il[h];
+      for (int d = 0; d < 4; ++d) {
+        o[d] = o01[d].x * il[0];
+        o[4 + d] = o01[d].y * il[1];
+        o[8 + d] = o23[d].x * il[2];
+        o[12 + d] = o23[d].y * il[3];
       }
     }
 
@@ -423,88 +436,130 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
       }
       NFB_RTC_BWD(RL_FC);
       NFB_RTC_WAIT();
-      float dO[16];
-      r_ld16(tl, 0, dO);
-      float Dh[4];
+      float2 dO01[4], dO23[4];
+      float2 Dh01, Dh23;
+      {
+        float dO[16];
+        r_ld16(tl, 0, dO);
+        float Dh[4];
 #pragma unroll
-      for (int h = 0; h < 4; ++h)
-        Dh[h] = dO[4 * h] * o[4 * h] + dO[4 * h + 1] * o[4 * h + 1] + dO[4 * h + 2] * o[4 * h + 2] + dO[4 * h + 3] * o[4 * h + 3];
-      // publish per-query quantities for the key-side pass
+        for (int h = 0; h < 4; ++h)
+          Dh[h] = dO[4 * h] * o[4 * h] + dO[4 * h + 1] * o[4 * h + 1] + dO[4 * h + 2] * o[4 * h + 2] + dO[4 * h + 3] * o[4 * h + 3];
+        Dh01 = make_float2(Dh[0], Dh[1]);
+        Dh23 = make_float2(Dh[2], Dh[3]);
+        // publish per-query quantities for the key-side pass (dimension-major like K / V)
+        const float vf = row_valid ? 1.f : 0.f;
 #pragma unroll
-      for (int c = 0; c < 16; c += 4) {
-        *reinterpret_cast<float4*>(sq + tg * 16 + c) = make_float4(q[c], q[c + 1], q[c + 2], q[c + 3]);
-        *reinterpret_cast<float4*>(sdo + tg * 16 + c) = make_float4(dO[c], dO[c + 1], dO[c + 2], dO[c + 3]);
+        for (int d = 0; d < 4; ++d) {
+          dO01[d] = make_float2(dO[d], dO[4 + d]);
+          dO23[d] = make_float2(dO[8 + d], dO[12 + d]);
+          *reinterpret_cast<float4*>(sq + tg * 16 + 4 * d) = make_float4(q01[d].x, q01[d].y, q23[d].x, q23[d].y);
+          *reinterpret_cast<float4*>(sdo + tg * 16 + 4 * d) = make_float4(dO[d], dO[4 + d], dO[8 + d], dO[12 + d]);
+        }
+        *reinterpret_cast<float4*>(sst + tg * 16) = make_float4(-m2[0], -m2[1], -m2[2], -m2[3]);
+        *reinterpret_cast<float4*>(sst + tg * 16 + 4) = make_float4(il[0], il[1], il[2], il[3]);
+        *reinterpret_cast<float4*>(sst + tg * 16 + 8) = make_float4(-Dh[0], -Dh[1], -Dh[2], -Dh[3]);
+        *reinterpret_cast<float4*>(sst + tg * 16 + 12) = make_float4(vf, vf, vf, vf);
       }
-#pragma unroll
-      for (int h = 0; h < 4; ++h)
-        *reinterpret_cast<float4*>(sst + (tg * 4 + h) * 4) = make_float4(m2[h], il[h], Dh[h], row_valid ? 1.f : 0.f);
       named_bar_sync(bar_id, GROUP);
 
       float dqkv[48];
-#pragma unroll
-      for (int c = 0; c < 48; ++c) dqkv[c] = 0.f;
       // query side: dq_i = sum_j dS_ij k_j  (zero for masked rows: masked_fill blocks the gradient)
-      if (row_valid) {
-        const float* kr = sk + kb * 16;
-        const float* vr = sv + kb * 16;
-        for (int j = 0; j < S; ++j) {
+      {
+        const float4* kr = reinterpret_cast<const float4*>(sk + kb * 16);
+        const float4* vr = reinterpret_cast<const float4*>(sv + kb * 16);
+        const float2 nm01 = make_float2(-m2[0], -m2[1]), nm23 = make_float2(-m2[2], -m2[3]);
+        const float2 il01 = make_float2(il[0], il[1]), il23 = make_float2(il[2], il[3]);
+        const float2 nD01 = make_float2(-Dh01.x, -Dh01.y), nD23 = make_float2(-Dh23.x, -Dh23.y);
+        float2 dq01[4], dq23[4];
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const float4 k = *reinterpret_cast<const float4*>(kr + j * 16 + 4 * h);
-            const float4 vj = *reinterpret_cast<const float4*>(vr + j * 16 + 4 * h);
-            const float sc = q[4 * h] * k.x + q[4 * h + 1] * k.y + q[4 * h + 2] * k.z + q[4 * h + 3] * k.w;
-            const float pj = ex2_approx(sc - m2[h]) * il[h];
-            const float dP = dO[4 * h] * vj.x + dO[4 * h + 1] * vj.y + dO[4 * h + 2] * vj.z + dO[4 * h + 3] * vj.w;
-            const float dS = pj * (dP - Dh[h]);
-            dqkv[4 * h] = fmaf(dS, k.x, dqkv[4 * h]);
-            dqkv[4 * h + 1] = fmaf(dS, k.y, dqkv[4 * h + 1]);
-            dqkv[4 * h + 2] = fmaf(dS, k.z, dqkv[4 * h + 2]);
-            dqkv[4 * h + 3] = fmaf(dS, k.w, dqkv[4 * h + 3]);
+        for (int d = 0; d < 4; ++d) dq01[d] = dq23[d] = make_float2(0.f, 0.f);
+        for (int j = 0; j < S; ++j) {
+          float2 s01, s23;
+          attn_scores(kr + 4 * j, q01, q23, s01, s23);
+          s01 = __fadd2_rn(s01, nm01);
+          s23 = __fadd2_rn(s23, nm23);
+          const float2 p01 = __fmul2_rn(make_float2(ex2_approx(s01.x), ex2_approx(s01.y)), il01);
+          const float2 p23 = __fmul2_rn(make_float2(ex2_approx(s23.x), ex2_approx(s23.y)), il23);
+          float2 dP01 = nD01, dP23 = nD23;                  // dP - D
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            const float4 vj = vr[4 * j + d];
+            dP01 = __ffma2_rn(dO01[d], make_float2(vj.x, vj.y), dP01);
+            dP23 = __ffma2_rn(dO23[d], make_float2(vj.z, vj.w), dP23);
+          }
+          const float2 dS01 = __fmul2_rn(p01, dP01), dS23 = __fmul2_rn(p23, dP23);
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            const float4 kj = kr[4 * j + d];
+            dq01[d] = __ffma2_rn(dS01, make_float2(kj.x, kj.y), dq01[d]);
+            dq23[d] = __ffma2_rn(dS23, make_float2(kj.z, kj.w), dq23[d]);
           }
         }
+        const float sc = row_valid ? INV_TEMP : 0.f;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) dqkv[c] *= INV_TEMP;
+        for (int d = 0; d < 4; ++d) {
+          dqkv[d] = dq01[d].x * sc;
+          dqkv[4 + d] = dq01[d].y * sc;
+          dqkv[8 + d] = dq23[d].x * sc;
+          dqkv[12 + d] = dq23[d].y * sc;
+        }
       }
       // key side: dk_j = sum_i dS_ij q_i ; dv_j = sum_i p_ij dO_i   (this thread is key j)
       {
-        const float invS = 1.f / (float)S;
-        float kk[16], vv[16];
+        float2 k01[4], k23[4], v01[4], v23[4];
 #pragma unroll
-        for (int c = 0; c < 16; c += 4) {
-          const float4 k4 = *reinterpret_cast<const float4*>(sk + tg * 16 + c);
-          const float4 v4 = *reinterpret_cast<const float4*>(sv + tg * 16 + c);
-          kk[c] = k4.x; kk[c + 1] = k4.y; kk[c + 2] = k4.z; kk[c + 3] = k4.w;
-          vv[c] = v4.x; vv[c + 1] = v4.y; vv[c + 2] = v4.z; vv[c + 3] = v4.w;
+        for (int d = 0; d < 4; ++d) {
+          const float4 k4 = *reinterpret_cast<const float4*>(sk + tg * 16 + 4 * d);
+          const float4 v4 = *reinterpret_cast<const float4*>(sv + tg * 16 + 4 * d);
+          k01[d] = make_float2(k4.x, k4.y); k23[d] = make_float2(k4.z, k4.w);
+          v01[d] = make_float2(v4.x, v4.y); v23[d] = make_float2(v4.z, v4.w);
         }
-        const float* qr = sq + kb * 16;
-        const float* dr_ = sdo + kb * 16;
-        const float* st = sst + kb * 16;
-        for (int i = 0; i < S; ++i) {
+        float2 dk01[4], dk23[4], dv01[4], dv23[4];
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const float4 qi = *reinterpret_cast<const float4*>(qr + i * 16 + 4 * h);
-            const float4 di = *reinterpret_cast<const float4*>(dr_ + i * 16 + 4 * h);
-            const float4 sti = *reinterpret_cast<const float4*>(st + (i * 4 + h) * 4);
-            float pij = invS, dS = 0.f;
-            if (sti.w != 0.f) {
-              const float sc = qi.x * kk[4 * h] + qi.y * kk[4 * h + 1] + qi.z * kk[4 * h + 2] + qi.w * kk[4 * h + 3];
-              pij = ex2_approx(sc - sti.x) * sti.y;
-              const float dP = di.x * vv[4 * h] + di.y * vv[4 * h + 1] + di.z * vv[4 * h + 2] + di.w * vv[4 * h + 3];
-              dS = pij * (dP - sti.z);
-            }
-            // q in shared memory carries the 0.5 * log2(e) score scale; d k = sum dS * q_scaled / log2(e)
-            dqkv[16 + 4 * h] = fmaf(dS, qi.x, dqkv[16 + 4 * h]);
-            dqkv[16 + 4 * h + 1] = fmaf(dS, qi.y, dqkv[16 + 4 * h + 1]);
-            dqkv[16 + 4 * h + 2] = fmaf(dS, qi.z, dqkv[16 + 4 * h + 2]);
-            dqkv[16 + 4 * h + 3] = fmaf(dS, qi.w, dqkv[16 + 4 * h + 3]);
-            dqkv[32 + 4 * h] = fmaf(pij, di.x, dqkv[32 + 4 * h]);
-            dqkv[32 + 4 * h + 1] = fmaf(pij, di.y, dqkv[32 + 4 * h + 1]);
-            dqkv[32 + 4 * h + 2] = fmaf(pij, di.z, dqkv[32 + 4 * h + 2]);
-            dqkv[32 + 4 * h + 3] = fmaf(pij, di.w, dqkv[32 + 4 * h + 3]);
+        for (int d = 0; d < 4; ++d) dk01[d] = dk23[d] = dv01[d] = dv23[d] = make_float2(0.f, 0.f);
+        const float4* qr = reinterpret_cast<const float4*>(sq + kb * 16);
+        const float4* gr = reinterpret_cast<const float4*>(sdo + kb * 16);
+        const float4* st = reinterpret_cast<const float4*>(sst + kb * 16);
+        for (int i = 0; i < S; ++i) {
+          float4 qi[4], gi[4];
+#pragma unroll
+          for (int d = 0; d < 4; ++d) { qi[d] = qr[4 * i + d]; gi[d] = gr[4 * i + d]; }
+          const float4 nm = st[4 * i], ili = st[4 * i + 1], nD = st[4 * i + 2], vf = st[4 * i + 3];
+          // masked query rows carry q = 0, -m = 0 and 1/l = 1/S: p = 1/S as the reference's uniform row, dS forced to 0
+          float2 s01 = make_float2(nm.x, nm.y), s23 = make_float2(nm.z, nm.w);
+          float2 dP01 = make_float2(nD.x, nD.y), dP23 = make_float2(nD.z, nD.w);
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            s01 = __ffma2_rn(make_float2(qi[d].x, qi[d].y), k01[d], s01);
+            s23 = __ffma2_rn(make_float2(qi[d].z, qi[d].w), k23[d], s23);
+            dP01 = __ffma2_rn(make_float2(gi[d].x, gi[d].y), v01[d], dP01);
+            dP23 = __ffma2_rn(make_float2(gi[d].z, gi[d].w), v23[d], dP23);
+          }
+          const float2 p01 = __fmul2_rn(make_float2(ex2_approx(s01.x), ex2_approx(s01.y)), make_float2(ili.x, ili.y));
+          const float2 p23 = __fmul2_rn(make_float2(ex2_approx(s23.x), ex2_approx(s23.y)), make_float2(ili.z, ili.w));
+          const float2 dS01 = __fmul2_rn(__fmul2_rn(p01, dP01), make_float2(vf.x, vf.y));
+          const float2 dS23 = __fmul2_rn(__fmul2_rn(p23, dP23), make_float2(vf.z, vf.w));
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            dk01[d] = __ffma2_rn(dS01, make_float2(qi[d].x, qi[d].y), dk01[d]);
+            dk23[d] = __ffma2_rn(dS23, make_float2(qi[d].z, qi[d].w), dk23[d]);
+            dv01[d] = __ffma2_rn(p01, make_float2(gi[d].x, gi[d].y), dv01[d]);
+            dv23[d] = __ffma2_rn(p23, make_float2(gi[d].z, gi[d].w), dv23[d]);
           }
         }
+        // q in shared memory carries the 0.5 * log2(e) score scale; d k = sum dS * q_scaled / log2(e)
 #pragma unroll
-        for (int c = 16; c < 32; ++c) dqkv[c] *= (1.f / LOG2E);
+        for (int d = 0; d < 4; ++d) {
+          dqkv[16 + d] = dk01[d].x * (1.f / LOG2E);
+          dqkv[16 + 4 + d] = dk01[d].y * (1.f / LOG2E);
+          dqkv[16 + 8 + d] = dk23[d].x * (1.f / LOG2E);
+          dqkv[16 + 12 + d] = dk23[d].y * (1.f / LOG2E);
+          dqkv[32 + d] = dv01[d].x;
+          dqkv[32 + 4 + d] = dv01[d].y;
+          dqkv[32 + 8 + d] = dv23[d].x;
+          dqkv[32 + 12 + d] = dv23[d].y;
+        }
       }
       // d xin = dy (residual) + [dq | dk | dv] Wqkv ; pos_encoding is a constant
 #pragma unroll

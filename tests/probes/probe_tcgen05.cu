@@ -2,12 +2,12 @@
 //   128 x N x K bf16 GEMM tiles, A from TMEM (.ts) or shared memory (.ss), B from shared memory in the canonical
 //   no-swizzle K-major layout, D read back with tcgen05.ld, compared with a host reference.
 // Usage: probe_tcgen05 <variant>   (one variant per process so that a trap in one does not poison the others)
-//   build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o probe_tcgen05 tests/probe_tcgen05.cu
+//   build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o probe_tcgen05 tests/probes/probe_tcgen05.cu
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
 #include <vector>
-#include "../nerfool_b200/csrc/nfb_tc.cuh"
+#include "../../nerfool_b200/csrc/nfb_tc.cuh"
 
 using namespace nfbtc;
 
