@@ -16,7 +16,9 @@ value       rays/s through forward + backward, inputs resident in HBM, CUDA-even
 e2e         the same step through the public API with the step's rays / target colours copied from pinned
             host memory and the loss read back, inside the timed region
 roofline    the dominant kernel (largest share of the step) against the measured HBM peak, algorithmic
-            gather/scatter bytes (560 B per (sample, view) row gathered, 512 B scattered)
+            gather/scatter bytes (SURVEY.md 8d: 560 B per (sample, view) row gathered, 512 B scattered);
+            "kernels" carries the same for all four IBRNet kernels, with the dense-FLOP rate against the
+            measured bf16 tensor peak (roofline_tensor)
 cpu_baseline / --impl reference : the CPU oracle (oracle/ibrnet_oracle.py, a port of the reference path)
             on a bounded ray sample with all host threads.
 """
@@ -50,6 +52,23 @@ def load_peaks():
             d = json.load(f)
         return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
     return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def load_tensor_peak():
+    path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f).get('bf16_tflops_sustained', 0) or 0) or None
+    return 1381.5      # fallback: sustained dense bf16 of this pool (B200_PROFILING.md)
+
+
+def load_traffic_table():
+    """DRAM bytes per unit measured ONCE with `ncu --set full` (profiles/traffic_r01.json, source named inside)."""
+    path = os.path.join(REPO, 'profiles', 'traffic_r01.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
 
 
 class ClockSampler:
@@ -212,31 +231,71 @@ def run_ours(a):
     barrier()
     e2e_total_ms = e2e_ev[0][0].elapsed_time(e2e_ev[-1][1])
 
+    # ---------------- the same step in plain-bf16 tensor-core mode (reported beside the headline) ----------------
+    bf16_ms = None
+    if not a.no_bf16:
+        saved_prec = _lib.get_precision()
+        _lib.set_precision('bf16')
+        step(batch)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(2):
+            step(batch)
+        s1.record()
+        barrier()
+        bf16_ms = s0.elapsed_time(s1) / 2
+        _lib.set_precision(saved_prec)
+
     # max over ranks
-    t = torch.tensor([total_ms, e2e_total_ms, statistics.median(fwd_ms)], device=device, dtype=torch.float64)
+    t = torch.tensor([total_ms, e2e_total_ms, statistics.median(fwd_ms), bf16_ms or 0.0], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_total_ms, fwd_med = t.tolist()
+    total_ms, e2e_total_ms, fwd_med, bf16_max = t.tolist()
+    bf16_ms = bf16_max if bf16_ms is not None else None
 
     if rank == 0:
         hbm_peak, peak_src = load_peaks()
-        rows_fwd = {  # (sample, view) rows per launch of each view-stage kernel, per level
-            'coarse': N_SAMPLES * a.views, 'fine': (N_SAMPLES + N_IMPORTANCE) * a.views}
-        # per-kernel totals over the timed region
+        tensor_peak = load_tensor_peak()
+        traffic_tab = load_traffic_table()
         ktot = {k: sum(v) for k, v in prof.items()}
         kshare = {k: v / sum(ktot.values()) for k, v in ktot.items()}
-        dom = max(ktot, key=ktot.get)
-        n_l = len(prof[dom])
-        avg_ms = ktot[dom] / n_l
-        # algorithmic bytes per launch of the dominant kernel: launches alternate coarse / fine chunks
-        chunks = [min(a.max_rays, R - lo) for lo in range(0, R, a.max_rays)]
-        rows_per_step = sum(chunks) * (rows_fwd['coarse'] + rows_fwd['fine'])
-        per_row = {'nfb_ibrnet_view_fwd': GATHER_B, 'nfb_ibrnet_view_bwd': GATHER_B + SCATTER_B}.get(dom, GATHER_B)
-        launches_per_step = n_l / a.steps
-        alg_bytes = rows_per_step * per_row / launches_per_step
-        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+        # units processed per step by the per-row (view stage) and per-sample (ray stage) kernels
+        samples_per_step = R * (N_SAMPLES + N_SAMPLES + N_IMPORTANCE)
+        rows_per_step = samples_per_step * a.views
+        # ALGORITHMIC bytes per unit (SURVEY.md 8d / DESIGN.md 3): gather 560 B and scatter 512 B per (sample, view) row;
+        # the view backward is charged the gather it replaces by reading the activation stash (which actually moves
+        # 768 B/row); ray stage: the 288-byte interface row in (fwd) / in + out (bwd) per sample
+        alg = {'nfb_ibrnet_view_fwd': (GATHER_B, rows_per_step), 'nfb_ibrnet_view_bwd': (GATHER_B + SCATTER_B, rows_per_step),
+               'nfb_ibrnet_ray_fwd': (288 + 16, samples_per_step), 'nfb_ibrnet_ray_bwd': (288 * 2 + 16, samples_per_step)}
+        # dense MACs per unit (SURVEY.md 8a FLOP model): 13,256 per row in the view stage, 6,480 + 32 S per sample in the
+        # ray stage; the data-gradient is ~1x the forward (dgrad only; the view backward reads the stash, no recompute)
+        ray_macs = R * (N_SAMPLES * (6480 + 32 * N_SAMPLES) + (N_SAMPLES + N_IMPORTANCE) * (6480 + 32 * (N_SAMPLES + N_IMPORTANCE)))
+        macs = {'nfb_ibrnet_view_fwd': 13256 * rows_per_step, 'nfb_ibrnet_view_bwd': 13256 * rows_per_step,
+                'nfb_ibrnet_ray_fwd': ray_macs, 'nfb_ibrnet_ray_bwd': 2 * ray_macs}
+        per_kernel = {}
+        for k, (bpu, units) in alg.items():
+            if k not in prof:
+                continue
+            n_l = len(prof[k])
+            avg_ms = ktot[k] / n_l
+            per_launch_units = units * a.steps / n_l
+            ach = bpu * per_launch_units / (avg_ms * 1e-3) / 1e9
+            tfl = 2 * macs[k] * a.steps / n_l / (avg_ms * 1e-3) / 1e12
+            tr = None
+            for tab, key in (('dram_bytes_per_row', 'nfb_ibrnet_view'), ('dram_bytes_per_sample', 'nfb_ibrnet_ray')):
+                if k.startswith(key) and traffic_tab and k in traffic_tab.get(tab, {}):
+                    tr = traffic_tab[tab][k] * per_launch_units
+            per_kernel[k] = {'ms_per_step': ktot[k] / a.steps, 'launches_per_step': n_l / a.steps, 'avg_launch_ms': avg_ms,
+                             'algorithmic_bytes_per_unit': bpu, 'units_per_launch': per_launch_units,
+                             'achieved_GBps': ach, 'hbm_frac': ach / hbm_peak,
+                             'dense_TFLOPs': tfl, 'tensor_frac': tfl / tensor_peak if tensor_peak else None,
+                             'traffic_bytes_per_launch': tr}
+        dom = max(per_kernel, key=lambda k: per_kernel[k]['ms_per_step'])
+        d = per_kernel[dom]
         ms_per_step = total_ms / a.steps
         rays_total = R * world
+        from nerfool_b200 import _lib as _l
         out = {
             'metric': 'rays/s', 'value': rays_total / (ms_per_step * 1e-3), 'unit': 'rays/s',
             'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms_per_step,
@@ -245,18 +304,29 @@ def run_ours(a):
                                    'bwd to source feature maps), 378x504 target view, all 190512 rays per step, '
                                    f'{a.views} source views, 64 coarse + 64 importance samples, random-init weights',
                        'rays_per_step_per_gpu': R, 'source_views': a.views, 'max_rays_per_launch': a.max_rays,
+                       'arithmetic': f'{_l.get_precision()}: fp32 data, dense layers on tcgen05 with bf16 hi+lo split operands '
+                                     '(3 MMA passes, fp32 accumulate) = fp32-equivalent results' if _l.get_precision() == 'bf16x3'
+                                     else _l.get_precision(),
                        'parallelism': f'one target view per GPU x{world}, 1 NCCL allreduce of d(featmaps)/step' if world > 1 else 'single GPU',
-                       'l2': 'per-step working set (per-sample workspaces, several GB) >> 126 MB L2; the 2x6.3 MB feature maps are L2-resident by design'},
+                       'l2': 'per-step working set (per-sample workspaces + activation stash, tens of GB) >> 126 MB L2; '
+                             'the 2x6.3 MB feature maps are L2-resident by design'},
             'pgd_iters_per_s': 1e3 / ms_per_step,
             'fwd_rays_per_s': rays_total / (fwd_med * 1e-3),
             'fwd_ms_per_frame': fwd_med,
             'encoder': 'not timed: the ResUNet stays on cuDNN in the reference and is outside this repo (north_star)',
             'wall_s_timed_region': t_wall,
             'step_ms': step_ms,
-            'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                         'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': peak_src,
-                         'avg_launch_ms': avg_ms, 'algorithmic_bytes_per_launch': alg_bytes,
-                         'note': 'fp32 CUDA-core MLP: the kernel is FMA-issue bound, not gather bound; see DESIGN.md'},
+            'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': d['achieved_GBps'], 'peak': hbm_peak, 'unit': 'GB/s',
+                         'frac': d['hbm_frac'], 'traffic': d['traffic_bytes_per_launch'], 'peak_source': peak_src,
+                         'avg_launch_ms': d['avg_launch_ms'],
+                         'algorithmic_bytes_per_launch': d['algorithmic_bytes_per_unit'] * d['units_per_launch'],
+                         'traffic_source': (traffic_tab or {}).get('source'),
+                         'note': 'algorithmic bytes = SURVEY.md 8(d) per-unit figure x units of the launch; the feature maps are '
+                                 'L2-resident, so the gather part of these bytes is served by L2, not DRAM'},
+            'roofline_tensor': {'bound': 'tensor', 'kernel': dom, 'achieved': d['dense_TFLOPs'], 'peak': tensor_peak,
+                                'unit': 'TFLOP/s', 'frac': d['tensor_frac'],
+                                'note': 'useful dense FLOPs of the reference network (not the 3x of the split passes)'},
+            'kernels': per_kernel,
             'kernel_share': {k: round(v, 4) for k, v in sorted(kshare.items(), key=lambda kv: -kv[1])},
             'kernel_ms_per_step': {k: v / a.steps for k, v in ktot.items()},
             'e2e': {'value': rays_total / (e2e_total_ms / a.steps * 1e-3), 'unit': 'rays/s',
@@ -265,6 +335,9 @@ def run_ours(a):
             'clocks': clocks,
             'loss_last': float(loss_host),
         }
+        if bf16_ms is not None:
+            out['bf16_mode'] = {'ms_per_step': bf16_ms, 'rays_per_s': rays_total / (bf16_ms * 1e-3),
+                                'note': 'same step with NFB_PREC_BF16 (single bf16 MMA pass; PSNR-parity mode, tests/test_gpu_parity.py::test_precision_modes)'}
         if world == 1 and not a.no_cpu_baseline:
             out['cpu_baseline'] = cpu_reference(a, sample_rays=a.cpu_rays, steps=1, warmup=1)
         print(json.dumps(out), flush=True)
@@ -328,6 +401,7 @@ def main():
     ap.add_argument('--max-rays', dest='max_rays', type=int, default=65536)
     ap.add_argument('--cpu-rays', dest='cpu_rays', type=int, default=2048)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-bf16', dest='no_bf16', action='store_true', help='skip the extra plain-bf16 measurement')
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == 'ours' else a.warmup
     if a.impl == 'reference':
