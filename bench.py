@@ -153,6 +153,8 @@ def run_ours(a):
     device = torch.device('cuda', local)
     group = None
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group('nccl', device_id=device)
         group = dist.group.WORLD
     _lib.load()

@@ -109,12 +109,15 @@ int nfb_ibrnet_view_fwd(int N, int S, int V, int anti_alias,
                         const float* xyz, const float* ray_o, const float* ray_d, const float* z,
                         const float* cam, const float* imgs, const float* feat,
                         const float* params, float* ps, float* stash, int precision, void* stream);
+/* The ray stage has the same optional activation stash (tensor-core form, S <= 128): 560 B per sample (q, k, v,
+ * attention output and softmax statistics, LayerNorm xhat / rstd, ELU-derivative codes). */
+size_t nfb_ray_stash_bytes(int R, int S);
 int nfb_ibrnet_ray_fwd(int R, int S, const float* ps, const float* params, const float* pos_enc /*[S][16]*/,
-                       float* raw /*[R][S][4]*/, int precision, void* stream);
+                       float* raw /*[R][S][4]*/, float* stash, int precision, void* stream);
 /* Backward (data gradients): d_raw[R][S][4] -> d_ps[N][72] -> d_rgb_feat[N][V][35] (tensor mode) or a
  * scatter into d_feat / d_imgs (fused mode, rgb_feat == NULL).                                         */
 int nfb_ibrnet_ray_bwd(int R, int S, const float* ps, const float* params, const float* pos_enc,
-                       const float* d_raw, float* d_ps, int precision, void* stream);
+                       const float* d_raw, float* d_ps, const float* stash, int precision, void* stream);
 int nfb_ibrnet_view_bwd(int N, int S, int V, int anti_alias,
                         const float* rgb_feat, const float* ray_diff, const float* mask,
                         int H, int W, int fh, int fw,

@@ -23,15 +23,15 @@ _SIGNATURES = {
     'nfb_project_gather_fwd': [_I] * 7 + [_P] * 11,
     'nfb_project_gather_bwd': [_I] * 7 + [_P] * 9,
     'nfb_ibrnet_view_fwd': [_I] * 4 + [_P] * 3 + [_I] * 4 + [_P] * 10 + [_I, _P],
-    'nfb_ibrnet_ray_fwd': [_I, _I, _P, _P, _P, _P, _I, _P],
-    'nfb_ibrnet_ray_bwd': [_I, _I, _P, _P, _P, _P, _P, _I, _P],
+    'nfb_ibrnet_ray_fwd': [_I, _I, _P, _P, _P, _P, _P, _I, _P],
+    'nfb_ibrnet_ray_bwd': [_I, _I, _P, _P, _P, _P, _P, _P, _I, _P],
     'nfb_ibrnet_view_bwd': [_I] * 4 + [_P] * 3 + [_I] * 4 + [_P] * 14 + [_I, _P],
     'nfb_composite_fwd': [_I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     'nfb_composite_bwd': [_I, _I, _I] + [_P] * 8,
     'nfb_sample_pdf': [_I, _I, _I, _P, _P, _P, _I, _P, _P, _P],
     'nfb_fine_depths': [_I, _I, _I, _I, _P, _P, _P, _I, _P, _P],
 }
-EXPORTS = ['nfb_version', 'nfb_last_error_string', 'nfb_ibrnet_param_offset', 'nfb_view_stash_bytes'] + list(_SIGNATURES)
+EXPORTS = ['nfb_version', 'nfb_last_error_string', 'nfb_ibrnet_param_offset', 'nfb_view_stash_bytes', 'nfb_ray_stash_bytes'] + list(_SIGNATURES)
 
 _lib = None
 
@@ -69,6 +69,14 @@ def stash_bytes(N: int, V: int) -> int:
     return n if n <= STASH_MAX_GIB * 2 ** 30 else 0
 
 
+def ray_stash_bytes(R: int, S: int) -> int:
+    """Size of the ray-stage activation stash (0 when disabled, fp32 mode or S > 128)."""
+    if _precision == PRECISIONS['fp32'] or STASH_MAX_GIB <= 0:
+        return 0
+    n = int(load().nfb_ray_stash_bytes(int(R), int(S)))
+    return n if n <= STASH_MAX_GIB * 2 ** 30 else 0
+
+
 def load():
     """Load (once) and return the ctypes library handle."""
     global _lib
@@ -87,6 +95,8 @@ def load():
     lib.nfb_ibrnet_param_offset.argtypes = [c_char_p]
     lib.nfb_view_stash_bytes.restype = ctypes.c_size_t
     lib.nfb_view_stash_bytes.argtypes = [c_int, c_int]
+    lib.nfb_ray_stash_bytes.restype = ctypes.c_size_t
+    lib.nfb_ray_stash_bytes.argtypes = [c_int, c_int]
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int

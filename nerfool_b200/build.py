@@ -43,6 +43,10 @@ UNITS = [
     ('nfb_ray_tc_inst1', 'nfb_ray_tc_inst.cu', ['-DNFB_RTC_INST=1']),
     ('nfb_ray_tc_inst2', 'nfb_ray_tc_inst.cu', ['-DNFB_RTC_INST=2']),
     ('nfb_ray_tc_inst3', 'nfb_ray_tc_inst.cu', ['-DNFB_RTC_INST=3']),
+    ('nfb_ray_tc_inst4', 'nfb_ray_tc_inst.cu', ['-DNFB_RTC_INST=4']),
+    ('nfb_ray_tc_inst5', 'nfb_ray_tc_inst.cu', ['-DNFB_RTC_INST=5']),
+    ('nfb_ray_tc_inst6', 'nfb_ray_tc_inst.cu', ['-DNFB_RTC_INST=6']),
+    ('nfb_ray_tc_inst7', 'nfb_ray_tc_inst.cu', ['-DNFB_RTC_INST=7']),
 ]
 
 

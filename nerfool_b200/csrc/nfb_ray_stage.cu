@@ -334,17 +334,28 @@ inline int ray_block(int S) { return ((S + 31) / 32) * 32; }
 
 }  // namespace
 
+extern "C" size_t nfb_ray_stash_bytes(int R, int S) {
+  if (R <= 0 || S < 1 || S > nfbrtc::GROUP) return 0;
+  const int rpg = nfbrtc::GROUP / S;
+  return (size_t)((R + rpg - 1) / rpg) * nfbrtc::RP_TILE_BYTES;
+}
+
 extern "C" int nfb_ibrnet_ray_fwd(int R, int S, const float* ps, const float* params, const float* pos_enc,
-                                  float* raw, int precision, void* stream) {
+                                  float* raw, float* stash, int precision, void* stream) {
   NFB_REQUIRE(R >= 0 && S >= 1, NFB_EINVAL, "nfb_ibrnet_ray_fwd: bad arguments (R=%d S=%d)", R, S);
   NFB_REQUIRE(S <= NFB_MAX_SAMPLES, NFB_EUNSUPPORTED, "nfb_ibrnet_ray_fwd: S=%d > %d samples per ray", S, NFB_MAX_SAMPLES);
   if (R == 0) return NFB_OK;
   NFB_REQUIRE(ps && params && pos_enc && raw, NFB_EINVAL, "nfb_ibrnet_ray_fwd: NULL buffer");
   NFB_REQUIRE(((uintptr_t)ps % 16) == 0 && ((uintptr_t)raw % 16) == 0, NFB_EINVAL, "nfb_ibrnet_ray_fwd: ps/raw must be 16-byte aligned");
   NFB_REQUIRE(precision >= NFB_PREC_FP32 && precision <= NFB_PREC_BF16, NFB_EINVAL, "nfb_ibrnet_ray_fwd: bad precision %d", precision);
+  if (stash)
+    NFB_REQUIRE(precision != NFB_PREC_FP32 && S <= nfbrtc::GROUP && ((uintptr_t)stash % 16) == 0, NFB_EUNSUPPORTED,
+                "nfb_ibrnet_ray_fwd: the activation stash exists for the tensor-core form (S <= 128) only, 16-byte aligned");
   if (precision != NFB_PREC_FP32 && S <= nfbrtc::GROUP) {     // longer rays: fp32 kernel below
-    nfbrtc::RayArgs a{R, S, ps, params, pos_enc, raw, nullptr, nullptr};
-    return precision == NFB_PREC_BF16 ? nfb_launch_ray_tc_fwd_p1(a, (cudaStream_t)stream) : nfb_launch_ray_tc_fwd_p3(a, (cudaStream_t)stream);
+    nfbrtc::RayArgs a{R, S, ps, params, pos_enc, raw, nullptr, nullptr, stash};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stash) return precision == NFB_PREC_BF16 ? nfb_launch_ray_tc_fwd_p1_save(a, st) : nfb_launch_ray_tc_fwd_p3_save(a, st);
+    return precision == NFB_PREC_BF16 ? nfb_launch_ray_tc_fwd_p1(a, st) : nfb_launch_ray_tc_fwd_p3(a, st);
   }
   const size_t smem = (size_t)(R_TOTAL + 2 * S * 16) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(k_ray_stage<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -358,7 +369,7 @@ extern "C" int nfb_ibrnet_ray_fwd(int R, int S, const float* ps, const float* pa
 }
 
 extern "C" int nfb_ibrnet_ray_bwd(int R, int S, const float* ps, const float* params, const float* pos_enc,
-                                  const float* d_raw, float* d_ps, int precision, void* stream) {
+                                  const float* d_raw, float* d_ps, const float* stash, int precision, void* stream) {
   NFB_REQUIRE(R >= 0 && S >= 1, NFB_EINVAL, "nfb_ibrnet_ray_bwd: bad arguments (R=%d S=%d)", R, S);
   NFB_REQUIRE(S <= NFB_MAX_SAMPLES, NFB_EUNSUPPORTED, "nfb_ibrnet_ray_bwd: S=%d > %d samples per ray", S, NFB_MAX_SAMPLES);
   if (R == 0) return NFB_OK;
@@ -366,9 +377,14 @@ extern "C" int nfb_ibrnet_ray_bwd(int R, int S, const float* ps, const float* pa
   NFB_REQUIRE(((uintptr_t)ps % 16) == 0 && ((uintptr_t)d_raw % 16) == 0 && ((uintptr_t)d_ps % 16) == 0, NFB_EINVAL,
               "nfb_ibrnet_ray_bwd: ps/d_raw/d_ps must be 16-byte aligned");
   NFB_REQUIRE(precision >= NFB_PREC_FP32 && precision <= NFB_PREC_BF16, NFB_EINVAL, "nfb_ibrnet_ray_bwd: bad precision %d", precision);
+  if (stash)
+    NFB_REQUIRE(precision != NFB_PREC_FP32 && S <= nfbrtc::GROUP && ((uintptr_t)stash % 16) == 0, NFB_EUNSUPPORTED,
+                "nfb_ibrnet_ray_bwd: the activation stash exists for the tensor-core form (S <= 128) only, 16-byte aligned");
   if (precision != NFB_PREC_FP32 && S <= nfbrtc::GROUP) {
-    nfbrtc::RayArgs a{R, S, ps, params, pos_enc, nullptr, d_raw, d_ps};
-    return precision == NFB_PREC_BF16 ? nfb_launch_ray_tc_bwd_p1(a, (cudaStream_t)stream) : nfb_launch_ray_tc_bwd_p3(a, (cudaStream_t)stream);
+    nfbrtc::RayArgs a{R, S, ps, params, pos_enc, nullptr, d_raw, d_ps, const_cast<float*>(stash)};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stash) return precision == NFB_PREC_BF16 ? nfb_launch_ray_tc_bwd_stash_p1(a, st) : nfb_launch_ray_tc_bwd_stash_p3(a, st);
+    return precision == NFB_PREC_BF16 ? nfb_launch_ray_tc_bwd_p1(a, st) : nfb_launch_ray_tc_bwd_p3(a, st);
   }
   const size_t smem = (size_t)(R_TOTAL + 4 * S * 16 + S * 12 + S) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(k_ray_stage<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

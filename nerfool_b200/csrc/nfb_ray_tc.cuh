@@ -168,9 +168,32 @@ struct RayArgs {
   float* raw;           // forward output
   const float* d_raw;   // backward input
   float* d_ps;          // backward output
+  float* stash;         // forward (SAVE): out; stash backward: in
 };
 
-template <int NPASS, bool BWD>
+// ---- activation stash of the ray stage (forward SAVE -> k_ray_tc_bwd_stash): per 128-sample tile RP_PLANES planes of
+// [128 samples][4 words], 560 B per sample ----
+//   0..3 q (scaled, log2 domain, dimension-major, 0 for masked rows)   4..7 k   8..11 v (dimension-major)
+//   12..15 o (normalised attention output)   16 -max   17 1/sum   18..21 xhat (LayerNorm)   22 rstd, z2, n_valid, -
+//   23..30 ELU' codes of geometry_fc.0 (64)   31..32 of geometry_fc.2 (16)   33..34 of out_geometry_fc.0 (16)
+enum : int { RP_Q = 0, RP_K = 4, RP_V = 8, RP_O = 12, RP_NM = 16, RP_IL = 17, RP_XHAT = 18, RP_MISC = 22, RP_H64 = 23,
+             RP_G16 = 31, RP_HH = 33, RP_PLANES = 35 };
+constexpr size_t RP_TILE_BYTES = (size_t)RP_PLANES * GROUP * 16;   // 71680
+
+__device__ __forceinline__ void rp_st(float4* sp, int plane, float a, float b, float c, float d) {
+  sp[plane * GROUP] = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void rp_st_codes8(float4* sp, int plane, const uint32_t (&q)[8]) {
+  sp[plane * GROUP] = make_float4(__uint_as_float(q[0]), __uint_as_float(q[1]), __uint_as_float(q[2]), __uint_as_float(q[3]));
+  sp[(plane + 1) * GROUP] = make_float4(__uint_as_float(q[4]), __uint_as_float(q[5]), __uint_as_float(q[6]), __uint_as_float(q[7]));
+}
+__device__ __forceinline__ void rp_ld_codes8(const float4* sp, int plane, uint32_t (&q)[8]) {
+  const float4 a = __ldcs(sp + plane * GROUP), b = __ldcs(sp + (plane + 1) * GROUP);
+  q[0] = __float_as_uint(a.x); q[1] = __float_as_uint(a.y); q[2] = __float_as_uint(a.z); q[3] = __float_as_uint(a.w);
+  q[4] = __float_as_uint(b.x); q[5] = __float_as_uint(b.y); q[6] = __float_as_uint(b.z); q[7] = __float_as_uint(b.w);
+}
+
+template <int NPASS, bool BWD, bool SAVE>
 __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayArgs a) {
   using C = Cfg<NPASS, BWD>;
   constexpr int NG = C::NG;
@@ -239,6 +262,8 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
     const bool act = (rl < RPG) && (ray < a.R);
     const size_t smp = act ? ((size_t)ray * S + s) : 0;
     const float* psrow = a.ps + smp * NFB_PS_STRIDE;
+    float4* sp = reinterpret_cast<float4*>(a.stash) + (size_t)tile * (RP_PLANES * GROUP) + tg;
+    const bool save = SAVE && act;
 
     // ---------------- geometry_fc.0 : 64 pooled statistics on the tensor cores, the mean weight on the CUDA cores ----
 #pragma unroll
@@ -263,11 +288,12 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         h[j] = elu_fast(h[j] + fmaf(tail.x, sf[RF_WCOL + 16 * kc + j], sf[RF_B_GEO0 + 16 * kc + j]));
-      if (BWD) {
+      if (BWD || SAVE) {
         uint32_t q[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) q[j] = elu_stash_pack(h[2 * j], h[2 * j + 1]);
-        tmem_st8(tl + RC_HQ + 8 * kc, q);
+        if (BWD) tmem_st8(tl + RC_HQ + 8 * kc, q);
+        if (save) rp_st_codes8(sp, RP_H64 + 2 * kc, q);
       }
       r_put16<NPASS>(tl, kc, h);
     }
@@ -279,9 +305,10 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
       r_ld16(tl, 0, xin);
 #pragma unroll
       for (int j = 0; j < 16; ++j) xin[j] = elu_fast(xin[j] + sf[RF_B_GEO2 + j]);
-      if (BWD) {
+      if (BWD || SAVE) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) gq[j] = elu_stash_pack(xin[2 * j], xin[2 * j + 1]);
+        if (save) rp_st_codes8(sp, RP_G16, gq);
       }
       const float* pe = s_pos + (act ? s : 0) * 16;
 #pragma unroll
@@ -310,6 +337,11 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
         q23[d] = make_float2(qq[8 + d] * qs, qq[12 + d] * qs);
         *reinterpret_cast<float4*>(sk + tg * 16 + 4 * d) = make_float4(kk[d], kk[4 + d], kk[8 + d], kk[12 + d]);
         *reinterpret_cast<float4*>(sv + tg * 16 + 4 * d) = make_float4(vv[d], vv[4 + d], vv[8 + d], vv[12 + d]);
+        if (save) {
+          rp_st(sp, RP_Q + d, q01[d].x, q01[d].y, q23[d].x, q23[d].y);
+          rp_st(sp, RP_K + d, kk[d], kk[4 + d], kk[8 + d], kk[12 + d]);
+          rp_st(sp, RP_V + d, vv[d], vv[4 + d], vv[8 + d], vv[12 + d]);
+        }
       }
     }
     named_bar_sync(bar_id, GROUP);
@@ -356,6 +388,12 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
       }
     }
 
+    if (save) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rp_st(sp, RP_O + j, o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      rp_st(sp, RP_NM, -m2[0], -m2[1], -m2[2], -m2[3]);
+      rp_st(sp, RP_IL, il[0], il[1], il[2], il[3]);
+    }
     // ---------------- fc + residual + LayerNorm + sigma head ----------------
     r_put16<NPASS>(tl, 0, o);
     NFB_RTC_FWD(RL_FC);
@@ -383,6 +421,10 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
         xhat[c] = (y[c] - mu) * rstd;
         ln[c] = fmaf(xhat[c], sf[RF_LNW + c], sf[RF_LNB + c]);
       }
+      if (save) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rp_st(sp, RP_XHAT + j, xhat[4 * j], xhat[4 * j + 1], xhat[4 * j + 2], xhat[4 * j + 3]);
+      }
       r_put16<NPASS>(tl, 0, ln);
     }
     NFB_RTC_FWD(RL_OG0);
@@ -396,6 +438,13 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
       z2 = fmaf(hh[c], sf[RF_W_OG2 + c], z2);
     }
 
+    if (save) {
+      uint32_t hq[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) hq[j] = elu_stash_pack(hh[2 * j], hh[2 * j + 1]);
+      rp_st_codes8(sp, RP_HH, hq);
+      rp_st(sp, RP_MISC, rstd, z2, nvalid, 0.f);
+    }
     if (!BWD) {
       float sigma = fmaxf(z2, 0.f);
       if (nvalid < 1.f) sigma = 0.f;                     // mlp_network.py:265
@@ -627,11 +676,11 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
   if (warp == 0) tmem_dealloc(*s_tmem, NG * C::GC);
 }
 
-template <int NPASS, bool BWD>
+template <int NPASS, bool BWD, bool SAVE = false>
 int launch_ray_tc(const RayArgs& a, cudaStream_t st) {
   using C = Cfg<NPASS, BWD>;
   const size_t smem = C::smem(a.S);
-  cudaError_t e = cudaFuncSetAttribute(k_ray_tc<NPASS, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_ray_tc<NPASS, BWD, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nfb_set_error(NFB_ECUDA, "k_ray_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int RPG = GROUP / a.S;
   const int ntiles = (a.R + RPG - 1) / RPG;
@@ -639,8 +688,400 @@ int launch_ray_tc(const RayArgs& a, cudaStream_t st) {
   const int cap = nfb_num_sms();
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  k_ray_tc<NPASS, BWD><<<grid, GROUP * C::NG, smem, st>>>(a);
+  k_ray_tc<NPASS, BWD, SAVE><<<grid, GROUP * C::NG, smem, st>>>(a);
   NFB_CHECK_LAUNCH("k_ray_tc");
+  return NFB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Data-gradient of the ray stage FROM THE STASH: no forward recompute, 128 registers, 4 groups (16 warps) per SM.
+// TMEM columns of a group (128): D [0,64) | A hi [64,96) | A lo [96,128); dy is parked in D columns [48,64) while the
+// attention passes run.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BS_NG = 4;
+constexpr int BS_GROUP_FLOATS = 4 * GROUP * 16 + GROUP * 16;    // K, V, Q, dO rows + statistics
+template <int NPASS>
+size_t bwd_stash_smem() {
+  return (size_t)R_SET_BYTES * (NPASS == 3 ? 2 : 1) + sizeof(float) * (RF_TOTAL + (size_t)BS_NG * BS_GROUP_FLOATS) + BS_NG * 8 + 16;
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int NPASS>
+__global__ void __launch_bounds__(GROUP * BS_NG, 1) k_ray_tc_bwd_stash(RayArgs a) {
+  constexpr int NG = BS_NG;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sB = smem_raw;
+  float* sf = reinterpret_cast<float*>(smem_raw + (size_t)R_SET_BYTES * (NPASS == 3 ? 2 : 1));
+  float* s_grp = sf + RF_TOTAL;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_grp + (size_t)NG * BS_GROUP_FLOATS);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + NG);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int grp = tid / GROUP, tg = tid % GROUP;
+  float* sk = s_grp + (size_t)grp * BS_GROUP_FLOATS;   // [128][16] each, dimension-major rows
+  float* sv = sk + GROUP * 16;
+  float* sq = sv + GROUP * 16;
+  float* sdo = sq + GROUP * 16;
+  float* sst = sdo + GROUP * 16;                        // [128][16]: -m[4] | 1/l[4] | -D[4] | valid x4
+  const int bar_id = 1 + grp;
+  uint64_t* mbar = s_bar + grp;
+
+  if (warp == 0) tmem_alloc(s_tmem, NG * 128);
+  if (tid == 0) {
+    for (int g = 0; g < NG; ++g) mbar_init(s_bar + g, 1);
+    mbar_init_fence();
+  }
+  {
+    const float* p = a.params;
+    load_rtile<NPASS>(sB, RL_GEO0, p + P_GEO0_W, 64, 65, tid, blockDim.x);
+    load_rtile<NPASS>(sB, RL_GEO2, p + P_GEO2_W, 16, 64, tid, blockDim.x);
+    load_rtile<NPASS>(sB, RL_QKV, p + P_ATT_Q, 48, 16, tid, blockDim.x);
+    load_rtile<NPASS>(sB, RL_FC, p + P_ATT_FC, 16, 16, tid, blockDim.x);
+    load_rtile<NPASS>(sB, RL_OG0, p + P_OG0_W, 16, 16, tid, blockDim.x);
+    for (int i = tid; i < 64; i += blockDim.x) {
+      sf[RF_B_GEO0 + i] = __ldg(p + P_GEO0_B + i);
+      sf[RF_WCOL + i] = __ldg(p + P_GEO0_W + i * 65 + 64);
+    }
+    for (int i = tid; i < 16; i += blockDim.x) {
+      sf[RF_LNW + i] = __ldg(p + P_LN_W + i);
+      sf[RF_W_OG2 + i] = __ldg(p + P_OG2_W + i);
+    }
+  }
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+
+  const uint32_t tb = *s_tmem + (uint32_t)(grp * 128);
+  const uint32_t tl = tb + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t sB_addr = smem_u32(sB);
+  uint32_t phase = 0;
+
+  const int S = a.S;
+  const int RPG = GROUP / S;
+  const int rl = tg / S, s = tg - rl * S;
+  const int kb = (rl < RPG ? rl : 0) * S;
+  const int ntiles = (a.R + RPG - 1) / RPG;
+
+  for (int tile = blockIdx.x * NG + grp; tile < ntiles; tile += gridDim.x * NG) {
+    const int ray = tile * RPG + rl;
+    const bool act = (rl < RPG) && (ray < a.R);
+    const size_t smp = act ? ((size_t)ray * S + s) : 0;
+    const float4* sp = reinterpret_cast<const float4*>(a.stash) + (size_t)tile * (RP_PLANES * GROUP) + tg;
+
+    // K / V / Q rows of this sample: global -> shared, asynchronously (rows of inactive samples are zero-filled)
+    if (act) {
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        cp_async16(sq + tg * 16 + 4 * d, sp + (RP_Q + d) * GROUP);
+        cp_async16(sk + tg * 16 + 4 * d, sp + (RP_K + d) * GROUP);
+        cp_async16(sv + tg * 16 + 4 * d, sp + (RP_V + d) * GROUP);
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        *reinterpret_cast<float4*>(sq + tg * 16 + 4 * d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(sk + tg * 16 + 4 * d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(sv + tg * 16 + 4 * d) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    // next tile of this group towards L2
+    {
+      const int nt = tile + gridDim.x * NG;
+      if (nt < ntiles && (tg & 7) == 0) {
+        const float4* np = reinterpret_cast<const float4*>(a.stash) + (size_t)nt * (RP_PLANES * GROUP) + tg;
+#pragma unroll 5
+        for (int pl = 0; pl < RP_PLANES; ++pl) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + pl * GROUP));
+      }
+    }
+
+    float4 misc = make_float4(1.f, 0.f, 0.f, 0.f);
+    float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t hq[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    float xhat[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) xhat[c] = 0.f;
+    if (act) {
+      misc = __ldcs(sp + RP_MISC * GROUP);
+      dr = __ldg(reinterpret_cast<const float4*>(a.d_raw) + smp);
+      rp_ld_codes8(sp, RP_HH, hq);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 q = __ldcs(sp + (RP_XHAT + j) * GROUP);
+        xhat[4 * j] = q.x; xhat[4 * j + 1] = q.y; xhat[4 * j + 2] = q.z; xhat[4 * j + 3] = q.w;
+      }
+    }
+    const float rstd = misc.x, z2 = misc.y, nvalid = misc.z;
+    const bool row_valid = act && nvalid > 1.f;
+    const float dz2 = (z2 > 0.f && !(nvalid < 1.f)) ? dr.w : 0.f;
+    // sigma head
+    {
+      float dh[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dh[2 * j] = dz2 * sf[RF_W_OG2 + 2 * j] * elu_stash_lo(hq[j]);
+        dh[2 * j + 1] = dz2 * sf[RF_W_OG2 + 2 * j + 1] * elu_stash_hi(hq[j]);
+      }
+      r_put16<NPASS>(tl, 0, dh);
+    }
+    NFB_RTC_BWD(RL_OG0);
+    NFB_RTC_WAIT();
+    // LayerNorm backward: dy = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dln * gamma
+    {
+      float dy[16];
+      r_ld16(tl, 0, dy);
+      float gsum = 0.f, gx = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        dy[c] *= sf[RF_LNW + c];
+        gsum += dy[c];
+        gx = fmaf(dy[c], xhat[c], gx);
+      }
+      gsum *= (1.f / 16.f); gx *= (1.f / 16.f);
+      uint32_t park[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        dy[c] = rstd * (dy[c] - gsum - xhat[c] * gx);
+        park[c] = __float_as_uint(dy[c]);
+      }
+      tmem_st16(tl + RC_D + 48, park);          // dy is needed again after the attention passes
+      r_put16<NPASS>(tl, 0, dy);
+    }
+    NFB_RTC_BWD(RL_FC);
+    NFB_RTC_WAIT();
+    float2 dO01[4], dO23[4];
+    float nm[4], il[4], nD[4];
+    {
+      float dO[16];
+      r_ld16(tl, 0, dO);
+      float o[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) o[c] = 0.f;
+      float4 nm4 = make_float4(0.f, 0.f, 0.f, 0.f), il4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (act) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 q = __ldcs(sp + (RP_O + j) * GROUP);
+          o[4 * j] = q.x; o[4 * j + 1] = q.y; o[4 * j + 2] = q.z; o[4 * j + 3] = q.w;
+        }
+        nm4 = __ldcs(sp + RP_NM * GROUP);
+        il4 = __ldcs(sp + RP_IL * GROUP);
+      }
+      nm[0] = nm4.x; nm[1] = nm4.y; nm[2] = nm4.z; nm[3] = nm4.w;
+      il[0] = il4.x; il[1] = il4.y; il[2] = il4.z; il[3] = il4.w;
+#pragma unroll
+      for (int h = 0; h < 4; ++h)
+        nD[h] = -(dO[4 * h] * o[4 * h] + dO[4 * h + 1] * o[4 * h + 1] + dO[4 * h + 2] * o[4 * h + 2] + dO[4 * h + 3] * o[4 * h + 3]);
+      const float vf = row_valid ? 1.f : 0.f;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        dO01[d] = make_float2(dO[d], dO[4 + d]);
+        dO23[d] = make_float2(dO[8 + d], dO[12 + d]);
+        *reinterpret_cast<float4*>(sdo + tg * 16 + 4 * d) = make_float4(dO[d], dO[4 + d], dO[8 + d], dO[12 + d]);
+      }
+      *reinterpret_cast<float4*>(sst + tg * 16) = nm4;
+      *reinterpret_cast<float4*>(sst + tg * 16 + 4) = il4;
+      *reinterpret_cast<float4*>(sst + tg * 16 + 8) = make_float4(nD[0], nD[1], nD[2], nD[3]);
+      *reinterpret_cast<float4*>(sst + tg * 16 + 12) = make_float4(vf, vf, vf, vf);
+    }
+    cp_async_wait_all();
+    named_bar_sync(bar_id, GROUP);
+
+    // query side: dq_i = sum_j dS_ij k_j  (zero for masked rows: masked_fill blocks the gradient)
+    {
+      float2 q01[4], q23[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const float4 q4 = *reinterpret_cast<const float4*>(sq + tg * 16 + 4 * d);
+        q01[d] = make_float2(q4.x, q4.y);
+        q23[d] = make_float2(q4.z, q4.w);
+      }
+      const float4* kr = reinterpret_cast<const float4*>(sk + kb * 16);
+      const float4* vr = reinterpret_cast<const float4*>(sv + kb * 16);
+      const float2 nm01 = make_float2(nm[0], nm[1]), nm23 = make_float2(nm[2], nm[3]);
+      const float2 il01 = make_float2(il[0], il[1]), il23 = make_float2(il[2], il[3]);
+      const float2 nD01 = make_float2(nD[0], nD[1]), nD23 = make_float2(nD[2], nD[3]);
+      float2 dq01[4], dq23[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) dq01[d] = dq23[d] = make_float2(0.f, 0.f);
+      for (int j = 0; j < S; ++j) {
+        float2 s01, s23;
+        attn_scores(kr + 4 * j, q01, q23, s01, s23);
+        s01 = __fadd2_rn(s01, nm01);
+        s23 = __fadd2_rn(s23, nm23);
+        const float2 p01 = __fmul2_rn(make_float2(ex2_approx(s01.x), ex2_approx(s01.y)), il01);
+        const float2 p23 = __fmul2_rn(make_float2(ex2_approx(s23.x), ex2_approx(s23.y)), il23);
+        float2 dP01 = nD01, dP23 = nD23;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const float4 vj = vr[4 * j + d];
+          dP01 = __ffma2_rn(dO01[d], make_float2(vj.x, vj.y), dP01);
+          dP23 = __ffma2_rn(dO23[d], make_float2(vj.z, vj.w), dP23);
+        }
+        const float2 dS01 = __fmul2_rn(p01, dP01), dS23 = __fmul2_rn(p23, dP23);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const float4 kj = kr[4 * j + d];
+          dq01[d] = __ffma2_rn(dS01, make_float2(kj.x, kj.y), dq01[d]);
+          dq23[d] = __ffma2_rn(dS23, make_float2(kj.z, kj.w), dq23[d]);
+        }
+      }
+      const float sc = row_valid ? INV_TEMP : 0.f;
+      float dq[16];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        dq[d] = dq01[d].x * sc;
+        dq[4 + d] = dq01[d].y * sc;
+        dq[8 + d] = dq23[d].x * sc;
+        dq[12 + d] = dq23[d].y * sc;
+      }
+      r_put16<NPASS>(tl, 0, dq);
+    }
+    // key side: dk_j = sum_i dS_ij q_i ; dv_j = sum_i p_ij dO_i   (this thread is key j)
+    {
+      float2 k01[4], k23[4], v01[4], v23[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const float4 k4 = *reinterpret_cast<const float4*>(sk + tg * 16 + 4 * d);
+        const float4 v4 = *reinterpret_cast<const float4*>(sv + tg * 16 + 4 * d);
+        k01[d] = make_float2(k4.x, k4.y); k23[d] = make_float2(k4.z, k4.w);
+        v01[d] = make_float2(v4.x, v4.y); v23[d] = make_float2(v4.z, v4.w);
+      }
+      float2 dk01[4], dk23[4], dv01[4], dv23[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) dk01[d] = dk23[d] = dv01[d] = dv23[d] = make_float2(0.f, 0.f);
+      const float4* qr = reinterpret_cast<const float4*>(sq + kb * 16);
+      const float4* gr = reinterpret_cast<const float4*>(sdo + kb * 16);
+      const float4* st = reinterpret_cast<const float4*>(sst + kb * 16);
+      for (int i = 0; i < S; ++i) {
+        float4 qi[4], gi[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) { qi[d] = qr[4 * i + d]; gi[d] = gr[4 * i + d]; }
+        const float4 nmi = st[4 * i], ili = st[4 * i + 1], nDi = st[4 * i + 2], vf = st[4 * i + 3];
+        float2 s01 = make_float2(nmi.x, nmi.y), s23 = make_float2(nmi.z, nmi.w);
+        float2 dP01 = make_float2(nDi.x, nDi.y), dP23 = make_float2(nDi.z, nDi.w);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          s01 = __ffma2_rn(make_float2(qi[d].x, qi[d].y), k01[d], s01);
+          s23 = __ffma2_rn(make_float2(qi[d].z, qi[d].w), k23[d], s23);
+          dP01 = __ffma2_rn(make_float2(gi[d].x, gi[d].y), v01[d], dP01);
+          dP23 = __ffma2_rn(make_float2(gi[d].z, gi[d].w), v23[d], dP23);
+        }
+        const float2 p01 = __fmul2_rn(make_float2(ex2_approx(s01.x), ex2_approx(s01.y)), make_float2(ili.x, ili.y));
+        const float2 p23 = __fmul2_rn(make_float2(ex2_approx(s23.x), ex2_approx(s23.y)), make_float2(ili.z, ili.w));
+        const float2 dS01 = __fmul2_rn(__fmul2_rn(p01, dP01), make_float2(vf.x, vf.y));
+        const float2 dS23 = __fmul2_rn(__fmul2_rn(p23, dP23), make_float2(vf.z, vf.w));
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          dk01[d] = __ffma2_rn(dS01, make_float2(qi[d].x, qi[d].y), dk01[d]);
+          dk23[d] = __ffma2_rn(dS23, make_float2(qi[d].z, qi[d].w), dk23[d]);
+          dv01[d] = __ffma2_rn(p01, make_float2(gi[d].x, gi[d].y), dv01[d]);
+          dv23[d] = __ffma2_rn(p23, make_float2(gi[d].z, gi[d].w), dv23[d]);
+        }
+      }
+      float t[16];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        t[d] = dk01[d].x * (1.f / LOG2E);
+        t[4 + d] = dk01[d].y * (1.f / LOG2E);
+        t[8 + d] = dk23[d].x * (1.f / LOG2E);
+        t[12 + d] = dk23[d].y * (1.f / LOG2E);
+      }
+      r_put16<NPASS>(tl, 1, t);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        t[d] = dv01[d].x; t[4 + d] = dv01[d].y; t[8 + d] = dv23[d].x; t[12 + d] = dv23[d].y;
+      }
+      r_put16<NPASS>(tl, 2, t);
+    }
+    // d xin = dy (residual) + [dq | dk | dv] Wqkv ; pos_encoding is a constant
+    NFB_RTC_BWD(RL_QKV);
+    uint32_t gq[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (act) rp_ld_codes8(sp, RP_G16, gq);
+    NFB_RTC_WAIT();
+    {
+      float dx[16];
+      r_ld16(tl, 0, dx);
+      uint32_t park[16];
+      tmem_ld16u(tl + RC_D + 48, park);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dx[2 * j] = (dx[2 * j] + __uint_as_float(park[2 * j])) * elu_stash_lo(gq[j]);
+        dx[2 * j + 1] = (dx[2 * j + 1] + __uint_as_float(park[2 * j + 1])) * elu_stash_hi(gq[j]);
+      }
+      r_put16<NPASS>(tl, 0, dx);
+    }
+    NFB_RTC_BWD(RL_GEO2);
+    uint32_t cq[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) cq[j] = 0u;
+    if (act) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 q = __ldcs(sp + (RP_H64 + j) * GROUP);
+        cq[4 * j] = __float_as_uint(q.x); cq[4 * j + 1] = __float_as_uint(q.y);
+        cq[4 * j + 2] = __float_as_uint(q.z); cq[4 * j + 3] = __float_as_uint(q.w);
+      }
+    }
+    NFB_RTC_WAIT();
+    float dwm = 0.f;
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+      float dh[16];
+      r_ld16(tl, 16 * kc, dh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dh[2 * j] *= elu_stash_lo(cq[8 * kc + j]);
+        dh[2 * j + 1] *= elu_stash_hi(cq[8 * kc + j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dwm = fmaf(dh[j], sf[RF_WCOL + 16 * kc + j], dwm);
+      r_put16<NPASS>(tl, kc, dh);
+    }
+    NFB_RTC_BWD(RL_GEO0);
+    NFB_RTC_WAIT();
+    {
+      float4* out = reinterpret_cast<float4*>(a.d_ps + smp * NFB_PS_STRIDE);
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        float t[16];
+        r_ld16(tl, 16 * kc, t);
+        if (act) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) out[4 * kc + j] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
+        }
+      }
+      if (act) {
+        out[16] = make_float4(dwm, dr.x, dr.y, dr.z);
+        out[17] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    named_bar_sync(bar_id, GROUP);                     // K / V / Q / dO rows are rewritten by the next tile
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(*s_tmem, NG * 128);
+}
+
+template <int NPASS>
+int launch_ray_tc_bwd_stash(const RayArgs& a, cudaStream_t st) {
+  const size_t smem = bwd_stash_smem<NPASS>();
+  cudaError_t e = cudaFuncSetAttribute(k_ray_tc_bwd_stash<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return nfb_set_error(NFB_ECUDA, "k_ray_tc_bwd_stash: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  const int RPG = GROUP / a.S;
+  const int ntiles = (a.R + RPG - 1) / RPG;
+  int grid = (ntiles + BS_NG - 1) / BS_NG;
+  const int cap = nfb_num_sms();
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  k_ray_tc_bwd_stash<NPASS><<<grid, GROUP * BS_NG, smem, st>>>(a);
+  NFB_CHECK_LAUNCH("k_ray_tc_bwd_stash");
   return NFB_OK;
 }
 
@@ -651,3 +1092,7 @@ int nfb_launch_ray_tc_fwd_p1(const nfbrtc::RayArgs& a, cudaStream_t st);
 int nfb_launch_ray_tc_fwd_p3(const nfbrtc::RayArgs& a, cudaStream_t st);
 int nfb_launch_ray_tc_bwd_p1(const nfbrtc::RayArgs& a, cudaStream_t st);
 int nfb_launch_ray_tc_bwd_p3(const nfbrtc::RayArgs& a, cudaStream_t st);
+int nfb_launch_ray_tc_fwd_p1_save(const nfbrtc::RayArgs& a, cudaStream_t st);
+int nfb_launch_ray_tc_fwd_p3_save(const nfbrtc::RayArgs& a, cudaStream_t st);
+int nfb_launch_ray_tc_bwd_stash_p1(const nfbrtc::RayArgs& a, cudaStream_t st);
+int nfb_launch_ray_tc_bwd_stash_p3(const nfbrtc::RayArgs& a, cudaStream_t st);

@@ -155,7 +155,7 @@ class IBRNetAggregate(torch.autograd.Function):
             st = stream_ptr(dev)
             call('nfb_ibrnet_view_fwd', N, S, V, int(anti_alias), ptr(rf), ptr(rd), ptr(mk), 0, 0, 0, 0,
                  None, None, None, None, None, None, None, ptr(params), ptr(ps), None, _lib.precision_code(), st)
-            call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), _lib.precision_code(), st)
+            call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), None, _lib.precision_code(), st)
         ctx.save_for_backward(rf, rd, mk, params, pos_enc, ps)
         ctx.dims = (R, S, V, int(anti_alias))
         ctx.precision = _lib.precision_code()
@@ -174,7 +174,7 @@ class IBRNetAggregate(torch.autograd.Function):
             d_rf = torch.empty_like(rf)
             with torch.cuda.device(dev):
                 st = stream_ptr(dev)
-                call('nfb_ibrnet_ray_bwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(g), ptr(d_ps), ctx.precision, st)
+                call('nfb_ibrnet_ray_bwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(g), ptr(d_ps), None, ctx.precision, st)
                 call('nfb_ibrnet_view_bwd', N, S, V, aa, ptr(rf), ptr(rd), ptr(mk), 0, 0, 0, 0,
                      None, None, None, None, None, None, None, ptr(params), ptr(ps), ptr(d_ps),
                      ptr(d_rf), None, None, None, ctx.precision, st)
@@ -288,15 +288,18 @@ class RenderLevel(torch.autograd.Function):
         # activation stash for the backward (768 B per (sample, view) row): written only when a gradient is wanted
         n_stash = _lib.stash_bytes(N, V) if need else 0
         stash = torch.empty(n_stash, device=dev, dtype=torch.uint8) if n_stash else None
+        n_rstash = _lib.ray_stash_bytes(R, S) if need else 0
+        rstash = torch.empty(n_rstash, device=dev, dtype=torch.uint8) if n_rstash else None
         with torch.cuda.device(dev):
             st = stream_ptr(dev)
             call('nfb_ibrnet_view_fwd', N, S, V, int(anti_alias), None, None, None, H, W, fh, fw,
                  None, ptr(o_c), ptr(d_c), ptr(z_c), ptr(cam), ptr(imgs_c), ptr(feat), ptr(params), ptr(ps),
                  ptr(stash), _lib.precision_code(), st)
-            call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), _lib.precision_code(), st)
+            call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), ptr(rstash), _lib.precision_code(), st)
             call('nfb_composite_fwd', R, S, int(white_bkgd), ptr(raw), ptr(z_c), None, ptr(ps[:, 68:]), PS_STRIDE,
                  ptr(rgb), ptr(depth), ptr(weights), ptr(alpha), ptr(ray_mask), st)
         ctx.stash = stash
+        ctx.rstash = rstash
         if need:
             ctx.save_for_backward(feat, imgs_c, o_c, d_c, z_c, cam, params, pos_enc, ps, raw)
         ctx.dims = (R, S, V, H, W, fh, fw, int(anti_alias), int(white_bkgd))
@@ -322,10 +325,11 @@ class RenderLevel(torch.autograd.Function):
             st = stream_ptr(dev)
             call('nfb_composite_bwd', R, S, white, ptr(raw), ptr(z_c), ptr(f32c(d_rgb)), ptr(f32c(d_depth)),
                  ptr(f32c(d_weights)), ptr(f32c(d_alpha)), ptr(d_raw), st)
-            call('nfb_ibrnet_ray_bwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(d_raw), ptr(d_ps), ctx.precision, st)
+            call('nfb_ibrnet_ray_bwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(d_raw), ptr(d_ps), ptr(ctx.rstash), ctx.precision, st)
             call('nfb_ibrnet_view_bwd', N, S, V, aa, None, None, None, H, W, fh, fw,
                  None, ptr(o_c), ptr(d_c), ptr(z_c), ptr(cam), ptr(imgs_c), ptr(feat), ptr(params), ptr(ps),
                  ptr(d_ps), None, ptr(d_feat), ptr(d_imgs), ptr(ctx.stash), ctx.precision, st)
         ctx.stash = None
+        ctx.rstash = None
         return (d_feat.permute(0, 3, 1, 2) if need_feat else None, d_imgs,
                 None, None, None, None, None, None, None, None, None, None)

@@ -446,7 +446,7 @@ def test_stash_backward_equals_recompute_backward(dev):
     saved = _lib.STASH_MAX_GIB
     try:
         _lib.STASH_MAX_GIB = 48.0
-        assert _lib.stash_bytes(77 * S, 5) > 0
+        assert _lib.stash_bytes(77 * S, 5) > 0 and _lib.ray_stash_bytes(77, S) > 0
         _, fm_s = _attack_grads(dev, scene, gb, model, S, NI)
         _lib.STASH_MAX_GIB = 0.0
         assert _lib.stash_bytes(77 * S, 5) == 0

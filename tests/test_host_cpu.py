@@ -61,7 +61,7 @@ def test_argument_validation_fails_loudly_without_touching_the_gpu(lib):
                   None, None, None, None, None, None)
     with pytest.raises(RuntimeError, match='> 256 samples'):
         _lib.call('nfb_ibrnet_ray_fwd', 1, 257, _lib.c_void_p(16), _lib.c_void_p(16), _lib.c_void_p(16),
-                  _lib.c_void_p(16), 0, None)
+                  _lib.c_void_p(16), None, 0, None)
     assert b'samples' in lib.nfb_last_error_string()
 
 
@@ -70,6 +70,8 @@ def test_stash_size_query(lib):
     assert lib.nfb_view_stash_bytes(6400, 4) == (6400 // 32) * 48 * 128 * 16
     assert lib.nfb_view_stash_bytes(100, 10) == -(-100 // 12) * 48 * 128 * 16
     assert lib.nfb_view_stash_bytes(0, 4) == 0 and lib.nfb_view_stash_bytes(10, 33) == 0
+    assert lib.nfb_ray_stash_bytes(100, 64) == 50 * 35 * 128 * 16 and lib.nfb_ray_stash_bytes(7, 128) == 7 * 35 * 128 * 16
+    assert lib.nfb_ray_stash_bytes(5, 33) == 2 * 35 * 128 * 16 and lib.nfb_ray_stash_bytes(5, 192) == 0
 
 
 def test_no_cpu_fallback():
