@@ -241,6 +241,46 @@ __device__ __forceinline__ void st_codes8(float4* sp, int plane, const uint32_t 
   st_plane(sp, plane + 1, q[4], q[5], q[6], q[7]);
 }
 
+// ---- cross-view reductions with instruction-level parallelism ---------------------------------------------
+// The V rows of a sample sit in consecutive exchange-buffer rows.  A thread owns channels c0, c0 + V, c0 + 2V, ...;
+// up to KMAX of them are accumulated side by side (independent chains, the loop over views outermost), so the
+// shared-memory latency of one channel hides behind the others.  row0 = ex + base * EXS.
+constexpr int POOL_K = 9;     // ceil(35 / V) for V >= 4; smaller V take several rounds
+// acc[k] = sum_u row_u[c0 + k V] * (WEIGHTED ? row_u[wslot] * scale : 1)
+template <bool WEIGHTED>
+__device__ __forceinline__ void pool_sum(const float* __restrict__ row0, int V, int c0, int cmax, int wslot, float scale,
+                                         float (&acc)[POOL_K]) {
+#pragma unroll
+  for (int k = 0; k < POOL_K; ++k) acc[k] = 0.f;
+  for (int u = 0; u < V; ++u) {
+    const float* r = row0 + u * EXS;
+    const float wu = WEIGHTED ? r[wslot] * scale : 1.f;
+#pragma unroll
+    for (int k = 0; k < POOL_K; ++k) {
+      const int c = c0 + k * V;
+      if (c < cmax) acc[k] = WEIGHTED ? fmaf(r[c], wu, acc[k]) : acc[k] + r[c];
+    }
+  }
+}
+// var[k] = sum_u (row_u[wslot] * scale) * (row_u[c] - mean[k])^2
+__device__ __forceinline__ void pool_var(const float* __restrict__ row0, int V, int c0, int cmax, int wslot, float scale,
+                                         const float (&mean)[POOL_K], float (&var)[POOL_K]) {
+#pragma unroll
+  for (int k = 0; k < POOL_K; ++k) var[k] = 0.f;
+  for (int u = 0; u < V; ++u) {
+    const float* r = row0 + u * EXS;
+    const float wu = r[wslot] * scale;
+#pragma unroll
+    for (int k = 0; k < POOL_K; ++k) {
+      const int c = c0 + k * V;
+      if (c < cmax) {
+        const float d = r[c] - mean[k];
+        var[k] = fmaf(wu * d, d, var[k]);
+      }
+    }
+  }
+}
+
 // all threads of the group: publish the A stores, let thread 0 issue + commit
 #define NFB_TC_ISSUE(LAYER, KS0, KS1, ACC0)                                   \
   do {                                                                        \
@@ -424,25 +464,29 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
     ex[tg * EXS + 35] = w;
     named_bar_sync(bar_id, GROUP);
     if (active) {
-      for (int c = v; c < NFB_ROW_CH; c += V) {
-        float m = 0.f;
-        for (int u = 0; u < V; ++u) m = fmaf(ex[(base + u) * EXS + c], ex[(base + u) * EXS + 35], m);
-        float vr = 0.f;
-        for (int u = 0; u < V; ++u) {
-          const float d = ex[(base + u) * EXS + c] - m;
-          vr = fmaf(ex[(base + u) * EXS + 35] * d, d, vr);
-        }
-        mvs[c] = m;
-        mvs[36 + c] = vr;
-        // the operand halves of this statistic, split once per sample instead of once per row
+      const float* row0 = ex + base * EXS;
+      for (int c0 = v; c0 < NFB_ROW_CH; c0 += POOL_K * V) {
+        float mk9[POOL_K], vk9[POOL_K];
+        pool_sum<true>(row0, V, c0, NFB_ROW_CH, 35, 1.f, mk9);
+        pool_var(row0, V, c0, NFB_ROW_CH, 35, 1.f, mk9, vk9);
         __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(mvps);
         __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(mvps + 36);
-        const __nv_bfloat16 mh = __float2bfloat16_rn(m), vh = __float2bfloat16_rn(vr);
-        ph[c] = mh;
-        ph[35 + c] = vh;
-        if (NPASS == 3) {
-          pl[c] = __float2bfloat16_rn(m - __bfloat162float(mh));
-          pl[35 + c] = __float2bfloat16_rn(vr - __bfloat162float(vh));
+#pragma unroll
+        for (int k = 0; k < POOL_K; ++k) {
+          const int c = c0 + k * V;
+          if (c < NFB_ROW_CH) {
+            const float m = mk9[k], vr = vk9[k];
+            mvs[c] = m;
+            mvs[36 + c] = vr;
+            // the operand halves of this statistic, split once per sample instead of once per row
+            const __nv_bfloat16 mh = __float2bfloat16_rn(m), vh = __float2bfloat16_rn(vr);
+            ph[c] = mh;
+            ph[35 + c] = vh;
+            if (NPASS == 3) {
+              pl[c] = __float2bfloat16_rn(m - __bfloat162float(mh));
+              pl[35 + c] = __float2bfloat16_rn(vr - __bfloat162float(vh));
+            }
+          }
         }
       }
     }
@@ -638,16 +682,19 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       for (int u = 0; u < V; ++u) D += ex[(base + u) * EXS + 32];
       const float invD = 1.f / D;
       float* out = a.ps + (size_t)p * NFB_PS_STRIDE;
-      for (int c = v; c < 32; c += V) {
-        float m = 0.f;
-        for (int u = 0; u < V; ++u) m = fmaf(ex[(base + u) * EXS + c], ex[(base + u) * EXS + 32] * invD, m);
-        float vr = 0.f;
-        for (int u = 0; u < V; ++u) {
-          const float d = ex[(base + u) * EXS + c] - m;
-          vr = fmaf((ex[(base + u) * EXS + 32] * invD) * d, d, vr);
+      const float* row0 = ex + base * EXS;
+      for (int c0 = v; c0 < 32; c0 += POOL_K * V) {
+        float mk9[POOL_K], vk9[POOL_K];
+        pool_sum<true>(row0, V, c0, 32, 32, invD, mk9);
+        pool_var(row0, V, c0, 32, 32, invD, mk9, vk9);
+#pragma unroll
+        for (int k = 0; k < POOL_K; ++k) {
+          const int c = c0 + k * V;
+          if (c < 32) {
+            out[PS_MEAN + c] = mk9[k];
+            out[PS_VAR + c] = vk9[k];
+          }
         }
-        out[PS_MEAN + c] = m;
-        out[PS_VAR + c] = vr;
       }
       if (v == 0) {
         float mx = -3.4e38f;

@@ -165,8 +165,11 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       if (nt < ntiles) {
         if ((tg & 7) == 0) {
           const float4* np = reinterpret_cast<const float4*>(a.stash) + (size_t)nt * (ST_PLANES * GROUP) + tg;
-#pragma unroll 8
-          for (int pl = 0; pl < ST_PLANES - 1; ++pl) prefetch_l2(np + pl * GROUP);
+#pragma unroll 5
+          for (int pl = 0; pl < SP_H1; ++pl) prefetch_l2(np + pl * GROUP);          // x0, x2, scalars
+          prefetch_l2(np + SP_G1 * GROUP);
+          prefetch_l2(np + (SP_G1 + 1) * GROUP);
+          prefetch_l2(np + SP_G2 * GROUP);
         }
         const int q0 = nt * TS;
         const int nn = (a.N - q0 < TS) ? (a.N - q0) : TS;
@@ -207,10 +210,13 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
     float wsum0 = 0.f;
     for (int u = 0; u < V; ++u) wsum0 += ex[(base + u) * EXS + 35];
     if (active) {
-      for (int c = v; c < NFB_ROW_CH; c += V) {
-        float m = 0.f;
-        for (int u = 0; u < V; ++u) m = fmaf(ex[(base + u) * EXS + c], ex[(base + u) * EXS + 35], m);
-        mvs[c] = m;
+      const float* row0 = ex + base * EXS;
+      for (int c0 = v; c0 < NFB_ROW_CH; c0 += POOL_K * V) {
+        float mk9[POOL_K];
+        pool_sum<true>(row0, V, c0, NFB_ROW_CH, 35, 1.f, mk9);
+#pragma unroll
+        for (int k = 0; k < POOL_K; ++k)
+          if (c0 + k * V < NFB_ROW_CH) mvs[c0 + k * V] = mk9[k];
       }
     }
     named_bar_sync(bar_id, GROUP);
@@ -443,10 +449,13 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
     // exchange round 1 (overlaps the MMA): per-sample sums of d mean0, parked in the (now dead) cotangent staging row
     float* dpw = dpb + (active ? sl : 0) * DPS;
     if (active) {
-      for (int c = v; c < NFB_ROW_CH; c += V) {
-        float dm = 0.f;
-        for (int u = 0; u < V; ++u) dm += ex[(base + u) * EXS + c];
-        dpw[c] = dm;
+      const float* row0 = ex + base * EXS;
+      for (int c0 = v; c0 < NFB_ROW_CH; c0 += POOL_K * V) {
+        float s9[POOL_K];
+        pool_sum<false>(row0, V, c0, NFB_ROW_CH, 0, 1.f, s9);
+#pragma unroll
+        for (int k = 0; k < POOL_K; ++k)
+          if (c0 + k * V < NFB_ROW_CH) dpw[c0 + k * V] = s9[k];
       }
     }
     named_bar_sync(bar_id, GROUP);
@@ -477,12 +486,19 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
     }
     named_bar_sync(bar_id, GROUP);
     if (active) {
-      for (int c = v; c < NFB_ROW_CH; c += V) {
-        float dv = 0.f;
-        for (int u = 0; u < V; ++u) dv += ex[(base + u) * EXS + c];
-        const float m0 = mvs[c];
-        mvs[c] = dpw[c] - 2.f * dv * m0 * (2.f - wsum0);
-        mvs[36 + c] = 2.f * dv;
+      const float* row0 = ex + base * EXS;
+      for (int c0 = v; c0 < NFB_ROW_CH; c0 += POOL_K * V) {
+        float s9[POOL_K];
+        pool_sum<false>(row0, V, c0, NFB_ROW_CH, 0, 1.f, s9);
+#pragma unroll
+        for (int k = 0; k < POOL_K; ++k) {
+          const int c = c0 + k * V;
+          if (c < NFB_ROW_CH) {
+            const float dv = s9[k], m0 = mvs[c];
+            mvs[c] = dpw[c] - 2.f * dv * m0 * (2.f - wsum0);
+            mvs[36 + c] = 2.f * dv;
+          }
+        }
       }
     }
     named_bar_sync(bar_id, GROUP);
