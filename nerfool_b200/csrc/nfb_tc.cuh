@@ -204,10 +204,38 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return r;
 }
 // split (a, b) into hi = bf16(x) and lo = bf16(x - hi): x = hi + lo to ~2^-17 relative
+// (the residual pair is one packed FFMA2: on sm_100 scalar fp32 instructions issue at half the packed rate)
 __device__ __forceinline__ void split_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
   hi = pack_bf16(a, b);
-  const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xFFFF0000u);
-  lo = pack_bf16(a - ah, b - bh);
+  const float2 h = make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xFFFF0000u));
+  const float2 l = __ffma2_rn(h, make_float2(-1.f, -1.f), make_float2(a, b));
+  lo = pack_bf16(l.x, l.y);
+}
+
+// ---- packed (two-lane) forms of the epilogue arithmetic ----
+__device__ __forceinline__ float2 elu_fast2(float2 x) {
+  const float2 t = __fmul2_rn(x, make_float2(1.4426950408889634f, 1.4426950408889634f));
+  const float2 em = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(-1.f, -1.f));
+  return make_float2(fmaxf(x.x, fminf(em.x, 0.f)), fmaxf(x.y, fminf(em.y, 0.f)));
+}
+// ELU of a pair and the 16-bit derivative codes of both (ELU' = min(e, 1) = 2 - t, t = max(1.9999999 - e, 1))
+__device__ __forceinline__ float2 elu_code2(float2 x, uint32_t& code) {
+  const float2 t = __fmul2_rn(x, make_float2(1.4426950408889634f, 1.4426950408889634f));
+  const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+  const float2 em = __fadd2_rn(e, make_float2(-1.f, -1.f));
+  const float2 c = __ffma2_rn(e, make_float2(-1.f, -1.f), make_float2(1.9999999f, 1.9999999f));
+  code = __byte_perm(__float_as_uint(fmaxf(c.x, 1.f)), __float_as_uint(fmaxf(c.y, 1.f)), 0x6521);
+  return make_float2(fmaxf(x.x, fminf(em.x, 0.f)), fmaxf(x.y, fminf(em.y, 0.f)));
+}
+// derivative pair of a code word: (ELU'_lo, ELU'_hi) = 2 - (t_lo, t_hi)
+__device__ __forceinline__ float2 elu_stash2(uint32_t w) {
+  const float2 t = make_float2(__uint_as_float(__byte_perm(w, 0x3F000000u, 0x7104)), __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7324)));
+  return __ffma2_rn(t, make_float2(-1.f, -1.f), make_float2(2.f, 2.f));
+}
+// (a, b) *= ELU' pair
+__device__ __forceinline__ void mul_stash2(float& a, float& b, uint32_t w) {
+  const float2 r = __fmul2_rn(make_float2(a, b), elu_stash2(w));
+  a = r.x; b = r.y;
 }
 
 }  // namespace nfbtc

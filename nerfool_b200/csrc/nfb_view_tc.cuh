@@ -152,10 +152,9 @@ __device__ __forceinline__ void epi16(uint32_t tl, int col, const float* __restr
 #pragma unroll
   for (int j = 0; j < 16; j += 4) {
     const float4 b = *reinterpret_cast<const float4*>(bias + j);
-    y[j + 0] = elu_fast(y[j + 0] + b.x);
-    y[j + 1] = elu_fast(y[j + 1] + b.y);
-    y[j + 2] = elu_fast(y[j + 2] + b.z);
-    y[j + 3] = elu_fast(y[j + 3] + b.w);
+    const float2 r0 = elu_fast2(__fadd2_rn(make_float2(y[j + 0], y[j + 1]), make_float2(b.x, b.y)));
+    const float2 r1 = elu_fast2(__fadd2_rn(make_float2(y[j + 2], y[j + 3]), make_float2(b.z, b.w)));
+    y[j + 0] = r0.x; y[j + 1] = r0.y; y[j + 2] = r1.x; y[j + 3] = r1.y;
   }
 }
 
@@ -219,13 +218,9 @@ __device__ __forceinline__ void epi16_code(uint32_t tl, int col, const float* __
 #pragma unroll
   for (int j = 0; j < 16; j += 4) {
     const float4 b = *reinterpret_cast<const float4*>(bias + j);
-    float t0, t1, t2, t3;
-    elu_with_t(y[j + 0] + b.x, y[j + 0], t0);
-    elu_with_t(y[j + 1] + b.y, y[j + 1], t1);
-    elu_with_t(y[j + 2] + b.z, y[j + 2], t2);
-    elu_with_t(y[j + 3] + b.w, y[j + 3], t3);
-    q[j / 2] = pack_t(t0, t1);
-    q[j / 2 + 1] = pack_t(t2, t3);
+    const float2 r0 = elu_code2(__fadd2_rn(make_float2(y[j + 0], y[j + 1]), make_float2(b.x, b.y)), q[j / 2]);
+    const float2 r1 = elu_code2(__fadd2_rn(make_float2(y[j + 2], y[j + 3]), make_float2(b.z, b.w)), q[j / 2 + 1]);
+    y[j + 0] = r0.x; y[j + 1] = r0.y; y[j + 2] = r1.x; y[j + 3] = r1.y;
   }
 }
 template <bool SAVE>

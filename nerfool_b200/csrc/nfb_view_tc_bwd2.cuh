@@ -273,8 +273,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       dense_T<16, 8>(sf + F_W_RGB2, dg2, dg1);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        dg1[2 * j] *= elu_stash_lo(q1[j]);
-        dg1[2 * j + 1] *= elu_stash_hi(q1[j]);
+        mul_stash2(dg1[2 * j], dg1[2 * j + 1], q1[j]);
       }
       a_store16<NPASS>(tl, 0, dg1);
     }
@@ -334,8 +333,9 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
         float dh[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          dh[2 * j] = dz * sf[F_W_VISB2 + 16 * kc + 2 * j] * elu_stash_lo(cq[8 * kc + j]);
-          dh[2 * j + 1] = dz * sf[F_W_VISB2 + 16 * kc + 2 * j + 1] * elu_stash_hi(cq[8 * kc + j]);
+          const float2 wv = *reinterpret_cast<const float2*>(sf + F_W_VISB2 + 16 * kc + 2 * j);
+          const float2 r = __fmul2_rn(__fmul2_rn(make_float2(dz, dz), wv), elu_stash2(cq[8 * kc + j]));
+          dh[2 * j] = r.x; dh[2 * j + 1] = r.y;
         }
         a_store16<NPASS>(tl, kc, dh);
       }
@@ -362,8 +362,8 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
         float dxv[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          dxv[2 * j] = d_x2[16 * kc + 2 * j] * elu_stash_lo(cq[8 * kc + j]);
-          dxv[2 * j + 1] = d_x2[16 * kc + 2 * j + 1] * elu_stash_hi(cq[8 * kc + j]);
+          const float2 r = __fmul2_rn(make_float2(d_x2[16 * kc + 2 * j], d_x2[16 * kc + 2 * j + 1]), elu_stash2(cq[8 * kc + j]));
+          dxv[2 * j] = r.x; dxv[2 * j + 1] = r.y;
         }
         a_store16<NPASS>(tl, kc, dxv);
       }
@@ -382,8 +382,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       d_raw16(tl, 16 * kc, dh);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        dh[2 * j] *= elu_stash_lo(cq[8 * kc + j]);
-        dh[2 * j + 1] *= elu_stash_hi(cq[8 * kc + j]);
+        mul_stash2(dh[2 * j], dh[2 * j + 1], cq[8 * kc + j]);
       }
       a_store16<NPASS>(tl, kc, dh);
     }
@@ -398,8 +397,10 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       d_raw16(tl, 16 * kc, dt);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        dt[2 * j] = fmaf(dt[2 * j], w, d_x2[16 * kc + 2 * j]) * elu_stash_lo(cq[8 * kc + j]);
-        dt[2 * j + 1] = fmaf(dt[2 * j + 1], w, d_x2[16 * kc + 2 * j + 1]) * elu_stash_hi(cq[8 * kc + j]);
+        const float2 r = __fmul2_rn(__ffma2_rn(make_float2(dt[2 * j], dt[2 * j + 1]), make_float2(w, w),
+                                               make_float2(d_x2[16 * kc + 2 * j], d_x2[16 * kc + 2 * j + 1])),
+                                    elu_stash2(cq[8 * kc + j]));
+        dt[2 * j] = r.x; dt[2 * j + 1] = r.y;
       }
       a_store16<NPASS>(tl, kc, dt);
     }
@@ -419,8 +420,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       d_raw16(tl, 16 * kc, dh);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        dh[2 * j] *= elu_stash_lo(hq[8 * kc + j]);
-        dh[2 * j + 1] *= elu_stash_hi(hq[8 * kc + j]);
+        mul_stash2(dh[2 * j], dh[2 * j + 1], hq[8 * kc + j]);
       }
       a_store16<NPASS>(tl, kc, dh);
     }
