@@ -1,0 +1,75 @@
+"""Drop-in for ``ibrnet.render_image`` (/root/reference/ibrnet/render_image.py:21-121): ``render_single_image`` with
+the reference's signature and return value, but device-resident -- the reference copies every output of every
+chunk to the host inside the loop (one device synchronisation per chunk and key, 47-157 chunks per frame), which
+throttles a fast renderer.  Here the chunks write into preallocated device buffers and the frame is copied to
+the host once at the end (the callers expect CPU tensors: eval.py / eval_adv.py index them with numpy)."""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import torch
+
+from .render_ray import render_rays, render_rays_hybrid
+
+_SHARED_KEYS = ('camera', 'depth_range', 'src_rgbs', 'src_cameras')
+
+
+def render_single_image(ray_sampler, ray_batch, model, projector, chunk_size, N_samples, inv_uniform=False,
+                        N_importance=0, det=False, white_bkgd=False, render_stride=1, featmaps=None, args=None,
+                        featmaps_clean=None, src_ray_batch=None):
+    '''
+    :param ray_sampler: RaySamplingSingleImage for this view
+    :param model:  {'net_coarse': , 'net_fine': , ...}
+    :param chunk_size: number of rays in a chunk
+    :param N_samples: samples along each ray (for both coarse and fine model)
+    :param inv_uniform: if True, uniformly sample inverse depth for coarse model
+    :param N_importance: additional samples along each ray produced by importance sampling (for fine model)
+    :return: {'outputs_coarse': {'rgb': [H, W, 3], 'depth': [H, W], ...}, 'outputs_fine': {}}   (CPU tensors)
+    '''
+    N_rays = ray_batch['ray_o'].shape[0]
+    hybrid = args is not None and (getattr(args, 'use_clean_color', False) or getattr(args, 'use_clean_density', False))
+    if hybrid:
+        assert featmaps_clean is not None
+    buf = {'outputs_coarse': None, 'outputs_fine': None}
+    for i in range(0, N_rays, chunk_size):
+        chunk = OrderedDict()
+        for k in ray_batch:
+            if k in _SHARED_KEYS:
+                chunk[k] = ray_batch[k]
+            elif ray_batch[k] is not None:
+                chunk[k] = ray_batch[k][i:i + chunk_size]
+            else:
+                chunk[k] = None
+        if hybrid:
+            ret = render_rays_hybrid(chunk, model, featmaps, projector=projector, N_samples=N_samples,
+                                     inv_uniform=inv_uniform, N_importance=N_importance, det=det, white_bkgd=white_bkgd,
+                                     args=args, featmaps_clean=featmaps_clean, src_ray_batch=src_ray_batch)
+        else:
+            ret = render_rays(chunk, model, featmaps, projector=projector, N_samples=N_samples, inv_uniform=inv_uniform,
+                              N_importance=N_importance, det=det, white_bkgd=white_bkgd, args=args,
+                              src_ray_batch=src_ray_batch)
+        for lvl in ('outputs_coarse', 'outputs_fine'):
+            out = ret[lvl]
+            if out is None:
+                continue
+            if buf[lvl] is None:      # first chunk: frame-sized device buffers, one per key
+                buf[lvl] = OrderedDict((k, torch.empty((N_rays,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device))
+                                       for k, v in out.items())
+            n = next(iter(out.values())).shape[0]
+            for k, v in out.items():
+                buf[lvl][k][i:i + n] = v.detach()
+
+    Hs = len(range(0, ray_sampler.H, render_stride))
+    Ws = len(range(0, ray_sampler.W, render_stride))
+    all_ret = OrderedDict([('outputs_coarse', OrderedDict()), ('outputs_fine', OrderedDict())])
+    for lvl in ('outputs_coarse', 'outputs_fine'):
+        if buf[lvl] is None:
+            all_ret[lvl] = None
+            continue
+        for k, v in buf[lvl].items():
+            if k == 'random_sigma':
+                continue
+            all_ret[lvl][k] = v.reshape(Hs, Ws, -1).squeeze().cpu()      # the one device -> host copy per key
+    # the reference paints masked-out pixels white in the coarse image only (render_image.py:109)
+    all_ret['outputs_coarse']['rgb'][all_ret['outputs_coarse']['mask'] == 0] = 1.
+    return all_ret

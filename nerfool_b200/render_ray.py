@@ -144,6 +144,39 @@ def render_rays(ray_batch, model, featmaps, projector, N_samples, inv_uniform=Fa
     return ret
 
 
-def render_rays_hybrid(*args, **kwargs):
-    raise NotImplementedError('render_rays_hybrid (render_ray.py:261-390, clean/adversarial mixing ablation) is a '
-                              '"next" row (SURVEY.md §8 f4) and is not built in this round')
+def render_rays_hybrid(ray_batch, model, featmaps, projector, N_samples, inv_uniform=False, N_importance=0, det=False,
+                       white_bkgd=False, args=None, src_ray_batch=None, featmaps_clean=None):
+    """
+    Clean / adversarial mixing ablation (render_ray.py:261-390): both feature-map sets are projected and aggregated at
+    the same points; colour and density are each taken from the clean or the adversarial pass (args.use_clean_color,
+    args.use_clean_density) before compositing.
+    :return: {'outputs_coarse': {}, 'outputs_fine': {}}
+    """
+    ret = {'outputs_coarse': None, 'outputs_fine': None}
+    src = ray_batch if src_ray_batch is None else src_ray_batch
+    ray_o, ray_d = ray_batch['ray_o'], ray_batch['ray_d']
+    _, z_vals = sample_along_camera_ray(ray_o=ray_o, ray_d=ray_d, depth_range=ray_batch['depth_range'],
+                                        N_samples=N_samples, inv_uniform=inv_uniform, det=det)
+
+    def level(net, fmap_adv, fmap_clean, z):
+        pts = z.unsqueeze(2) * ray_d.unsqueeze(1) + ray_o.unsqueeze(1)
+        raws = []
+        pixel_mask = None
+        for fmap in (fmap_adv, fmap_clean):
+            rgb_feat, ray_diff, mask = projector.compute(pts, ray_batch['camera'], src['src_rgbs'], src['src_cameras'],
+                                                         featmaps=fmap)
+            if pixel_mask is None:                       # the reference composites with the adversarial pass's mask
+                pixel_mask = mask[..., 0].sum(dim=2) > 1
+            raws.append(net(rgb_feat, ray_diff, mask))
+        raw_adv, raw_clean = raws
+        color = raw_clean[:, :, :3] if args.use_clean_color else raw_adv[:, :, :3]
+        sigma = raw_clean[:, :, 3:4] if args.use_clean_density else raw_adv[:, :, 3:4]
+        return raw2outputs(torch.cat([color, sigma], dim=2), z, pixel_mask, white_bkgd=white_bkgd)
+
+    ret['outputs_coarse'] = level(model.net_coarse, featmaps[0], featmaps_clean[0], z_vals)
+    if N_importance > 0:
+        assert model.net_fine is not None
+        weights = ret['outputs_coarse']['weights'].clone().detach()
+        z_fine = _fine_z(z_vals, weights, N_importance, inv_uniform, det)
+        ret['outputs_fine'] = level(model.net_fine, featmaps[1], featmaps_clean[1], z_fine)
+    return ret

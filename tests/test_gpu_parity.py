@@ -457,6 +457,71 @@ def test_stash_backward_equals_recompute_backward(dev):
         assert relerr(a.grad.cpu(), b.grad.cpu()) < 2e-4
 
 
+def test_render_single_image_device_resident(dev):
+    """render_image.py:21-121 mirror: same dict / shapes / CPU tensors as the reference's chunk loop, equal to one
+    un-chunked render_rays over the frame, masked pixels of the coarse image painted white."""
+    from nerfool_b200.projection import Projector
+    from nerfool_b200.render_ray import render_rays
+    from nerfool_b200.render_image import render_single_image
+    from nerfool_b200.synthetic import make_scene, ray_batch_for
+    Hh, Ww, V, S, NI = 24, 40, 4, 32, 16
+    scene = make_scene(Hh, Ww, V, seed=13, kind='llff')
+    batch = ray_batch_for(scene, np.arange(Hh * Ww))
+    gb = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    model = types.SimpleNamespace(net_coarse=_net(_params(S, 3), S, dev), net_fine=_net(_params(S + NI, 4), S + NI, dev))
+    fm = tuple(f.to(dev) for f in scene['featmaps'])
+    sampler = types.SimpleNamespace(H=Hh, W=Ww)
+    with torch.no_grad():
+        img = render_single_image(sampler, gb, model, Projector(dev), 157, S, inv_uniform=True, N_importance=NI, det=True,
+                                  featmaps=fm)
+        full = render_rays(gb, model, fm, Projector(dev), S, inv_uniform=True, N_importance=NI, det=True)
+    for lvl in ('outputs_coarse', 'outputs_fine'):
+        assert list(img[lvl].keys()) == ['rgb', 'depth', 'weights', 'mask', 'alpha', 'z_vals']
+        assert img[lvl]['rgb'].shape == (Hh, Ww, 3) and img[lvl]['depth'].shape == (Hh, Ww) and not img[lvl]['rgb'].is_cuda
+        assert torch.equal(img[lvl]['depth'], full[lvl]['depth'].cpu().reshape(Hh, Ww))
+        assert torch.equal(img[lvl]['mask'], full[lvl]['mask'].cpu().reshape(Hh, Ww))
+    want = full['outputs_coarse']['rgb'].cpu().reshape(Hh, Ww, 3).clone()
+    want[full['outputs_coarse']['mask'].cpu().reshape(Hh, Ww) == 0] = 1.
+    assert torch.equal(img['outputs_coarse']['rgb'], want)
+    assert torch.equal(img['outputs_fine']['rgb'], full['outputs_fine']['rgb'].cpu().reshape(Hh, Ww, 3))
+
+
+def test_render_rays_hybrid(dev):
+    """render_ray.py:261-390: with identical clean / adversarial maps the hybrid path is the plain (composed) render;
+    with different maps colour and density come from the pass the flags name."""
+    from nerfool_b200.projection import Projector
+    from nerfool_b200.render_ray import render_rays, render_rays_hybrid, raw2outputs
+    scene, batch = _scene(4, 96, 96, 128, 'llff', seed=17)
+    gb = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    S, NI = 32, 16
+    model = types.SimpleNamespace(net_coarse=_net(_params(S, 5), S, dev), net_fine=_net(_params(S + NI, 6), S + NI, dev))
+    fm = tuple(f.to(dev) for f in scene['featmaps'])
+    fm_adv = tuple(f + 0.05 * torch.randn_like(f) for f in fm)
+    proj = Projector(dev)
+    with torch.no_grad():
+        flags = types.SimpleNamespace(use_clean_color=True, use_clean_density=True)
+        same = render_rays_hybrid(gb, model, fm, proj, S, inv_uniform=True, N_importance=NI, det=True, args=flags, featmaps_clean=fm)
+        os.environ['NFB_FUSED'] = '0'
+        try:
+            plain = render_rays(gb, model, fm, proj, S, inv_uniform=True, N_importance=NI, det=True)
+        finally:
+            os.environ['NFB_FUSED'] = '1'
+        for lvl in ('outputs_coarse', 'outputs_fine'):
+            for k in ('rgb', 'depth', 'weights', 'mask'):
+                assert torch.equal(same[lvl][k], plain[lvl][k]), (lvl, k)
+        # colour from the clean maps, density from the adversarial ones (coarse level, checked by hand)
+        flags = types.SimpleNamespace(use_clean_color=True, use_clean_density=False)
+        mix = render_rays_hybrid(gb, model, fm_adv, proj, S, inv_uniform=True, N_importance=0, det=True, args=flags, featmaps_clean=fm)
+        z = mix['outputs_coarse']['z_vals']
+        pts = z.unsqueeze(2) * gb['ray_d'].unsqueeze(1) + gb['ray_o'].unsqueeze(1)
+        ra = proj.compute(pts, gb['camera'], gb['src_rgbs'], gb['src_cameras'], featmaps=fm_adv[0])
+        rc = proj.compute(pts, gb['camera'], gb['src_rgbs'], gb['src_cameras'], featmaps=fm[0])
+        raw = torch.cat([model.net_coarse(*rc)[..., :3], model.net_coarse(*ra)[..., 3:4]], dim=2)
+        want = raw2outputs(raw, z, ra[2][..., 0].sum(dim=2) > 1)
+        assert torch.equal(mix['outputs_coarse']['rgb'], want['rgb'])
+        assert not torch.equal(mix['outputs_coarse']['rgb'], same['outputs_coarse']['rgb'])
+
+
 def test_full_size_properties(dev):
     """BASELINE-size chunk (4096 rays, V=4, 64+64): size-independent properties instead of an oracle run:
     weights in [0,1] and sum <= 1, rgb in the convex hull of source colours, determinism, linearity of the

@@ -232,5 +232,7 @@ def test_dropin_overlay_resolves_hot_path_modules_and_falls_through(tmp_path, mo
     rr = importlib.import_module('ibrnet.render_ray')
     for name in ('render_rays', 'render_rays_hybrid', 'sample_pdf', 'raw2outputs', 'sample_along_camera_ray'):
         assert callable(getattr(rr, name))
+    from nerfool_b200.render_image import render_single_image
+    assert importlib.import_module('ibrnet.render_image').render_single_image is render_single_image
     for m in [k for k in sys.modules if k == 'ibrnet' or k.startswith('ibrnet.')]:
         monkeypatch.delitem(sys.modules, m)
