@@ -44,8 +44,7 @@ typedef enum {
   NFB_ECUDA = -3          /* a CUDA runtime call or launch failed; text carries cudaGetErrorString */
 } NfbStatus;
 
-/* Arithmetic of the dense layers of the IBRNet view and ray stages (`precision` argument; the ray stage takes its
- * tensor-core form for S <= 128 samples per ray and the fp32 form beyond):
+/* Arithmetic of the dense layers of the IBRNet view and ray stages (`precision` argument):
  *   NFB_PREC_FP32   fp32 FMA on the CUDA cores (the exactness reference of this library)
  *   NFB_PREC_BF16X3 tcgen05 tensor cores, operands split hi+lo in bf16, 3 MMA passes, fp32 accumulation:
  *                   products exact to ~2^-17 -> results inside the reference's fp32 tolerance (default)
@@ -109,7 +108,7 @@ int nfb_ibrnet_view_fwd(int N, int S, int V, int anti_alias,
                         const float* xyz, const float* ray_o, const float* ray_d, const float* z,
                         const float* cam, const float* imgs, const float* feat,
                         const float* params, float* ps, float* stash, int precision, void* stream);
-/* The ray stage has the same optional activation stash (tensor-core form, S <= 128): 560 B per sample (q, k, v,
+/* The ray stage has the same optional activation stash (tensor-core forms): 560 B per sample (q, k, v,
  * attention output and softmax statistics, LayerNorm xhat / rstd, ELU-derivative codes). */
 size_t nfb_ray_stash_bytes(int R, int S);
 int nfb_ibrnet_ray_fwd(int R, int S, const float* ps, const float* params, const float* pos_enc /*[S][16]*/,

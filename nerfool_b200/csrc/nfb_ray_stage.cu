@@ -335,7 +335,8 @@ inline int ray_block(int S) { return ((S + 31) / 32) * 32; }
 }  // namespace
 
 extern "C" size_t nfb_ray_stash_bytes(int R, int S) {
-  if (R <= 0 || S < 1 || S > nfbrtc::GROUP) return 0;
+  if (R <= 0 || S < 1 || S > NFB_MAX_SAMPLES) return 0;
+  if (S > nfbrtc::GROUP) return (size_t)R * 2 * nfbrtc::RP_TILE_BYTES;     // two 128-row tiles per ray
   const int rpg = nfbrtc::GROUP / S;
   return (size_t)((R + rpg - 1) / rpg) * nfbrtc::RP_TILE_BYTES;
 }
@@ -349,9 +350,9 @@ extern "C" int nfb_ibrnet_ray_fwd(int R, int S, const float* ps, const float* pa
   NFB_REQUIRE(((uintptr_t)ps % 16) == 0 && ((uintptr_t)raw % 16) == 0, NFB_EINVAL, "nfb_ibrnet_ray_fwd: ps/raw must be 16-byte aligned");
   NFB_REQUIRE(precision >= NFB_PREC_FP32 && precision <= NFB_PREC_BF16, NFB_EINVAL, "nfb_ibrnet_ray_fwd: bad precision %d", precision);
   if (stash)
-    NFB_REQUIRE(precision != NFB_PREC_FP32 && S <= nfbrtc::GROUP && ((uintptr_t)stash % 16) == 0, NFB_EUNSUPPORTED,
-                "nfb_ibrnet_ray_fwd: the activation stash exists for the tensor-core form (S <= 128) only, 16-byte aligned");
-  if (precision != NFB_PREC_FP32 && S <= nfbrtc::GROUP) {     // longer rays: fp32 kernel below
+    NFB_REQUIRE(precision != NFB_PREC_FP32 && ((uintptr_t)stash % 16) == 0, NFB_EUNSUPPORTED,
+                "nfb_ibrnet_ray_fwd: the activation stash exists for the tensor-core forms only, 16-byte aligned");
+  if (precision != NFB_PREC_FP32) {
     nfbrtc::RayArgs a{R, S, ps, params, pos_enc, raw, nullptr, nullptr, stash};
     cudaStream_t st = (cudaStream_t)stream;
     if (stash) return precision == NFB_PREC_BF16 ? nfb_launch_ray_tc_fwd_p1_save(a, st) : nfb_launch_ray_tc_fwd_p3_save(a, st);
@@ -378,9 +379,9 @@ extern "C" int nfb_ibrnet_ray_bwd(int R, int S, const float* ps, const float* pa
               "nfb_ibrnet_ray_bwd: ps/d_raw/d_ps must be 16-byte aligned");
   NFB_REQUIRE(precision >= NFB_PREC_FP32 && precision <= NFB_PREC_BF16, NFB_EINVAL, "nfb_ibrnet_ray_bwd: bad precision %d", precision);
   if (stash)
-    NFB_REQUIRE(precision != NFB_PREC_FP32 && S <= nfbrtc::GROUP && ((uintptr_t)stash % 16) == 0, NFB_EUNSUPPORTED,
-                "nfb_ibrnet_ray_bwd: the activation stash exists for the tensor-core form (S <= 128) only, 16-byte aligned");
-  if (precision != NFB_PREC_FP32 && S <= nfbrtc::GROUP) {
+    NFB_REQUIRE(precision != NFB_PREC_FP32 && ((uintptr_t)stash % 16) == 0, NFB_EUNSUPPORTED,
+                "nfb_ibrnet_ray_bwd: the activation stash exists for the tensor-core forms only, 16-byte aligned");
+  if (precision != NFB_PREC_FP32) {
     nfbrtc::RayArgs a{R, S, ps, params, pos_enc, nullptr, d_raw, d_ps, const_cast<float*>(stash)};
     cudaStream_t st = (cudaStream_t)stream;
     if (stash) return precision == NFB_PREC_BF16 ? nfb_launch_ray_tc_bwd_stash_p1(a, st) : nfb_launch_ray_tc_bwd_stash_p3(a, st);

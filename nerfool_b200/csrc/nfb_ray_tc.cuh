@@ -2,8 +2,8 @@
 // geometry_fc, + pos_encoding, 4-head d_k = 4 self-attention over the samples of a ray (row-masked), fc + residual +
 // LayerNorm(eps 1e-6), sigma head (mlp_network.py:259-265, 69-119, 23-43).
 //
-// Mapping: one thread per sample; a 128-thread group owns floor(128 / S) whole rays per tile (S <= 128; longer rays
-// take the fp32 kernels in nfb_ray_stage.cu).  Dense layers run as 128 x N x K tcgen05.mma tiles exactly like the view
+// Mapping: one thread per sample; a 128-thread group owns floor(128 / S) whole rays per tile (S <= 128); rays of
+// 129..256 samples are owned by a pair of groups sharing one 256-row attention buffer.  Dense layers run as 128 x N x K tcgen05.mma tiles exactly like the view
 // stage (A operand = the rows' activations written to TMEM by their threads, B = weight tiles resident in shared
 // memory, D read back with tcgen05.ld); the backward products dX = dY W read the same tiles MN-major.  The attention
 // itself (d_k = 4 per head: too thin for an MMA) stays on the CUDA cores with K / V (backward: Q, dO, softmax
@@ -207,12 +207,21 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int grp = tid / GROUP, tg = tid % GROUP;
-  float* sk = s_grp + (size_t)grp * C::GROUP_FLOATS;   // [128][16]
-  float* sv = sk + GROUP * 16;
-  float* sq = sv + GROUP * 16;                          // backward only
-  float* sdo = sq + GROUP * 16;
-  float* sst = sdo + GROUP * 16;                        // [128][4] float4 {m2, 1/l, D, valid}
+  // Rays longer than 128 samples are owned by a PAIR of groups (256 rows): the pair shares one K / V (/ Q / dO /
+  // statistics) buffer of 256 rows and synchronises on its own 256-thread named barrier around the attention; the
+  // dense layers stay per group (one M = 128 tile each).
+  const bool pair_mode = a.S > GROUP;
+  const int pair = grp >> 1, gp = grp & 1;
+  const int AR = pair_mode ? 2 * GROUP : GROUP;                       // rows of the attention buffers
+  float* abase = s_grp + (size_t)(pair_mode ? 2 * pair : grp) * C::GROUP_FLOATS;
+  float* sk = abase;                                                  // [AR][16]
+  float* sv = sk + AR * 16;
+  float* sq = sv + AR * 16;                                           // backward only
+  float* sdo = sq + AR * 16;
+  float* sst = sdo + AR * 16;                                         // [AR][16]: -m | 1/l | -D | valid
+  const int row = pair_mode ? gp * GROUP + tg : tg;                   // this thread's row in those buffers
   const int bar_id = 1 + grp;
+  const int att_bar = pair_mode ? 9 + pair : bar_id, att_n = pair_mode ? 2 * GROUP : GROUP;
   uint64_t* mbar = s_bar + grp;
 
   if (warp == 0) tmem_alloc(s_tmem, NG * C::GC);
@@ -252,17 +261,20 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
   uint32_t phase = 0;
 
   const int S = a.S;
-  const int RPG = GROUP / S;                       // whole rays per group tile (>= 1)
-  const int rl = tg / S, s = tg - rl * S;          // ray within the tile, sample within the ray
+  const int RPG = pair_mode ? 1 : GROUP / S;       // whole rays per tile (>= 1)
+  const int rl = pair_mode ? 0 : tg / S;           // ray within the tile
+  const int s = pair_mode ? row : tg - rl * S;     // sample within the ray
   const int kb = (rl < RPG ? rl : 0) * S;          // first K / V row of this thread's ray
   const int ntiles = (a.R + RPG - 1) / RPG;
+  const int tile0 = pair_mode ? blockIdx.x * (NG / 2) + pair : blockIdx.x * NG + grp;
+  const int tstep = pair_mode ? gridDim.x * (NG / 2) : gridDim.x * NG;
 
-  for (int tile = blockIdx.x * NG + grp; tile < ntiles; tile += gridDim.x * NG) {
+  for (int tile = tile0; tile < ntiles; tile += tstep) {
     const int ray = tile * RPG + rl;
-    const bool act = (rl < RPG) && (ray < a.R);
+    const bool act = (rl < RPG) && (s < S) && (ray < a.R);
     const size_t smp = act ? ((size_t)ray * S + s) : 0;
     const float* psrow = a.ps + smp * NFB_PS_STRIDE;
-    float4* sp = reinterpret_cast<float4*>(a.stash) + (size_t)tile * (RP_PLANES * GROUP) + tg;
+    float4* sp = reinterpret_cast<float4*>(a.stash) + (size_t)(pair_mode ? 2 * tile + gp : tile) * (RP_PLANES * GROUP) + tg;
     const bool save = SAVE && act;
 
     // ---------------- geometry_fc.0 : 64 pooled statistics on the tensor cores, the mean weight on the CUDA cores ----
@@ -335,8 +347,8 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
       for (int d = 0; d < 4; ++d) {
         q01[d] = make_float2(qq[d] * qs, qq[4 + d] * qs);
         q23[d] = make_float2(qq[8 + d] * qs, qq[12 + d] * qs);
-        *reinterpret_cast<float4*>(sk + tg * 16 + 4 * d) = make_float4(kk[d], kk[4 + d], kk[8 + d], kk[12 + d]);
-        *reinterpret_cast<float4*>(sv + tg * 16 + 4 * d) = make_float4(vv[d], vv[4 + d], vv[8 + d], vv[12 + d]);
+        *reinterpret_cast<float4*>(sk + row * 16 + 4 * d) = make_float4(kk[d], kk[4 + d], kk[8 + d], kk[12 + d]);
+        *reinterpret_cast<float4*>(sv + row * 16 + 4 * d) = make_float4(vv[d], vv[4 + d], vv[8 + d], vv[12 + d]);
         if (save) {
           rp_st(sp, RP_Q + d, q01[d].x, q01[d].y, q23[d].x, q23[d].y);
           rp_st(sp, RP_K + d, kk[d], kk[4 + d], kk[8 + d], kk[12 + d]);
@@ -344,7 +356,7 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
         }
       }
     }
-    named_bar_sync(bar_id, GROUP);
+    named_bar_sync(att_bar, att_n);
     float o[16], m2[4], il[4];
     {
       const float4* kr = reinterpret_cast<const float4*>(sk + kb * 16);
@@ -449,7 +461,7 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
       float sigma = fmaxf(z2, 0.f);
       if (nvalid < 1.f) sigma = 0.f;                     // mlp_network.py:265
       if (act) reinterpret_cast<float4*>(a.raw)[smp] = make_float4(tail.y, tail.z, tail.w, sigma);
-      named_bar_sync(bar_id, GROUP);                     // K / V rows are rewritten by the next tile
+      named_bar_sync(att_bar, att_n);                    // K / V rows are rewritten by the next tile
       continue;
     }
 
@@ -502,15 +514,15 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
         for (int d = 0; d < 4; ++d) {
           dO01[d] = make_float2(dO[d], dO[4 + d]);
           dO23[d] = make_float2(dO[8 + d], dO[12 + d]);
-          *reinterpret_cast<float4*>(sq + tg * 16 + 4 * d) = make_float4(q01[d].x, q01[d].y, q23[d].x, q23[d].y);
-          *reinterpret_cast<float4*>(sdo + tg * 16 + 4 * d) = make_float4(dO[d], dO[4 + d], dO[8 + d], dO[12 + d]);
+          *reinterpret_cast<float4*>(sq + row * 16 + 4 * d) = make_float4(q01[d].x, q01[d].y, q23[d].x, q23[d].y);
+          *reinterpret_cast<float4*>(sdo + row * 16 + 4 * d) = make_float4(dO[d], dO[4 + d], dO[8 + d], dO[12 + d]);
         }
-        *reinterpret_cast<float4*>(sst + tg * 16) = make_float4(-m2[0], -m2[1], -m2[2], -m2[3]);
-        *reinterpret_cast<float4*>(sst + tg * 16 + 4) = make_float4(il[0], il[1], il[2], il[3]);
-        *reinterpret_cast<float4*>(sst + tg * 16 + 8) = make_float4(-Dh[0], -Dh[1], -Dh[2], -Dh[3]);
-        *reinterpret_cast<float4*>(sst + tg * 16 + 12) = make_float4(vf, vf, vf, vf);
+        *reinterpret_cast<float4*>(sst + row * 16) = make_float4(-m2[0], -m2[1], -m2[2], -m2[3]);
+        *reinterpret_cast<float4*>(sst + row * 16 + 4) = make_float4(il[0], il[1], il[2], il[3]);
+        *reinterpret_cast<float4*>(sst + row * 16 + 8) = make_float4(-Dh[0], -Dh[1], -Dh[2], -Dh[3]);
+        *reinterpret_cast<float4*>(sst + row * 16 + 12) = make_float4(vf, vf, vf, vf);
       }
-      named_bar_sync(bar_id, GROUP);
+      named_bar_sync(att_bar, att_n);
 
       float dqkv[48];
       // query side: dq_i = sum_j dS_ij k_j  (zero for masked rows: masked_fill blocks the gradient)
@@ -559,8 +571,8 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
         float2 k01[4], k23[4], v01[4], v23[4];
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-          const float4 k4 = *reinterpret_cast<const float4*>(sk + tg * 16 + 4 * d);
-          const float4 v4 = *reinterpret_cast<const float4*>(sv + tg * 16 + 4 * d);
+          const float4 k4 = *reinterpret_cast<const float4*>(sk + row * 16 + 4 * d);
+          const float4 v4 = *reinterpret_cast<const float4*>(sv + row * 16 + 4 * d);
           k01[d] = make_float2(k4.x, k4.y); k23[d] = make_float2(k4.z, k4.w);
           v01[d] = make_float2(v4.x, v4.y); v23[d] = make_float2(v4.z, v4.w);
         }
@@ -667,7 +679,7 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
           out[17] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      named_bar_sync(bar_id, GROUP);                     // K / V / Q / dO rows are rewritten by the next tile
+      named_bar_sync(att_bar, att_n);                    // K / V / Q / dO rows are rewritten by the next tile
     }
   }
 
@@ -682,9 +694,11 @@ int launch_ray_tc(const RayArgs& a, cudaStream_t st) {
   const size_t smem = C::smem(a.S);
   cudaError_t e = cudaFuncSetAttribute(k_ray_tc<NPASS, BWD, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nfb_set_error(NFB_ECUDA, "k_ray_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  const int RPG = GROUP / a.S;
+  const bool pair_mode = a.S > GROUP;
+  const int RPG = pair_mode ? 1 : GROUP / a.S;
   const int ntiles = (a.R + RPG - 1) / RPG;
-  int grid = (ntiles + C::NG - 1) / C::NG;
+  const int per_cta = pair_mode ? C::NG / 2 : C::NG;
+  int grid = (ntiles + per_cta - 1) / per_cta;
   const int cap = nfb_num_sms();
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
@@ -722,12 +736,18 @@ __global__ void __launch_bounds__(GROUP * BS_NG, 1) k_ray_tc_bwd_stash(RayArgs a
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int grp = tid / GROUP, tg = tid % GROUP;
-  float* sk = s_grp + (size_t)grp * BS_GROUP_FLOATS;   // [128][16] each, dimension-major rows
-  float* sv = sk + GROUP * 16;
-  float* sq = sv + GROUP * 16;
-  float* sdo = sq + GROUP * 16;
-  float* sst = sdo + GROUP * 16;                        // [128][16]: -m[4] | 1/l[4] | -D[4] | valid x4
+  const bool pair_mode = a.S > GROUP;                   // rays of 129..256 samples: two groups per ray (see k_ray_tc)
+  const int pair = grp >> 1, gp = grp & 1;
+  const int AR = pair_mode ? 2 * GROUP : GROUP;
+  float* abase = s_grp + (size_t)(pair_mode ? 2 * pair : grp) * BS_GROUP_FLOATS;
+  float* sk = abase;                                    // [AR][16] each, dimension-major rows
+  float* sv = sk + AR * 16;
+  float* sq = sv + AR * 16;
+  float* sdo = sq + AR * 16;
+  float* sst = sdo + AR * 16;                           // [AR][16]: -m[4] | 1/l[4] | -D[4] | valid x4
+  const int row = pair_mode ? gp * GROUP + tg : tg;
   const int bar_id = 1 + grp;
+  const int att_bar = pair_mode ? 9 + pair : bar_id, att_n = pair_mode ? 2 * GROUP : GROUP;
   uint64_t* mbar = s_bar + grp;
 
   if (warp == 0) tmem_alloc(s_tmem, NG * 128);
@@ -762,38 +782,41 @@ __global__ void __launch_bounds__(GROUP * BS_NG, 1) k_ray_tc_bwd_stash(RayArgs a
   uint32_t phase = 0;
 
   const int S = a.S;
-  const int RPG = GROUP / S;
-  const int rl = tg / S, s = tg - rl * S;
+  const int RPG = pair_mode ? 1 : GROUP / S;
+  const int rl = pair_mode ? 0 : tg / S;
+  const int s = pair_mode ? row : tg - rl * S;
   const int kb = (rl < RPG ? rl : 0) * S;
   const int ntiles = (a.R + RPG - 1) / RPG;
+  const int tile0 = pair_mode ? blockIdx.x * (NG / 2) + pair : blockIdx.x * NG + grp;
+  const int tstep = pair_mode ? gridDim.x * (NG / 2) : gridDim.x * NG;
 
-  for (int tile = blockIdx.x * NG + grp; tile < ntiles; tile += gridDim.x * NG) {
+  for (int tile = tile0; tile < ntiles; tile += tstep) {
     const int ray = tile * RPG + rl;
-    const bool act = (rl < RPG) && (ray < a.R);
+    const bool act = (rl < RPG) && (s < S) && (ray < a.R);
     const size_t smp = act ? ((size_t)ray * S + s) : 0;
-    const float4* sp = reinterpret_cast<const float4*>(a.stash) + (size_t)tile * (RP_PLANES * GROUP) + tg;
+    const float4* sp = reinterpret_cast<const float4*>(a.stash) + (size_t)(pair_mode ? 2 * tile + gp : tile) * (RP_PLANES * GROUP) + tg;
 
     // K / V / Q rows of this sample: global -> shared, asynchronously (rows of inactive samples are zero-filled)
     if (act) {
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
-        cp_async16(sq + tg * 16 + 4 * d, sp + (RP_Q + d) * GROUP);
-        cp_async16(sk + tg * 16 + 4 * d, sp + (RP_K + d) * GROUP);
-        cp_async16(sv + tg * 16 + 4 * d, sp + (RP_V + d) * GROUP);
+        cp_async16(sq + row * 16 + 4 * d, sp + (RP_Q + d) * GROUP);
+        cp_async16(sk + row * 16 + 4 * d, sp + (RP_K + d) * GROUP);
+        cp_async16(sv + row * 16 + 4 * d, sp + (RP_V + d) * GROUP);
       }
     } else {
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
-        *reinterpret_cast<float4*>(sq + tg * 16 + 4 * d) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(sk + tg * 16 + 4 * d) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(sv + tg * 16 + 4 * d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(sq + row * 16 + 4 * d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(sk + row * 16 + 4 * d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(sv + row * 16 + 4 * d) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     // next tile of this group towards L2
     {
-      const int nt = tile + gridDim.x * NG;
+      const int nt = tile + tstep;
       if (nt < ntiles && (tg & 7) == 0) {
-        const float4* np = reinterpret_cast<const float4*>(a.stash) + (size_t)nt * (RP_PLANES * GROUP) + tg;
+        const float4* np = reinterpret_cast<const float4*>(a.stash) + (size_t)(pair_mode ? 2 * nt + gp : nt) * (RP_PLANES * GROUP) + tg;
 #pragma unroll 5
         for (int pl = 0; pl < RP_PLANES; ++pl) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + pl * GROUP));
       }
@@ -881,22 +904,22 @@ __global__ void __launch_bounds__(GROUP * BS_NG, 1) k_ray_tc_bwd_stash(RayArgs a
       for (int d = 0; d < 4; ++d) {
         dO01[d] = make_float2(dO[d], dO[4 + d]);
         dO23[d] = make_float2(dO[8 + d], dO[12 + d]);
-        *reinterpret_cast<float4*>(sdo + tg * 16 + 4 * d) = make_float4(dO[d], dO[4 + d], dO[8 + d], dO[12 + d]);
+        *reinterpret_cast<float4*>(sdo + row * 16 + 4 * d) = make_float4(dO[d], dO[4 + d], dO[8 + d], dO[12 + d]);
       }
-      *reinterpret_cast<float4*>(sst + tg * 16) = nm4;
-      *reinterpret_cast<float4*>(sst + tg * 16 + 4) = il4;
-      *reinterpret_cast<float4*>(sst + tg * 16 + 8) = make_float4(nD[0], nD[1], nD[2], nD[3]);
-      *reinterpret_cast<float4*>(sst + tg * 16 + 12) = make_float4(vf, vf, vf, vf);
+      *reinterpret_cast<float4*>(sst + row * 16) = nm4;
+      *reinterpret_cast<float4*>(sst + row * 16 + 4) = il4;
+      *reinterpret_cast<float4*>(sst + row * 16 + 8) = make_float4(nD[0], nD[1], nD[2], nD[3]);
+      *reinterpret_cast<float4*>(sst + row * 16 + 12) = make_float4(vf, vf, vf, vf);
     }
     cp_async_wait_all();
-    named_bar_sync(bar_id, GROUP);
+    named_bar_sync(att_bar, att_n);
 
     // query side: dq_i = sum_j dS_ij k_j  (zero for masked rows: masked_fill blocks the gradient)
     {
       float2 q01[4], q23[4];
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
-        const float4 q4 = *reinterpret_cast<const float4*>(sq + tg * 16 + 4 * d);
+        const float4 q4 = *reinterpret_cast<const float4*>(sq + row * 16 + 4 * d);
         q01[d] = make_float2(q4.x, q4.y);
         q23[d] = make_float2(q4.z, q4.w);
       }
@@ -946,8 +969,8 @@ __global__ void __launch_bounds__(GROUP * BS_NG, 1) k_ray_tc_bwd_stash(RayArgs a
       float2 k01[4], k23[4], v01[4], v23[4];
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
-        const float4 k4 = *reinterpret_cast<const float4*>(sk + tg * 16 + 4 * d);
-        const float4 v4 = *reinterpret_cast<const float4*>(sv + tg * 16 + 4 * d);
+        const float4 k4 = *reinterpret_cast<const float4*>(sk + row * 16 + 4 * d);
+        const float4 v4 = *reinterpret_cast<const float4*>(sv + row * 16 + 4 * d);
         k01[d] = make_float2(k4.x, k4.y); k23[d] = make_float2(k4.z, k4.w);
         v01[d] = make_float2(v4.x, v4.y); v23[d] = make_float2(v4.z, v4.w);
       }
@@ -1061,7 +1084,7 @@ __global__ void __launch_bounds__(GROUP * BS_NG, 1) k_ray_tc_bwd_stash(RayArgs a
         out[17] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    named_bar_sync(bar_id, GROUP);                     // K / V / Q / dO rows are rewritten by the next tile
+    named_bar_sync(att_bar, att_n);                    // K / V / Q / dO rows are rewritten by the next tile
   }
 
   fence_before_sync();
@@ -1074,9 +1097,11 @@ int launch_ray_tc_bwd_stash(const RayArgs& a, cudaStream_t st) {
   const size_t smem = bwd_stash_smem<NPASS>();
   cudaError_t e = cudaFuncSetAttribute(k_ray_tc_bwd_stash<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nfb_set_error(NFB_ECUDA, "k_ray_tc_bwd_stash: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  const int RPG = GROUP / a.S;
+  const bool pair_mode = a.S > GROUP;
+  const int RPG = pair_mode ? 1 : GROUP / a.S;
   const int ntiles = (a.R + RPG - 1) / RPG;
-  int grid = (ntiles + BS_NG - 1) / BS_NG;
+  const int per_cta = pair_mode ? BS_NG / 2 : BS_NG;
+  int grid = (ntiles + per_cta - 1) / per_cta;
   const int cap = nfb_num_sms();
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;

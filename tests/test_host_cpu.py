@@ -71,7 +71,7 @@ def test_stash_size_query(lib):
     assert lib.nfb_view_stash_bytes(100, 10) == -(-100 // 12) * 48 * 128 * 16
     assert lib.nfb_view_stash_bytes(0, 4) == 0 and lib.nfb_view_stash_bytes(10, 33) == 0
     assert lib.nfb_ray_stash_bytes(100, 64) == 50 * 35 * 128 * 16 and lib.nfb_ray_stash_bytes(7, 128) == 7 * 35 * 128 * 16
-    assert lib.nfb_ray_stash_bytes(5, 33) == 2 * 35 * 128 * 16 and lib.nfb_ray_stash_bytes(5, 192) == 0
+    assert lib.nfb_ray_stash_bytes(5, 33) == 2 * 35 * 128 * 16 and lib.nfb_ray_stash_bytes(5, 192) == 10 * 35 * 128 * 16 and lib.nfb_ray_stash_bytes(5, 257) == 0
 
 
 def test_no_cpu_fallback():
