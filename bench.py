@@ -41,6 +41,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 H, W = 378, 504
+SCENE_KIND = 'llff'
 N_SAMPLES, N_IMPORTANCE = 64, 64
 GATHER_B, SCATTER_B = 560, 512          # algorithmic bytes per (sample, view) row, SURVEY.md 8(d)
 
@@ -122,7 +123,7 @@ def build_workload(device, rank, V, seed=0):
     from nerfool_b200.mlp_network import IBRNet
     from nerfool_b200.projection import Projector
     world = int(os.environ.get('WORLD_SIZE', '1'))
-    scene = make_scene(H, W, V, seed=seed, kind='llff', n_targets=max(world, 1))
+    scene = make_scene(H, W, V, seed=seed, kind=SCENE_KIND, n_targets=max(world, 1))
     ray_o, ray_d = rays_for_view(scene['camera'][rank], H, W)
     args = types.SimpleNamespace(anti_alias_pooling=1)
     torch.manual_seed(seed)
@@ -302,9 +303,9 @@ def run_ours(a):
             'metric': 'rays/s', 'value': rays_total / (ms_per_step * 1e-3), 'unit': 'rays/s',
             'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'BASELINE configs[1]: IBRNet view-specific PGD hot-path step (render_rays fwd + masked-MSE + '
-                                   'bwd to source feature maps), 378x504 target view, all 190512 rays per step, '
-                                   f'{a.views} source views, 64 coarse + 64 importance samples, random-init weights',
+            'config': {'workload': f'BASELINE configs[{a.config}]: IBRNet PGD hot-path step (render_rays fwd + masked-MSE + '
+                                   f'bwd to source feature maps), {H}x{W} target view, all {R} rays per step, '
+                                   f'{a.views} source views, {N_SAMPLES} coarse + {N_IMPORTANCE} importance samples, random-init weights',
                        'rays_per_step_per_gpu': R, 'source_views': a.views, 'max_rays_per_launch': a.max_rays,
                        'arithmetic': f'{_l.get_precision()}: fp32 data, dense layers on tcgen05 with bf16 hi+lo split operands '
                                      '(3 MMA passes, fp32 accumulate) = fp32-equivalent results' if _l.get_precision() == 'bf16x3'
@@ -355,7 +356,7 @@ def cpu_reference(a, sample_rays, steps, warmup):
     from oracle import ibrnet_oracle as O
     from nerfool_b200.synthetic import make_scene, ray_batch_for
     torch.set_num_threads(os.cpu_count() or 1)
-    scene = make_scene(H, W, a.views, seed=0, kind='llff')
+    scene = make_scene(H, W, a.views, seed=0, kind=SCENE_KIND)
     ids = np.sort(np.random.RandomState(1).choice(H * W, sample_rays, replace=False))
     batch = ray_batch_for(scene, ids)
     pc = O.random_ibrnet_params(N_SAMPLES, 1, sigma_bias=0.3)
@@ -372,7 +373,7 @@ def cpu_reference(a, sample_rays, steps, warmup):
             times.append(dt)
     sec = sum(times) / len(times)
     return {'value': sample_rays / sec, 'unit': 'rays/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': f'{sample_rays} random rays of the 378x504 view, same step (fwd + loss + bwd to feature maps), '
+            'sample': f'{sample_rays} random rays of the {H}x{W} view, same step (fwd + loss + bwd to feature maps), '
                       f'{warmup} warm-up + mean of {steps}', 'ms_per_step': sec * 1e3}
 
 
@@ -385,8 +386,8 @@ def run_reference(a):
     out = {'impl': 'reference', 'metric': 'rays/s', 'value': cb['value'], 'unit': 'rays/s', 'n_gpus': world,
            'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': cb['ms_per_step'], 'higher_is_better': True,
            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': 'BASELINE configs[1]: IBRNet view-specific PGD hot-path step, 378x504 target view, '
-                                  f'{a.views} source views, 64 + 64 samples; CPU port of the reference path on a bounded sample',
+           'config': {'workload': f'BASELINE configs[{a.config}]: IBRNet PGD hot-path step, {H}x{W} target view, '
+                                  f'{a.views} source views, {N_SAMPLES} + {N_IMPORTANCE} samples; CPU port of the reference path on a bounded sample',
                       'rays_per_step': a.cpu_rays, 'source_views': a.views},
            'cpu_baseline': cb,
            'e2e': {'value': cb['value'], 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
@@ -400,11 +401,24 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--views', type=int, default=4)
-    ap.add_argument('--max-rays', dest='max_rays', type=int, default=65536)
+    ap.add_argument('--max-rays', dest='max_rays', type=int, default=0, help='rays per launch (0 = sized from the stash budget)')
     ap.add_argument('--cpu-rays', dest='cpu_rays', type=int, default=2048)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-bf16', dest='no_bf16', action='store_true', help='skip the extra plain-bf16 measurement')
+    ap.add_argument('--config', type=int, default=1, choices=[1, 2, 3],
+                    help='BASELINE.json configs index: 1 = headline (378x504, 4 views, 64+64); 2 = universal-attack shape '
+                         '(378x504, 10 views, one target view per GPU); 3 = NeRF-Synthetic shape (800x800, 10 views, 64+128)')
     a = ap.parse_args()
+    global H, W, N_SAMPLES, N_IMPORTANCE, SCENE_KIND
+    if a.config == 2:
+        a.views = 10
+    elif a.config == 3:
+        H, W, N_IMPORTANCE, SCENE_KIND = 800, 800, 128, 'synthetic'
+        a.views = 10
+    if a.max_rays <= 0:
+        # bound the two activation stashes of a chunk (768 B per (sample, view) row) to ~40 GB
+        per_ray = (2 * N_SAMPLES + N_IMPORTANCE) * a.views * 768 + (2 * N_SAMPLES + N_IMPORTANCE) * 560
+        a.max_rays = max(4096, min(65536, 1 << int(np.log2(40e9 / per_ray))))
     a.warmup = max(a.warmup, 3) if a.impl == 'ours' else a.warmup
     if a.impl == 'reference':
         run_reference(a)
