@@ -352,6 +352,41 @@ def test_render_rays_featmap_gradients(dev, V, R, S, NI, kind, H, W):
         assert e_f <= 5e-3, (mode, 'fine vs fp32 oracle', e_f)
 
 
+def test_render_rays_source_image_gradient(dev):
+    """eval_adv.py perturbs src_rgbs: besides the path through the encoder (d featmaps) the colours enter the
+    renderer directly (projection.py:119 -> mlp_network.py:233,272).  d loss / d src_rgbs of the fused path (stash
+    and recompute backward) against the fp64 oracle, coarse level (the fine level's depths are not pinned here)."""
+    from nerfool_b200 import _lib
+    from nerfool_b200.projection import Projector
+    from nerfool_b200.render_ray import render_rays
+    V, R, S = 4, 150, 48
+    scene, batch = _scene(V, R, 96, 128, 'llff', seed=31)
+    pc = _params(S, 9)
+    b32 = dict(batch); b32['src_rgbs'] = batch['src_rgbs'].clone().requires_grad_(True)
+    b64 = _dbl(batch); b64['src_rgbs'] = batch['src_rgbs'].double().requires_grad_(True)
+    fm = scene['featmaps']
+    r32 = O.render_rays(b32, pc, None, fm, S, True, 0, det=True)
+    O.masked_mse(r32['outputs_coarse']['rgb'], batch['rgb'], r32['outputs_coarse']['mask'].float()).backward()
+    r64 = O.render_rays(b64, _dbl(pc), None, tuple(f.double() for f in fm), S, True, 0, det=True)
+    O.masked_mse(r64['outputs_coarse']['rgb'], batch['rgb'].double(), r64['outputs_coarse']['mask'].double()).backward()
+    e_ref = relerr(b32['src_rgbs'].grad, b64['src_rgbs'].grad)
+    model = types.SimpleNamespace(net_coarse=_net(pc, S, dev), net_fine=None)
+    saved = _lib.STASH_MAX_GIB
+    try:
+        for cap in (48.0, 0.0):                     # activation-stash backward, then forward-recompute backward
+            _lib.STASH_MAX_GIB = cap
+            gb = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+            gb['src_rgbs'] = gb['src_rgbs'].clone().requires_grad_(True)
+            out = render_rays(gb, model, tuple(f.to(dev) for f in fm), Projector(dev), S, inv_uniform=True, N_importance=0, det=True)
+            m = out['outputs_coarse']['mask'].float()
+            loss = torch.sum((out['outputs_coarse']['rgb'] - gb['rgb']) ** 2 * m.unsqueeze(-1)) / (torch.sum(m) * 3 + 1e-6)
+            loss.backward()
+            e = relerr(gb['src_rgbs'].grad.cpu(), b64['src_rgbs'].grad)
+            assert e <= max(1e-3, 3 * e_ref), (cap, e, e_ref)
+    finally:
+        _lib.STASH_MAX_GIB = saved
+
+
 def test_render_rays_golden_end_to_end(dev):
     """The reference's own outputs (golden) through the fused CUDA path."""
     from nerfool_b200.projection import Projector
