@@ -288,6 +288,13 @@ __device__ __forceinline__ void pool_var(const float* __restrict__ row0, int V, 
       mma_commit(mbar);                                                       \
     }                                                                         \
   } while (0)
+// Exchange-buffer synchronisation.  When V divides 32 the V rows of a sample are lanes of ONE warp, so the cross-view
+// exchanges only need a warp barrier; otherwise the whole 128-row group synchronises.
+#define NFB_EX_SYNC()                                   \
+  do {                                                  \
+    if (warp_local) __syncwarp();                       \
+    else named_bar_sync(bar_id, GROUP);                 \
+  } while (0)
 #define NFB_TC_WAIT()          \
   do {                         \
     mbar_wait(mbar, phase);    \
@@ -348,6 +355,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
   uint32_t phase = 0;
 
   const int V = a.V;
+  const bool warp_local = (32 % V) == 0;
   const int TS = (GROUP / V < TS_MAX) ? GROUP / V : TS_MAX;
   const int sl = tg / V, v = tg - sl * V;
   const int ntiles = (a.N + TS - 1) / TS;
@@ -423,7 +431,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       const float e = a.anti_alias ? (float)exp((double)__fmul_rn(s_abs, __fsub_rn(rd[3], 1.f))) : 1.f;
       ex[tg * EXS + 35] = e;
       ex[tg * EXS + 36] = mk;
-      named_bar_sync(bar_id, GROUP);
+      NFB_EX_SYNC();
       float mn = 3.4e38f, nv = 0.f;
       for (int u = 0; u < V; ++u) {
         mn = fminf(mn, ex[(base + u) * EXS + 35]);
@@ -434,7 +442,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       for (int u = 0; u < V; ++u) sum += (ex[(base + u) * EXS + 35] - mn) * ex[(base + u) * EXS + 36];
       w = (e - mn) * mk / (sum + 1e-8f);
       n_valid = nv;
-      named_bar_sync(bar_id, GROUP);
+      NFB_EX_SYNC();
     }
 
     // ---------------- x0 = rgb_feat + direction_feat ----------------
@@ -457,7 +465,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
 #pragma unroll
     for (int c = 0; c < NFB_ROW_CH; ++c) ex[tg * EXS + c] = x[c];
     ex[tg * EXS + 35] = w;
-    named_bar_sync(bar_id, GROUP);
+    NFB_EX_SYNC();
     if (active) {
       const float* row0 = ex + base * EXS;
       for (int c0 = v; c0 < NFB_ROW_CH; c0 += POOL_K * V) {
@@ -485,7 +493,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
         }
       }
     }
-    named_bar_sync(bar_id, GROUP);
+    NFB_EX_SYNC();
 
     // ---------------- base_fc.0 : [mean | var | x0] (105 -> 64) ----------------
     // operand words 0..34 = packed [mean | var] of the sample (shared memory), words 35..52 = x0 pairs, 53..55 = 0
@@ -671,7 +679,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
     ex[tg * EXS + 34] = rgb_in0;
     ex[tg * EXS + 35] = rgb_in1;
     ex[tg * EXS + 36] = rgb_in2;
-    named_bar_sync(bar_id, GROUP);
+    NFB_EX_SYNC();
     if (active) {
       float D = 1e-8f;
       for (int u = 0; u < V; ++u) D += ex[(base + u) * EXS + 32];
@@ -711,7 +719,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
         out[69] = 0.f; out[70] = 0.f; out[71] = 0.f;
       }
     }
-    named_bar_sync(bar_id, GROUP);            // exchange buffer is reused by the next tile
+    if (FUSED) NFB_EX_SYNC(); else named_bar_sync(bar_id, GROUP);            // exchange buffer is reused by the next tile
   }
 
   fence_before_sync();

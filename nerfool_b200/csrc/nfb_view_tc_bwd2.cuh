@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
   uint32_t phase = 0;
 
   const int V = a.V;
+  const bool warp_local = (32 % V) == 0;       // NFB_EX_SYNC (nfb_view_tc.cuh): warp barrier when a sample's rows share a warp
   const int TS = (GROUP / V < TS_MAX) ? GROUP / V : TS_MAX;
   const int sl = tg / V, v = tg - sl * V;
   const int ntiles = (a.N + TS - 1) / TS;
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
         }
       }
       ex[tg * EXS + 35] = w;
-      named_bar_sync(bar_id, GROUP);
+      NFB_EX_SYNC();
     }
     float wsum0 = 0.f;
     for (int u = 0; u < V; ++u) wsum0 += ex[(base + u) * EXS + 35];
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
           if (c0 + k * V < NFB_ROW_CH) mvs[c0 + k * V] = mk9[k];
       }
     }
-    named_bar_sync(bar_id, GROUP);
+    NFB_EX_SYNC();
 
     // ---------------- exchange vis2 / logit / rgb_in ; blending softmax ----------------
     ex[tg * EXS + 32] = vis2;
@@ -299,9 +300,9 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
         d_x2[c] = w2 * (dm - 2.f * dv * mean * (1.f - w2sum)) + 2.f * w2 * diff * dv;
       }
     }
-    named_bar_sync(bar_id, GROUP);          // all reads of slots 33..36 above are done
+    NFB_EX_SYNC();          // all reads of slots 33..36 above are done
     ex[tg * EXS + 33] = d_w2 * vis2;
-    named_bar_sync(bar_id, GROUP);
+    NFB_EX_SYNC();
     float d_vis2;
     {
       float sdv = 0.f;
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
           if (c0 + k * V < NFB_ROW_CH) dpw[c0 + k * V] = s9[k];
       }
     }
-    named_bar_sync(bar_id, GROUP);
+    NFB_EX_SYNC();
     float x0[36];
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
 #pragma unroll
       for (int j = 0; j < 9; ++j) d_row[26 + j] = t[j];
     }
-    named_bar_sync(bar_id, GROUP);
+    NFB_EX_SYNC();
     if (active) {
       const float* row0 = ex + base * EXS;
       for (int c0 = v; c0 < NFB_ROW_CH; c0 += POOL_K * V) {
@@ -501,7 +502,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
         }
       }
     }
-    named_bar_sync(bar_id, GROUP);
+    NFB_EX_SYNC();
     if (active) {
 #pragma unroll
       for (int c = 0; c < NFB_ROW_CH; ++c) d_row[c] += w * (mvs[c] + x0[c] * mvs[36 + c]);
