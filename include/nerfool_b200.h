@@ -125,6 +125,23 @@ int nfb_ibrnet_view_bwd(int N, int S, int V, int anti_alias,
                         const float* params, const float* ps, const float* d_ps,
                         float* d_rgb_feat, float* d_feat, float* d_imgs, const float* stash, int precision,
                         void* stream);
+/* Backward WITH parameter gradients (training: train.py:317-327 back-propagates the rendering loss into the IBRNet
+ * weights; mlp_network.py:153-208 lists them).  Same data-gradient outputs as the two functions above (d_feat /
+ * d_imgs / d_rgb_feat may be NULL when only the weights train) and, in addition, the gradient of every tensor of
+ * the parameter blob, ACCUMULATED (+=) into d_params[NFB_IBRNET_PARAM_FLOATS] in the blob's layout -- the view
+ * stage fills s, ray_dir_fc, base_fc, vis_fc, vis_fc2 and rgb_fc, the ray stage geometry_fc, ray_attention.* and
+ * out_geometry_fc; pos_encoding is a buffer and has no gradient.  fp32 CUDA-core kernels that recompute the forward
+ * per tile (no stash): per-row outer products are reduced over the 32 rows of a warp with an exchange butterfly,
+ * summed per CTA in shared memory and added to d_params with one float atomic per weight and CTA.              */
+int nfb_ibrnet_ray_wgrad(int R, int S, const float* ps, const float* params, const float* pos_enc,
+                         const float* d_raw, float* d_ps, float* d_params, void* stream);
+int nfb_ibrnet_view_wgrad(int N, int S, int V, int anti_alias,
+                          const float* rgb_feat, const float* ray_diff, const float* mask,
+                          int H, int W, int fh, int fw,
+                          const float* xyz, const float* ray_o, const float* ray_d, const float* z,
+                          const float* cam, const float* imgs, const float* feat,
+                          const float* params, const float* ps, const float* d_ps,
+                          float* d_rgb_feat, float* d_feat, float* d_imgs, float* d_params, void* stream);
 
 /* ---- raw2outputs  (render_ray.py:123-170) ------------------------------------------------------------
  * pixel_mask: uint8 [R][S] (the `mask` argument), or NULL with n_valid (stride n_valid_stride floats per

@@ -26,6 +26,8 @@ _SIGNATURES = {
     'nfb_ibrnet_ray_fwd': [_I, _I, _P, _P, _P, _P, _P, _I, _P],
     'nfb_ibrnet_ray_bwd': [_I, _I, _P, _P, _P, _P, _P, _P, _I, _P],
     'nfb_ibrnet_view_bwd': [_I] * 4 + [_P] * 3 + [_I] * 4 + [_P] * 14 + [_I, _P],
+    'nfb_ibrnet_ray_wgrad': [_I, _I, _P, _P, _P, _P, _P, _P, _P],
+    'nfb_ibrnet_view_wgrad': [_I] * 4 + [_P] * 3 + [_I] * 4 + [_P] * 15,
     'nfb_composite_fwd': [_I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     'nfb_composite_bwd': [_I, _I, _I] + [_P] * 8,
     'nfb_sample_pdf': [_I, _I, _I, _P, _P, _P, _I, _P, _P, _P],
@@ -116,6 +118,7 @@ def stream_ptr(device=None):
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+PARAM_FLOATS = 20136  # NFB_IBRNET_PARAM_FLOATS (include/nerfool_b200.h)
 LAUNCHES = 0          # kernels launched through the C ABI since import (every entry point = one launch)
 _profile = None       # when a dict: entry-point name -> list of (start_event, end_event)
 

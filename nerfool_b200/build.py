@@ -27,6 +27,8 @@ UNITS = [
     ('nfb_view_inst1', 'nfb_view_inst.cu', ['-DNFB_VIEW_INST=1']),
     ('nfb_view_inst2', 'nfb_view_inst.cu', ['-DNFB_VIEW_INST=2']),
     ('nfb_view_inst3', 'nfb_view_inst.cu', ['-DNFB_VIEW_INST=3']),
+    ('nfb_view_inst4', 'nfb_view_inst.cu', ['-DNFB_VIEW_INST=4']),
+    ('nfb_view_inst5', 'nfb_view_inst.cu', ['-DNFB_VIEW_INST=5']),
     ('nfb_view_tc_inst0', 'nfb_view_tc_inst.cu', ['-DNFB_VTC_INST=0']),
     ('nfb_view_tc_inst1', 'nfb_view_tc_inst.cu', ['-DNFB_VTC_INST=1']),
     ('nfb_view_tc_inst2', 'nfb_view_tc_inst.cu', ['-DNFB_VTC_INST=2']),

@@ -43,6 +43,24 @@ static __device__ void load_ray_weights(float* sw, const float* __restrict__ p, 
   load_vec_padded(sw + RB_OG2, p + P_OG2_B, 1, 4, tid, nt);
 }
 
+// adds the per-CTA accumulators (shared-memory weight layout) into the torch-layout gradient blob
+static __device__ void flush_ray_grads(float* __restrict__ dp, const float* sg, int tid, int nt) {
+  flush_wt_transposed(dp + P_GEO0_W, sg + R_GEO0, 64, 65, 64, tid, nt);
+  flush_vec(dp + P_GEO0_B, sg + RB_GEO0, 64, tid, nt);
+  flush_wt_transposed(dp + P_GEO2_W, sg + R_GEO2, 16, 64, 16, tid, nt);
+  flush_vec(dp + P_GEO2_B, sg + RB_GEO2, 16, tid, nt);
+  flush_wt_transposed(dp + P_ATT_Q, sg + R_Q, 16, 16, 16, tid, nt);
+  flush_wt_transposed(dp + P_ATT_K, sg + R_K, 16, 16, 16, tid, nt);
+  flush_wt_transposed(dp + P_ATT_V, sg + R_V, 16, 16, 16, tid, nt);
+  flush_wt_transposed(dp + P_ATT_FC, sg + R_FC, 16, 16, 16, tid, nt);
+  flush_vec(dp + P_LN_W, sg + R_LNW, 16, tid, nt);
+  flush_vec(dp + P_LN_B, sg + R_LNB, 16, tid, nt);
+  flush_wt_transposed(dp + P_OG0_W, sg + R_OG0, 16, 16, 16, tid, nt);
+  flush_vec(dp + P_OG0_B, sg + RB_OG0, 16, tid, nt);
+  flush_vec(dp + P_OG2_W, sg + R_OG2, 16, tid, nt);
+  flush_vec(dp + P_OG2_B, sg + RB_OG2, 1, tid, nt);
+}
+
 constexpr float INV_TEMP = 0.5f;   // 1 / sqrt(d_k), d_k = 4 (mlp_network.py:84)
 constexpr float LN_EPS = 1e-6f;    // mlp_network.py:87
 
@@ -103,11 +121,13 @@ __device__ __forceinline__ void attend(const float (&q)[16], bool row_valid, int
   }
 }
 
-template <bool BWD>
+template <bool BWD, bool WG = false>
 __global__ void __launch_bounds__(256) k_ray_stage(int R, int S, const float* __restrict__ ps,
                                                     const float* __restrict__ params,
                                                     const float* __restrict__ pos_enc, float* __restrict__ raw,
-                                                    const float* __restrict__ d_raw, float* __restrict__ d_ps) {
+                                                    const float* __restrict__ d_raw, float* __restrict__ d_ps,
+                                                    float* __restrict__ d_params = nullptr) {
+  static_assert(!WG || BWD, "parameter gradients are part of the backward");
   extern __shared__ __align__(16) float smem[];
   float* sw = smem;
   float* sk = smem + R_TOTAL;          // [S][16]
@@ -117,6 +137,9 @@ __global__ void __launch_bounds__(256) k_ray_stage(int R, int S, const float* __
   float* sdo = sq + (size_t)S * 16;    // [S][16] d(attention output)
   float* sst = sdo + (size_t)S * 16;   // [S][12]: m[4], 1/l[4], D[4]
   float* svalid = sst + (size_t)S * 12;  // [S]
+  float* sg = svalid + (((size_t)S + 3) & ~(size_t)3);   // WG: [R_TOTAL] parameter-gradient accumulators
+  if (WG)
+    for (int i = threadIdx.x; i < R_TOTAL; i += blockDim.x) sg[i] = 0.f;
 
   load_ray_weights(sw, params, threadIdx.x, blockDim.x);
   __syncthreads();
@@ -193,6 +216,7 @@ __global__ void __launch_bounds__(256) k_ray_stage(int R, int S, const float* __
       float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
       if (act) dr = __ldg(reinterpret_cast<const float4*>(d_raw) + (size_t)r * S + s);
       const float dz2 = (z2 > 0.f && !(nvalid < 1.f)) ? dr.w : 0.f;
+      const float gate = act ? 1.f : 0.f;
       // sigma head
       float dln[16];
       {
@@ -200,6 +224,18 @@ __global__ void __launch_bounds__(256) k_ray_stage(int R, int S, const float* __
 #pragma unroll
         for (int k = 0; k < 16; ++k) dh[k] = dz2 * sw[R_OG2 + k] * elu_grad_from_out(hh[k]);
         dense_T<16, 16>(sw + R_OG0, dh, dln);
+        if (WG) {
+          wgrad_vec<16>(sg + R_OG2, hh, dz2 * gate);
+          const float dbz[4] = {dz2, 0.f, 0.f, 0.f};
+          wgrad_vec<4>(sg + RB_OG2, dbz, gate);
+          wgrad_acc<16, 16>(sg + R_OG0, ln, dh, gate);
+          wgrad_vec<16>(sg + RB_OG0, dh, gate);
+          float t[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) t[c] = dln[c] * xhat[c];
+          wgrad_vec<16>(sg + R_LNW, t, gate);
+          wgrad_vec<16>(sg + R_LNB, dln, gate);
+        }
       }
       // LayerNorm backward: dy = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dln * gamma
       float dy[16];
@@ -218,6 +254,7 @@ __global__ void __launch_bounds__(256) k_ray_stage(int R, int S, const float* __
       // y = fc(o) + xin
       float dO[16];
       dense_T<16, 16>(sw + R_FC, dy, dO);
+      if (WG) wgrad_acc<16, 16>(sg + R_FC, at.o, dy, gate);
       // publish per-query quantities for the key-side pass
       if (act) {
 #pragma unroll
@@ -289,6 +326,11 @@ __global__ void __launch_bounds__(256) k_ray_stage(int R, int S, const float* __
           dv[4 * h] = av0; dv[4 * h + 1] = av1; dv[4 * h + 2] = av2; dv[4 * h + 3] = av3;
         }
       }
+      if (WG) {
+        wgrad_acc<16, 16>(sg + R_Q, xin, dq, gate);
+        wgrad_acc<16, 16>(sg + R_K, xin, dk, gate);
+        wgrad_acc<16, 16>(sg + R_V, xin, dv, gate);
+      }
       // d xin = dy (residual) + Wq^T dq + Wk^T dk + Wv^T dv ; pos_encoding is a constant
       float dx[16];
       {
@@ -310,6 +352,15 @@ __global__ void __launch_bounds__(256) k_ray_stage(int R, int S, const float* __
       dense_T<64, 16>(sw + R_GEO2, dx, dh64);
 #pragma unroll
       for (int k = 0; k < 64; ++k) dh64[k] *= elu_grad_from_out(h64[k]);
+      if (WG) {
+        wgrad_acc<64, 16>(sg + R_GEO2, h64, dx, gate);
+        wgrad_vec<16>(sg + RB_GEO2, dx, gate);
+        float xin65[65];
+#pragma unroll
+        for (int k = 0; k < 65; ++k) xin65[k] = __ldg(psrow + k);
+        wgrad_acc<65, 64>(sg + R_GEO0, xin65, dh64, gate);
+        wgrad_vec<64>(sg + RB_GEO0, dh64, gate);
+      }
       if (act) {
         float* out = d_ps + ((size_t)r * S + s) * NFB_PS_STRIDE;
 #pragma unroll
@@ -327,6 +378,10 @@ __global__ void __launch_bounds__(256) k_ray_stage(int R, int S, const float* __
       }
       __syncthreads();
     }
+  }
+  if (WG) {
+    __syncthreads();
+    flush_ray_grads(d_params, sg, threadIdx.x, blockDim.x);
   }
 }
 
@@ -395,5 +450,24 @@ extern "C" int nfb_ibrnet_ray_bwd(int R, int S, const float* ps, const float* pa
   int grid = nfb_num_sms() * per_sm; if (grid > R) grid = R;
   k_ray_stage<true><<<grid, block, smem, (cudaStream_t)stream>>>(R, S, ps, params, pos_enc, nullptr, d_raw, d_ps);
   NFB_CHECK_LAUNCH("k_ray_stage<bwd>");
+  return NFB_OK;
+}
+
+extern "C" int nfb_ibrnet_ray_wgrad(int R, int S, const float* ps, const float* params, const float* pos_enc,
+                                    const float* d_raw, float* d_ps, float* d_params, void* stream) {
+  NFB_REQUIRE(R >= 0 && S >= 1, NFB_EINVAL, "nfb_ibrnet_ray_wgrad: bad arguments (R=%d S=%d)", R, S);
+  NFB_REQUIRE(S <= NFB_MAX_SAMPLES, NFB_EUNSUPPORTED, "nfb_ibrnet_ray_wgrad: S=%d > %d samples per ray", S, NFB_MAX_SAMPLES);
+  if (R == 0) return NFB_OK;
+  NFB_REQUIRE(ps && params && pos_enc && d_raw && d_ps && d_params, NFB_EINVAL, "nfb_ibrnet_ray_wgrad: NULL buffer");
+  NFB_REQUIRE(((uintptr_t)ps % 16) == 0 && ((uintptr_t)d_raw % 16) == 0 && ((uintptr_t)d_ps % 16) == 0, NFB_EINVAL,
+              "nfb_ibrnet_ray_wgrad: ps/d_raw/d_ps must be 16-byte aligned");
+  const size_t smem = (size_t)(R_TOTAL * 2 + 4 * S * 16 + S * 12 + ((S + 3) & ~3)) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(k_ray_stage<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return nfb_set_error(NFB_ECUDA, "nfb_ibrnet_ray_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  const int block = ray_block(S);
+  int per_sm = 2048 / block; if (per_sm > 2) per_sm = 2;
+  int grid = nfb_num_sms() * per_sm; if (grid > R) grid = R;
+  k_ray_stage<true, true><<<grid, block, smem, (cudaStream_t)stream>>>(R, S, ps, params, pos_enc, nullptr, d_raw, d_ps, d_params);
+  NFB_CHECK_LAUNCH("k_ray_stage<bwd,wgrad>");
   return NFB_OK;
 }

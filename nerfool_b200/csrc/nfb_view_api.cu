@@ -101,3 +101,28 @@ extern "C" int nfb_ibrnet_view_bwd(int N, int S, int V, int anti_alias, const fl
   if (rgb_feat) return nfb_launch_view_tensor_bwd(a, st);
   return nfb_launch_view_fused_bwd(a, st);
 }
+
+extern "C" int nfb_ibrnet_view_wgrad(int N, int S, int V, int anti_alias, const float* rgb_feat, const float* ray_diff,
+                                     const float* mask, int H, int W, int fh, int fw, const float* xyz,
+                                     const float* ray_o, const float* ray_d, const float* z, const float* cam,
+                                     const float* imgs, const float* feat, const float* params, const float* ps,
+                                     const float* d_ps, float* d_rgb_feat, float* d_feat, float* d_imgs,
+                                     float* d_params, void* stream) {
+  int rc = check_view_args("nfb_ibrnet_view_wgrad", N, S, V, rgb_feat, ray_diff, mask, H, W, fh, fw, xyz, ray_o, ray_d,
+                           z, cam, imgs, feat, params);
+  if (rc) return rc;
+  if (N == 0) return NFB_OK;
+  NFB_REQUIRE(ps && d_ps && d_params, NFB_EINVAL, "nfb_ibrnet_view_wgrad: ps / d_ps / d_params is NULL");
+  if (rgb_feat) NFB_REQUIRE(d_rgb_feat, NFB_EINVAL, "nfb_ibrnet_view_wgrad: tensor mode needs d_rgb_feat");
+  else NFB_REQUIRE(((uintptr_t)d_feat % 16) == 0, NFB_EINVAL, "nfb_ibrnet_view_wgrad: d_feat must be 16-byte aligned");
+  NFB_REQUIRE(((uintptr_t)ps % 16) == 0 && ((uintptr_t)d_ps % 16) == 0, NFB_EINVAL, "nfb_ibrnet_view_wgrad: ps / d_ps must be 16-byte aligned");
+  ViewArgs a{};
+  a.N = N; a.S = S; a.V = V; a.anti_alias = anti_alias;
+  a.rgb_feat = rgb_feat; a.ray_diff = ray_diff; a.mask = mask;
+  a.H = H; a.W = W; a.fh = fh; a.fw = fw;
+  a.pts = PointSrc{xyz, ray_o, ray_d, z, S};
+  a.cam = cam; a.imgs = imgs; a.feat = feat; a.params = params; a.ps = const_cast<float*>(ps);
+  a.d_ps = d_ps; a.d_rgb_feat = d_rgb_feat; a.d_feat = d_feat; a.d_imgs = d_imgs; a.d_params = d_params;
+  cudaStream_t st = (cudaStream_t)stream;
+  return rgb_feat ? nfb_launch_view_tensor_wgrad(a, st) : nfb_launch_view_fused_wgrad(a, st);
+}

@@ -72,6 +72,32 @@ static __device__ void load_view_weights(float* sw, const float* __restrict__ p,
   if (tid == 0) sw[W_S] = fabsf(__ldg(p + P_S));
 }
 
+// adds the per-CTA accumulators (shared-memory weight layout) into the torch-layout gradient blob
+static __device__ void flush_view_grads(float* __restrict__ dp, const float* sg, int tid, int nt) {
+  flush_wt_transposed(dp + P_DIR0_W, sg + W_DIR0, 16, 4, 16, tid, nt);
+  flush_vec(dp + P_DIR0_B, sg + B_DIR0, 16, tid, nt);
+  flush_wt_transposed(dp + P_DIR2_W, sg + W_DIR2, 35, 16, 36, tid, nt);
+  flush_vec(dp + P_DIR2_B, sg + B_DIR2, 35, tid, nt);
+  flush_wt_transposed(dp + P_BASE0_W, sg + W_BASE0, 64, 105, 64, tid, nt);
+  flush_vec(dp + P_BASE0_B, sg + B_BASE0, 64, tid, nt);
+  flush_wt_transposed(dp + P_BASE2_W, sg + W_BASE2, 32, 64, 32, tid, nt);
+  flush_vec(dp + P_BASE2_B, sg + B_BASE2, 32, tid, nt);
+  flush_wt_transposed(dp + P_VIS0_W, sg + W_VIS0, 32, 32, 32, tid, nt);
+  flush_vec(dp + P_VIS0_B, sg + B_VIS0, 32, tid, nt);
+  flush_wt_transposed(dp + P_VIS2_W, sg + W_VIS2, 33, 32, 36, tid, nt);
+  flush_vec(dp + P_VIS2_B, sg + B_VIS2, 33, tid, nt);
+  flush_wt_transposed(dp + P_VISB0_W, sg + W_VISB0, 32, 32, 32, tid, nt);
+  flush_vec(dp + P_VISB0_B, sg + B_VISB0, 32, tid, nt);
+  flush_vec(dp + P_VISB2_W, sg + W_VISB2, 32, tid, nt);
+  flush_vec(dp + P_VISB2_B, sg + B_VISB2, 1, tid, nt);
+  flush_wt_transposed(dp + P_RGB0_W, sg + W_RGB0, 16, 37, 16, tid, nt);
+  flush_vec(dp + P_RGB0_B, sg + B_RGB0, 16, tid, nt);
+  flush_wt_transposed(dp + P_RGB2_W, sg + W_RGB2, 8, 16, 8, tid, nt);
+  flush_vec(dp + P_RGB2_B, sg + B_RGB2, 8, tid, nt);
+  flush_vec(dp + P_RGB4_W, sg + W_RGB4, 8, tid, nt);
+  flush_vec(dp + P_RGB4_B, sg + B_RGB4, 1, tid, nt);
+}
+
 struct ViewArgs {
   int N, S, V, anti_alias;
   // tensor mode
@@ -88,13 +114,16 @@ struct ViewArgs {
   float* d_rgb_feat; float* d_feat; float* d_imgs;
   // tensor-core fused mode: activation stash written by the forward, read by the backward (nfb_view_tc.cuh)
   float* stash;
+  // training: parameter-gradient blob (NFB_IBRNET_PARAM_FLOATS, torch layout), accumulated into (WG kernels only)
+  float* d_params;
 };
 
 // ---------------------------------------------------------------------------------------------------
 // one kernel body for forward (BWD=false) and forward-recompute + backward (BWD=true)
 // ---------------------------------------------------------------------------------------------------
-template <bool FUSED, bool BWD, int NG>
+template <bool FUSED, bool BWD, int NG, bool WG = false>
 __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
+  static_assert(!WG || BWD, "parameter gradients are part of the backward");
   extern __shared__ __align__(16) float smem[];
   float* sw = smem;
   float* s_cam = smem + W_TOTAL;                               // 16*V+4 floats (fused mode)
@@ -103,6 +132,11 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
   float* ex = ex_all + (size_t)grp * GROUP * EXS;
   float* mv = ex_all + (size_t)NG * GROUP * EXS + (size_t)grp * TS_MAX * MVS;   // per-sample mean0 / var0
   const int bar_id = 1 + grp;
+  // WG: per-CTA parameter-gradient accumulators, same (transposed) layout as the weights
+  float* sg = ex_all + (size_t)NG * GROUP * EXS + (size_t)NG * TS_MAX * MVS;
+  float ds_acc = 0.f;                                          // d loss / d |s| of this thread's rows
+  if (WG)
+    for (int i = threadIdx.x; i < W_TOTAL; i += blockDim.x) sg[i] = 0.f;
 
   load_view_weights(sw, a.params, threadIdx.x, blockDim.x);
   if (FUSED)
@@ -180,6 +214,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
 
     // ---------------- pooling weights (:234-241) ----------------
     float w, n_valid;
+    float e_aa = 1.f, mn_aa = 0.f, den_aa = 1.f;               // WG: exp term, its minimum over views, normaliser
     {
       // exp_dot_prod = exp(|s| * (dot - 1)) (:236).  The weights are DIFFERENCES of these exponentials
       // (:237), which cancel when the source views see the point under similar angles, so the exponential
@@ -198,6 +233,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
       for (int u = 0; u < V; ++u) sum += (ex[(base + u) * EXS + 35] - mn) * ex[(base + u) * EXS + 36];
       w = (e - mn) * mk / (sum + 1e-8f);
       n_valid = nv;
+      e_aa = e; mn_aa = mn; den_aa = sum + 1e-8f;
       named_bar_sync(bar_id, GROUP);
     }
 
@@ -346,6 +382,8 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
 
     // =================================== backward ===================================
     if (BWD) {
+      const float gate = active ? 1.f : 0.f;       // WG: rows outside the problem contribute nothing
+      float d_w = 0.f;                             // WG: d loss / d (first pooling weight of this row)
       const float* dps = a.d_ps + (size_t)(active ? p : 0) * NFB_PS_STRIDE;
       const float* fps = a.ps + (size_t)(active ? p : 0) * NFB_PS_STRIDE;
       const float w2 = vis2 / D;
@@ -378,6 +416,19 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
         for (int k = 0; k < 16; ++k) dg1[k] *= elu_grad_from_out(g1[k]);
         dense_T<32, 16>(sw + W_RGB0, dg1, d_x2);
         d_vis2 = dot_row<16>(dg1, sw + W_RGB0 + 32 * 16);
+        if (WG) {
+          wgrad_vec<8>(sg + W_RGB4, g2, d_logit * gate);
+          const float db4[4] = {d_logit, 0.f, 0.f, 0.f};
+          wgrad_vec<4>(sg + B_RGB4, db4, gate);
+          wgrad_acc<16, 8>(sg + W_RGB2, g1, dg2, gate);
+          wgrad_vec<8>(sg + B_RGB2, dg2, gate);
+          float xin[37];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) xin[c] = x2[c];
+          xin[32] = vis2; xin[33] = rd[0]; xin[34] = rd[1]; xin[35] = rd[2]; xin[36] = rd[3];
+          wgrad_acc<37, 16>(sg + W_RGB0, xin, dg1, gate);
+          wgrad_vec<16>(sg + B_RGB0, dg1, gate);
+        }
       }
 
       // (3) second pooling backward (fused_mean_variance + weight normalisation, :255-258)
@@ -409,6 +460,16 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
         for (int k = 0; k < 32; ++k) dh[k] = dz * sw[W_VISB2 + k] * elu_grad_from_out(hv2[k]);
         float dt[32];
         dense_T<32, 32>(sw + W_VISB0, dh, dt);
+        if (WG) {
+          wgrad_vec<32>(sg + W_VISB2, hv2, dz * gate);
+          const float dbz[4] = {dz, 0.f, 0.f, 0.f};
+          wgrad_vec<4>(sg + B_VISB2, dbz, gate);
+          float t2[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) t2[c] = x2[c] * vis1;
+          wgrad_acc<32, 32>(sg + W_VISB0, t2, dh, gate);
+          wgrad_vec<32>(sg + B_VISB0, dh, gate);
+        }
         d_vis1 = 0.f;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
@@ -433,6 +494,18 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
         dense_T<32, 32>(sw + W_VIS0, dh, dt);
 #pragma unroll
         for (int c = 0; c < 32; ++c) d_x1[c] = fmaf(dt[c], w, d_x2[c]);
+        if (WG) {
+          wgrad_acc<32, 36>(sg + W_VIS2, hv, dxv, gate);
+          wgrad_vec<36>(sg + B_VIS2, dxv, gate);
+          float t1[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            t1[c] = x1[c] * w;
+            d_w = fmaf(dt[c], x1[c], d_w);         // vis_fc sees x * weight (:250)
+          }
+          wgrad_acc<32, 32>(sg + W_VIS0, t1, dh, gate);
+          wgrad_vec<32>(sg + B_VIS0, dh, gate);
+        }
       }
 
       // (6) base_fc backward -> d[mean0 | var0 | x0]
@@ -443,6 +516,19 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
         dense_T<64, 32>(sw + W_BASE2, d_x1, d_h1);
 #pragma unroll
         for (int k = 0; k < 64; ++k) d_h1[k] *= elu_grad_from_out(h1[k]);
+      }
+      float m0[NFB_ROW_CH];                        // WG: mean0 of this sample (the buffer is overwritten in (7))
+      if (WG) {
+        wgrad_acc<64, 32>(sg + W_BASE2, h1, d_x1, gate);
+        wgrad_vec<32>(sg + B_BASE2, d_x1, gate);
+        float xin[105];
+#pragma unroll
+        for (int c = 0; c < NFB_ROW_CH; ++c) {
+          m0[c] = mvs[c];
+          xin[c] = mvs[c]; xin[35 + c] = mvs[36 + c]; xin[70 + c] = x[c];
+        }
+        wgrad_acc<105, 64>(sg + W_BASE0, xin, d_h1, gate);
+        wgrad_vec<64>(sg + B_BASE0, d_h1, gate);
       }
 
       // (7) first pooling backward.  With Dm_c = sum_v d mean0_vc, Dv_c = sum_v d var0_vc:
@@ -480,11 +566,53 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
 #pragma unroll
         for (int c = 0; c < NFB_ROW_CH; ++c)
           d_row[c] = dot_row<64>(d_h1, sw + W_BASE0 + (70 + c) * 64) + w * (mvs[c] + x[c] * mvs[36 + c]);
+        if (WG) {
+          // d w_v of the first pooling: sum_c x0_vc A_c + B_c/2 (x0_vc^2 + mean0_c^2)   (A_c, B_c as above)
+#pragma unroll
+          for (int c = 0; c < NFB_ROW_CH; ++c)
+            d_w += x[c] * mvs[c] + 0.5f * mvs[36 + c] * (x[c] * x[c] + m0[c] * m0[c]);
+          // ray_dir_fc (:231): d direction_feat = d x0 (d_row before the direct rgb_in term below)
+          float a1[16];
+          load_bias<16>(a1, sw + B_DIR0);
+          dense_acc<4, 16>(sw + W_DIR0, rd, a1);
+          elu_inplace<16>(a1);
+          float ddf[36];
+          load_bias<36>(ddf, sw + B_DIR2);
+          dense_acc<16, 36>(sw + W_DIR2, a1, ddf);
+#pragma unroll
+          for (int c = 0; c < NFB_ROW_CH; ++c) ddf[c] = d_row[c] * elu_grad_from_out(elu_f(ddf[c]));
+          ddf[35] = 0.f;
+          wgrad_acc<16, 36>(sg + W_DIR2, a1, ddf, gate);
+          wgrad_vec<36>(sg + B_DIR2, ddf, gate);
+          float da1[16];
+          dense_T<16, 36>(sw + W_DIR2, ddf, da1);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) da1[k] *= elu_grad_from_out(a1[k]);
+          wgrad_acc<4, 16>(sg + W_DIR0, rd, da1, gate);
+          wgrad_vec<16>(sg + B_DIR0, da1, gate);
+        }
         // rgb_in enters the blend directly (:233,272)
         d_row[0] = fmaf(blend, d_r0, d_row[0]);
         d_row[1] = fmaf(blend, d_r1, d_row[1]);
         d_row[2] = fmaf(blend, d_r2, d_row[2]);
         named_bar_sync(bar_id, GROUP);
+        if (WG && a.anti_alias) {
+          // s (:236-238): w_v = n_v / (sum_u n_u + 1e-8), n_v = (e_v - min_u e_u) mask_v, e_v = exp(|s| (dot_v - 1))
+          const float ge = e_aa * (rd[3] - 1.f);   // d e_v / d |s|
+          ex[tg * EXS + 0] = d_w;
+          ex[tg * EXS + 1] = w;
+          ex[tg * EXS + 2] = e_aa;
+          ex[tg * EXS + 3] = ge;
+          named_bar_sync(bar_id, GROUP);
+          float dww = 0.f, emin = 3.4e38f, gmin = 0.f;
+          for (int u = 0; u < V; ++u) {
+            dww = fmaf(ex[(base + u) * EXS + 0], ex[(base + u) * EXS + 1], dww);
+            const float eu = ex[(base + u) * EXS + 2];
+            if (eu < emin) { emin = eu; gmin = ex[(base + u) * EXS + 3]; }
+          }
+          ds_acc += gate * ((d_w - dww) / den_aa) * mk * (ge - gmin);
+          named_bar_sync(bar_id, GROUP);
+        }
       }
 
       // (8) hand the row cotangent on
@@ -510,16 +638,28 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
       }
     }
   }
+  if (WG) {
+    if (a.anti_alias) {
+      const float t = warp_sum(ds_acc);
+      if ((threadIdx.x & 31) == 0) atomicAdd(sg + W_S, t);
+    }
+    __syncthreads();
+    flush_view_grads(a.d_params, sg, threadIdx.x, blockDim.x);
+    if (threadIdx.x == 0 && a.anti_alias) {
+      const float sv = __ldg(a.params + P_S);
+      atomicAdd(a.d_params + P_S, (sv > 0.f ? 1.f : (sv < 0.f ? -1.f : 0.f)) * sg[W_S]);
+    }
+  }
 }
 
-constexpr size_t view_smem_bytes(int ng) {
-  return (size_t)(W_TOTAL + 16 * NFB_MAX_VIEWS + 4 + ng * GROUP * EXS + ng * TS_MAX * MVS) * sizeof(float);
+constexpr size_t view_smem_bytes(int ng, bool wg = false) {
+  return (size_t)(W_TOTAL * (wg ? 2 : 1) + 16 * NFB_MAX_VIEWS + 4 + ng * GROUP * EXS + ng * TS_MAX * MVS) * sizeof(float);
 }
 
-template <bool FUSED, bool BWD, int NG>
+template <bool FUSED, bool BWD, int NG, bool WG = false>
 int launch_view(const ViewArgs& a, cudaStream_t st, const char* name) {
-  const size_t smem = view_smem_bytes(NG);
-  cudaError_t e = cudaFuncSetAttribute(k_view_stage<FUSED, BWD, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = view_smem_bytes(NG, WG);
+  cudaError_t e = cudaFuncSetAttribute(k_view_stage<FUSED, BWD, NG, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nfb_set_error(NFB_ECUDA, "%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
   const int TS = (GROUP / a.V < TS_MAX) ? GROUP / a.V : TS_MAX;
   const int ntiles = (a.N + TS - 1) / TS;
@@ -527,7 +667,7 @@ int launch_view(const ViewArgs& a, cudaStream_t st, const char* name) {
   const int cap = nfb_num_sms();
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  k_view_stage<FUSED, BWD, NG><<<grid, GROUP * NG, smem, st>>>(a);
+  k_view_stage<FUSED, BWD, NG, WG><<<grid, GROUP * NG, smem, st>>>(a);
   NFB_CHECK_LAUNCH(name);
   return NFB_OK;
 }
@@ -539,3 +679,5 @@ int nfb_launch_view_tensor_fwd(const nfbview::ViewArgs& a, cudaStream_t st);
 int nfb_launch_view_fused_fwd(const nfbview::ViewArgs& a, cudaStream_t st);
 int nfb_launch_view_tensor_bwd(const nfbview::ViewArgs& a, cudaStream_t st);
 int nfb_launch_view_fused_bwd(const nfbview::ViewArgs& a, cudaStream_t st);
+int nfb_launch_view_tensor_wgrad(const nfbview::ViewArgs& a, cudaStream_t st);   // data + parameter gradients
+int nfb_launch_view_fused_wgrad(const nfbview::ViewArgs& a, cudaStream_t st);

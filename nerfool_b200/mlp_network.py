@@ -2,7 +2,9 @@
 
 An ``nn.Module`` with the reference's parameter / buffer names and shapes (so checkpoints load, DDP /
 DataParallel wrapping and ``.to()`` work) whose ``forward`` runs the CUDA view-stage + ray-stage kernels.
-The sub-modules exist only as parameter containers; their ``forward`` is never called."""
+The sub-modules exist only as parameter containers; their ``forward`` is never called.  Gradients: data gradients
+(feature maps / source images, what the PGD attack optimises) always; parameter gradients (training) whenever a
+parameter has ``requires_grad`` -- then the backward runs the wgrad kernels (nfb_ibrnet_{view,ray}_wgrad)."""
 from __future__ import annotations
 
 import numpy as np
@@ -102,8 +104,20 @@ class IBRNet(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def param_blob(self) -> torch.Tensor:
-        """Flat fp32 copy of the parameters in the C-ABI order, rebuilt only when a parameter changed."""
+        """Flat fp32 copy of the parameters in the C-ABI order.  Inference / attack (no parameter requires a
+        gradient, or grad mode is off): a detached blob, rebuilt only when a parameter changed.  Training
+        (train.py:317-327): a differentiable ``torch.cat`` of the parameters, so the gradient blob the wgrad
+        kernels return is split back onto ``.grad`` of every tensor by autograd."""
         sd = dict(self.named_parameters())
+        if torch.is_grad_enabled() and any(p.requires_grad for p in sd.values()):
+            dev = next(self.parameters()).device
+            parts = []
+            for name in PARAM_ORDER:
+                if name == 's' and name not in sd:
+                    parts.append(torch.zeros(1, device=dev))
+                else:
+                    parts.append(sd[name].reshape(-1).float())
+            return torch.cat(parts)
         key = tuple((p.data_ptr(), p._version) for p in sd.values())
         if self._blob is None or key != self._blob_key:
             dev = next(self.parameters()).device
@@ -118,14 +132,5 @@ class IBRNet(nn.Module):
         :param mask: [n_rays, n_samples, n_views, 1]
         :return: rgb and density output, [n_rays, n_samples, 4]
         """
-        self._check_weight_grad()
         return ops.IBRNetAggregate.apply(rgb_feat, ray_diff, mask, self.param_blob(), self.pos_encoding[0],
                                          bool(self.anti_alias_pooling))
-
-    def _check_weight_grad(self):
-        # The CUDA backward produces data gradients (what the PGD attack optimises).  Parameter gradients
-        # (train.py) are not produced yet: refuse loudly in training mode instead of silently not learning.
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                'nerfool_b200.IBRNet: parameter gradients (training) are not implemented in this round; '
-                'call .eval() (the attack drivers do, eval_adv.py:541) or freeze the parameters')

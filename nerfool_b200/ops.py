@@ -156,7 +156,7 @@ class IBRNetAggregate(torch.autograd.Function):
             call('nfb_ibrnet_view_fwd', N, S, V, int(anti_alias), ptr(rf), ptr(rd), ptr(mk), 0, 0, 0, 0,
                  None, None, None, None, None, None, None, ptr(params), ptr(ps), None, _lib.precision_code(), st)
             call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), None, _lib.precision_code(), st)
-        ctx.save_for_backward(rf, rd, mk, params, pos_enc, ps)
+        ctx.save_for_backward(rf, rd, mk, params.detach(), pos_enc, ps)
         ctx.dims = (R, S, V, int(anti_alias))
         ctx.precision = _lib.precision_code()
         return raw
@@ -168,6 +168,19 @@ class IBRNetAggregate(torch.autograd.Function):
         N = R * S
         dev = rf.device
         d_rf = None
+        if ctx.needs_input_grad[3]:
+            # training: data + parameter gradients from the fp32 recompute kernels
+            g = f32c(d_raw)
+            d_ps = torch.empty(N, PS_STRIDE, device=dev, dtype=torch.float32)
+            d_rf = torch.empty_like(rf)
+            d_params = torch.zeros(_lib.PARAM_FLOATS, device=dev, dtype=torch.float32)
+            with torch.cuda.device(dev):
+                st = stream_ptr(dev)
+                call('nfb_ibrnet_ray_wgrad', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(g), ptr(d_ps), ptr(d_params), st)
+                call('nfb_ibrnet_view_wgrad', N, S, V, aa, ptr(rf), ptr(rd), ptr(mk), 0, 0, 0, 0,
+                     None, None, None, None, None, None, None, ptr(params), ptr(ps), ptr(d_ps),
+                     ptr(d_rf), None, None, ptr(d_params), st)
+            return (d_rf if ctx.needs_input_grad[0] else None), None, None, d_params, None, None
         if ctx.needs_input_grad[0]:
             g = f32c(d_raw)
             d_ps = torch.empty(N, PS_STRIDE, device=dev, dtype=torch.float32)
@@ -284,11 +297,14 @@ class RenderLevel(torch.autograd.Function):
         weights = torch.empty(R, S, device=dev, dtype=torch.float32)
         alpha = torch.empty(R, S, device=dev, dtype=torch.float32)
         ray_mask = torch.empty(R, device=dev, dtype=torch.uint8)
-        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        # activation stash for the backward (768 B per (sample, view) row): written only when a gradient is wanted
-        n_stash = _lib.stash_bytes(N, V) if need else 0
+        need_params = ctx.needs_input_grad[6]
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or need_params
+        # activation stash for the backward (768 B per (sample, view) row): written only when a data gradient is
+        # wanted and no parameter trains (the wgrad kernels recompute the forward)
+        use_stash = need and not need_params
+        n_stash = _lib.stash_bytes(N, V) if use_stash else 0
         stash = torch.empty(n_stash, device=dev, dtype=torch.uint8) if n_stash else None
-        n_rstash = _lib.ray_stash_bytes(R, S) if need else 0
+        n_rstash = _lib.ray_stash_bytes(R, S) if use_stash else 0
         rstash = torch.empty(n_rstash, device=dev, dtype=torch.uint8) if n_rstash else None
         with torch.cuda.device(dev):
             st = stream_ptr(dev)
@@ -301,7 +317,7 @@ class RenderLevel(torch.autograd.Function):
         ctx.stash = stash
         ctx.rstash = rstash
         if need:
-            ctx.save_for_backward(feat, imgs_c, o_c, d_c, z_c, cam, params, pos_enc, ps, raw)
+            ctx.save_for_backward(feat, imgs_c, o_c, d_c, z_c, cam, params.detach(), pos_enc, ps, raw)
         ctx.dims = (R, S, V, H, W, fh, fw, int(anti_alias), int(white_bkgd))
         ctx.precision = _lib.precision_code()
         ctx.imgs_shape = imgs.shape
@@ -316,7 +332,8 @@ class RenderLevel(torch.autograd.Function):
         R, S, V, H, W, fh, fw, aa, white = ctx.dims
         N = R * S
         dev = z_c.device
-        need_feat, need_imgs = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_feat, need_imgs, need_params = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[6]
+        d_params = torch.zeros(_lib.PARAM_FLOATS, device=dev, dtype=torch.float32) if need_params else None
         d_feat = torch.zeros(V, fh, fw, FEAT_CH, device=dev, dtype=torch.float32) if need_feat else None
         d_imgs = torch.zeros(ctx.imgs_shape, device=dev, dtype=torch.float32) if need_imgs else None
         d_raw = torch.empty(R, S, 4, device=dev, dtype=torch.float32)
@@ -325,11 +342,17 @@ class RenderLevel(torch.autograd.Function):
             st = stream_ptr(dev)
             call('nfb_composite_bwd', R, S, white, ptr(raw), ptr(z_c), ptr(f32c(d_rgb)), ptr(f32c(d_depth)),
                  ptr(f32c(d_weights)), ptr(f32c(d_alpha)), ptr(d_raw), st)
-            call('nfb_ibrnet_ray_bwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(d_raw), ptr(d_ps), ptr(ctx.rstash), ctx.precision, st)
-            call('nfb_ibrnet_view_bwd', N, S, V, aa, None, None, None, H, W, fh, fw,
-                 None, ptr(o_c), ptr(d_c), ptr(z_c), ptr(cam), ptr(imgs_c), ptr(feat), ptr(params), ptr(ps),
-                 ptr(d_ps), None, ptr(d_feat), ptr(d_imgs), ptr(ctx.stash), ctx.precision, st)
+            if need_params:
+                call('nfb_ibrnet_ray_wgrad', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(d_raw), ptr(d_ps), ptr(d_params), st)
+                call('nfb_ibrnet_view_wgrad', N, S, V, aa, None, None, None, H, W, fh, fw,
+                     None, ptr(o_c), ptr(d_c), ptr(z_c), ptr(cam), ptr(imgs_c), ptr(feat), ptr(params), ptr(ps),
+                     ptr(d_ps), None, ptr(d_feat), ptr(d_imgs), ptr(d_params), st)
+            else:
+                call('nfb_ibrnet_ray_bwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(d_raw), ptr(d_ps), ptr(ctx.rstash), ctx.precision, st)
+                call('nfb_ibrnet_view_bwd', N, S, V, aa, None, None, None, H, W, fh, fw,
+                     None, ptr(o_c), ptr(d_c), ptr(z_c), ptr(cam), ptr(imgs_c), ptr(feat), ptr(params), ptr(ps),
+                     ptr(d_ps), None, ptr(d_feat), ptr(d_imgs), ptr(ctx.stash), ctx.precision, st)
         ctx.stash = None
         ctx.rstash = None
         return (d_feat.permute(0, 3, 1, 2) if need_feat else None, d_imgs,
-                None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, d_params, None, None, None, None, None)

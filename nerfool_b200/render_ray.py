@@ -120,7 +120,6 @@ def render_rays(ray_batch, model, featmaps, projector, N_samples, inv_uniform=Fa
 
         def level(net, fmap, z):
             net = _unwrap(net)
-            net._check_weight_grad()
             rgb, depth, weights, alpha, mask = ops.RenderLevel.apply(
                 fmap, src_rgbs[0], ray_o, ray_d, z, cam, net.param_blob(), net.pos_encoding[0], H, W,
                 bool(net.anti_alias_pooling), bool(white_bkgd))

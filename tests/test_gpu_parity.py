@@ -156,6 +156,128 @@ def test_ibrnet_forward_backward(dev, V, S, kind, H, W, R):
     assert e_ours <= max(1e-3, 3 * e_ref), (e_ours, e_ref)
 
 
+def _grad_params(p, dtype):
+    """leaf copies of the float parameters of an oracle parameter dict (pos_encoding stays a constant)."""
+    q = {}
+    for k, v in p.items():
+        if k == 'pos_encoding' or not v.is_floating_point():
+            q[k] = v.to(dtype) if v.is_floating_point() else v
+        else:
+            q[k] = v.detach().to(dtype).clone().requires_grad_(True)
+    return q
+
+
+def _check_param_grads(net, p32, p64, what, floor=2e-3):
+    """every parameter gradient of our module within max(floor, 3 x the fp32 oracle's own distance) of the fp64 truth
+    (relative L2 per tensor; tensors whose true gradient is ~0 are compared absolutely)."""
+    worst = {}
+    for name, prm in net.named_parameters():
+        assert prm.grad is not None, f'{what}: no gradient for {name}'
+        g, g32, g64 = prm.grad.detach().cpu().double(), p32[name].grad.double(), p64[name].grad
+        scale = g64.norm().item()
+        if scale < 1e-9:
+            # e.g. rgb_fc.4.bias: the blending softmax is shift invariant, the true gradient is exactly 0 and what is
+            # left is the fp32 rounding of a sum over all rows
+            assert (g - g64).norm().item() < max(1e-4, 3 * (g32 - g64).norm().item()), (what, name, 'zero gradient expected')
+            continue
+        e_ours = ((g - g64).norm() / scale).item()
+        e_ref = ((g32 - g64).norm() / scale).item()
+        worst[name] = (e_ours, e_ref)
+        assert e_ours <= max(floor, 3 * e_ref), f'{what}: d {name}: ours {e_ours:.3e}, fp32 oracle {e_ref:.3e}'
+    return worst
+
+
+@pytest.mark.parametrize('V,S,kind,H,W,R,aa', [(4, 64, 'llff', 378, 504, 100, 1), (10, 192, 'synthetic', 200, 200, 20, 1),
+                                               (5, 33, 'llff', 96, 128, 67, 1), (3, 40, 'llff', 96, 128, 50, 0)])
+def test_ibrnet_parameter_gradients(dev, V, S, kind, H, W, R, aa):
+    """Training (train.py:317-327): d loss / d every IBRNet parameter through IBRNet.forward (tensor form) equals autograd
+    of the oracle; the data gradient that comes out of the same kernels is checked too."""
+    from nerfool_b200.mlp_network import IBRNet
+    scene, batch = _scene(V, R, H, W, kind, seed=V + S)
+    pts, _ = O.coarse_depths(batch['ray_o'], batch['ray_d'], batch['depth_range'], S, inv_uniform=True, det=True)
+    rf, rd, mk = O.projector_compute(pts, batch['camera'], batch['src_rgbs'], batch['src_cameras'], scene['featmaps'][0])
+    p = _params(S, 5)
+    cot = torch.randn(R, S, 4, generator=torch.Generator().manual_seed(8))
+    p32, p64 = _grad_params(p, torch.float32), _grad_params(p, torch.float64)
+    r32 = rf.clone().requires_grad_(True)
+    (O.ibrnet_forward(p32, p['pos_encoding'], r32, rd, mk, anti_alias_pooling=bool(aa)) * cot).sum().backward()
+    r64 = rf.double().requires_grad_(True)
+    (O.ibrnet_forward(p64, p['pos_encoding'].double(), r64, rd.double(), mk.double(), anti_alias_pooling=bool(aa))
+     * cot.double()).sum().backward()
+    net = IBRNet(types.SimpleNamespace(anti_alias_pooling=aa), 32, S)
+    net.load_state_dict({k: v.clone() for k, v in p.items() if aa or k != 's'})
+    net = net.to(dev).train()
+    rg = rf.to(dev).requires_grad_(True)
+    raw = net(rg, rd.to(dev), mk.to(dev))
+    (raw * cot.to(dev)).sum().backward()
+    _check_param_grads(net, p32, p64, f'V={V} S={S}')
+    e_ours, e_ref = relerr(rg.grad.cpu(), r64.grad), relerr(r32.grad, r64.grad)
+    assert e_ours <= max(1e-3, 3 * e_ref), (e_ours, e_ref)
+    # frozen parameters + data gradient only: the module must not produce parameter gradients
+    net.zero_grad(set_to_none=True)
+    for q in net.parameters():
+        q.requires_grad_(False)
+    rg2 = rf.to(dev).requires_grad_(True)
+    (net(rg2, rd.to(dev), mk.to(dev)) * cot.to(dev)).sum().backward()
+    assert all(q.grad is None for q in net.parameters())
+    assert relerr(rg2.grad.cpu(), r64.grad) <= max(1e-3, 3 * e_ref)
+
+
+def test_render_rays_parameter_gradients(dev):
+    """One training step of the fused render_rays: masked-MSE loss -> gradients of both networks' parameters AND of
+    the feature maps, against the oracle (coarse level vs the fp64 truth, fine level vs the fp32 oracle at the
+    oracle's fine depths)."""
+    from nerfool_b200.mlp_network import IBRNet
+    from nerfool_b200.projection import Projector
+    from nerfool_b200 import render_ray as RR
+    from nerfool_b200.attack import rgb_loss
+    V, R, S, NI = 4, 96, 32, 32
+    scene, batch = _scene(V, R, 378, 504, 'llff', seed=3)
+    pc, pf = _params(S, 21), _params(S + NI, 22)
+    runs = {}
+    for dt in (torch.float32, torch.float64):
+        qc, qf = _grad_params(pc, dt), _grad_params(pf, dt)
+        fm = tuple(f.detach().clone().to(dt).requires_grad_(True) for f in scene['featmaps'])
+        b = batch if dt == torch.float32 else _dbl(batch)
+        out = O.render_rays(b, qc, qf, fm, S, True, NI, det=True)
+        if dt == torch.float64:      # truth for the coarse level only (the fine depths differ between precisions)
+            O.masked_mse(out['outputs_coarse']['rgb'], b['rgb'], out['outputs_coarse']['mask'].double()).backward()
+        else:
+            O.attack_loss(out, b['rgb']).backward()
+        runs[dt] = (qc, qf, fm, out)
+    gb = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    nets = []
+    for p, n in ((pc, S), (pf, S + NI)):
+        net = IBRNet(types.SimpleNamespace(anti_alias_pooling=1), 32, n)
+        net.load_state_dict({k: v.clone() for k, v in p.items()})
+        nets.append(net.to(dev).train())
+    model = types.SimpleNamespace(net_coarse=nets[0], net_fine=nets[1])
+    fm_g = tuple(f.detach().to(dev).requires_grad_(True) for f in scene['featmaps'])
+    saved = RR._fine_z
+    RR._fine_z = lambda z, w, n, iu, det: runs[torch.float32][3]['outputs_fine']['z_vals'].to(dev)
+    try:
+        out = RR.render_rays(gb, model, fm_g, Projector(dev), S, inv_uniform=True, N_importance=NI, det=True)
+    finally:
+        RR._fine_z = saved
+    rgb_loss(out, gb['rgb']).backward()
+    _check_param_grads(nets[0], runs[torch.float32][0], runs[torch.float64][0], 'coarse net')
+    for name, prm in nets[1].named_parameters():          # fine net: fp32 oracle at identical depths
+        ref = runs[torch.float32][1][name].grad
+        if ref.norm() > 1e-9:
+            assert relerr(prm.grad.cpu(), ref) < 5e-3, ('fine net', name, relerr(prm.grad.cpu(), ref))
+    e_c = relerr(fm_g[0].grad.cpu(), runs[torch.float64][2][0].grad)
+    e_r = relerr(runs[torch.float32][2][0].grad, runs[torch.float64][2][0].grad)
+    assert e_c <= max(1e-3, 3 * e_r), (e_c, e_r)
+    assert relerr(fm_g[1].grad.cpu(), runs[torch.float32][2][1].grad) < 5e-3
+    # an optimiser step changes the parameters and the next forward sees them (blob cache invalidation)
+    before = out['outputs_fine']['rgb'].detach().clone()
+    opt = torch.optim.Adam([q for n in nets for q in n.parameters()], lr=1e-2)
+    opt.step()
+    with torch.no_grad():
+        out2 = RR.render_rays(gb, model, fm_g, Projector(dev), S, inv_uniform=True, N_importance=NI, det=True)
+    assert maxabs(out2['outputs_fine']['rgb'].cpu(), before.cpu()) > 1e-4
+
+
 def test_ibrnet_golden_and_no_anti_alias(dev):
     g = load_golden('render_llff_v3')
     p = params_from_golden(g, 'nc')

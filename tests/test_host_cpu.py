@@ -97,14 +97,22 @@ def test_ibrnet_module_interface_matches_reference_checkpoint_contract():
     missing, unexpected = net.load_state_dict(sd, strict=True)
     assert not missing and not unexpected
     assert sum(p.numel() for p in net.parameters()) == 20136
-    blob = net.param_blob()
-    assert blob.numel() == 20136 and blob is net.param_blob()          # cached until a parameter changes
     with torch.no_grad():
+        blob = net.param_blob()
+        assert blob.numel() == 20136 and blob is net.param_blob()      # cached until a parameter changes
         net.s.add_(1.0)
-    assert net.param_blob()[0].item() == pytest.approx(float(g['nc.s']) + 1.0)
+        assert net.param_blob()[0].item() == pytest.approx(float(g['nc.s']) + 1.0)
+    # training: with grad enabled and trainable parameters the blob is a differentiable concatenation (autograd splits
+    # the gradient blob of the wgrad kernels back onto the tensors); under no_grad it is the cached detached copy
     net.train()
-    with pytest.raises(NotImplementedError):
-        net._check_weight_grad()
+    tb = net.param_blob()
+    assert tb.requires_grad and tb.numel() == 20136 and torch.equal(tb.detach()[1:], blob[1:])
+    (tb * torch.arange(20136.)).sum().backward()
+    assert net.s.grad.item() == 0.0 and net.rgb_fc[4].bias.grad.item() == 20135.0
+    off = 1 + 64 + 16
+    assert torch.equal(net.ray_dir_fc[2].weight.grad.reshape(-1), torch.arange(off, off + 35 * 16.))
+    with torch.no_grad():
+        assert not net.param_blob().requires_grad and net.param_blob() is net.param_blob()
 
 
 def test_camera_block_matches_reference_projection_matrices():
