@@ -250,6 +250,26 @@ def run_ours(a):
         bf16_ms = s0.elapsed_time(s1) / 2
         _lib.set_precision(saved_prec)
 
+    # ---------------- PGD iterations/s at the reference's ray-batch sizes (N_rand, config.py:55 default 512) ----------------
+    nrand = {}
+    if world == 1 and not a.no_nrand:
+        gen = torch.Generator(device='cpu').manual_seed(3)
+        for n in (512, 4096, 32768):
+            sel = torch.randperm(R, generator=gen)[:n].sort().values.to(device)
+            nb = dict(static)
+            for k in ('ray_o', 'ray_d', 'rgb'):
+                nb[k] = resident[k][sel].contiguous()
+            for _ in range(3):
+                step(nb)
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(10):
+                step(nb)
+            s1.record()
+            torch.cuda.synchronize()
+            nrand[str(n)] = {'ms_per_iter': s0.elapsed_time(s1) / 10, 'iters_per_s': 1e4 / s0.elapsed_time(s1)}
+
     # max over ranks
     t = torch.tensor([total_ms, e2e_total_ms, statistics.median(fwd_ms), bf16_ms or 0.0], device=device, dtype=torch.float64)
     if world > 1:
@@ -314,6 +334,7 @@ def run_ours(a):
                        'l2': 'per-step working set (per-sample workspaces + activation stash, tens of GB) >> 126 MB L2; '
                              'the 2x6.3 MB feature maps are L2-resident by design'},
             'pgd_iters_per_s': 1e3 / ms_per_step,
+            'pgd_iters_per_s_by_n_rand': nrand or None,
             'fwd_rays_per_s': rays_total / (fwd_med * 1e-3),
             'fwd_ms_per_frame': fwd_med,
             'encoder': 'not timed: the ResUNet stays on cuDNN in the reference and is outside this repo (north_star)',
@@ -343,6 +364,7 @@ def run_ours(a):
                                 'note': 'same step with NFB_PREC_BF16 (single bf16 MMA pass; PSNR-parity mode, tests/test_gpu_parity.py::test_precision_modes)'}
         if world == 1 and not a.no_cpu_baseline:
             out['cpu_baseline'] = cpu_reference(a, sample_rays=a.cpu_rays, steps=1, warmup=1)
+            out['torch_eager_b200'] = eager_gpu_reference(a, device)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
@@ -377,6 +399,45 @@ def cpu_reference(a, sample_rays, steps, warmup):
                       f'{warmup} warm-up + mean of {steps}', 'ms_per_step': sec * 1e3}
 
 
+def eager_gpu_reference(a, device, rays=4096, steps=3):
+    """The reference algorithm as eager PyTorch ON THE SAME B200 (the oracle port moved to CUDA, TF32 off): what a
+    user of the reference gets today on this GPU.  Same step (render_rays fwd + masked MSE + backward to the feature
+    maps) on a chunk of `rays` rays (the reference's own chunking: autograd keeps ~1 GB per 1k rays alive)."""
+    from oracle import ibrnet_oracle as O
+    from nerfool_b200.synthetic import make_scene, ray_batch_for
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        scene = make_scene(H, W, a.views, seed=0, kind=SCENE_KIND)
+        ids = np.sort(np.random.RandomState(1).choice(H * W, rays, replace=False))
+        batch = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in ray_batch_for(scene, ids).items()}
+        pc = {k: v.to(device) for k, v in O.random_ibrnet_params(N_SAMPLES, 1, sigma_bias=0.3).items()}
+        pf = {k: v.to(device) for k, v in O.random_ibrnet_params(N_SAMPLES + N_IMPORTANCE, 2, sigma_bias=0.3).items()}
+        ms = []
+        for i in range(1 + steps):
+            fm = tuple(f.to(device).clone().requires_grad_(True) for f in scene['featmaps'])
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = O.render_rays(batch, pc, pf, fm, N_SAMPLES, inv_uniform=True, n_importance=N_IMPORTANCE, det=True)
+            O.attack_loss(out, batch['rgb']).backward()
+            e.record()
+            torch.cuda.synchronize()
+            if i > 0:
+                ms.append(s.elapsed_time(e))
+            del out, fm
+        t = statistics.median(ms)
+        return {'value': rays / (t * 1e-3), 'unit': 'rays/s', 'ms_per_chunk': t, 'rays_per_chunk': rays,
+                'what': 'eager PyTorch (CUDA, fp32, TF32 off) port of the reference path on the same B200, same step; '
+                        'reported baseline, not part of the product path'}
+    except Exception as ex:       # never let the baseline break the bench line
+        return {'unavailable': f'{type(ex).__name__}: {ex}'[:200]}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        torch.cuda.empty_cache()
+
+
 def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -404,6 +465,7 @@ def main():
     ap.add_argument('--max-rays', dest='max_rays', type=int, default=0, help='rays per launch (0 = sized from the stash budget)')
     ap.add_argument('--cpu-rays', dest='cpu_rays', type=int, default=2048)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-nrand', dest='no_nrand', action='store_true', help='skip the N_rand = 512/4096/32768 PGD iteration timings')
     ap.add_argument('--no-bf16', dest='no_bf16', action='store_true', help='skip the extra plain-bf16 measurement')
     ap.add_argument('--config', type=int, default=1, choices=[1, 2, 3],
                     help='BASELINE.json configs index: 1 = headline (378x504, 4 views, 64+64); 2 = universal-attack shape '

@@ -104,12 +104,15 @@ class IBRNet(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def param_blob(self) -> torch.Tensor:
-        """Flat fp32 copy of the parameters in the C-ABI order.  Inference / attack (no parameter requires a
-        gradient, or grad mode is off): a detached blob, rebuilt only when a parameter changed.  Training
-        (train.py:317-327): a differentiable ``torch.cat`` of the parameters, so the gradient blob the wgrad
-        kernels return is split back onto ``.grad`` of every tensor by autograd."""
+        """Flat fp32 copy of the parameters in the C-ABI order.  Inference / attack (``.eval()`` -- the attack
+        drivers call model.switch_to_eval(), eval_adv.py:541 --, or no parameter requires a gradient, or grad mode
+        is off): a detached blob, rebuilt only when a parameter changed; the backward then runs the fast
+        data-gradient kernels only.  (The reference's eager ``loss.backward()`` would also fill the parameters'
+        ``.grad`` in eval mode; nothing in the attack reads them, so they are not produced.)  Training
+        (``.train()``, train.py:317-327): a differentiable ``torch.cat`` of the parameters, so the gradient blob
+        the wgrad kernels return is split back onto ``.grad`` of every tensor by autograd."""
         sd = dict(self.named_parameters())
-        if torch.is_grad_enabled() and any(p.requires_grad for p in sd.values()):
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in sd.values()):
             dev = next(self.parameters()).device
             parts = []
             for name in PARAM_ORDER:

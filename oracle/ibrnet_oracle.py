@@ -285,9 +285,9 @@ def sample_pdf(bins, weights, n_samples, det=False, u=None, return_inds=False):
     cdf = cdf_from_weights(weights)
     if u is None:
         if det:
-            u = torch.linspace(0., 1., n_samples).unsqueeze(0).repeat(bins.shape[0], 1)
+            u = torch.linspace(0., 1., n_samples).to(bins.device).unsqueeze(0).repeat(bins.shape[0], 1)
         else:
-            u = torch.rand(bins.shape[0], n_samples)
+            u = torch.rand(bins.shape[0], n_samples, device=bins.device)
     samples, above = invert_cdf(bins, cdf, u)
     return (samples, above) if return_inds else samples
 

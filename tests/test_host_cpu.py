@@ -113,6 +113,8 @@ def test_ibrnet_module_interface_matches_reference_checkpoint_contract():
     assert torch.equal(net.ray_dir_fc[2].weight.grad.reshape(-1), torch.arange(off, off + 35 * 16.))
     with torch.no_grad():
         assert not net.param_blob().requires_grad and net.param_blob() is net.param_blob()
+    net.eval()                                                          # attack mode: data gradients only
+    assert not net.param_blob().requires_grad and net.param_blob() is net.param_blob()
 
 
 def test_camera_block_matches_reference_projection_matrices():
