@@ -143,6 +143,27 @@ int nfb_ibrnet_view_wgrad(int N, int S, int V, int anti_alias,
                           const float* params, const float* ps, const float* d_ps,
                           float* d_rgb_feat, float* d_feat, float* d_imgs, float* d_params, void* stream);
 
+/* ---- GNT.forward  (gnt/transformer_network.py:270-309; SURVEY.md 8 row a15, BASELINE config 5) ------------------
+ * View transformer (Attention2D: subtraction attention over the V source views, softmax per channel) + ray
+ * transformer (4-head self-attention over the S samples), netwidth 64, `depth` layers, q_fc with 63-d positional
+ * encodings of the points / view directions on even layers.  Inputs are what Projector.compute returns
+ * (rgb_feat[R][S][V][35], ray_diff[R][S][V][4], mask[R][S][V][1]) plus pts[R][S][3] and ray_d[R][3].
+ * out: [R][3] or, with ret_alpha, [R][3+S] (rgb | attention row of query 0 of the last ray transformer, the
+ * "learned density" gnt/render_ray.py:249-250 turns into depth).  Forward only in this round (eval mode: dropout is
+ * the identity); fp32 CUDA-core kernels.
+ * params: one flat fp32 blob of nfb_gnt_param_floats(depth) floats: header (rgbfeat_fc), `depth` layer blocks
+ * (view_crosstrans.i | q_fcs.i | view_selftrans.i), tail (norm, rgb_fc); nfb_gnt_param_offset(depth, name) gives the
+ * offset of a header / tail tensor ("rgbfeat_fc.0.weight", "norm.bias", ...), of the first layer block ("layer0"),
+ * the block size ("layer_size") and of a tensor inside a block ("view.attn.q_fc.weight", "q_fc.0.bias",
+ * "ray.ff.fc2.weight", ...).  workspace: nfb_gnt_workspace_bytes(R, S, V) bytes, 16-byte aligned (projected view
+ * features F[R*S*V][64] + the running query q[R*S][64]).                                                          */
+int nfb_gnt_param_floats(int depth);
+int nfb_gnt_param_offset(int depth, const char* name);
+size_t nfb_gnt_workspace_bytes(int R, int S, int V);
+int nfb_gnt_fwd(int R, int S, int V, int depth, int ret_alpha,
+                const float* rgb_feat, const float* ray_diff, const float* mask, const float* pts, const float* ray_d,
+                const float* params, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- raw2outputs  (render_ray.py:123-170) ------------------------------------------------------------
  * pixel_mask: uint8 [R][S] (the `mask` argument), or NULL with n_valid (stride n_valid_stride floats per
  * sample) from which pixel_mask = n_valid > 1 (render_ray.py:210).  Outputs rgb[R][3], depth[R],

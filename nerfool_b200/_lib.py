@@ -32,8 +32,10 @@ _SIGNATURES = {
     'nfb_composite_bwd': [_I, _I, _I] + [_P] * 8,
     'nfb_sample_pdf': [_I, _I, _I, _P, _P, _P, _I, _P, _P, _P],
     'nfb_fine_depths': [_I, _I, _I, _I, _P, _P, _P, _I, _P, _P],
+    'nfb_gnt_fwd': [_I] * 5 + [_P] * 8 + [ctypes.c_size_t, _P],
 }
-EXPORTS = ['nfb_version', 'nfb_last_error_string', 'nfb_ibrnet_param_offset', 'nfb_view_stash_bytes', 'nfb_ray_stash_bytes'] + list(_SIGNATURES)
+EXPORTS = ['nfb_version', 'nfb_last_error_string', 'nfb_ibrnet_param_offset', 'nfb_view_stash_bytes', 'nfb_ray_stash_bytes',
+           'nfb_gnt_param_floats', 'nfb_gnt_param_offset', 'nfb_gnt_workspace_bytes'] + list(_SIGNATURES)
 
 _lib = None
 
@@ -99,6 +101,12 @@ def load():
     lib.nfb_view_stash_bytes.argtypes = [c_int, c_int]
     lib.nfb_ray_stash_bytes.restype = ctypes.c_size_t
     lib.nfb_ray_stash_bytes.argtypes = [c_int, c_int]
+    lib.nfb_gnt_param_floats.restype = c_int
+    lib.nfb_gnt_param_floats.argtypes = [c_int]
+    lib.nfb_gnt_param_offset.restype = c_int
+    lib.nfb_gnt_param_offset.argtypes = [c_int, c_char_p]
+    lib.nfb_gnt_workspace_bytes.restype = ctypes.c_size_t
+    lib.nfb_gnt_workspace_bytes.argtypes = [c_int, c_int, c_int]
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int

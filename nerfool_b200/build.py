@@ -22,6 +22,7 @@ UNITS = [
     ('nfb_api', 'nfb_api.cu', []),
     ('nfb_geom', 'nfb_geom.cu', []),
     ('nfb_ray_stage', 'nfb_ray_stage.cu', []),
+    ('nfb_gnt', 'nfb_gnt.cu', []),
     ('nfb_view_api', 'nfb_view_api.cu', []),
     ('nfb_view_inst0', 'nfb_view_inst.cu', ['-DNFB_VIEW_INST=0']),
     ('nfb_view_inst1', 'nfb_view_inst.cu', ['-DNFB_VIEW_INST=1']),

@@ -103,51 +103,38 @@ __device__ __forceinline__ Taps bilinear_taps(float gx, float gy, int w, int h) 
 __device__ __forceinline__ void gather_row(const ViewGeom& g, int v, int H, int W, int fh, int fw,
                                            const float* __restrict__ imgs, const float* __restrict__ feat,
                                            float (&row)[NFB_ROW_CH]) {
-  // Branch-free: a tap outside the source reads texel 0 of the view with weight 0 (adds +0, bit-identical to
-  // skipping it), so the 12 + 32 loads of a row are independent of any predicate and can all be in flight
-  // together instead of one L2 round trip per tap.
+#pragma unroll
+  for (int c = 0; c < NFB_ROW_CH; ++c) row[c] = 0.f;
   {
     const Taps t = bilinear_taps(g.gx, g.gy, W, H);
     const float* base = imgs + (size_t)v * H * W * 3;
-    float q[4][3], wt[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float* p = base + (size_t)max(t.off[i], 0) * 3;
-      wt[i] = t.off[i] >= 0 ? t.wt[i] : 0.f;
-      q[i][0] = __ldg(p + 0); q[i][1] = __ldg(p + 1); q[i][2] = __ldg(p + 2);
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float acc = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc += q[i][c] * wt[i];
-      row[c] = acc;
+      if (t.off[i] >= 0) {
+        const float* p = base + (size_t)t.off[i] * 3;
+        row[0] += __ldg(p + 0) * t.wt[i];
+        row[1] += __ldg(p + 1) * t.wt[i];
+        row[2] += __ldg(p + 2) * t.wt[i];
+      }
     }
   }
   {
     const Taps t = bilinear_taps(g.gx, g.gy, fw, fh);
     const float4* base = reinterpret_cast<const float4*>(feat + (size_t)v * fh * fw * NFB_FEAT_CH);
-    const float4* p[4];
-    float wt[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      p[i] = base + (size_t)max(t.off[i], 0) * (NFB_FEAT_CH / 4);
-      wt[i] = t.off[i] >= 0 ? t.wt[i] : 0.f;
-    }
+      if (t.off[i] >= 0) {
+        const float4* p = base + (size_t)t.off[i] * (NFB_FEAT_CH / 4);
+        const float wgt = t.wt[i];
 #pragma unroll
-    for (int j = 0; j < NFB_FEAT_CH / 4; ++j) {
-      float4 q[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) q[i] = __ldg(p[i] + j);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        acc.x += q[i].x * wt[i];
-        acc.y += q[i].y * wt[i];
-        acc.z += q[i].z * wt[i];
-        acc.w += q[i].w * wt[i];
+        for (int j = 0; j < NFB_FEAT_CH / 4; ++j) {
+          const float4 q = __ldg(p + j);
+          row[3 + 4 * j + 0] += q.x * wgt;
+          row[3 + 4 * j + 1] += q.y * wgt;
+          row[3 + 4 * j + 2] += q.z * wgt;
+          row[3 + 4 * j + 3] += q.w * wgt;
+        }
       }
-      row[3 + 4 * j + 0] = acc.x; row[3 + 4 * j + 1] = acc.y; row[3 + 4 * j + 2] = acc.z; row[3 + 4 * j + 3] = acc.w;
     }
   }
 }

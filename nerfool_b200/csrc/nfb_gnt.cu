@@ -1,0 +1,589 @@
+// GNT forward (gnt/transformer_network.py:205-309): view transformer (subtraction attention over the source
+// views, softmax per channel) + ray transformer (4-head self-attention over the samples of a ray), netwidth 64.
+// First CUDA form of SURVEY 8 row a15 / f3: fp32 on the CUDA cores, one thread per sample, layer weights resident
+// in shared memory (transposed, nfb_dense.cuh), activations q[N][64] and the projected view features F[N][V][64]
+// in a caller-provided workspace.  Forward only (the render path of BASELINE config 5); the tcgen05 form and the
+// data-gradient are the next step.
+//
+// Launch sequence of nfb_gnt_fwd: embed (rgbfeat_fc + max over views) -> per layer { view attention, FFN,
+// [q_fc with positional encodings on even layers], ray attention, FFN } -> head (LayerNorm, mean over samples,
+// rgb_fc).  Dropout is the identity (eval mode, transformer_network.py:45,72,136).
+#include "nfb_dense.cuh"
+
+namespace {
+
+constexpr int D = 64;          // netwidth (eval/gnt/config.py:111)
+constexpr int DH = 256;        // feed-forward hidden width (4 x netwidth)
+constexpr int PE = 63;         // 3 + 3 * 2 * 10 positional-encoding width (transformer_network.py:253-268)
+constexpr int QIN = D + 2 * PE;  // 190
+
+// ---- parameter blob layout (floats; every tensor in torch's [out][in] layout) ------------------------------
+enum : int {
+  G_RF0_W = 0,                       // rgbfeat_fc.0.weight [64][35]
+  G_RF0_B = G_RF0_W + D * 35,
+  G_RF2_W = G_RF0_B + D,             // rgbfeat_fc.2.weight [64][64]
+  G_RF2_B = G_RF2_W + D * D,
+  G_HEAD = G_RF2_B + D               // end of the header block
+};
+// per-layer block
+enum : int {
+  L_V_LN1_W = 0,                     // view_crosstrans.i.attn_norm
+  L_V_LN1_B = L_V_LN1_W + D,
+  L_V_Q = L_V_LN1_B + D,             // attn.q_fc / k_fc / v_fc .weight [64][64]
+  L_V_K = L_V_Q + D * D,
+  L_V_V = L_V_K + D * D,
+  L_V_POS0_W = L_V_V + D * D,        // attn.pos_fc.0 [8][4]
+  L_V_POS0_B = L_V_POS0_W + 32,
+  L_V_POS2_W = L_V_POS0_B + 8,       // attn.pos_fc.2 [64][8]
+  L_V_POS2_B = L_V_POS2_W + D * 8,
+  L_V_AT0_W = L_V_POS2_B + D,        // attn.attn_fc.0 [8][64]
+  L_V_AT0_B = L_V_AT0_W + 8 * D,
+  L_V_AT2_W = L_V_AT0_B + 8,         // attn.attn_fc.2 [64][8]
+  L_V_AT2_B = L_V_AT2_W + D * 8,
+  L_V_O_W = L_V_AT2_B + D,           // attn.out_fc [64][64] + bias
+  L_V_O_B = L_V_O_W + D * D,
+  L_V_LN2_W = L_V_O_B + D,           // ff_norm
+  L_V_LN2_B = L_V_LN2_W + D,
+  L_V_FF1_W = L_V_LN2_B + D,         // ff.fc1 [256][64]
+  L_V_FF1_B = L_V_FF1_W + DH * D,
+  L_V_FF2_W = L_V_FF1_B + DH,        // ff.fc2 [64][256]
+  L_V_FF2_B = L_V_FF2_W + D * DH,
+  L_Q0_W = L_V_FF2_B + D,            // q_fcs.i.0 [64][190]   (even layers; the slot is unused on odd layers)
+  L_Q0_B = L_Q0_W + D * QIN,
+  L_Q2_W = L_Q0_B + D,               // q_fcs.i.2 [64][64]
+  L_Q2_B = L_Q2_W + D * D,
+  L_R_LN1_W = L_Q2_B + D,            // view_selftrans.i.attn_norm
+  L_R_LN1_B = L_R_LN1_W + D,
+  L_R_Q = L_R_LN1_B + D,             // attn.q_fc / k_fc / v_fc [64][64]
+  L_R_K = L_R_Q + D * D,
+  L_R_V = L_R_K + D * D,
+  L_R_O_W = L_R_V + D * D,           // attn.out_fc + bias
+  L_R_O_B = L_R_O_W + D * D,
+  L_R_LN2_W = L_R_O_B + D,           // ff_norm
+  L_R_LN2_B = L_R_LN2_W + D,
+  L_R_FF1_W = L_R_LN2_B + D,
+  L_R_FF1_B = L_R_FF1_W + DH * D,
+  L_R_FF2_W = L_R_FF1_B + DH,
+  L_R_FF2_B = L_R_FF2_W + D * DH,
+  L_SIZE = L_R_FF2_B + D
+};
+// tail block (after depth layers): norm.weight, norm.bias, rgb_fc.weight [3][64], rgb_fc.bias [3]
+enum : int { T_LN_W = 0, T_LN_B = D, T_RGB_W = 2 * D, T_RGB_B = 2 * D + 3 * D, T_SIZE = 2 * D + 3 * D + 3 };
+
+constexpr float LN_EPS_T = 1e-6f;   // Transformer / Transformer2D norms (transformer_network.py:96-97,182-183)
+constexpr float LN_EPS_HEAD = 1e-5f;  // GNT.norm = nn.LayerNorm default (:250)
+
+__device__ __forceinline__ void layer_norm64(const float (&x)[D], const float* __restrict__ w, const float* __restrict__ b,
+                                             float eps, float (&y)[D]) {
+  float mu = 0.f;
+#pragma unroll
+  for (int c = 0; c < D; ++c) mu += x[c];
+  mu *= (1.f / D);
+  float var = 0.f;
+#pragma unroll
+  for (int c = 0; c < D; ++c) var = fmaf(x[c] - mu, x[c] - mu, var);
+  var *= (1.f / D);
+  const float rstd = 1.f / sqrtf(var + eps);
+#pragma unroll
+  for (int c = 0; c < D; ++c) y[c] = fmaf((x[c] - mu) * rstd, w[c], b[c]);
+}
+
+__device__ __forceinline__ void load_row64(const float* __restrict__ p, float (&x)[D]) {
+#pragma unroll
+  for (int c = 0; c < D; c += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p + c);
+    x[c] = t.x; x[c + 1] = t.y; x[c + 2] = t.z; x[c + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void store_row64(float* __restrict__ p, const float (&x)[D]) {
+#pragma unroll
+  for (int c = 0; c < D; c += 4) *reinterpret_cast<float4*>(p + c) = make_float4(x[c], x[c + 1], x[c + 2], x[c + 3]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// embed: F[row] = rgbfeat_fc(rgb_feat[row])  (35 -> 64 ReLU -> 64), one thread per (sample, view) row
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_gnt_embed(size_t rows, const float* __restrict__ rgb_feat,
+                                                    const float* __restrict__ params, float* __restrict__ F) {
+  extern __shared__ __align__(16) float sm[];
+  float* w0 = sm;                 // [35][64]
+  float* b0 = w0 + 35 * D;
+  float* w2 = b0 + D;             // [64][64]
+  float* b2 = w2 + D * D;
+  load_wt_transposed(w0, params + G_RF0_W, D, 35, D, threadIdx.x, blockDim.x);
+  load_vec_padded(b0, params + G_RF0_B, D, D, threadIdx.x, blockDim.x);
+  load_wt_transposed(w2, params + G_RF2_W, D, D, D, threadIdx.x, blockDim.x);
+  load_vec_padded(b2, params + G_RF2_B, D, D, threadIdx.x, blockDim.x);
+  __syncthreads();
+  for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (size_t)gridDim.x * blockDim.x) {
+    float h[D];
+    load_bias<D>(h, b0);
+    const float* x = rgb_feat + r * NFB_ROW_CH;
+#pragma unroll
+    for (int k = 0; k < NFB_ROW_CH; ++k) axpy_row<D>(h, __ldg(x + k), w0 + k * D);
+#pragma unroll
+    for (int c = 0; c < D; ++c) h[c] = fmaxf(h[c], 0.f);
+    float f[D];
+    load_bias<D>(f, b2);
+    dense_acc<D, D>(w2, h, f);
+    store_row64(F + r * D, f);
+  }
+}
+
+// q[n] = max over the V views of F[n][v]   (transformer_network.py:286: no mask)
+__global__ void __launch_bounds__(256) k_gnt_qinit(size_t n_elems, int V, const float* __restrict__ F, float* __restrict__ q) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / D;
+    const int c = (int)(i - n * D);
+    float m = -3.4e38f;
+    for (int v = 0; v < V; ++v) m = fmaxf(m, F[(n * V + v) * D + c]);
+    q[i] = m;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// view transformer attention block (Transformer2D first half + Attention2D, :55-113), one thread per sample:
+//   x = LN(q);  qq = q_fc(x);  per view: k = k_fc(F_v), v = v_fc(k), pos = pos_fc(ray_diff_v),
+//   a = attn_fc(k - qq + pos) (masked_fill -1e9), softmax over views PER CHANNEL, out = sum_v (v + pos) a;
+//   q <- out_fc(out) + q.   The softmax over views runs online (running max / sum / weighted accumulator).
+// ---------------------------------------------------------------------------------------------------
+enum : int {
+  VS_LN_W = 0, VS_LN_B = D, VS_Q = 2 * D, VS_K = VS_Q + D * D, VS_V = VS_K + D * D, VS_O = VS_V + D * D,
+  VS_O_B = VS_O + D * D, VS_P0 = VS_O_B + D /*[4][8]*/, VS_P0_B = VS_P0 + 32, VS_P2 = VS_P0_B + 8 /*[8][64]*/,
+  VS_P2_B = VS_P2 + 8 * D, VS_A0 = VS_P2_B + D /*[64][8]*/, VS_A0_B = VS_A0 + D * 8, VS_A2 = VS_A0_B + 8 /*[8][64]*/,
+  VS_A2_B = VS_A2 + 8 * D, VS_TOTAL = VS_A2_B + D
+};
+
+__global__ void __launch_bounds__(128) k_gnt_view_attn(int N, int V, const float* __restrict__ F,
+                                                        const float* __restrict__ ray_diff, const float* __restrict__ mask,
+                                                        const float* __restrict__ lp, float* __restrict__ q) {
+  extern __shared__ __align__(16) float sm[];
+  const int t = threadIdx.x, nt = blockDim.x;
+  load_vec_padded(sm + VS_LN_W, lp + L_V_LN1_W, D, D, t, nt);
+  load_vec_padded(sm + VS_LN_B, lp + L_V_LN1_B, D, D, t, nt);
+  load_wt_transposed(sm + VS_Q, lp + L_V_Q, D, D, D, t, nt);
+  load_wt_transposed(sm + VS_K, lp + L_V_K, D, D, D, t, nt);
+  load_wt_transposed(sm + VS_V, lp + L_V_V, D, D, D, t, nt);
+  load_wt_transposed(sm + VS_O, lp + L_V_O_W, D, D, D, t, nt);
+  load_vec_padded(sm + VS_O_B, lp + L_V_O_B, D, D, t, nt);
+  load_wt_transposed(sm + VS_P0, lp + L_V_POS0_W, 8, 4, 8, t, nt);
+  load_vec_padded(sm + VS_P0_B, lp + L_V_POS0_B, 8, 8, t, nt);
+  load_wt_transposed(sm + VS_P2, lp + L_V_POS2_W, D, 8, D, t, nt);
+  load_vec_padded(sm + VS_P2_B, lp + L_V_POS2_B, D, D, t, nt);
+  load_wt_transposed(sm + VS_A0, lp + L_V_AT0_W, 8, D, 8, t, nt);
+  load_vec_padded(sm + VS_A0_B, lp + L_V_AT0_B, 8, 8, t, nt);
+  load_wt_transposed(sm + VS_A2, lp + L_V_AT2_W, D, 8, D, t, nt);
+  load_vec_padded(sm + VS_A2_B, lp + L_V_AT2_B, D, D, t, nt);
+  __syncthreads();
+
+  for (int n = blockIdx.x * blockDim.x + t; n < N; n += gridDim.x * blockDim.x) {
+    float q0[D];
+    load_row64(q + (size_t)n * D, q0);
+    float qq[D];
+    {
+      float x[D];
+      layer_norm64(q0, sm + VS_LN_W, sm + VS_LN_B, LN_EPS_T, x);
+#pragma unroll
+      for (int c = 0; c < D; ++c) qq[c] = 0.f;
+      dense_acc<D, D>(sm + VS_Q, x, qq);
+    }
+    float m[D], l[D], acc[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) { m[c] = -3.4e38f; l[c] = 0.f; acc[c] = 0.f; }
+    for (int v = 0; v < V; ++v) {
+      const size_t row = (size_t)n * V + v;
+      float k[D], vv[D], pos[D];
+      {
+        float f[D];
+        load_row64(F + row * D, f);
+#pragma unroll
+        for (int c = 0; c < D; ++c) k[c] = 0.f;
+        dense_acc<D, D>(sm + VS_K, f, k);
+      }
+#pragma unroll
+      for (int c = 0; c < D; ++c) vv[c] = 0.f;
+      dense_acc<D, D>(sm + VS_V, k, vv);              // v = v_fc(k): applied to the projected k (:76-77)
+      {
+        const float4 rd4 = __ldg(reinterpret_cast<const float4*>(ray_diff) + row);
+        const float rd[4] = {rd4.x, rd4.y, rd4.z, rd4.w};
+        float p8[8];
+        load_bias<8>(p8, sm + VS_P0_B);
+        dense_acc<4, 8>(sm + VS_P0, rd, p8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p8[j] = fmaxf(p8[j], 0.f);
+        load_bias<D>(pos, sm + VS_P2_B);
+        dense_acc<8, D>(sm + VS_P2, p8, pos);
+      }
+      float a8[8];
+      load_bias<8>(a8, sm + VS_A0_B);
+#pragma unroll
+      for (int c = 0; c < D; ++c) axpy_row<8>(a8, k[c] - qq[c] + pos[c], sm + VS_A0 + c * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a8[j] = fmaxf(a8[j], 0.f);
+      const bool valid = __ldg(mask + row) != 0.f;
+      float a[D];
+      load_bias<D>(a, sm + VS_A2_B);
+      dense_acc<8, D>(sm + VS_A2, a8, a);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const float s = valid ? a[c] : -1e9f;
+        const float mn = fmaxf(m[c], s);
+        const float sc = __expf(m[c] - mn), e = __expf(s - mn);
+        l[c] = fmaf(l[c], sc, e);
+        acc[c] = fmaf(acc[c], sc, (vv[c] + pos[c]) * e);
+        m[c] = mn;
+      }
+    }
+    float o[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = acc[c] / l[c];
+    load_bias<D>(o, sm + VS_O_B);
+    dense_acc<D, D>(sm + VS_O, acc, o);
+#pragma unroll
+    for (int c = 0; c < D; ++c) o[c] += q0[c];
+    store_row64(q + (size_t)n * D, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// feed-forward block (second half of Transformer2D / Transformer): q <- fc2(ReLU(fc1(LN(q)))) + q
+// lp points at the block's {ff_norm.w, ff_norm.b, fc1.w, fc1.b, fc2.w, fc2.b} (contiguous in the blob)
+// ---------------------------------------------------------------------------------------------------
+enum : int { FS_LN_W = 0, FS_LN_B = D, FS_W1 = 2 * D /*[64][256]*/, FS_B1 = FS_W1 + D * DH, FS_W2 = FS_B1 + DH /*[256][64]*/,
+             FS_B2 = FS_W2 + DH * D, FS_TOTAL = FS_B2 + D };
+
+__global__ void __launch_bounds__(128) k_gnt_ffn(int N, const float* __restrict__ lp, float* __restrict__ q) {
+  extern __shared__ __align__(16) float sm[];
+  const int t = threadIdx.x, nt = blockDim.x;
+  load_vec_padded(sm + FS_LN_W, lp, D, D, t, nt);
+  load_vec_padded(sm + FS_LN_B, lp + D, D, D, t, nt);
+  load_wt_transposed(sm + FS_W1, lp + 2 * D, DH, D, DH, t, nt);
+  load_vec_padded(sm + FS_B1, lp + 2 * D + DH * D, DH, DH, t, nt);
+  load_wt_transposed(sm + FS_W2, lp + 2 * D + DH * D + DH, D, DH, D, t, nt);
+  load_vec_padded(sm + FS_B2, lp + 2 * D + DH * D + DH + D * DH, D, D, t, nt);
+  __syncthreads();
+  for (int n = blockIdx.x * blockDim.x + t; n < N; n += gridDim.x * blockDim.x) {
+    float q0[D], x[D], y[D];
+    load_row64(q + (size_t)n * D, q0);
+    layer_norm64(q0, sm + FS_LN_W, sm + FS_LN_B, LN_EPS_T, x);
+    load_bias<D>(y, sm + FS_B2);
+#pragma unroll 1
+    for (int j0 = 0; j0 < DH; j0 += 32) {
+      float h[32];
+      load_bias<32>(h, sm + FS_B1 + j0);
+#pragma unroll
+      for (int k = 0; k < D; ++k) axpy_row<32>(h, x[k], sm + FS_W1 + k * DH + j0);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) axpy_row<D>(y, fmaxf(h[j], 0.f), sm + FS_W2 + (j0 + j) * D);
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) y[c] += q0[c];
+    store_row64(q + (size_t)n * D, y);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// q_fc on even layers (:295-297): q <- fc2(ReLU(fc1([q, posenc(pts), posenc(ray_d / |ray_d|)])))
+// Embedder order (:12-37): [x, sin(x f0), cos(x f0), sin(x f1), ...], f_k = 2^k, k = 0..9, 3 components each.
+// ---------------------------------------------------------------------------------------------------
+enum : int { QS_W0 = 0 /*[190][64]*/, QS_B0 = QIN * D, QS_W2 = QS_B0 + D, QS_B2 = QS_W2 + D * D, QS_TOTAL = QS_B2 + D };
+
+__device__ __forceinline__ void posenc_axpy(float (&h)[D], const float (&x3)[3], const float* __restrict__ w /*[63][64]*/) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) axpy_row<D>(h, x3[i], w + i * D);
+#pragma unroll 1
+  for (int f = 0; f < 10; ++f) {
+    const float fr = (float)(1 << f);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float ang = __fmul_rn(x3[i], fr);
+      axpy_row<D>(h, sinf(ang), w + (3 + 6 * f + i) * D);
+      axpy_row<D>(h, cosf(ang), w + (3 + 6 * f + 3 + i) * D);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_gnt_qfc(int N, int S, const float* __restrict__ pts, const float* __restrict__ ray_d,
+                                                  const float* __restrict__ lp, float* __restrict__ q) {
+  extern __shared__ __align__(16) float sm[];
+  const int t = threadIdx.x, nt = blockDim.x;
+  load_wt_transposed(sm + QS_W0, lp + L_Q0_W, D, QIN, D, t, nt);
+  load_vec_padded(sm + QS_B0, lp + L_Q0_B, D, D, t, nt);
+  load_wt_transposed(sm + QS_W2, lp + L_Q2_W, D, D, D, t, nt);
+  load_vec_padded(sm + QS_B2, lp + L_Q2_B, D, D, t, nt);
+  __syncthreads();
+  for (int n = blockIdx.x * blockDim.x + t; n < N; n += gridDim.x * blockDim.x) {
+    float h[D];
+    load_bias<D>(h, sm + QS_B0);
+    {
+      float q0[D];
+      load_row64(q + (size_t)n * D, q0);
+      dense_acc<D, D>(sm + QS_W0, q0, h);
+    }
+    const float p3[3] = {__ldg(pts + (size_t)n * 3), __ldg(pts + (size_t)n * 3 + 1), __ldg(pts + (size_t)n * 3 + 2)};
+    posenc_axpy(h, p3, sm + QS_W0 + D * D);
+    const int r = n / S;
+    const float dx = __ldg(ray_d + (size_t)r * 3), dy = __ldg(ray_d + (size_t)r * 3 + 1), dz = __ldg(ray_d + (size_t)r * 3 + 2);
+    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const float d3[3] = {__fdiv_rn(dx, nrm), __fdiv_rn(dy, nrm), __fdiv_rn(dz, nrm)};
+    posenc_axpy(h, d3, sm + QS_W0 + (D + PE) * D);
+#pragma unroll
+    for (int c = 0; c < D; ++c) h[c] = fmaxf(h[c], 0.f);
+    float y[D];
+    load_bias<D>(y, sm + QS_B2);
+    dense_acc<D, D>(sm + QS_W2, h, y);
+    store_row64(q + (size_t)n * D, y);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ray transformer attention block (Transformer first half + Attention "qk", :121-202): one CTA per ray, one thread per
+// sample; K / V rows of the ray in shared memory; 4 heads x 16, scores / sqrt(16), softmax over the samples, no mask.
+// q <- out_fc(attn) + q.   attn_out (optional): mean over heads of the probabilities of QUERY 0 (:200) -> [R][S].
+// ---------------------------------------------------------------------------------------------------
+enum : int { RS_LN_W = 0, RS_LN_B = D, RS_Q = 2 * D, RS_K = RS_Q + D * D, RS_V = RS_K + D * D, RS_O = RS_V + D * D,
+             RS_O_B = RS_O + D * D, RS_Q0 = RS_O_B + D /*query 0, scaled*/, RS_ST = RS_Q0 + D /*m[4], 1/l[4]*/, RS_TOTAL = RS_ST + 8 };
+
+__global__ void __launch_bounds__(256) k_gnt_ray_attn(int R, int S, const float* __restrict__ lp, float* __restrict__ q,
+                                                       float* __restrict__ attn_out, int attn_stride) {
+  extern __shared__ __align__(16) float sm[];
+  float* sk = sm + RS_TOTAL;            // [S][64]
+  float* sv = sk + (size_t)S * D;       // [S][64]
+  const int t = threadIdx.x, nt = blockDim.x;
+  load_vec_padded(sm + RS_LN_W, lp + L_R_LN1_W, D, D, t, nt);
+  load_vec_padded(sm + RS_LN_B, lp + L_R_LN1_B, D, D, t, nt);
+  load_wt_transposed(sm + RS_Q, lp + L_R_Q, D, D, D, t, nt);
+  load_wt_transposed(sm + RS_K, lp + L_R_K, D, D, D, t, nt);
+  load_wt_transposed(sm + RS_V, lp + L_R_V, D, D, D, t, nt);
+  load_wt_transposed(sm + RS_O, lp + L_R_O_W, D, D, D, t, nt);
+  load_vec_padded(sm + RS_O_B, lp + L_R_O_B, D, D, t, nt);
+  __syncthreads();
+  const bool act = t < S;
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    float* qrow = q + ((size_t)r * S + (act ? t : 0)) * D;
+    float q0[D], qv[D];
+    load_row64(qrow, q0);
+    {
+      float x[D], kk[D];
+      layer_norm64(q0, sm + RS_LN_W, sm + RS_LN_B, LN_EPS_T, x);
+#pragma unroll
+      for (int c = 0; c < D; ++c) { qv[c] = 0.f; kk[c] = 0.f; }
+      dense_acc<D, D>(sm + RS_Q, x, qv);
+      dense_acc<D, D>(sm + RS_K, x, kk);
+      if (act) store_row64(sk + (size_t)t * D, kk);
+#pragma unroll
+      for (int c = 0; c < D; ++c) kk[c] = 0.f;
+      dense_acc<D, D>(sm + RS_V, x, kk);
+      if (act) store_row64(sv + (size_t)t * D, kk);
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) qv[c] *= 0.25f;          // 1 / sqrt(16)
+    if (t == 0) store_row64(sm + RS_Q0, qv);
+    __syncthreads();
+    float o[D];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float mx = -3.4e38f;
+      for (int j = 0; j < S; ++j) {
+        const float* kj = sk + (size_t)j * D + 16 * h;
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) s = fmaf(qv[16 * h + c], kj[c], s);
+        mx = fmaxf(mx, s);
+      }
+      float l = 0.f, a16[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) a16[c] = 0.f;
+      for (int j = 0; j < S; ++j) {
+        const float* kj = sk + (size_t)j * D + 16 * h;
+        const float* vj = sv + (size_t)j * D + 16 * h;
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) s = fmaf(qv[16 * h + c], kj[c], s);
+        const float p = __expf(s - mx);
+        l += p;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) a16[c] = fmaf(p, vj[c], a16[c]);
+      }
+      const float il = 1.f / l;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) o[16 * h + c] = a16[c] * il;
+      if (t == 0) { sm[RS_ST + h] = mx; sm[RS_ST + 4 + h] = il; }
+    }
+    float y[D];
+    load_bias<D>(y, sm + RS_O_B);
+    dense_acc<D, D>(sm + RS_O, o, y);
+#pragma unroll
+    for (int c = 0; c < D; ++c) y[c] += q0[c];
+    if (act) store_row64(qrow, y);
+    if (attn_out) {
+      __syncthreads();                                     // query 0's statistics are published
+      if (act) {
+        float pm = 0.f;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float* kj = sk + (size_t)t * D + 16 * h;
+          float s = 0.f;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) s = fmaf(sm[RS_Q0 + 16 * h + c], kj[c], s);
+          pm += __expf(s - sm[RS_ST + h]) * sm[RS_ST + 4 + h];
+        }
+        attn_out[(size_t)r * attn_stride + t] = 0.25f * pm;
+      }
+    }
+    __syncthreads();                                       // sk / sv / q0 are rewritten by the next ray
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// head (:303-305): h = LayerNorm(q) (eps 1e-5), rgb = rgb_fc(mean over samples of h).  One CTA per ray.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gnt_head(int R, int S, const float* __restrict__ tp, const float* __restrict__ q,
+                                                   float* __restrict__ out, int out_stride) {
+  extern __shared__ __align__(16) float sm[];
+  float* sh = sm;                        // [S][65]
+  float* smean = sm + (size_t)S * 65;    // [64]
+  const int t = threadIdx.x;
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    if (t < S) {
+      float q0[D], h[D];
+      load_row64(q + ((size_t)r * S + t) * D, q0);
+      float w[D], b[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) { w[c] = __ldg(tp + T_LN_W + c); b[c] = __ldg(tp + T_LN_B + c); }
+      layer_norm64(q0, w, b, LN_EPS_HEAD, h);
+#pragma unroll
+      for (int c = 0; c < D; ++c) sh[t * 65 + c] = h[c];
+    }
+    __syncthreads();
+    if (t < D) {
+      float s = 0.f;
+      for (int j = 0; j < S; ++j) s += sh[j * 65 + t];
+      smean[t] = s / (float)S;
+    }
+    __syncthreads();
+    if (t < 3) {
+      float a = __ldg(tp + T_RGB_B + t);
+      for (int c = 0; c < D; ++c) a = fmaf(smean[c], __ldg(tp + T_RGB_W + t * D + c), a);
+      out[(size_t)r * out_stride + t] = a;
+    }
+    __syncthreads();
+  }
+}
+
+template <typename K>
+int set_smem(K kern, size_t bytes, const char* name) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return nfb_set_error(NFB_ECUDA, "%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
+  return NFB_OK;
+}
+
+}  // namespace
+
+extern "C" int nfb_gnt_param_floats(int depth) { return depth < 1 ? 0 : G_HEAD + depth * L_SIZE + T_SIZE; }
+
+extern "C" int nfb_gnt_param_offset(int depth, const char* name) {
+  // offsets of the header / tail tensors and of the per-layer block, for the host-side packer and its test
+  if (!name) return -1;
+  struct E { const char* n; int off; };
+  static const E head[] = {{"rgbfeat_fc.0.weight", G_RF0_W}, {"rgbfeat_fc.0.bias", G_RF0_B},
+                           {"rgbfeat_fc.2.weight", G_RF2_W}, {"rgbfeat_fc.2.bias", G_RF2_B}, {"layer0", G_HEAD}};
+  for (const E& e : head)
+    if (strcmp(e.n, name) == 0) return e.off;
+  static const E lay[] = {
+      {"view.attn_norm.weight", L_V_LN1_W}, {"view.attn_norm.bias", L_V_LN1_B}, {"view.attn.q_fc.weight", L_V_Q},
+      {"view.attn.k_fc.weight", L_V_K}, {"view.attn.v_fc.weight", L_V_V}, {"view.attn.pos_fc.0.weight", L_V_POS0_W},
+      {"view.attn.pos_fc.0.bias", L_V_POS0_B}, {"view.attn.pos_fc.2.weight", L_V_POS2_W}, {"view.attn.pos_fc.2.bias", L_V_POS2_B},
+      {"view.attn.attn_fc.0.weight", L_V_AT0_W}, {"view.attn.attn_fc.0.bias", L_V_AT0_B},
+      {"view.attn.attn_fc.2.weight", L_V_AT2_W}, {"view.attn.attn_fc.2.bias", L_V_AT2_B},
+      {"view.attn.out_fc.weight", L_V_O_W}, {"view.attn.out_fc.bias", L_V_O_B}, {"view.ff_norm.weight", L_V_LN2_W},
+      {"view.ff_norm.bias", L_V_LN2_B}, {"view.ff.fc1.weight", L_V_FF1_W}, {"view.ff.fc1.bias", L_V_FF1_B},
+      {"view.ff.fc2.weight", L_V_FF2_W}, {"view.ff.fc2.bias", L_V_FF2_B}, {"q_fc.0.weight", L_Q0_W}, {"q_fc.0.bias", L_Q0_B},
+      {"q_fc.2.weight", L_Q2_W}, {"q_fc.2.bias", L_Q2_B}, {"ray.attn_norm.weight", L_R_LN1_W}, {"ray.attn_norm.bias", L_R_LN1_B},
+      {"ray.attn.q_fc.weight", L_R_Q}, {"ray.attn.k_fc.weight", L_R_K}, {"ray.attn.v_fc.weight", L_R_V},
+      {"ray.attn.out_fc.weight", L_R_O_W}, {"ray.attn.out_fc.bias", L_R_O_B}, {"ray.ff_norm.weight", L_R_LN2_W},
+      {"ray.ff_norm.bias", L_R_LN2_B}, {"ray.ff.fc1.weight", L_R_FF1_W}, {"ray.ff.fc1.bias", L_R_FF1_B},
+      {"ray.ff.fc2.weight", L_R_FF2_W}, {"ray.ff.fc2.bias", L_R_FF2_B}, {"layer_size", L_SIZE}};
+  for (const E& e : lay)
+    if (strcmp(e.n, name) == 0) return e.off;
+  const int tail = G_HEAD + depth * L_SIZE;
+  static const E tl[] = {{"norm.weight", T_LN_W}, {"norm.bias", T_LN_B}, {"rgb_fc.weight", T_RGB_W}, {"rgb_fc.bias", T_RGB_B}};
+  for (const E& e : tl)
+    if (strcmp(e.n, name) == 0) return tail + e.off;
+  return -1;
+}
+
+extern "C" size_t nfb_gnt_workspace_bytes(int R, int S, int V) {
+  if (R <= 0 || S < 1 || V < 1) return 0;
+  return ((size_t)R * S * V * D + (size_t)R * S * D) * sizeof(float);
+}
+
+extern "C" int nfb_gnt_fwd(int R, int S, int V, int depth, int ret_alpha, const float* rgb_feat, const float* ray_diff,
+                           const float* mask, const float* pts, const float* ray_d, const float* params, float* out,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  NFB_REQUIRE(R >= 0 && S >= 1 && V >= 1 && depth >= 1, NFB_EINVAL, "nfb_gnt_fwd: bad arguments (R=%d S=%d V=%d depth=%d)", R, S, V, depth);
+  NFB_REQUIRE(S <= NFB_MAX_SAMPLES, NFB_EUNSUPPORTED, "nfb_gnt_fwd: S=%d > %d samples per ray", S, NFB_MAX_SAMPLES);
+  NFB_REQUIRE(V <= NFB_MAX_VIEWS, NFB_EUNSUPPORTED, "nfb_gnt_fwd: V=%d > %d views", V, NFB_MAX_VIEWS);
+  if (R == 0) return NFB_OK;
+  NFB_REQUIRE(rgb_feat && ray_diff && mask && pts && ray_d && params && out && workspace, NFB_EINVAL, "nfb_gnt_fwd: NULL buffer");
+  NFB_REQUIRE(workspace_bytes >= nfb_gnt_workspace_bytes(R, S, V), NFB_EINVAL, "nfb_gnt_fwd: workspace too small (%zu < %zu bytes)",
+              workspace_bytes, nfb_gnt_workspace_bytes(R, S, V));
+  NFB_REQUIRE(((uintptr_t)ray_diff % 16) == 0 && ((uintptr_t)workspace % 16) == 0 && ((uintptr_t)params % 16) == 0, NFB_EINVAL,
+              "nfb_gnt_fwd: ray_diff / workspace / params must be 16-byte aligned");
+  NFB_REQUIRE((long long)R * S * V < (1ll << 31), NFB_EUNSUPPORTED, "nfb_gnt_fwd: more than 2^31 rows per call; chunk the rays");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = R * S;
+  const size_t rows = (size_t)N * V;
+  float* F = reinterpret_cast<float*>(workspace);
+  float* q = F + rows * D;
+  const int sms = nfb_num_sms();
+  int rc;
+
+  const size_t sm_embed = (size_t)(35 * D + D + D * D + D) * sizeof(float);
+  if ((rc = set_smem(k_gnt_embed, sm_embed, "k_gnt_embed"))) return rc;
+  {
+    size_t g = (rows + 127) / 128;
+    if (g > (size_t)sms * 8) g = (size_t)sms * 8;
+    k_gnt_embed<<<(int)g, 128, sm_embed, st>>>(rows, rgb_feat, params, F);
+    NFB_CHECK_LAUNCH("k_gnt_embed");
+    size_t g2 = ((size_t)N * D + 255) / 256;
+    if (g2 > (size_t)sms * 16) g2 = (size_t)sms * 16;
+    k_gnt_qinit<<<(int)g2, 256, 0, st>>>((size_t)N * D, V, F, q);
+    NFB_CHECK_LAUNCH("k_gnt_qinit");
+  }
+  const size_t sm_view = (size_t)VS_TOTAL * sizeof(float), sm_ffn = (size_t)FS_TOTAL * sizeof(float),
+               sm_qfc = (size_t)QS_TOTAL * sizeof(float), sm_ray = (size_t)(RS_TOTAL + 2 * S * D) * sizeof(float),
+               sm_head = (size_t)(S * 65 + D) * sizeof(float);
+  if ((rc = set_smem(k_gnt_view_attn, sm_view, "k_gnt_view_attn"))) return rc;
+  if ((rc = set_smem(k_gnt_ffn, sm_ffn, "k_gnt_ffn"))) return rc;
+  if ((rc = set_smem(k_gnt_qfc, sm_qfc, "k_gnt_qfc"))) return rc;
+  if ((rc = set_smem(k_gnt_ray_attn, sm_ray, "k_gnt_ray_attn"))) return rc;
+  if ((rc = set_smem(k_gnt_head, sm_head, "k_gnt_head"))) return rc;
+  auto grid_for = [&](int per_sm) {
+    int g = (N + 127) / 128;
+    if (g > sms * per_sm) g = sms * per_sm;
+    return g < 1 ? 1 : g;
+  };
+  const int ray_block = ((S + 31) / 32) * 32;
+  const int ray_grid = R < sms ? R : sms;
+  const int out_stride = ret_alpha ? 3 + S : 3;
+  for (int i = 0; i < depth; ++i) {
+    const float* lp = params + G_HEAD + (size_t)i * L_SIZE;
+    k_gnt_view_attn<<<grid_for(3), 128, sm_view, st>>>(N, V, F, ray_diff, mask, lp, q);
+    NFB_CHECK_LAUNCH("k_gnt_view_attn");
+    k_gnt_ffn<<<grid_for(1), 128, sm_ffn, st>>>(N, lp + L_V_LN2_W, q);
+    NFB_CHECK_LAUNCH("k_gnt_ffn<view>");
+    if ((i & 1) == 0) {
+      k_gnt_qfc<<<grid_for(3), 128, sm_qfc, st>>>(N, S, pts, ray_d, lp, q);
+      NFB_CHECK_LAUNCH("k_gnt_qfc");
+    }
+    const bool last = ret_alpha && i == depth - 1;
+    k_gnt_ray_attn<<<ray_grid, ray_block, sm_ray, st>>>(R, S, lp, q, last ? out + 3 : nullptr, out_stride);
+    NFB_CHECK_LAUNCH("k_gnt_ray_attn");
+    k_gnt_ffn<<<grid_for(1), 128, sm_ffn, st>>>(N, lp + L_R_LN2_W, q);
+    NFB_CHECK_LAUNCH("k_gnt_ffn<ray>");
+  }
+  k_gnt_head<<<ray_grid, ray_block < 64 ? 64 : ray_block, sm_head, st>>>(R, S, params + G_HEAD + (size_t)depth * L_SIZE, q, out, out_stride);
+  NFB_CHECK_LAUNCH("k_gnt_head");
+  return NFB_OK;
+}

@@ -1,0 +1,156 @@
+"""Drop-in for ``gnt.transformer_network.GNT`` (/root/reference/gnt/transformer_network.py:205-309).
+
+An ``nn.Module`` with the reference's parameter names, shapes and construction order (checkpoints load strictly, the
+same torch seed gives the same initial weights) whose ``forward`` runs ``nfb_gnt_fwd``.  The sub-modules are parameter
+containers; their ``forward`` is never called.  Forward only: asking for a gradient raises (no silent fallback)."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from .._lib import call, f32c, ptr, stream_ptr
+
+
+class _FeedForward(nn.Module):          # transformer_network.py:40-46
+    def __init__(self, dim, hid_dim):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hid_dim)
+        self.fc2 = nn.Linear(hid_dim, dim)
+
+
+class _Attention2D(nn.Module):          # :55-72
+    def __init__(self, dim):
+        super().__init__()
+        self.q_fc = nn.Linear(dim, dim, bias=False)
+        self.k_fc = nn.Linear(dim, dim, bias=False)
+        self.v_fc = nn.Linear(dim, dim, bias=False)
+        self.pos_fc = nn.Sequential(nn.Linear(4, dim // 8), nn.ReLU(), nn.Linear(dim // 8, dim))
+        self.attn_fc = nn.Sequential(nn.Linear(dim, dim // 8), nn.ReLU(), nn.Linear(dim // 8, dim))
+        self.out_fc = nn.Linear(dim, dim)
+
+
+class _Attention(nn.Module):            # :121-139, attn_mode "qk"
+    def __init__(self, dim, n_heads):
+        super().__init__()
+        self.q_fc = nn.Linear(dim, dim, bias=False)
+        self.k_fc = nn.Linear(dim, dim, bias=False)
+        self.v_fc = nn.Linear(dim, dim, bias=False)
+        self.out_fc = nn.Linear(dim, dim)
+        self.n_heads = n_heads
+
+
+class _TransformerParams(nn.Module):    # Transformer2D :93-100 / Transformer :175-183 (same member order)
+    def __init__(self, dim, make_attn):
+        super().__init__()
+        self.attn_norm = nn.LayerNorm(dim, eps=1e-6)
+        self.ff_norm = nn.LayerNorm(dim, eps=1e-6)
+        self.ff = _FeedForward(dim, 4 * dim)
+        self.attn = make_attn()          # created after ff, as in the reference (RNG consumption order)
+
+
+# (block-relative name inside the C-ABI layer block, state_dict name pattern)
+_VIEW = ['attn_norm.weight', 'attn_norm.bias', 'attn.q_fc.weight', 'attn.k_fc.weight', 'attn.v_fc.weight',
+         'attn.pos_fc.0.weight', 'attn.pos_fc.0.bias', 'attn.pos_fc.2.weight', 'attn.pos_fc.2.bias',
+         'attn.attn_fc.0.weight', 'attn.attn_fc.0.bias', 'attn.attn_fc.2.weight', 'attn.attn_fc.2.bias',
+         'attn.out_fc.weight', 'attn.out_fc.bias', 'ff_norm.weight', 'ff_norm.bias',
+         'ff.fc1.weight', 'ff.fc1.bias', 'ff.fc2.weight', 'ff.fc2.bias']
+_QFC = ['0.weight', '0.bias', '2.weight', '2.bias']
+_RAY = ['attn_norm.weight', 'attn_norm.bias', 'attn.q_fc.weight', 'attn.k_fc.weight', 'attn.v_fc.weight',
+        'attn.out_fc.weight', 'attn.out_fc.bias', 'ff_norm.weight', 'ff_norm.bias',
+        'ff.fc1.weight', 'ff.fc1.bias', 'ff.fc2.weight', 'ff.fc2.bias']
+_HEAD = ['rgbfeat_fc.0.weight', 'rgbfeat_fc.0.bias', 'rgbfeat_fc.2.weight', 'rgbfeat_fc.2.bias']
+_TAIL = ['norm.weight', 'norm.bias', 'rgb_fc.weight', 'rgb_fc.bias']
+
+
+def blob_layout(depth: int):
+    """[(state_dict name, offset in floats)] of every tensor in the nfb_gnt_fwd parameter blob (from the library)."""
+    lib = _lib.load()
+    off = lambda n: int(lib.nfb_gnt_param_offset(depth, n.encode()))     # noqa: E731
+    out = [(n, off(n)) for n in _HEAD]
+    base, size = off('layer0'), off('layer_size')
+    for i in range(depth):
+        out += [(f'view_crosstrans.{i}.{n}', base + i * size + off('view.' + n)) for n in _VIEW]
+        if i % 2 == 0:
+            out += [(f'q_fcs.{i}.{n}', base + i * size + off('q_fc.' + n)) for n in _QFC]
+        out += [(f'view_selftrans.{i}.{n}', base + i * size + off('ray.' + n)) for n in _RAY]
+    out += [(n, off(n)) for n in _TAIL]
+    assert all(o >= 0 for _, o in out)
+    return out
+
+
+def pack_params(tensors: dict, depth: int, device=None) -> torch.Tensor:
+    """state_dict-like mapping -> flat fp32 blob in the C-ABI layout (unused q_fc slots of odd layers stay zero)."""
+    n = int(_lib.load().nfb_gnt_param_floats(depth))
+    blob = torch.zeros(n, dtype=torch.float32, device=device)
+    for name, o in blob_layout(depth):
+        t = tensors[name].detach().reshape(-1).float()
+        blob[o:o + t.numel()] = t.to(blob.device)
+    return blob
+
+
+class GNT(nn.Module):
+    def __init__(self, args, in_feat_ch=32, posenc_dim=3, viewenc_dim=3, ret_alpha=False):
+        super().__init__()
+        if in_feat_ch != 32 or args.netwidth != 64:
+            raise NotImplementedError('nerfool_b200 GNT kernels are built for in_feat_ch=32, netwidth=64 '
+                                      '(every shipped GNT config: eval/gnt/config.py:111, configs/gnt/*.txt)')
+        if posenc_dim != 63 or viewenc_dim != 63:
+            raise NotImplementedError('nerfool_b200 GNT kernels are built for the 63-d positional encodings the '
+                                      'reference constructs the model with (gnt/model.py:25-26)')
+        w = args.netwidth
+        self.rgbfeat_fc = nn.Sequential(nn.Linear(in_feat_ch + 3, w), nn.ReLU(), nn.Linear(w, w))
+        # construction order == the reference's (:215-246), so the same torch seed gives the same initial weights
+        self.view_selftrans = nn.ModuleList([])
+        self.view_crosstrans = nn.ModuleList([])
+        self.q_fcs = nn.ModuleList([])
+        for i in range(args.trans_depth):
+            self.view_crosstrans.append(_TransformerParams(w, lambda: _Attention2D(w)))
+            self.view_selftrans.append(_TransformerParams(w, lambda: _Attention(w, 4)))
+            if i % 2 == 0:
+                self.q_fcs.append(nn.Sequential(nn.Linear(w + posenc_dim + viewenc_dim, w), nn.ReLU(), nn.Linear(w, w)))
+            else:
+                self.q_fcs.append(nn.Identity())
+        self.posenc_dim = posenc_dim
+        self.viewenc_dim = viewenc_dim
+        self.ret_alpha = ret_alpha
+        self.depth = args.trans_depth
+        self.norm = nn.LayerNorm(w)
+        self.rgb_fc = nn.Linear(w, 3)
+        self._blob = None
+        self._blob_key = None
+
+    def param_blob(self) -> torch.Tensor:
+        sd = dict(self.named_parameters())
+        key = tuple((p.data_ptr(), p._version) for p in sd.values())
+        if self._blob is None or key != self._blob_key:
+            self._blob = pack_params(sd, self.depth, device=next(self.parameters()).device)
+            self._blob_key = key
+        return self._blob
+
+    def forward(self, rgb_feat, ray_diff, mask, pts, ray_d):
+        """
+        :param rgb_feat: [n_rays, n_samples, n_views, 35]   :param ray_diff: [.., n_views, 4]   :param mask: [.., n_views, 1]
+        :param pts: [n_rays, n_samples, 3]                  :param ray_d: [n_rays, 3]
+        :return: [n_rays, 3] or, with ret_alpha, [n_rays, 3 + n_samples]
+        """
+        _lib.require_cuda(rgb_feat, ray_diff, mask, pts, ray_d)
+        if torch.is_grad_enabled() and (rgb_feat.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
+            raise NotImplementedError('nerfool_b200.gnt.GNT: only the forward (render) path is implemented in this round; '
+                                      'wrap the call in torch.no_grad() (gradients of the GNT path are listed as next in DESIGN.md)')
+        if self.training:
+            raise NotImplementedError('nerfool_b200.gnt.GNT runs in eval mode only (dropout is the identity); call .eval()')
+        if rgb_feat.shape[-1] != 35:
+            raise RuntimeError(f'GNT kernels are built for 35-channel rows, got {rgb_feat.shape[-1]}')
+        R, S, V = rgb_feat.shape[:3]
+        rf, rd, mk, pt, dd = f32c(rgb_feat.detach()), f32c(ray_diff.detach()), f32c(mask.detach()), f32c(pts.detach()), f32c(ray_d.detach())
+        dev = rf.device
+        out = torch.empty(R, 3 + S if self.ret_alpha else 3, device=dev, dtype=torch.float32)
+        nbytes = int(_lib.load().nfb_gnt_workspace_bytes(R, S, V))
+        ws = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            call('nfb_gnt_fwd', R, S, V, self.depth, int(bool(self.ret_alpha)), ptr(rf), ptr(rd), ptr(mk), ptr(pt), ptr(dd),
+                 ptr(self.param_blob()), ptr(out), ptr(ws), ctypes.c_size_t(nbytes), stream_ptr(dev))
+        return out

@@ -246,3 +246,29 @@ def test_dropin_overlay_resolves_hot_path_modules_and_falls_through(tmp_path, mo
     assert importlib.import_module('ibrnet.render_image').render_single_image is render_single_image
     for m in [k for k in sys.modules if k == 'ibrnet' or k.startswith('ibrnet.')]:
         monkeypatch.delitem(sys.modules, m)
+
+
+def test_gnt_module_interface_and_blob_layout():
+    """GNT drop-in: reference parameter names / shapes (444,739 parameters at depth 4), strict load of the
+    reference's own state dict, and a parameter blob whose layout comes from the library (no overlap, full coverage)."""
+    from nerfool_b200 import _lib
+    from nerfool_b200.gnt.transformer_network import GNT, blob_layout, pack_params
+    lib = _lib.load()
+    g = load_golden('gnt_d2')
+    p = {k[2:]: t(v) for k, v in g.items() if k.startswith('p.')}
+    net = GNT(types.SimpleNamespace(netwidth=64, trans_depth=2), 32, 63, 63, True)
+    missing, unexpected = net.load_state_dict(p, strict=True)
+    assert not missing and not unexpected
+    assert sum(q.numel() for q in GNT(types.SimpleNamespace(netwidth=64, trans_depth=4), 32, 63, 63, True).parameters()) == 444739
+    lay = blob_layout(2)
+    assert sorted(n for n, _ in lay) == sorted(p)
+    iv = sorted((o, o + p[n].numel()) for n, o in lay)
+    assert all(iv[i][1] <= iv[i + 1][0] for i in range(len(iv) - 1)) and iv[-1][1] == lib.nfb_gnt_param_floats(2)
+    blob = pack_params(p, 2)
+    for n, o in lay:
+        assert torch.equal(blob[o:o + p[n].numel()], p[n].reshape(-1))
+    assert lib.nfb_gnt_param_offset(2, b'no.such.tensor') == -1 and lib.nfb_gnt_workspace_bytes(2, 3, 4) == (2 * 3 * 4 * 64 + 2 * 3 * 64) * 4
+    with pytest.raises(NotImplementedError):
+        GNT(types.SimpleNamespace(netwidth=32, trans_depth=2), 32, 63, 63, True)
+    with pytest.raises(RuntimeError, match='workspace'):
+        _lib.call('nfb_gnt_fwd', 1, 4, 2, 2, 1, *[_lib.c_void_p(16)] * 8, _lib.ctypes.c_size_t(0), None)
