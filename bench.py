@@ -438,10 +438,172 @@ def eager_gpu_reference(a, device, rays=4096, steps=3):
         torch.cuda.empty_cache()
 
 
+# ----------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: GNT render (forward only) of a 378x504 view, 8 source views, 64 samples, trans_depth 4
+# ----------------------------------------------------------------------------------------------------
+GNT_DEPTH, GNT_VIEWS, GNT_SAMPLES = 4, 8, 64
+
+
+def gnt_flops_per_ray(S, V, depth):
+    # MAC/ray = S [6336 V + depth (9760 V + 90112 + 128 S) + ceil(depth/2) 16256]
+    return 2 * S * (6336 * V + depth * (9760 * V + 90112 + 128 * S) + ((depth + 1) // 2) * 16256)
+
+
+def gnt_cpu_reference(rays, steps=1, warmup=1):
+    from oracle import gnt_oracle as G
+    from oracle import ibrnet_oracle as O
+    from nerfool_b200.synthetic import make_scene, ray_batch_for
+    torch.set_num_threads(os.cpu_count() or 1)
+    scene = make_scene(H, W, GNT_VIEWS, seed=0, kind='llff')
+    ids = np.sort(np.random.RandomState(1).choice(H * W, rays, replace=False))
+    batch = ray_batch_for(scene, ids)
+    p = G.random_gnt_params(GNT_DEPTH, 1)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            pts, z = O.coarse_depths(batch['ray_o'], batch['ray_d'], batch['depth_range'], GNT_SAMPLES, inv_uniform=True, det=True)
+            rf, rd, mk = O.projector_compute(pts, batch['camera'], batch['src_rgbs'], batch['src_cameras'], scene['featmaps'][0])
+            G.gnt_forward(p, GNT_DEPTH, rf, rd, mk, pts, batch['ray_d'], ret_alpha=True)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {'value': rays / sec, 'unit': 'rays/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': f'{rays} random rays of the {H}x{W} view, GNT forward render (projector + network), {warmup} warm-up + mean of {steps}',
+            'ms_per_step': sec * 1e3}
+
+
+def run_gnt(a):
+    """One step = the forward render of ALL rays of one 378x504 target view through gnt.render_rays (coarse depths,
+    projection + gather, GNT network with ret_alpha, single_net, N_importance = 0: configs/gnt/gnt_llff.txt)."""
+    import torch.distributed as dist
+    from nerfool_b200 import _lib
+    from nerfool_b200.gnt import GNT, render_rays as gnt_render_rays
+    from nerfool_b200.projection import Projector
+    from nerfool_b200.synthetic import make_scene, rays_for_view
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: nerfool_b200 has no CPU path')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
+        dist.init_process_group('nccl', device_id=device)
+    _lib.load()
+    scene = make_scene(H, W, GNT_VIEWS, seed=0, kind='llff', n_targets=max(world, 1))
+    ray_o, ray_d = rays_for_view(scene['camera'][rank], H, W)
+    torch.manual_seed(0)
+    net = GNT(types.SimpleNamespace(netwidth=64, trans_depth=GNT_DEPTH), 32, 63, 63, ret_alpha=True).to(device).eval()
+    model = types.SimpleNamespace(net_coarse=net, net_fine=None)
+    projector = Projector(device)
+    host = {'ray_o': ray_o.pin_memory(), 'ray_d': ray_d.pin_memory()}
+    static = {'depth_range': scene['depth_range'].to(device), 'camera': scene['camera'][rank:rank + 1].to(device),
+              'src_rgbs': scene['src_rgbs'].to(device), 'src_cameras': scene['src_cameras'].to(device)}
+    featmaps = [f.to(device).contiguous() for f in scene['featmaps']]
+    R = ray_o.shape[0]
+    chunk = min(a.max_rays, 32768) if a.max_rays > 0 else 16384
+    resident = {k: v.to(device) for k, v in host.items()}
+
+    def step(src):
+        acc = torch.zeros((), device=device)
+        with torch.no_grad():
+            for lo in range(0, R, chunk):
+                b = dict(static)
+                b['ray_o'], b['ray_d'] = src['ray_o'][lo:lo + chunk], src['ray_d'][lo:lo + chunk]
+                out = gnt_render_rays(b, model, featmaps, projector, GNT_SAMPLES, inv_uniform=True, N_importance=0, det=True,
+                                      ret_alpha=True, single_net=True)
+                acc = acc + out['outputs_coarse']['rgb'].sum()
+        return acc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step(resident)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = _lib.LAUNCHES
+    _lib.profile_start()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s0.record()
+    for _ in range(a.steps):
+        step(resident)
+    s1.record()
+    barrier()
+    prof = _lib.profile_stop()
+    launches = _lib.LAUNCHES - launches0
+    clocks = sampler.stop() if sampler else None
+    total_ms = s0.elapsed_time(s1)
+    # e2e: rays from pinned host memory, checksum of the rendered colours read back
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        chk = step({k: v.to(device, non_blocking=True) for k, v in host.items()}).to('cpu')
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([total_ms, e2e_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = t.tolist()
+    if rank == 0:
+        tensor_peak = load_tensor_peak()
+        ms_per_step = total_ms / a.steps
+        ktot = {k: sum(v) / a.steps for k, v in prof.items()}
+        net_ms = ktot.get('nfb_gnt_fwd', 0.0)
+        fl = gnt_flops_per_ray(GNT_SAMPLES, GNT_VIEWS, GNT_DEPTH) * R
+        ach = fl / (net_ms * 1e-3) / 1e12 if net_ms else None
+        # nfb_gnt_fwd launches 3 + depth * 4.5 kernels per call: count them for gpu_launches
+        per_call = 3 + GNT_DEPTH * 4 + (GNT_DEPTH + 1) // 2
+        n_calls = len(prof.get('nfb_gnt_fwd', []))
+        out = {'metric': 'rays/s', 'value': R * world / (ms_per_step * 1e-3), 'unit': 'rays/s', 'n_gpus': world, 'steps': a.steps,
+               'warmup': a.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+               'dtype': 'f32', 'data': 'synthetic',
+               'config': {'workload': f'BASELINE configs[4]: GNT forward render of one {H}x{W} view (all {R} rays), {GNT_VIEWS} source views, '
+                                      f'{GNT_SAMPLES} samples, trans_depth {GNT_DEPTH}, netwidth 64, ret_alpha, single_net, N_importance 0, '
+                                      'random-init weights', 'rays_per_step_per_gpu': R, 'source_views': GNT_VIEWS,
+                          'max_rays_per_launch': chunk, 'arithmetic': 'fp32 CUDA-core kernels (first form of the GNT path)',
+                          'parallelism': f'one target view per GPU x{world}, no collective (render)' if world > 1 else 'single GPU',
+                          'l2': 'per-chunk working set (projected view features, ~2 GB) >> 126 MB L2'},
+               'roofline': {'bound': 'tensor', 'kernel': 'nfb_gnt_fwd (all kernels of the GNT network, one C-ABI call)',
+                            'achieved': ach, 'peak': tensor_peak, 'unit': 'TFLOP/s', 'frac': (ach / tensor_peak) if ach and tensor_peak else None,
+                            'traffic': None, 'avg_launch_ms': net_ms / max(n_calls / a.steps, 1),
+                            'note': 'algorithmic FLOPs = SURVEY.md Appendix B formula (101 MFLOP/ray at depth 4, S 64, V 8); the kernels '
+                                    'run on the CUDA cores in this round, so the fraction of the bf16 tensor peak is the distance to go'},
+               'kernel_ms_per_step': ktot,
+               'e2e': {'value': R * world / (e2e_ms / a.steps * 1e-3), 'unit': 'rays/s',
+                       'h2d_bytes_per_step': sum(v.numel() * v.element_size() for v in host.values()), 'd2h_bytes_per_step': 4,
+                       'ms_per_step': e2e_ms / a.steps},
+               'gpu_launches': launches - n_calls + n_calls * per_call, 'clocks': clocks, 'checksum': float(chk)}
+        if world == 1 and not a.no_cpu_baseline:
+            out['cpu_baseline'] = gnt_cpu_reference(min(a.cpu_rays, 512))
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if rank != 0:
+        return
+    if a.config == 4:
+        cb = gnt_cpu_reference(min(a.cpu_rays, 512), steps=a.steps, warmup=1)
+        print(json.dumps({'impl': 'reference', 'metric': 'rays/s', 'value': cb['value'], 'unit': 'rays/s', 'n_gpus': world,
+                          'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': cb['ms_per_step'], 'higher_is_better': True,
+                          'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                          'config': {'workload': f'BASELINE configs[4]: GNT forward render, {H}x{W}, {GNT_VIEWS} source views, '
+                                                 f'{GNT_SAMPLES} samples, depth {GNT_DEPTH}; CPU port of the reference on a bounded sample'},
+                          'cpu_baseline': cb, 'e2e': {'value': cb['value'], 'unit': 'rays/s', 'h2d_bytes_per_step': 0,
+                                                      'd2h_bytes_per_step': 0}}), flush=True)
         return
     cb = cpu_reference(a, sample_rays=a.cpu_rays, steps=a.steps, warmup=max(1, min(a.warmup, 2)))
     out = {'impl': 'reference', 'metric': 'rays/s', 'value': cb['value'], 'unit': 'rays/s', 'n_gpus': world,
@@ -467,9 +629,10 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-nrand', dest='no_nrand', action='store_true', help='skip the N_rand = 512/4096/32768 PGD iteration timings')
     ap.add_argument('--no-bf16', dest='no_bf16', action='store_true', help='skip the extra plain-bf16 measurement')
-    ap.add_argument('--config', type=int, default=1, choices=[1, 2, 3],
+    ap.add_argument('--config', type=int, default=1, choices=[1, 2, 3, 4],
                     help='BASELINE.json configs index: 1 = headline (378x504, 4 views, 64+64); 2 = universal-attack shape '
-                         '(378x504, 10 views, one target view per GPU); 3 = NeRF-Synthetic shape (800x800, 10 views, 64+128)')
+                         '(378x504, 10 views, one target view per GPU); 3 = NeRF-Synthetic shape (800x800, 10 views, 64+128); '
+                         '4 = GNT forward render (378x504, 8 views, 64 samples, depth 4)')
     a = ap.parse_args()
     global H, W, N_SAMPLES, N_IMPORTANCE, SCENE_KIND
     if a.config == 2:
@@ -484,6 +647,8 @@ def main():
     a.warmup = max(a.warmup, 3) if a.impl == 'ours' else a.warmup
     if a.impl == 'reference':
         run_reference(a)
+    elif a.config == 4:
+        run_gnt(a)
     else:
         run_ours(a)
 

@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(128) k_gnt_view_attn(int N, int V, const float
 enum : int { FS_LN_W = 0, FS_LN_B = D, FS_W1 = 2 * D /*[64][256]*/, FS_B1 = FS_W1 + D * DH, FS_W2 = FS_B1 + DH /*[256][64]*/,
              FS_B2 = FS_W2 + DH * D, FS_TOTAL = FS_B2 + D };
 
-__global__ void __launch_bounds__(128) k_gnt_ffn(int N, const float* __restrict__ lp, float* __restrict__ q) {
+__global__ void __launch_bounds__(256, 1) k_gnt_ffn(int N, const float* __restrict__ lp, float* __restrict__ q) {
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, nt = blockDim.x;
   load_vec_padded(sm + FS_LN_W, lp, D, D, t, nt);
@@ -342,25 +342,32 @@ __global__ void __launch_bounds__(128) k_gnt_qfc(int N, int S, const float* __re
 // q <- out_fc(attn) + q.   attn_out (optional): mean over heads of the probabilities of QUERY 0 (:200) -> [R][S].
 // ---------------------------------------------------------------------------------------------------
 enum : int { RS_LN_W = 0, RS_LN_B = D, RS_Q = 2 * D, RS_K = RS_Q + D * D, RS_V = RS_K + D * D, RS_O = RS_V + D * D,
-             RS_O_B = RS_O + D * D, RS_Q0 = RS_O_B + D /*query 0, scaled*/, RS_ST = RS_Q0 + D /*m[4], 1/l[4]*/, RS_TOTAL = RS_ST + 8 };
+             RS_O_B = RS_O + D * D, RS_W_TOTAL = RS_O_B + D,
+             // per ray of the CTA: query 0 (scaled) [64], its softmax statistics m[4], 1/l[4]; then K [S][64], V [S][64]
+             RS_Q0 = 0, RS_ST = D, RS_PER_RAY = D + 8 };
 
-__global__ void __launch_bounds__(256) k_gnt_ray_attn(int R, int S, const float* __restrict__ lp, float* __restrict__ q,
-                                                       float* __restrict__ attn_out, int attn_stride) {
+__global__ void __launch_bounds__(256, 1) k_gnt_ray_attn(int R, int S, int rpc, const float* __restrict__ lp, float* __restrict__ q,
+                                                          float* __restrict__ attn_out, int attn_stride) {
   extern __shared__ __align__(16) float sm[];
-  float* sk = sm + RS_TOTAL;            // [S][64]
+  const int nt = blockDim.x;
+  const int rb = nt / rpc;               // threads per ray (S rounded up to a warp multiple)
+  const int lr = threadIdx.x / rb;       // ray of the CTA this thread works on
+  const int t = threadIdx.x - lr * rb;   // sample index
+  float* sq0 = sm + RS_W_TOTAL + (size_t)lr * (RS_PER_RAY + 2 * S * D);   // this ray's query-0 block
+  float* sk = sq0 + RS_PER_RAY;         // [S][64]
   float* sv = sk + (size_t)S * D;       // [S][64]
-  const int t = threadIdx.x, nt = blockDim.x;
-  load_vec_padded(sm + RS_LN_W, lp + L_R_LN1_W, D, D, t, nt);
-  load_vec_padded(sm + RS_LN_B, lp + L_R_LN1_B, D, D, t, nt);
-  load_wt_transposed(sm + RS_Q, lp + L_R_Q, D, D, D, t, nt);
-  load_wt_transposed(sm + RS_K, lp + L_R_K, D, D, D, t, nt);
-  load_wt_transposed(sm + RS_V, lp + L_R_V, D, D, D, t, nt);
-  load_wt_transposed(sm + RS_O, lp + L_R_O_W, D, D, D, t, nt);
-  load_vec_padded(sm + RS_O_B, lp + L_R_O_B, D, D, t, nt);
+  load_vec_padded(sm + RS_LN_W, lp + L_R_LN1_W, D, D, threadIdx.x, nt);
+  load_vec_padded(sm + RS_LN_B, lp + L_R_LN1_B, D, D, threadIdx.x, nt);
+  load_wt_transposed(sm + RS_Q, lp + L_R_Q, D, D, D, threadIdx.x, nt);
+  load_wt_transposed(sm + RS_K, lp + L_R_K, D, D, D, threadIdx.x, nt);
+  load_wt_transposed(sm + RS_V, lp + L_R_V, D, D, D, threadIdx.x, nt);
+  load_wt_transposed(sm + RS_O, lp + L_R_O_W, D, D, D, threadIdx.x, nt);
+  load_vec_padded(sm + RS_O_B, lp + L_R_O_B, D, D, threadIdx.x, nt);
   __syncthreads();
-  const bool act = t < S;
-  for (int r = blockIdx.x; r < R; r += gridDim.x) {
-    float* qrow = q + ((size_t)r * S + (act ? t : 0)) * D;
+  for (int r0 = blockIdx.x * rpc; r0 < R; r0 += gridDim.x * rpc) {
+    const int r = r0 + lr;
+    const bool act = (t < S) && (r < R);
+    float* qrow = q + ((size_t)(r < R ? r : 0) * S + (t < S ? t : 0)) * D;
     float q0[D], qv[D];
     load_row64(qrow, q0);
     {
@@ -378,7 +385,7 @@ __global__ void __launch_bounds__(256) k_gnt_ray_attn(int R, int S, const float*
     }
 #pragma unroll
     for (int c = 0; c < D; ++c) qv[c] *= 0.25f;          // 1 / sqrt(16)
-    if (t == 0) store_row64(sm + RS_Q0, qv);
+    if (t == 0) store_row64(sq0 + RS_Q0, qv);
     __syncthreads();
     float o[D];
 #pragma unroll
@@ -408,7 +415,7 @@ __global__ void __launch_bounds__(256) k_gnt_ray_attn(int R, int S, const float*
       const float il = 1.f / l;
 #pragma unroll
       for (int c = 0; c < 16; ++c) o[16 * h + c] = a16[c] * il;
-      if (t == 0) { sm[RS_ST + h] = mx; sm[RS_ST + 4 + h] = il; }
+      if (t == 0) { sq0[RS_ST + h] = mx; sq0[RS_ST + 4 + h] = il; }
     }
     float y[D];
     load_bias<D>(y, sm + RS_O_B);
@@ -425,8 +432,8 @@ __global__ void __launch_bounds__(256) k_gnt_ray_attn(int R, int S, const float*
           const float* kj = sk + (size_t)t * D + 16 * h;
           float s = 0.f;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) s = fmaf(sm[RS_Q0 + 16 * h + c], kj[c], s);
-          pm += __expf(s - sm[RS_ST + h]) * sm[RS_ST + 4 + h];
+          for (int c = 0; c < 16; ++c) s = fmaf(sq0[RS_Q0 + 16 * h + c], kj[c], s);
+          pm += __expf(s - sq0[RS_ST + h]) * sq0[RS_ST + 4 + h];
         }
         attn_out[(size_t)r * attn_stride + t] = 0.25f * pm;
       }
@@ -552,7 +559,7 @@ extern "C" int nfb_gnt_fwd(int R, int S, int V, int depth, int ret_alpha, const 
     NFB_CHECK_LAUNCH("k_gnt_qinit");
   }
   const size_t sm_view = (size_t)VS_TOTAL * sizeof(float), sm_ffn = (size_t)FS_TOTAL * sizeof(float),
-               sm_qfc = (size_t)QS_TOTAL * sizeof(float), sm_ray = (size_t)(RS_TOTAL + 2 * S * D) * sizeof(float),
+               sm_qfc = (size_t)QS_TOTAL * sizeof(float), sm_ray = (size_t)(RS_W_TOTAL + (size_t)(256 / (((S + 31) / 32) * 32) > 0 ? 256 / (((S + 31) / 32) * 32) : 1) * (2 * S * D + RS_PER_RAY)) * sizeof(float),
                sm_head = (size_t)(S * 65 + D) * sizeof(float);
   if ((rc = set_smem(k_gnt_view_attn, sm_view, "k_gnt_view_attn"))) return rc;
   if ((rc = set_smem(k_gnt_ffn, sm_ffn, "k_gnt_ffn"))) return rc;
@@ -564,26 +571,35 @@ extern "C" int nfb_gnt_fwd(int R, int S, int V, int depth, int ret_alpha, const 
     if (g > sms * per_sm) g = sms * per_sm;
     return g < 1 ? 1 : g;
   };
+  const int ffn_grid = (N + 255) / 256 < sms ? (N + 255) / 256 : sms;
   const int ray_block = ((S + 31) / 32) * 32;
-  const int ray_grid = R < sms ? R : sms;
+  // rays per CTA of the ray-attention kernel: up to 256 threads, K/V of every ray of the CTA in shared memory
+  int rpc = 256 / ray_block;
+  const int rpc_smem = (int)((200 * 1024 - (size_t)RS_W_TOTAL * sizeof(float)) / ((size_t)(2 * S * D + RS_PER_RAY) * sizeof(float)));
+  if (rpc > rpc_smem) rpc = rpc_smem;
+  if (rpc < 1) rpc = 1;
+  const int ray_ctas = (R + rpc - 1) / rpc;
+  const int ray_grid = ray_ctas < sms ? ray_ctas : sms;
+  const int head_grid = R < sms * 4 ? R : sms * 4;
   const int out_stride = ret_alpha ? 3 + S : 3;
   for (int i = 0; i < depth; ++i) {
     const float* lp = params + G_HEAD + (size_t)i * L_SIZE;
     k_gnt_view_attn<<<grid_for(3), 128, sm_view, st>>>(N, V, F, ray_diff, mask, lp, q);
     NFB_CHECK_LAUNCH("k_gnt_view_attn");
-    k_gnt_ffn<<<grid_for(1), 128, sm_ffn, st>>>(N, lp + L_V_LN2_W, q);
+    k_gnt_ffn<<<ffn_grid, 256, sm_ffn, st>>>(N, lp + L_V_LN2_W, q);
     NFB_CHECK_LAUNCH("k_gnt_ffn<view>");
     if ((i & 1) == 0) {
       k_gnt_qfc<<<grid_for(3), 128, sm_qfc, st>>>(N, S, pts, ray_d, lp, q);
       NFB_CHECK_LAUNCH("k_gnt_qfc");
     }
     const bool last = ret_alpha && i == depth - 1;
-    k_gnt_ray_attn<<<ray_grid, ray_block, sm_ray, st>>>(R, S, lp, q, last ? out + 3 : nullptr, out_stride);
+    k_gnt_ray_attn<<<ray_grid, ray_block * rpc, (size_t)(RS_W_TOTAL + (size_t)rpc * (2 * S * D + RS_PER_RAY)) * sizeof(float), st>>>(
+        R, S, rpc, lp, q, last ? out + 3 : nullptr, out_stride);
     NFB_CHECK_LAUNCH("k_gnt_ray_attn");
-    k_gnt_ffn<<<grid_for(1), 128, sm_ffn, st>>>(N, lp + L_R_LN2_W, q);
+    k_gnt_ffn<<<ffn_grid, 256, sm_ffn, st>>>(N, lp + L_R_LN2_W, q);
     NFB_CHECK_LAUNCH("k_gnt_ffn<ray>");
   }
-  k_gnt_head<<<ray_grid, ray_block < 64 ? 64 : ray_block, sm_head, st>>>(R, S, params + G_HEAD + (size_t)depth * L_SIZE, q, out, out_stride);
+  k_gnt_head<<<head_grid, ray_block < 64 ? 64 : ray_block, sm_head, st>>>(R, S, params + G_HEAD + (size_t)depth * L_SIZE, q, out, out_stride);
   NFB_CHECK_LAUNCH("k_gnt_head");
   return NFB_OK;
 }
