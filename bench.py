@@ -269,6 +269,24 @@ def run_ours(a):
             s1.record()
             torch.cuda.synchronize()
             nrand[str(n)] = {'ms_per_iter': s0.elapsed_time(s1) / 10, 'iters_per_s': 1e4 / s0.elapsed_time(s1)}
+            # the same step captured in a CUDA graph (attack.GraphedPGDStep): launch / host overhead removed
+            try:
+                from nerfool_b200.attack import GraphedPGDStep
+                gstep = GraphedPGDStep(model, projector, nb, featmaps, N_SAMPLES, N_IMPORTANCE, inv_uniform=True, det=True,
+                                       max_rays=a.max_rays)
+                for _ in range(3):
+                    gstep(nb['ray_o'], nb['ray_d'], nb['rgb'], featmaps)
+                torch.cuda.synchronize()
+                s0.record()
+                for _ in range(20):
+                    gstep(nb['ray_o'], nb['ray_d'], nb['rgb'], featmaps)
+                s1.record()
+                torch.cuda.synchronize()
+                nrand[str(n)]['graph_ms_per_iter'] = s0.elapsed_time(s1) / 20
+                nrand[str(n)]['graph_iters_per_s'] = 2e4 / s0.elapsed_time(s1)
+                del gstep
+            except Exception as ex:
+                nrand[str(n)]['graph_error'] = f'{type(ex).__name__}: {ex}'[:160]
 
     # max over ranks
     t = torch.tensor([total_ms, e2e_total_ms, statistics.median(fwd_ms), bf16_ms or 0.0], device=device, dtype=torch.float64)

@@ -93,3 +93,46 @@ def pgd_hot_step(model, projector, ray_batch, featmaps, N_samples, N_importance,
     else:
         total = loss
     return total, g_c, g_f
+
+
+class GraphedPGDStep:
+    """``pgd_hot_step`` for a FIXED ray-batch size, captured once into a CUDA graph and replayed.
+
+    At the reference's ray-batch sizes (``N_rand`` = 512 by default, config.py:55) one attack step is ~14 kernel launches
+    plus the autograd bookkeeping around them and the kernels themselves take ~0.3 ms: the step is launch / host bound.
+    The graph removes that: per call only the ray batch and the feature maps are copied into the graph's static
+    buffers, the captured kernels are replayed, and the results are read from static output tensors (valid until
+    the next call).  Single-GPU (a collective inside the capture is not attempted); the library's entry points are
+    stream-ordered and allocate nothing, so the capture only involves PyTorch's graph-private allocator.
+    """
+
+    def __init__(self, model, projector, ray_batch, featmaps, N_samples, N_importance, inv_uniform=True, det=True,
+                 white_bkgd=False, max_rays=65536):
+        if not det:
+            raise ValueError('GraphedPGDStep needs det=True (the stochastic sampler draws new random numbers per step)')
+        self._batch = dict(ray_batch)
+        for k in ('ray_o', 'ray_d', 'rgb'):
+            self._batch[k] = ray_batch[k].detach().clone()
+        self._fm = [f.detach().clone() for f in featmaps]
+        args = (model, projector, self._batch, self._fm, N_samples, N_importance)
+        kw = dict(inv_uniform=inv_uniform, det=det, white_bkgd=white_bkgd, max_rays=max_rays)
+        # warm-up on a side stream (fills the camera-block / depth-range caches, sizes the allocator), then capture
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                pgd_hot_step(*args, **kw)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._out = pgd_hot_step(*args, **kw)
+
+    def __call__(self, ray_o, ray_d, rgb, featmaps):
+        """Same result as pgd_hot_step on a batch with these rays (shapes must equal the captured ones)."""
+        self._batch['ray_o'].copy_(ray_o, non_blocking=True)
+        self._batch['ray_d'].copy_(ray_d, non_blocking=True)
+        self._batch['rgb'].copy_(rgb, non_blocking=True)
+        for dst, src in zip(self._fm, featmaps):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self._out

@@ -24,10 +24,16 @@ _cam_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
 _CAM_CACHE_MAX = 32
 
 
+def _tensor_key(t: torch.Tensor):
+    """Identity of the memory a tensor (or a view such as ``src_cameras[0]``, a fresh Python object on every call) looks
+    at, plus the version counter views share with their base: equal keys <=> same bytes, as long as the tensor is alive."""
+    return (t.untyped_storage().data_ptr(), t.storage_offset(), tuple(t.shape), tuple(t.stride()), t._version, str(t.device))
+
+
 def camera_block(train_cameras: torch.Tensor, query_camera: torch.Tensor, device) -> torch.Tensor:
     """train_cameras [V,34], query_camera [34] (any device) -> device float32 [16*V+4].
-    Cached per (tensor object, version); the cache keeps the key tensors alive so ids cannot be reused."""
-    key = (id(train_cameras), train_cameras._version, id(query_camera), query_camera._version, str(device))
+    Cached per (storage, view geometry, version); the cache keeps the key tensors alive so addresses cannot be reused."""
+    key = (_tensor_key(train_cameras), _tensor_key(query_camera), str(device))
     hit = _cam_cache.get(key)
     if hit is not None:
         _cam_cache.move_to_end(key)

@@ -39,10 +39,18 @@ def sample_pdf(bins, weights, N_samples, det=False):
     return ops.sample_pdf_op(bins, w_in, u)
 
 
+_linspace_cache = {}
+
+
 def _uniforms(R, n, det, device):
     if det:
-        # torch.linspace on CPU then copy: the values the reference's CPU path sees (render_ray.py:42)
-        return torch.linspace(0., 1., n).to(device)
+        # torch.linspace on CPU then copy: the values the reference's CPU path sees (render_ray.py:42); the device
+        # copy is cached per (n, device) -- no host->device copy per step (and none inside a CUDA-graph capture)
+        key = (int(n), str(device))
+        u = _linspace_cache.get(key)
+        if u is None:
+            u = _linspace_cache[key] = torch.linspace(0., 1., n).to(device)
+        return u
     return torch.rand(R, n, device=device)
 
 

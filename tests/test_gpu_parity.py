@@ -721,3 +721,33 @@ def test_full_size_properties(dev):
 def test_graft_smoke(dev):
     import __graft_entry__ as ge
     ge.smoke()
+
+
+def test_graphed_pgd_step_equals_eager(dev):
+    """CUDA-graph replay of the attack step (GraphedPGDStep) == the eager step, on new rays and new feature maps."""
+    from nerfool_b200.attack import pgd_hot_step, GraphedPGDStep
+    from nerfool_b200.projection import Projector
+    V, R, S, NI = 4, 512, 64, 64
+    scene, batch = _scene(V, 2 * R, 378, 504, 'llff', seed=9)
+    model = types.SimpleNamespace(net_coarse=_net(_params(S, 31), S, dev), net_fine=_net(_params(S + NI, 32), S + NI, dev))
+    gb = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    fm = [f.to(dev) for f in scene['featmaps']]
+    first = dict(gb)
+    for k in ('ray_o', 'ray_d', 'rgb'):
+        first[k] = gb[k][:R].contiguous()
+    proj = Projector(dev)
+    step = GraphedPGDStep(model, proj, first, fm, S, NI, inv_uniform=True, det=True)
+    # replay on the OTHER half of the rays and perturbed feature maps
+    second = dict(gb)
+    for k in ('ray_o', 'ray_d', 'rgb'):
+        second[k] = gb[k][R:].contiguous()
+    fm2 = [f + 0.01 * torch.randn_like(f) for f in fm]
+    loss_g, gc_g, gf_g = step(second['ray_o'], second['ray_d'], second['rgb'], fm2)
+    loss_e, gc_e, gf_e = pgd_hot_step(model, proj, second, fm2, S, NI, inv_uniform=True, det=True)
+    assert abs(loss_g.item() - loss_e.item()) < 1e-6
+    assert relerr(gc_g.cpu(), gc_e.cpu()) < 1e-5 and relerr(gf_g.cpu(), gf_e.cpu()) < 1e-5     # float-atomic order only
+    # and again on the first half: the static buffers are really re-read
+    loss_g1, gc_g1, _ = step(first['ray_o'], first['ray_d'], first['rgb'], fm)
+    loss_e1, gc_e1, _ = pgd_hot_step(model, proj, first, fm, S, NI, inv_uniform=True, det=True)
+    assert abs(loss_g1.item() - loss_e1.item()) < 1e-6 and relerr(gc_g1.cpu(), gc_e1.cpu()) < 1e-5
+    assert abs(loss_g1.item() - loss_e.item()) > 1e-6
