@@ -751,3 +751,44 @@ def test_graphed_pgd_step_equals_eager(dev):
     loss_e1, gc_e1, _ = pgd_hot_step(model, proj, first, fm, S, NI, inv_uniform=True, det=True)
     assert abs(loss_g1.item() - loss_e1.item()) < 1e-6 and relerr(gc_g1.cpu(), gc_e1.cpu()) < 1e-5
     assert abs(loss_g1.item() - loss_e.item()) > 1e-6
+
+
+def test_delta_gradient_step_end_to_end(dev):
+    """attack.delta_gradient_step on the GPU (encoder stub -> fused render_rays -> masked MSE; both paths from the
+    perturbation to the loss: through the feature maps and through the blended source colours) against plain autograd
+    of the oracle with the same encoder on the CPU."""
+    from nerfool_b200.attack import delta_gradient_step
+    from nerfool_b200.projection import Projector
+    V, R, S, NI = 4, 200, 32, 32
+    scene, batch = _scene(V, R, 96, 128, 'llff', seed=13)
+    pc, pf = _params(S, 41), _params(S + NI, 42)
+    torch.manual_seed(5)
+    conv, norm = torch.nn.Conv2d(3, 64, 3, stride=4, padding=1), torch.nn.InstanceNorm2d(64)
+
+    def make_enc(c, n):
+        def enc(x):
+            y = n(c(x))
+            return y[:, :32], y[:, 32:]
+        return enc
+    delta = (torch.rand(batch['src_rgbs'].shape, generator=torch.Generator().manual_seed(6)) * 2 - 1) * (8. / 255.)
+    adv = (batch['src_rgbs'] + delta).requires_grad_(True)
+    fc, ff = make_enc(conv, norm)(adv[0].permute(0, 3, 1, 2))
+    b2 = dict(batch)
+    b2['src_rgbs'] = adv
+    ro = O.render_rays(b2, pc, pf, (fc, ff), S, True, NI, det=True)
+    loss0 = O.attack_loss(ro, batch['rgb'])
+    loss0.backward()
+    import copy
+    from nerfool_b200 import render_ray as RR
+    model = types.SimpleNamespace(net_coarse=_net(pc, S, dev), net_fine=_net(pf, S + NI, dev))
+    gb = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    saved = RR._fine_z
+    RR._fine_z = lambda z, w, n, iu, det: ro['outputs_fine']['z_vals'].detach().to(dev)
+    try:
+        loss, dd = delta_gradient_step(make_enc(copy.deepcopy(conv).to(dev), copy.deepcopy(norm).to(dev)), model, Projector(dev), gb,
+                                       delta.to(dev), S, NI, inv_uniform=True, det=True, max_rays=256)
+    finally:
+        RR._fine_z = saved
+    assert dd.shape == delta.shape
+    assert abs(loss.item() - loss0.item()) < 5e-5
+    assert relerr(dd.cpu(), adv.grad) < 5e-3, relerr(dd.cpu(), adv.grad)
