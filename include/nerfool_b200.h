@@ -150,19 +150,22 @@ int nfb_ibrnet_view_wgrad(int N, int S, int V, int anti_alias,
  * (rgb_feat[R][S][V][35], ray_diff[R][S][V][4], mask[R][S][V][1]) plus pts[R][S][3] and ray_d[R][3].
  * out: [R][3] or, with ret_alpha, [R][3+S] (rgb | attention row of query 0 of the last ray transformer, the
  * "learned density" gnt/render_ray.py:249-250 turns into depth).  Forward only in this round (eval mode: dropout is
- * the identity); fp32 CUDA-core kernels.
+ * the identity).  precision (NfbPrecision): NFB_PREC_FP32 = CUDA-core kernels; NFB_PREC_BF16X3 / NFB_PREC_BF16 = every
+ * 64-wide linear layer (q/k/v/out projections of both attentions, the feed-forward blocks) as tcgen05 128 x 64 x 64 tiles
+ * with split (fp32-equivalent) or plain bf16 operands; the per-channel view softmax, the d = 16 ray attention, the
+ * embedding and the positional q_fc stay on the CUDA cores.
  * params: one flat fp32 blob of nfb_gnt_param_floats(depth) floats: header (rgbfeat_fc), `depth` layer blocks
  * (view_crosstrans.i | q_fcs.i | view_selftrans.i), tail (norm, rgb_fc); nfb_gnt_param_offset(depth, name) gives the
  * offset of a header / tail tensor ("rgbfeat_fc.0.weight", "norm.bias", ...), of the first layer block ("layer0"),
  * the block size ("layer_size") and of a tensor inside a block ("view.attn.q_fc.weight", "q_fc.0.bias",
  * "ray.ff.fc2.weight", ...).  workspace: nfb_gnt_workspace_bytes(R, S, V) bytes, 16-byte aligned (projected view
- * features F[R*S*V][64] + the running query q[R*S][64]).                                                          */
+ * features F, per-row k / v [R*S*V][64]; the running query q and five per-sample buffers [R*S][64]).                                                          */
 int nfb_gnt_param_floats(int depth);
 int nfb_gnt_param_offset(int depth, const char* name);
 size_t nfb_gnt_workspace_bytes(int R, int S, int V);
 int nfb_gnt_fwd(int R, int S, int V, int depth, int ret_alpha,
                 const float* rgb_feat, const float* ray_diff, const float* mask, const float* pts, const float* ray_d,
-                const float* params, float* out, void* workspace, size_t workspace_bytes, void* stream);
+                const float* params, float* out, void* workspace, size_t workspace_bytes, int precision, void* stream);
 
 /* ---- raw2outputs  (render_ray.py:123-170) ------------------------------------------------------------
  * pixel_mask: uint8 [R][S] (the `mask` argument), or NULL with n_valid (stride n_valid_stride floats per

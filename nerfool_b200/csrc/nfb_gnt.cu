@@ -9,6 +9,7 @@
 // [q_fc with positional encodings on even layers], ray attention, FFN } -> head (LayerNorm, mean over samples,
 // rgb_fc).  Dropout is the identity (eval mode, transformer_network.py:45,72,136).
 #include "nfb_dense.cuh"
+#include "nfb_gnt_tc.cuh"
 
 namespace {
 
@@ -478,6 +479,176 @@ __global__ void __launch_bounds__(256) k_gnt_head(int R, int S, const float* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// tensor-core form: the 64 x 64 projections run in k_gnt_lin_tc (nfb_gnt_tc.cuh); what stays on the CUDA cores is
+// the part of the two attentions that is not a dense contraction.
+// view core: per sample, given qq = q_fc(LN(q)) [N][64] and the per-row k, v [N*V][64]:
+//   pos = pos_fc(ray_diff), a = attn_fc(k - qq + pos) (masked), softmax over views per channel, x = sum_v (v + pos) a
+// ---------------------------------------------------------------------------------------------------
+enum : int { CS_P0 = 0 /*[4][8]*/, CS_P0_B = 32, CS_P2 = 40 /*[8][64]*/, CS_P2_B = CS_P2 + 8 * D, CS_A0 = CS_P2_B + D /*[64][8]*/,
+             CS_A0_B = CS_A0 + D * 8, CS_A2 = CS_A0_B + 8 /*[8][64]*/, CS_A2_B = CS_A2 + 8 * D, CS_TOTAL = CS_A2_B + D };
+
+__global__ void __launch_bounds__(128) k_gnt_view_core(int N, int V, const float* __restrict__ qq, const float* __restrict__ Kv,
+                                                        const float* __restrict__ Vv, const float* __restrict__ ray_diff,
+                                                        const float* __restrict__ mask, const float* __restrict__ lp,
+                                                        float* __restrict__ xout) {
+  __shared__ __align__(16) float sm[CS_TOTAL];
+  const int t = threadIdx.x, nt = blockDim.x;
+  load_wt_transposed(sm + CS_P0, lp + L_V_POS0_W, 8, 4, 8, t, nt);
+  load_vec_padded(sm + CS_P0_B, lp + L_V_POS0_B, 8, 8, t, nt);
+  load_wt_transposed(sm + CS_P2, lp + L_V_POS2_W, D, 8, D, t, nt);
+  load_vec_padded(sm + CS_P2_B, lp + L_V_POS2_B, D, D, t, nt);
+  load_wt_transposed(sm + CS_A0, lp + L_V_AT0_W, 8, D, 8, t, nt);
+  load_vec_padded(sm + CS_A0_B, lp + L_V_AT0_B, 8, 8, t, nt);
+  load_wt_transposed(sm + CS_A2, lp + L_V_AT2_W, D, 8, D, t, nt);
+  load_vec_padded(sm + CS_A2_B, lp + L_V_AT2_B, D, D, t, nt);
+  __syncthreads();
+  for (int n = blockIdx.x * blockDim.x + t; n < N; n += gridDim.x * blockDim.x) {
+    float qv[D];
+    load_row64(qq + (size_t)n * D, qv);
+    float m[D], l[D], acc[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) { m[c] = -3.4e38f; l[c] = 0.f; acc[c] = 0.f; }
+    for (int v = 0; v < V; ++v) {
+      const size_t row = (size_t)n * V + v;
+      float pos[D];
+      {
+        const float4 rd4 = __ldg(reinterpret_cast<const float4*>(ray_diff) + row);
+        const float rd[4] = {rd4.x, rd4.y, rd4.z, rd4.w};
+        float p8[8];
+        load_bias<8>(p8, sm + CS_P0_B);
+        dense_acc<4, 8>(sm + CS_P0, rd, p8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p8[j] = fmaxf(p8[j], 0.f);
+        load_bias<D>(pos, sm + CS_P2_B);
+        dense_acc<8, D>(sm + CS_P2, p8, pos);
+      }
+      float a8[8];
+      load_bias<8>(a8, sm + CS_A0_B);
+      const float4* kr = reinterpret_cast<const float4*>(Kv + row * D);
+#pragma unroll
+      for (int c = 0; c < D; c += 4) {
+        const float4 k4 = __ldg(kr + c / 4);
+        axpy_row<8>(a8, k4.x - qv[c] + pos[c], sm + CS_A0 + c * 8);
+        axpy_row<8>(a8, k4.y - qv[c + 1] + pos[c + 1], sm + CS_A0 + (c + 1) * 8);
+        axpy_row<8>(a8, k4.z - qv[c + 2] + pos[c + 2], sm + CS_A0 + (c + 2) * 8);
+        axpy_row<8>(a8, k4.w - qv[c + 3] + pos[c + 3], sm + CS_A0 + (c + 3) * 8);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a8[j] = fmaxf(a8[j], 0.f);
+      const bool valid = __ldg(mask + row) != 0.f;
+      const float4* vr = reinterpret_cast<const float4*>(Vv + row * D);
+#pragma unroll
+      for (int c0 = 0; c0 < D; c0 += 16) {
+        float a[16];
+        load_bias<16>(a, sm + CS_A2_B + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) axpy_row<16>(a, a8[j], sm + CS_A2 + j * D + c0);
+        float vv[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v4 = __ldg(vr + c0 / 4 + j);
+          vv[4 * j] = v4.x; vv[4 * j + 1] = v4.y; vv[4 * j + 2] = v4.z; vv[4 * j + 3] = v4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int c = c0 + j;
+          const float s = valid ? a[j] : -1e9f;
+          const float mn = fmaxf(m[c], s);
+          const float sc = __expf(m[c] - mn), e = __expf(s - mn);
+          l[c] = fmaf(l[c], sc, e);
+          acc[c] = fmaf(acc[c], sc, (vv[j] + pos[c]) * e);
+          m[c] = mn;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = acc[c] / l[c];
+    store_row64(xout + (size_t)n * D, acc);
+  }
+}
+
+// ray core: scaled-dot-product attention of the ray's samples given the projected Q, K, V [N][64]; o -> [N][64]
+// (same CTA / thread mapping as k_gnt_ray_attn; the projections and out_fc run in k_gnt_lin_tc)
+__global__ void __launch_bounds__(256, 1) k_gnt_ray_core(int R, int S, int rpc, const float* __restrict__ Q, const float* __restrict__ K,
+                                                          const float* __restrict__ Vp, float* __restrict__ O,
+                                                          float* __restrict__ attn_out, int attn_stride) {
+  extern __shared__ __align__(16) float sm[];
+  const int nt = blockDim.x;
+  const int rb = nt / rpc;
+  const int lr = threadIdx.x / rb;
+  const int t = threadIdx.x - lr * rb;
+  float* sq0 = sm + (size_t)lr * (RS_PER_RAY + 2 * S * D);
+  float* sk = sq0 + RS_PER_RAY;
+  float* sv = sk + (size_t)S * D;
+  for (int r0 = blockIdx.x * rpc; r0 < R; r0 += gridDim.x * rpc) {
+    const int r = r0 + lr;
+    const bool act = (t < S) && (r < R);
+    const size_t n = (size_t)(r < R ? r : 0) * S + (t < S ? t : 0);
+    float qv[D];
+    load_row64(Q + n * D, qv);
+    if (act) {
+      float tmp[D];
+      load_row64(K + n * D, tmp);
+      store_row64(sk + (size_t)t * D, tmp);
+      load_row64(Vp + n * D, tmp);
+      store_row64(sv + (size_t)t * D, tmp);
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) qv[c] *= 0.25f;          // 1 / sqrt(16)
+    if (t == 0) store_row64(sq0 + RS_Q0, qv);
+    __syncthreads();
+    float o[D];
+    const int Sr = (r < R) ? S : 0;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float mx = -3.4e38f;
+      for (int j = 0; j < Sr; ++j) {
+        const float* kj = sk + (size_t)j * D + 16 * h;
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) s = fmaf(qv[16 * h + c], kj[c], s);
+        mx = fmaxf(mx, s);
+      }
+      float l = 0.f, a16[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) a16[c] = 0.f;
+      for (int j = 0; j < Sr; ++j) {
+        const float* kj = sk + (size_t)j * D + 16 * h;
+        const float* vj = sv + (size_t)j * D + 16 * h;
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) s = fmaf(qv[16 * h + c], kj[c], s);
+        const float p = __expf(s - mx);
+        l += p;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) a16[c] = fmaf(p, vj[c], a16[c]);
+      }
+      const float il = 1.f / l;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) o[16 * h + c] = a16[c] * il;
+      if (t == 0) { sq0[RS_ST + h] = mx; sq0[RS_ST + 4 + h] = il; }
+    }
+    if (act) store_row64(O + n * D, o);
+    if (attn_out) {
+      __syncthreads();
+      if (act) {
+        float pm = 0.f;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float* kj = sk + (size_t)t * D + 16 * h;
+          float s = 0.f;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) s = fmaf(sq0[RS_Q0 + 16 * h + c], kj[c], s);
+          pm += __expf(s - sq0[RS_ST + h]) * sq0[RS_ST + 4 + h];
+        }
+        attn_out[(size_t)r * attn_stride + t] = 0.25f * pm;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <typename K>
 int set_smem(K kern, size_t bytes, const char* name) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -521,13 +692,72 @@ extern "C" int nfb_gnt_param_offset(int depth, const char* name) {
 }
 
 extern "C" size_t nfb_gnt_workspace_bytes(int R, int S, int V) {
+  // F[rows][64] + q[N][64]  |  tensor-core form in addition: k, v [rows][64] and five per-sample [N][64] buffers
   if (R <= 0 || S < 1 || V < 1) return 0;
-  return ((size_t)R * S * V * D + (size_t)R * S * D) * sizeof(float);
+  return ((size_t)R * S * V * D * 3 + (size_t)R * S * D * 6) * sizeof(float);
+}
+
+template <int NPASS>
+static int gnt_layer_tc(int i, int R, int S, int V, const float* ray_diff, const float* mask, const float* pts, const float* ray_d,
+                        const float* lp, float* F, float* q, float* ws, float* attn_out, int out_stride, int rpc, int ray_grid,
+                        int ray_block, int sms, cudaStream_t st) {
+  using namespace gnttc;
+  const int N = R * S;
+  const size_t rows = (size_t)N * V;
+  float* Kv = ws;                       // [rows][64]
+  float* Vv = Kv + rows * D;            // [rows][64]
+  float* b0 = Vv + rows * D;            // five [N][64] per-sample buffers
+  float* b1 = b0 + (size_t)N * D;
+  float* b2 = b1 + (size_t)N * D;
+  float* b3 = b2 + (size_t)N * D;
+  int rc;
+  // ---- view transformer: qq = q_fc(LN(q)); k = k_fc(F), v = v_fc(k); core; q = out_fc(x) + b + q; FFN
+  LinArgs a{};
+  a.M = N; a.x = q; a.y0 = b0; a.w[0] = lp + L_V_Q; a.ln_w = lp + L_V_LN1_W; a.ln_b = lp + L_V_LN1_B;
+  if ((rc = launch_lin<NPASS, LIN_PRE>(a, st, "k_gnt_lin_tc<pre>"))) return rc;
+  a = LinArgs{};
+  a.M = (long long)rows; a.x = F; a.y0 = Kv; a.y1 = Vv; a.w[0] = lp + L_V_K; a.w[1] = lp + L_V_V;
+  if ((rc = launch_lin<NPASS, LIN_KV>(a, st, "k_gnt_lin_tc<kv>"))) return rc;
+  {
+    int g = (N + 127) / 128;
+    if (g > sms * 4) g = sms * 4;
+    k_gnt_view_core<<<g, 128, 0, st>>>(N, V, b0, Kv, Vv, ray_diff, mask, lp, b1);
+    NFB_CHECK_LAUNCH("k_gnt_view_core");
+  }
+  a = LinArgs{};
+  a.M = N; a.x = b1; a.res = q; a.y0 = q; a.w[0] = lp + L_V_O_W; a.b0 = lp + L_V_O_B;
+  if ((rc = launch_lin<NPASS, LIN_POST>(a, st, "k_gnt_lin_tc<post>"))) return rc;
+  a = LinArgs{};
+  a.M = N; a.x = q; a.y0 = q; a.w[0] = lp + L_V_FF1_W; a.w[1] = lp + L_V_FF2_W; a.b0 = lp + L_V_FF1_B; a.b1 = lp + L_V_FF2_B;
+  a.ln_w = lp + L_V_LN2_W; a.ln_b = lp + L_V_LN2_B;
+  if ((rc = launch_lin<NPASS, LIN_FFN>(a, st, "k_gnt_lin_tc<ffn>"))) return rc;
+  if ((i & 1) == 0) {
+    int g = (N + 127) / 128;
+    if (g > sms * 3) g = sms * 3;
+    k_gnt_qfc<<<g, 128, (size_t)QS_TOTAL * sizeof(float), st>>>(N, S, pts, ray_d, lp, q);
+    NFB_CHECK_LAUNCH("k_gnt_qfc");
+  }
+  // ---- ray transformer: Q, K, V = projections of LN(q); core; q = out_fc(o) + b + q; FFN
+  a = LinArgs{};
+  a.M = N; a.x = q; a.y0 = b0; a.y1 = b1; a.y2 = b2; a.w[0] = lp + L_R_Q; a.w[1] = lp + L_R_K; a.w[2] = lp + L_R_V;
+  a.ln_w = lp + L_R_LN1_W; a.ln_b = lp + L_R_LN1_B;
+  if ((rc = launch_lin<NPASS, LIN_QKV>(a, st, "k_gnt_lin_tc<qkv>"))) return rc;
+  k_gnt_ray_core<<<ray_grid, ray_block * rpc, (size_t)rpc * (2 * S * D + RS_PER_RAY) * sizeof(float), st>>>(
+      R, S, rpc, b0, b1, b2, b3, attn_out, out_stride);
+  NFB_CHECK_LAUNCH("k_gnt_ray_core");
+  a = LinArgs{};
+  a.M = N; a.x = b3; a.res = q; a.y0 = q; a.w[0] = lp + L_R_O_W; a.b0 = lp + L_R_O_B;
+  if ((rc = launch_lin<NPASS, LIN_POST>(a, st, "k_gnt_lin_tc<post>"))) return rc;
+  a = LinArgs{};
+  a.M = N; a.x = q; a.y0 = q; a.w[0] = lp + L_R_FF1_W; a.w[1] = lp + L_R_FF2_W; a.b0 = lp + L_R_FF1_B; a.b1 = lp + L_R_FF2_B;
+  a.ln_w = lp + L_R_LN2_W; a.ln_b = lp + L_R_LN2_B;
+  return launch_lin<NPASS, LIN_FFN>(a, st, "k_gnt_lin_tc<ffn>");
 }
 
 extern "C" int nfb_gnt_fwd(int R, int S, int V, int depth, int ret_alpha, const float* rgb_feat, const float* ray_diff,
                            const float* mask, const float* pts, const float* ray_d, const float* params, float* out,
-                           void* workspace, size_t workspace_bytes, void* stream) {
+                           void* workspace, size_t workspace_bytes, int precision, void* stream) {
+  NFB_REQUIRE(precision >= NFB_PREC_FP32 && precision <= NFB_PREC_BF16, NFB_EINVAL, "nfb_gnt_fwd: bad precision %d", precision);
   NFB_REQUIRE(R >= 0 && S >= 1 && V >= 1 && depth >= 1, NFB_EINVAL, "nfb_gnt_fwd: bad arguments (R=%d S=%d V=%d depth=%d)", R, S, V, depth);
   NFB_REQUIRE(S <= NFB_MAX_SAMPLES, NFB_EUNSUPPORTED, "nfb_gnt_fwd: S=%d > %d samples per ray", S, NFB_MAX_SAMPLES);
   NFB_REQUIRE(V <= NFB_MAX_VIEWS, NFB_EUNSUPPORTED, "nfb_gnt_fwd: V=%d > %d views", V, NFB_MAX_VIEWS);
@@ -566,6 +796,7 @@ extern "C" int nfb_gnt_fwd(int R, int S, int V, int depth, int ret_alpha, const 
   if ((rc = set_smem(k_gnt_qfc, sm_qfc, "k_gnt_qfc"))) return rc;
   if ((rc = set_smem(k_gnt_ray_attn, sm_ray, "k_gnt_ray_attn"))) return rc;
   if ((rc = set_smem(k_gnt_head, sm_head, "k_gnt_head"))) return rc;
+  if ((rc = set_smem(k_gnt_ray_core, sm_ray, "k_gnt_ray_core"))) return rc;
   auto grid_for = [&](int per_sm) {
     int g = (N + 127) / 128;
     if (g > sms * per_sm) g = sms * per_sm;
@@ -584,6 +815,15 @@ extern "C" int nfb_gnt_fwd(int R, int S, int V, int depth, int ret_alpha, const 
   const int out_stride = ret_alpha ? 3 + S : 3;
   for (int i = 0; i < depth; ++i) {
     const float* lp = params + G_HEAD + (size_t)i * L_SIZE;
+    if (precision != NFB_PREC_FP32) {
+      float* ws = q + (size_t)N * D;
+      float* attn = (ret_alpha && i == depth - 1) ? out + 3 : nullptr;
+      rc = precision == NFB_PREC_BF16
+               ? gnt_layer_tc<1>(i, R, S, V, ray_diff, mask, pts, ray_d, lp, F, q, ws, attn, out_stride, rpc, ray_grid, ray_block, sms, st)
+               : gnt_layer_tc<3>(i, R, S, V, ray_diff, mask, pts, ray_d, lp, F, q, ws, attn, out_stride, rpc, ray_grid, ray_block, sms, st);
+      if (rc) return rc;
+      continue;
+    }
     k_gnt_view_attn<<<grid_for(3), 128, sm_view, st>>>(N, V, F, ray_diff, mask, lp, q);
     NFB_CHECK_LAUNCH("k_gnt_view_attn");
     k_gnt_ffn<<<ffn_grid, 256, sm_ffn, st>>>(N, lp + L_V_LN2_W, q);

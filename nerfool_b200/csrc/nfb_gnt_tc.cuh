@@ -1,0 +1,289 @@
+// GNT dense layers on the 5th-generation tensor cores (tcgen05 + TMEM): one generic kernel for every 64-wide linear
+// layer of the GNT network (gnt/transformer_network.py), in the operand scheme of nfb_view_tc.cuh:
+//   * one thread per row (a (sample, view) row or a sample), 128-row groups = one M = 128 MMA tile,
+//   * the thread writes its (optionally LayerNorm-ed) input row as bf16 hi / lo halves into TMEM (A operand),
+//   * one thread of the group issues the K/16 MMAs against 64 x 64 weight tiles resident in shared memory
+//     (canonical no-swizzle K-major layout) and commits to the group's mbarrier,
+//   * every thread reads its fp32 accumulator row back for bias / ReLU / residual and stores it to HBM.
+// NPASS = 3: x = hi + lo split of activations and weights, D = hi*hi + lo*hi + hi*lo in fp32 (fp32-equivalent);
+// NPASS = 1: plain bf16 operands.
+//
+// Modes (what one launch computes per row; every weight is a 64 x 64 tile, torch layout [out][in]):
+//   LIN_PRE   y0 = W0 LN(x)                                   view attention: qq = q_fc(attn_norm(q))
+//   LIN_KV    y0 = W0 x ; y1 = W1 y0                          view attention: k = k_fc(F), v = v_fc(k)   (per (sample, view) row)
+//   LIN_QKV   y0 = W0 LN(x) ; y1 = W1 LN(x) ; y2 = W2 LN(x)   ray attention:  q, k, v projections
+//   LIN_POST  y0 = W0 x + b + res                             out_fc + residual (view and ray attention)
+//   LIN_FFN   y0 = W2 ReLU(W1 LN(x) + b1) + b2 + x            feed-forward block: fc1 [256][64] = 4 N-chunks, fc2 [64][256] = 4 K-chunks
+#pragma once
+#include "nfb_common.cuh"
+#include "nfb_tc.cuh"
+
+namespace gnttc {
+using namespace nfbtc;
+
+constexpr int GROUP = 128;
+constexpr int TD = 64;                           // tile edge = netwidth
+constexpr int TILE_BYTES = TD * TD * 2;          // one bf16 64 x 64 tile
+enum : int { LIN_PRE = 0, LIN_KV = 1, LIN_QKV = 2, LIN_POST = 3, LIN_FFN = 4 };
+
+__host__ __device__ constexpr int mode_tiles(int mode) { return mode == LIN_PRE || mode == LIN_POST ? 1 : mode == LIN_KV ? 2 : mode == LIN_QKV ? 3 : 8; }
+__host__ __device__ constexpr int mode_groups(int mode) { return mode == LIN_FFN ? 2 : 4; }       // FFN needs 256 TMEM columns per group
+__host__ __device__ constexpr int mode_cols(int mode) { return mode == LIN_FFN ? 256 : 128; }
+// TMEM columns of a group: D0 [0,64) | A hi [64,96) | A lo [96,128) | FFN only: D1 [128,192) | A2 hi [192,224) | A2 lo [224,256)
+constexpr int C_D0 = 0, C_A = 64, C_ALO = 96, C_D1 = 128, C_A2 = 192, C_A2LO = 224;
+
+struct LinArgs {
+  long long M;                 // rows
+  const float* x;              // [M][64] input rows
+  const float* res;            // LIN_POST: residual rows [M][64]
+  float* y0; float* y1; float* y2;
+  const float* w[3];           // 64 x 64 tiles (LIN_FFN: w[0] = fc1 [256][64], w[1] = fc2 [64][256])
+  const float* b0;             // LIN_POST: bias [64]; LIN_FFN: fc1 bias [256]
+  const float* b1;             // LIN_FFN: fc2 bias [64]
+  const float* ln_w; const float* ln_b;   // LayerNorm of the input (LIN_PRE, LIN_QKV, LIN_FFN), eps 1e-6
+};
+
+template <int NPASS, int MODE>
+__host__ __device__ constexpr size_t lin_smem_bytes() {
+  return (size_t)mode_tiles(MODE) * TILE_BYTES * (NPASS == 3 ? 2 : 1) + sizeof(float) * (256 + 64 + 128) + mode_groups(MODE) * 8 + 16;
+}
+
+__host__ __device__ constexpr uint32_t canon_off(int n, int k) {      // element (n, k) of a [64][64] K-major tile
+  return (uint32_t)((k >> 3) * (TD * 16) + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2);
+}
+
+// w: element (n, k) at w[n * ldw + k]
+template <int NPASS>
+static __device__ void load_tile64(uint8_t* hi, uint8_t* lo, const float* __restrict__ w, int ldw, int tid, int nt) {
+  for (int i = tid; i < TD * TD; i += nt) {
+    const int n = i >> 6, k = i & 63;
+    const float v = __ldg(w + (size_t)n * ldw + k);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const uint32_t off = canon_off(n, k);
+    *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
+    if (NPASS == 3) *reinterpret_cast<__nv_bfloat16*>(lo + off) = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// this thread's 64-value row -> A operand (4 K-chunks of 16) at column base ca (hi) / calo (lo)
+template <int NPASS>
+__device__ __forceinline__ void a_store_row(uint32_t tl, int ca, int calo, const float (&v)[TD]) {
+#pragma unroll
+  for (int kc = 0; kc < 4; ++kc) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (NPASS == 3) split_bf16(v[16 * kc + 2 * j], v[16 * kc + 2 * j + 1], hi[j], lo[j]);
+      else hi[j] = pack_bf16(v[16 * kc + 2 * j], v[16 * kc + 2 * j + 1]);
+    }
+    tmem_st8(tl + ca + 8 * kc, hi);
+    if (NPASS == 3) tmem_st8(tl + calo + 8 * kc, lo);
+  }
+}
+
+// D[dcol .. dcol+64) (+)= A[64 values at ca / calo] x tile^T ; one thread
+template <int NPASS>
+__device__ __forceinline__ void issue_tile(uint32_t tb, int dcol, int ca, int calo, uint32_t tile_hi, uint32_t tile_lo, bool acc0) {
+  constexpr uint32_t idesc = idesc_bf16(128, TD);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint64_t dh = smem_desc(tile_hi + ks * 2 * TD * 16, TD * 16, 128);
+    mma_ts(tb + dcol, tb + ca + 8 * ks, dh, idesc, acc0 || ks > 0);
+    if (NPASS == 3) {
+      const uint64_t dl = smem_desc(tile_lo + ks * 2 * TD * 16, TD * 16, 128);
+      mma_ts(tb + dcol, tb + calo + 8 * ks, dh, idesc, true);
+      mma_ts(tb + dcol, tb + ca + 8 * ks, dl, idesc, true);
+    }
+  }
+}
+
+__device__ __forceinline__ void d_load_row(uint32_t tl, int dcol, float (&y)[TD]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float t[16];
+    tmem_ld16(tl + dcol + 16 * c, t);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[16 * c + j] = t[j];
+  }
+}
+
+__device__ __forceinline__ void row_load(const float* __restrict__ p, float (&x)[TD]) {
+#pragma unroll
+  for (int c = 0; c < TD; c += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p + c));
+    x[c] = t.x; x[c + 1] = t.y; x[c + 2] = t.z; x[c + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void row_store(float* __restrict__ p, const float (&x)[TD]) {
+#pragma unroll
+  for (int c = 0; c < TD; c += 4) *reinterpret_cast<float4*>(p + c) = make_float4(x[c], x[c + 1], x[c + 2], x[c + 3]);
+}
+__device__ __forceinline__ void row_layer_norm(float (&x)[TD], const float* __restrict__ w, const float* __restrict__ b) {
+  float mu = 0.f;
+#pragma unroll
+  for (int c = 0; c < TD; ++c) mu += x[c];
+  mu *= (1.f / TD);
+  float var = 0.f;
+#pragma unroll
+  for (int c = 0; c < TD; ++c) var = fmaf(x[c] - mu, x[c] - mu, var);
+  var *= (1.f / TD);
+  const float rstd = 1.f / sqrtf(var + 1e-6f);
+#pragma unroll
+  for (int c = 0; c < TD; ++c) x[c] = fmaf((x[c] - mu) * rstd, w[c], b[c]);
+}
+
+#define GNT_TC_ISSUE(DCOL, CA, CALO, TILE, ACC0)                                                        \
+  do {                                                                                                  \
+    tmem_st_wait();                                                                                     \
+    fence_before_sync();                                                                                \
+    named_bar_sync(bar_id, GROUP);                                                                      \
+    if (tg == 0) {                                                                                      \
+      fence_after_sync();                                                                               \
+      issue_tile<NPASS>(tb, DCOL, CA, CALO, sB_addr + (TILE) * TILE_BYTES, sB_addr + (NT + (TILE)) * TILE_BYTES, ACC0); \
+      mma_commit(mbar);                                                                                 \
+    }                                                                                                   \
+  } while (0)
+#define GNT_TC_WAIT()          \
+  do {                         \
+    mbar_wait(mbar, phase);    \
+    phase ^= 1u;               \
+    fence_after_sync();        \
+  } while (0)
+
+template <int NPASS, int MODE>
+__global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(LinArgs a) {
+  constexpr int NG = mode_groups(MODE), GC = mode_cols(MODE), NT = mode_tiles(MODE);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sB = smem_raw;                                                    // NT hi tiles, then NT lo tiles
+  float* sf = reinterpret_cast<float*>(smem_raw + (size_t)NT * TILE_BYTES * (NPASS == 3 ? 2 : 1));
+  float* s_b0 = sf;            // 256
+  float* s_b1 = sf + 256;      // 64
+  float* s_ln = sf + 320;      // 64 + 64
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(sf + 448);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + NG);
+
+  const int tid = threadIdx.x, warp = tid >> 5, nt = blockDim.x;
+  const int grp = tid / GROUP, tg = tid % GROUP;
+  const int bar_id = 1 + grp;
+  uint64_t* mbar = s_bar + grp;
+
+  if (warp == 0) tmem_alloc(s_tmem, NG * GC);
+  if (tid == 0) {
+    for (int g = 0; g < NG; ++g) mbar_init(s_bar + g, 1);
+    mbar_init_fence();
+  }
+  if (MODE == LIN_FFN) {
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      load_tile64<NPASS>(sB + j * TILE_BYTES, sB + (NT + j) * TILE_BYTES, a.w[0] + (size_t)j * TD * TD, TD, tid, nt);        // fc1 rows 64j..
+      load_tile64<NPASS>(sB + (4 + j) * TILE_BYTES, sB + (NT + 4 + j) * TILE_BYTES, a.w[1] + j * TD, 4 * TD, tid, nt);         // fc2 cols 64j..
+    }
+    for (int i = tid; i < 256; i += nt) s_b0[i] = __ldg(a.b0 + i);
+    for (int i = tid; i < 64; i += nt) s_b1[i] = __ldg(a.b1 + i);
+  } else {
+#pragma unroll 1
+    for (int j = 0; j < NT; ++j) load_tile64<NPASS>(sB + j * TILE_BYTES, sB + (NT + j) * TILE_BYTES, a.w[j], TD, tid, nt);
+    if (MODE == LIN_POST)
+      for (int i = tid; i < 64; i += nt) s_b0[i] = __ldg(a.b0 + i);
+  }
+  if (MODE == LIN_PRE || MODE == LIN_QKV || MODE == LIN_FFN)
+    for (int i = tid; i < 64; i += nt) { s_ln[i] = __ldg(a.ln_w + i); s_ln[64 + i] = __ldg(a.ln_b + i); }
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+
+  const uint32_t tb = *s_tmem + (uint32_t)(grp * GC);
+  const uint32_t tl = tb + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t sB_addr = smem_u32(sB);
+  uint32_t phase = 0;
+  const long long ntiles = (a.M + GROUP - 1) / GROUP;
+
+  for (long long tile = (long long)blockIdx.x * NG + grp; tile < ntiles; tile += (long long)gridDim.x * NG) {
+    const long long row = tile * GROUP + tg;
+    const bool active = row < a.M;
+    float x[TD];
+    if (active) row_load(a.x + row * TD, x);
+    else {
+#pragma unroll
+      for (int c = 0; c < TD; ++c) x[c] = 0.f;
+    }
+    if (MODE == LIN_PRE || MODE == LIN_QKV) row_layer_norm(x, s_ln, s_ln + 64);
+    if (MODE == LIN_FFN) {
+      float xn[TD];
+#pragma unroll
+      for (int c = 0; c < TD; ++c) xn[c] = x[c];
+      row_layer_norm(xn, s_ln, s_ln + 64);
+      a_store_row<NPASS>(tl, C_A, C_ALO, xn);
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        GNT_TC_ISSUE(C_D0, C_A, C_ALO, j, false);                 // h_j = fc1[64j .. 64j+64) . LN(x)
+        GNT_TC_WAIT();
+        float h[TD];
+        d_load_row(tl, C_D0, h);
+#pragma unroll
+        for (int c = 0; c < TD; ++c) h[c] = fmaxf(h[c] + s_b0[64 * j + c], 0.f);
+        a_store_row<NPASS>(tl, C_A2, C_A2LO, h);
+        GNT_TC_ISSUE(C_D1, C_A2, C_A2LO, 4 + j, j > 0);           // y += fc2[:, 64j .. 64j+64) . h_j
+        GNT_TC_WAIT();
+      }
+      float y[TD];
+      d_load_row(tl, C_D1, y);
+#pragma unroll
+      for (int c = 0; c < TD; ++c) y[c] += s_b1[c] + x[c];
+      if (active) row_store(a.y0 + row * TD, y);
+    } else {
+      a_store_row<NPASS>(tl, C_A, C_ALO, x);
+      GNT_TC_ISSUE(C_D0, C_A, C_ALO, 0, false);
+      GNT_TC_WAIT();
+      float y[TD];
+      d_load_row(tl, C_D0, y);
+      if (MODE == LIN_POST) {
+        float r[TD];
+        if (active) row_load(a.res + row * TD, r);
+#pragma unroll
+        for (int c = 0; c < TD; ++c) y[c] += s_b0[c] + (active ? r[c] : 0.f);
+      }
+      if (active) row_store(a.y0 + row * TD, y);
+      if (MODE == LIN_KV) {
+        a_store_row<NPASS>(tl, C_A, C_ALO, y);                     // v = v_fc(k): the projected k is the next input
+        GNT_TC_ISSUE(C_D0, C_A, C_ALO, 1, false);
+        GNT_TC_WAIT();
+        d_load_row(tl, C_D0, y);
+        if (active) row_store(a.y1 + row * TD, y);
+      }
+      if (MODE == LIN_QKV) {
+        GNT_TC_ISSUE(C_D0, C_A, C_ALO, 1, false);                  // A (LN(x)) is unchanged
+        GNT_TC_WAIT();
+        d_load_row(tl, C_D0, y);
+        if (active) row_store(a.y1 + row * TD, y);
+        GNT_TC_ISSUE(C_D0, C_A, C_ALO, 2, false);
+        GNT_TC_WAIT();
+        d_load_row(tl, C_D0, y);
+        if (active) row_store(a.y2 + row * TD, y);
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(*s_tmem, NG * GC);
+}
+
+template <int NPASS, int MODE>
+int launch_lin(const LinArgs& a, cudaStream_t st, const char* name) {
+  constexpr size_t smem = lin_smem_bytes<NPASS, MODE>();
+  cudaError_t e = cudaFuncSetAttribute(k_gnt_lin_tc<NPASS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return nfb_set_error(NFB_ECUDA, "%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
+  constexpr int NG = mode_groups(MODE);
+  const long long ntiles = (a.M + GROUP - 1) / GROUP;
+  long long grid = (ntiles + NG - 1) / NG;
+  const int cap = nfb_num_sms();
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  k_gnt_lin_tc<NPASS, MODE><<<(int)grid, GROUP * NG, smem, st>>>(a);
+  NFB_CHECK_LAUNCH(name);
+  return NFB_OK;
+}
+
+}  // namespace gnttc

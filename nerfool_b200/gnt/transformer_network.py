@@ -152,5 +152,5 @@ class GNT(nn.Module):
         ws = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
         with torch.cuda.device(dev):
             call('nfb_gnt_fwd', R, S, V, self.depth, int(bool(self.ret_alpha)), ptr(rf), ptr(rd), ptr(mk), ptr(pt), ptr(dd),
-                 ptr(self.param_blob()), ptr(out), ptr(ws), ctypes.c_size_t(nbytes), stream_ptr(dev))
+                 ptr(self.param_blob()), ptr(out), ptr(ws), ctypes.c_size_t(nbytes), _lib.precision_code(), stream_ptr(dev))
         return out

@@ -357,8 +357,8 @@ def test_gnt_module_interface_and_blob_layout():
     blob = pack_params(p, 2)
     for n, o in lay:
         assert torch.equal(blob[o:o + p[n].numel()], p[n].reshape(-1))
-    assert lib.nfb_gnt_param_offset(2, b'no.such.tensor') == -1 and lib.nfb_gnt_workspace_bytes(2, 3, 4) == (2 * 3 * 4 * 64 + 2 * 3 * 64) * 4
+    assert lib.nfb_gnt_param_offset(2, b'no.such.tensor') == -1 and lib.nfb_gnt_workspace_bytes(2, 3, 4) == (3 * 2 * 3 * 4 * 64 + 6 * 2 * 3 * 64) * 4
     with pytest.raises(NotImplementedError):
         GNT(types.SimpleNamespace(netwidth=32, trans_depth=2), 32, 63, 63, True)
     with pytest.raises(RuntimeError, match='workspace'):
-        _lib.call('nfb_gnt_fwd', 1, 4, 2, 2, 1, *[_lib.c_void_p(16)] * 8, _lib.ctypes.c_size_t(0), None)
+        _lib.call('nfb_gnt_fwd', 1, 4, 2, 2, 1, *[_lib.c_void_p(16)] * 8, _lib.ctypes.c_size_t(0), 1, None)
