@@ -579,7 +579,9 @@ def run_gnt(a):
         fl = gnt_flops_per_ray(GNT_SAMPLES, GNT_VIEWS, GNT_DEPTH) * R
         ach = fl / (net_ms * 1e-3) / 1e12 if net_ms else None
         # nfb_gnt_fwd launches 3 + depth * 4.5 kernels per call: count them for gpu_launches
-        per_call = 3 + GNT_DEPTH * 4 + (GNT_DEPTH + 1) // 2
+        # fp32 form: 4 kernels per layer; tensor-core form: 9 (pre, k/v, view core, post, FFN, qkv, ray core, post, FFN)
+        per_layer = 4 if _lib.get_precision() == 'fp32' else 9
+        per_call = 3 + GNT_DEPTH * per_layer + (GNT_DEPTH + 1) // 2
         n_calls = len(prof.get('nfb_gnt_fwd', []))
         out = {'metric': 'rays/s', 'value': R * world / (ms_per_step * 1e-3), 'unit': 'rays/s', 'n_gpus': world, 'steps': a.steps,
                'warmup': a.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -587,14 +589,17 @@ def run_gnt(a):
                'config': {'workload': f'BASELINE configs[4]: GNT forward render of one {H}x{W} view (all {R} rays), {GNT_VIEWS} source views, '
                                       f'{GNT_SAMPLES} samples, trans_depth {GNT_DEPTH}, netwidth 64, ret_alpha, single_net, N_importance 0, '
                                       'random-init weights', 'rays_per_step_per_gpu': R, 'source_views': GNT_VIEWS,
-                          'max_rays_per_launch': chunk, 'arithmetic': 'fp32 CUDA-core kernels (first form of the GNT path)',
+                          'max_rays_per_launch': chunk,
+                          'arithmetic': ('fp32 CUDA-core kernels' if _lib.get_precision() == 'fp32' else
+                                         f'{_lib.get_precision()}: every 64-wide linear layer on tcgen05 (bf16 hi+lo split operands, fp32 accumulate '
+                                         '= fp32-equivalent), attention cores / positional q_fc on the CUDA cores'),
                           'parallelism': f'one target view per GPU x{world}, no collective (render)' if world > 1 else 'single GPU',
                           'l2': 'per-chunk working set (projected view features, ~2 GB) >> 126 MB L2'},
                'roofline': {'bound': 'tensor', 'kernel': 'nfb_gnt_fwd (all kernels of the GNT network, one C-ABI call)',
                             'achieved': ach, 'peak': tensor_peak, 'unit': 'TFLOP/s', 'frac': (ach / tensor_peak) if ach and tensor_peak else None,
                             'traffic': None, 'avg_launch_ms': net_ms / max(n_calls / a.steps, 1),
-                            'note': 'algorithmic FLOPs = SURVEY.md Appendix B formula (101 MFLOP/ray at depth 4, S 64, V 8); the kernels '
-                                    'run on the CUDA cores in this round, so the fraction of the bf16 tensor peak is the distance to go'},
+                            'note': 'algorithmic FLOPs = SURVEY.md Appendix B formula (101 MFLOP/ray at depth 4, S 64, V 8), useful FLOPs only '
+                                    '(not the 3x of the split passes); the unfused linear kernels are HBM-bound (rows in / out per layer)'},
                'kernel_ms_per_step': ktot,
                'e2e': {'value': R * world / (e2e_ms / a.steps * 1e-3), 'unit': 'rays/s',
                        'h2d_bytes_per_step': sum(v.numel() * v.element_size() for v in host.values()), 'd2h_bytes_per_step': 4,

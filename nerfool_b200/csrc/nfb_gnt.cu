@@ -488,10 +488,13 @@ __global__ void __launch_bounds__(256) k_gnt_head(int R, int S, const float* __r
 enum : int { CS_P0 = 0 /*[4][8]*/, CS_P0_B = 32, CS_P2 = 40 /*[8][64]*/, CS_P2_B = CS_P2 + 8 * D, CS_A0 = CS_P2_B + D /*[64][8]*/,
              CS_A0_B = CS_A0 + D * 8, CS_A2 = CS_A0_B + 8 /*[8][64]*/, CS_A2_B = CS_A2 + 8 * D, CS_TOTAL = CS_A2_B + D };
 
+// Two adjacent lanes share a sample: each owns 32 of the 64 channels (softmax state, pos, a), the 64-term sums of
+// attn_fc.0 are completed with one shuffle -- half the registers per thread, twice the threads.
 __global__ void __launch_bounds__(128) k_gnt_view_core(int N, int V, const float* __restrict__ qq, const float* __restrict__ Kv,
                                                         const float* __restrict__ Vv, const float* __restrict__ ray_diff,
                                                         const float* __restrict__ mask, const float* __restrict__ lp,
                                                         float* __restrict__ xout) {
+  constexpr int HC = D / 2;
   __shared__ __align__(16) float sm[CS_TOTAL];
   const int t = threadIdx.x, nt = blockDim.x;
   load_wt_transposed(sm + CS_P0, lp + L_V_POS0_W, 8, 4, 8, t, nt);
@@ -503,15 +506,24 @@ __global__ void __launch_bounds__(128) k_gnt_view_core(int N, int V, const float
   load_wt_transposed(sm + CS_A2, lp + L_V_AT2_W, D, 8, D, t, nt);
   load_vec_padded(sm + CS_A2_B, lp + L_V_AT2_B, D, D, t, nt);
   __syncthreads();
-  for (int n = blockIdx.x * blockDim.x + t; n < N; n += gridDim.x * blockDim.x) {
-    float qv[D];
-    load_row64(qq + (size_t)n * D, qv);
-    float m[D], l[D], acc[D];
+  const int half = t & 1, c0 = half * HC;
+  // every thread of a warp runs the same number of iterations (the pair exchanges with a full-warp shuffle)
+  for (int base = blockIdx.x * (blockDim.x / 2); base < N; base += gridDim.x * (blockDim.x / 2)) {
+    const int n = base + (t >> 1);
+    const bool act = n < N;
+    const int ns = act ? n : 0;
+    float qv[HC];
 #pragma unroll
-    for (int c = 0; c < D; ++c) { m[c] = -3.4e38f; l[c] = 0.f; acc[c] = 0.f; }
+    for (int c = 0; c < HC; c += 4) {
+      const float4 q4 = __ldg(reinterpret_cast<const float4*>(qq + (size_t)ns * D + c0 + c));
+      qv[c] = q4.x; qv[c + 1] = q4.y; qv[c + 2] = q4.z; qv[c + 3] = q4.w;
+    }
+    float m[HC], l[HC], acc[HC];
+#pragma unroll
+    for (int c = 0; c < HC; ++c) { m[c] = -3.4e38f; l[c] = 0.f; acc[c] = 0.f; }
     for (int v = 0; v < V; ++v) {
-      const size_t row = (size_t)n * V + v;
-      float pos[D];
+      const size_t row = (size_t)ns * V + v;
+      float pos[HC];
       {
         const float4 rd4 = __ldg(reinterpret_cast<const float4*>(ray_diff) + row);
         const float rd[4] = {rd4.x, rd4.y, rd4.z, rd4.w};
@@ -520,39 +532,44 @@ __global__ void __launch_bounds__(128) k_gnt_view_core(int N, int V, const float
         dense_acc<4, 8>(sm + CS_P0, rd, p8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) p8[j] = fmaxf(p8[j], 0.f);
-        load_bias<D>(pos, sm + CS_P2_B);
-        dense_acc<8, D>(sm + CS_P2, p8, pos);
+        load_bias<HC>(pos, sm + CS_P2_B + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) axpy_row<HC>(pos, p8[j], sm + CS_P2 + j * D + c0);
       }
       float a8[8];
-      load_bias<8>(a8, sm + CS_A0_B);
-      const float4* kr = reinterpret_cast<const float4*>(Kv + row * D);
 #pragma unroll
-      for (int c = 0; c < D; c += 4) {
+      for (int j = 0; j < 8; ++j) a8[j] = 0.f;
+      const float4* kr = reinterpret_cast<const float4*>(Kv + row * D + c0);
+#pragma unroll
+      for (int c = 0; c < HC; c += 4) {
         const float4 k4 = __ldg(kr + c / 4);
-        axpy_row<8>(a8, k4.x - qv[c] + pos[c], sm + CS_A0 + c * 8);
-        axpy_row<8>(a8, k4.y - qv[c + 1] + pos[c + 1], sm + CS_A0 + (c + 1) * 8);
-        axpy_row<8>(a8, k4.z - qv[c + 2] + pos[c + 2], sm + CS_A0 + (c + 2) * 8);
-        axpy_row<8>(a8, k4.w - qv[c + 3] + pos[c + 3], sm + CS_A0 + (c + 3) * 8);
+        axpy_row<8>(a8, k4.x - qv[c] + pos[c], sm + CS_A0 + (c0 + c) * 8);
+        axpy_row<8>(a8, k4.y - qv[c + 1] + pos[c + 1], sm + CS_A0 + (c0 + c + 1) * 8);
+        axpy_row<8>(a8, k4.z - qv[c + 2] + pos[c + 2], sm + CS_A0 + (c0 + c + 2) * 8);
+        axpy_row<8>(a8, k4.w - qv[c + 3] + pos[c + 3], sm + CS_A0 + (c0 + c + 3) * 8);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a8[j] = fmaxf(a8[j], 0.f);
+      for (int j = 0; j < 8; ++j) {
+        a8[j] += __shfl_xor_sync(0xffffffffu, a8[j], 1);            // the other half of the 64-term sum
+        a8[j] = fmaxf(a8[j] + sm[CS_A0_B + j], 0.f);
+      }
       const bool valid = __ldg(mask + row) != 0.f;
-      const float4* vr = reinterpret_cast<const float4*>(Vv + row * D);
+      const float4* vr = reinterpret_cast<const float4*>(Vv + row * D + c0);
 #pragma unroll
-      for (int c0 = 0; c0 < D; c0 += 16) {
+      for (int cc = 0; cc < HC; cc += 16) {
         float a[16];
-        load_bias<16>(a, sm + CS_A2_B + c0);
+        load_bias<16>(a, sm + CS_A2_B + c0 + cc);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) axpy_row<16>(a, a8[j], sm + CS_A2 + j * D + c0);
+        for (int j = 0; j < 8; ++j) axpy_row<16>(a, a8[j], sm + CS_A2 + j * D + c0 + cc);
         float vv[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 v4 = __ldg(vr + c0 / 4 + j);
+          const float4 v4 = __ldg(vr + cc / 4 + j);
           vv[4 * j] = v4.x; vv[4 * j + 1] = v4.y; vv[4 * j + 2] = v4.z; vv[4 * j + 3] = v4.w;
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int c = c0 + j;
+          const int c = cc + j;
           const float s = valid ? a[j] : -1e9f;
           const float mn = fmaxf(m[c], s);
           const float sc = __expf(m[c] - mn), e = __expf(s - mn);
@@ -562,9 +579,12 @@ __global__ void __launch_bounds__(128) k_gnt_view_core(int N, int V, const float
         }
       }
     }
+    if (act) {
 #pragma unroll
-    for (int c = 0; c < D; ++c) acc[c] = acc[c] / l[c];
-    store_row64(xout + (size_t)n * D, acc);
+      for (int c = 0; c < HC; c += 4)
+        *reinterpret_cast<float4*>(xout + (size_t)n * D + c0 + c) =
+            make_float4(acc[c] / l[c], acc[c + 1] / l[c + 1], acc[c + 2] / l[c + 2], acc[c + 3] / l[c + 3]);
+    }
   }
 }
 
@@ -719,8 +739,8 @@ static int gnt_layer_tc(int i, int R, int S, int V, const float* ray_diff, const
   a.M = (long long)rows; a.x = F; a.y0 = Kv; a.y1 = Vv; a.w[0] = lp + L_V_K; a.w[1] = lp + L_V_V;
   if ((rc = launch_lin<NPASS, LIN_KV>(a, st, "k_gnt_lin_tc<kv>"))) return rc;
   {
-    int g = (N + 127) / 128;
-    if (g > sms * 4) g = sms * 4;
+    int g = (N + 63) / 64;                      // 2 threads per sample
+    if (g > sms * 8) g = sms * 8;
     k_gnt_view_core<<<g, 128, 0, st>>>(N, V, b0, Kv, Vv, ray_diff, mask, lp, b1);
     NFB_CHECK_LAUNCH("k_gnt_view_core");
   }
@@ -779,10 +799,20 @@ extern "C" int nfb_gnt_fwd(int R, int S, int V, int depth, int ret_alpha, const 
   const size_t sm_embed = (size_t)(35 * D + D + D * D + D) * sizeof(float);
   if ((rc = set_smem(k_gnt_embed, sm_embed, "k_gnt_embed"))) return rc;
   {
-    size_t g = (rows + 127) / 128;
-    if (g > (size_t)sms * 8) g = (size_t)sms * 8;
-    k_gnt_embed<<<(int)g, 128, sm_embed, st>>>(rows, rgb_feat, params, F);
-    NFB_CHECK_LAUNCH("k_gnt_embed");
+    if (precision != NFB_PREC_FP32) {
+      // rgbfeat_fc as two tensor-core tiles (35 -> 64 zero-padded to K = 64, ReLU, 64 -> 64)
+      gnttc::LinArgs a{};
+      a.M = (long long)rows; a.x = rgb_feat; a.y0 = F; a.w[0] = params + G_RF0_W; a.w[1] = params + G_RF2_W;
+      a.b0 = params + G_RF0_B; a.b1 = params + G_RF2_B;
+      rc = precision == NFB_PREC_BF16 ? gnttc::launch_lin<1, gnttc::LIN_EMBED>(a, st, "k_gnt_lin_tc<embed>")
+                                      : gnttc::launch_lin<3, gnttc::LIN_EMBED>(a, st, "k_gnt_lin_tc<embed>");
+      if (rc) return rc;
+    } else {
+      size_t g = (rows + 127) / 128;
+      if (g > (size_t)sms * 8) g = (size_t)sms * 8;
+      k_gnt_embed<<<(int)g, 128, sm_embed, st>>>(rows, rgb_feat, params, F);
+      NFB_CHECK_LAUNCH("k_gnt_embed");
+    }
     size_t g2 = ((size_t)N * D + 255) / 256;
     if (g2 > (size_t)sms * 16) g2 = (size_t)sms * 16;
     k_gnt_qinit<<<(int)g2, 256, 0, st>>>((size_t)N * D, V, F, q);

@@ -14,6 +14,7 @@
 //   LIN_QKV   y0 = W0 LN(x) ; y1 = W1 LN(x) ; y2 = W2 LN(x)   ray attention:  q, k, v projections
 //   LIN_POST  y0 = W0 x + b + res                             out_fc + residual (view and ray attention)
 //   LIN_FFN   y0 = W2 ReLU(W1 LN(x) + b1) + b2 + x            feed-forward block: fc1 [256][64] = 4 N-chunks, fc2 [64][256] = 4 K-chunks
+//   LIN_EMBED y0 = W1 ReLU(W0 x35 + b0) + b1                   rgbfeat_fc on the 35-channel rows (W0 [64][35] zero-padded to K = 64)
 #pragma once
 #include "nfb_common.cuh"
 #include "nfb_tc.cuh"
@@ -24,9 +25,9 @@ using namespace nfbtc;
 constexpr int GROUP = 128;
 constexpr int TD = 64;                           // tile edge = netwidth
 constexpr int TILE_BYTES = TD * TD * 2;          // one bf16 64 x 64 tile
-enum : int { LIN_PRE = 0, LIN_KV = 1, LIN_QKV = 2, LIN_POST = 3, LIN_FFN = 4 };
+enum : int { LIN_PRE = 0, LIN_KV = 1, LIN_QKV = 2, LIN_POST = 3, LIN_FFN = 4, LIN_EMBED = 5 };
 
-__host__ __device__ constexpr int mode_tiles(int mode) { return mode == LIN_PRE || mode == LIN_POST ? 1 : mode == LIN_KV ? 2 : mode == LIN_QKV ? 3 : 8; }
+__host__ __device__ constexpr int mode_tiles(int mode) { return mode == LIN_PRE || mode == LIN_POST ? 1 : (mode == LIN_KV || mode == LIN_EMBED) ? 2 : mode == LIN_QKV ? 3 : 8; }
 __host__ __device__ constexpr int mode_groups(int mode) { return mode == LIN_FFN ? 2 : 4; }       // FFN needs 256 TMEM columns per group
 __host__ __device__ constexpr int mode_cols(int mode) { return mode == LIN_FFN ? 256 : 128; }
 // TMEM columns of a group: D0 [0,64) | A hi [64,96) | A lo [96,128) | FFN only: D1 [128,192) | A2 hi [192,224) | A2 lo [224,256)
@@ -54,10 +55,10 @@ __host__ __device__ constexpr uint32_t canon_off(int n, int k) {      // element
 
 // w: element (n, k) at w[n * ldw + k]
 template <int NPASS>
-static __device__ void load_tile64(uint8_t* hi, uint8_t* lo, const float* __restrict__ w, int ldw, int tid, int nt) {
+static __device__ void load_tile64(uint8_t* hi, uint8_t* lo, const float* __restrict__ w, int ldw, int tid, int nt, int k_real = TD) {
   for (int i = tid; i < TD * TD; i += nt) {
     const int n = i >> 6, k = i & 63;
-    const float v = __ldg(w + (size_t)n * ldw + k);
+    const float v = k < k_real ? __ldg(w + (size_t)n * ldw + k) : 0.f;
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     const uint32_t off = canon_off(n, k);
     *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
@@ -181,6 +182,10 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
     }
     for (int i = tid; i < 256; i += nt) s_b0[i] = __ldg(a.b0 + i);
     for (int i = tid; i < 64; i += nt) s_b1[i] = __ldg(a.b1 + i);
+  } else if (MODE == LIN_EMBED) {
+    load_tile64<NPASS>(sB, sB + NT * TILE_BYTES, a.w[0], NFB_ROW_CH, tid, nt, NFB_ROW_CH);
+    load_tile64<NPASS>(sB + TILE_BYTES, sB + (NT + 1) * TILE_BYTES, a.w[1], TD, tid, nt);
+    for (int i = tid; i < 64; i += nt) { s_b0[i] = __ldg(a.b0 + i); s_b1[i] = __ldg(a.b1 + i); }
   } else {
 #pragma unroll 1
     for (int j = 0; j < NT; ++j) load_tile64<NPASS>(sB + j * TILE_BYTES, sB + (NT + j) * TILE_BYTES, a.w[j], TD, tid, nt);
@@ -204,7 +209,10 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
     const long long row = tile * GROUP + tg;
     const bool active = row < a.M;
     float x[TD];
-    if (active) row_load(a.x + row * TD, x);
+    if (MODE == LIN_EMBED) {
+#pragma unroll
+      for (int c = 0; c < TD; ++c) x[c] = (active && c < NFB_ROW_CH) ? __ldg(a.x + row * NFB_ROW_CH + c) : 0.f;
+    } else if (active) row_load(a.x + row * TD, x);
     else {
 #pragma unroll
       for (int c = 0; c < TD; ++c) x[c] = 0.f;
@@ -244,6 +252,16 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
         if (active) row_load(a.res + row * TD, r);
 #pragma unroll
         for (int c = 0; c < TD; ++c) y[c] += s_b0[c] + (active ? r[c] : 0.f);
+      }
+      if (MODE == LIN_EMBED) {
+#pragma unroll
+        for (int c = 0; c < TD; ++c) y[c] = fmaxf(y[c] + s_b0[c], 0.f);
+        a_store_row<NPASS>(tl, C_A, C_ALO, y);
+        GNT_TC_ISSUE(C_D0, C_A, C_ALO, 1, false);
+        GNT_TC_WAIT();
+        d_load_row(tl, C_D0, y);
+#pragma unroll
+        for (int c = 0; c < TD; ++c) y[c] += s_b1[c];
       }
       if (active) row_store(a.y0 + row * TD, y);
       if (MODE == LIN_KV) {
