@@ -488,79 +488,35 @@ __global__ void __launch_bounds__(256) k_gnt_head(int R, int S, const float* __r
 enum : int { CS_P0 = 0 /*[4][8]*/, CS_P0_B = 32, CS_P2 = 40 /*[8][64]*/, CS_P2_B = CS_P2 + 8 * D, CS_A0 = CS_P2_B + D /*[64][8]*/,
              CS_A0_B = CS_A0 + D * 8, CS_A2 = CS_A0_B + 8 /*[8][64]*/, CS_A2_B = CS_A2 + 8 * D, CS_TOTAL = CS_A2_B + D };
 
-// Two adjacent lanes share a sample: each owns 32 of the 64 channels (softmax state, pos, a), the 64-term sums of
-// attn_fc.0 are completed with one shuffle -- half the registers per thread, twice the threads.
-__global__ void __launch_bounds__(128) k_gnt_view_core(int N, int V, const float* __restrict__ qq, const float* __restrict__ Kv,
-                                                        const float* __restrict__ Vv, const float* __restrict__ ray_diff,
+// Input per (sample, view) row from k_gnt_lin_tc<LIN_KV>: a8 = ReLU(attn_fc.0(k - qq + pos)) [8] and vp = v + pos [64].
+// Two adjacent lanes share a sample, each owns 32 of the 64 channels: a = attn_fc.2(a8) (masked), softmax over the
+// views per channel (online), x = sum_v vp a.
+__global__ void __launch_bounds__(128) k_gnt_view_core(int N, int V, const float* __restrict__ A8, const float* __restrict__ VP,
                                                         const float* __restrict__ mask, const float* __restrict__ lp,
                                                         float* __restrict__ xout) {
   constexpr int HC = D / 2;
-  __shared__ __align__(16) float sm[CS_TOTAL];
+  __shared__ __align__(16) float sm[8 * D + D];          // attn_fc.2 transposed [8][64], bias [64]
   const int t = threadIdx.x, nt = blockDim.x;
-  load_wt_transposed(sm + CS_P0, lp + L_V_POS0_W, 8, 4, 8, t, nt);
-  load_vec_padded(sm + CS_P0_B, lp + L_V_POS0_B, 8, 8, t, nt);
-  load_wt_transposed(sm + CS_P2, lp + L_V_POS2_W, D, 8, D, t, nt);
-  load_vec_padded(sm + CS_P2_B, lp + L_V_POS2_B, D, D, t, nt);
-  load_wt_transposed(sm + CS_A0, lp + L_V_AT0_W, 8, D, 8, t, nt);
-  load_vec_padded(sm + CS_A0_B, lp + L_V_AT0_B, 8, 8, t, nt);
-  load_wt_transposed(sm + CS_A2, lp + L_V_AT2_W, D, 8, D, t, nt);
-  load_vec_padded(sm + CS_A2_B, lp + L_V_AT2_B, D, D, t, nt);
+  load_wt_transposed(sm, lp + L_V_AT2_W, D, 8, D, t, nt);
+  load_vec_padded(sm + 8 * D, lp + L_V_AT2_B, D, D, t, nt);
   __syncthreads();
-  const int half = t & 1, c0 = half * HC;
-  // every thread of a warp runs the same number of iterations (the pair exchanges with a full-warp shuffle)
-  for (int base = blockIdx.x * (blockDim.x / 2); base < N; base += gridDim.x * (blockDim.x / 2)) {
-    const int n = base + (t >> 1);
-    const bool act = n < N;
-    const int ns = act ? n : 0;
-    float qv[HC];
-#pragma unroll
-    for (int c = 0; c < HC; c += 4) {
-      const float4 q4 = __ldg(reinterpret_cast<const float4*>(qq + (size_t)ns * D + c0 + c));
-      qv[c] = q4.x; qv[c + 1] = q4.y; qv[c + 2] = q4.z; qv[c + 3] = q4.w;
-    }
+  const int c0 = (t & 1) * HC;
+  for (int n = blockIdx.x * (blockDim.x / 2) + (t >> 1); n < N; n += gridDim.x * (blockDim.x / 2)) {
     float m[HC], l[HC], acc[HC];
 #pragma unroll
     for (int c = 0; c < HC; ++c) { m[c] = -3.4e38f; l[c] = 0.f; acc[c] = 0.f; }
     for (int v = 0; v < V; ++v) {
-      const size_t row = (size_t)ns * V + v;
-      float pos[HC];
-      {
-        const float4 rd4 = __ldg(reinterpret_cast<const float4*>(ray_diff) + row);
-        const float rd[4] = {rd4.x, rd4.y, rd4.z, rd4.w};
-        float p8[8];
-        load_bias<8>(p8, sm + CS_P0_B);
-        dense_acc<4, 8>(sm + CS_P0, rd, p8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) p8[j] = fmaxf(p8[j], 0.f);
-        load_bias<HC>(pos, sm + CS_P2_B + c0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) axpy_row<HC>(pos, p8[j], sm + CS_P2 + j * D + c0);
-      }
-      float a8[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) a8[j] = 0.f;
-      const float4* kr = reinterpret_cast<const float4*>(Kv + row * D + c0);
-#pragma unroll
-      for (int c = 0; c < HC; c += 4) {
-        const float4 k4 = __ldg(kr + c / 4);
-        axpy_row<8>(a8, k4.x - qv[c] + pos[c], sm + CS_A0 + (c0 + c) * 8);
-        axpy_row<8>(a8, k4.y - qv[c + 1] + pos[c + 1], sm + CS_A0 + (c0 + c + 1) * 8);
-        axpy_row<8>(a8, k4.z - qv[c + 2] + pos[c + 2], sm + CS_A0 + (c0 + c + 2) * 8);
-        axpy_row<8>(a8, k4.w - qv[c + 3] + pos[c + 3], sm + CS_A0 + (c0 + c + 3) * 8);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a8[j] += __shfl_xor_sync(0xffffffffu, a8[j], 1);            // the other half of the 64-term sum
-        a8[j] = fmaxf(a8[j] + sm[CS_A0_B + j], 0.f);
-      }
+      const size_t row = (size_t)n * V + v;
+      const float4 h0 = __ldg(reinterpret_cast<const float4*>(A8 + row * 8)), h1 = __ldg(reinterpret_cast<const float4*>(A8 + row * 8) + 1);
+      const float a8[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
       const bool valid = __ldg(mask + row) != 0.f;
-      const float4* vr = reinterpret_cast<const float4*>(Vv + row * D + c0);
+      const float4* vr = reinterpret_cast<const float4*>(VP + row * D + c0);
 #pragma unroll
       for (int cc = 0; cc < HC; cc += 16) {
         float a[16];
-        load_bias<16>(a, sm + CS_A2_B + c0 + cc);
+        load_bias<16>(a, sm + 8 * D + c0 + cc);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) axpy_row<16>(a, a8[j], sm + CS_A2 + j * D + c0 + cc);
+        for (int j = 0; j < 8; ++j) axpy_row<16>(a, a8[j], sm + j * D + c0 + cc);
         float vv[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -574,17 +530,15 @@ __global__ void __launch_bounds__(128) k_gnt_view_core(int N, int V, const float
           const float mn = fmaxf(m[c], s);
           const float sc = __expf(m[c] - mn), e = __expf(s - mn);
           l[c] = fmaf(l[c], sc, e);
-          acc[c] = fmaf(acc[c], sc, (vv[j] + pos[c]) * e);
+          acc[c] = fmaf(acc[c], sc, vv[j] * e);
           m[c] = mn;
         }
       }
     }
-    if (act) {
 #pragma unroll
-      for (int c = 0; c < HC; c += 4)
-        *reinterpret_cast<float4*>(xout + (size_t)n * D + c0 + c) =
-            make_float4(acc[c] / l[c], acc[c + 1] / l[c + 1], acc[c + 2] / l[c + 2], acc[c + 3] / l[c + 3]);
-    }
+    for (int c = 0; c < HC; c += 4)
+      *reinterpret_cast<float4*>(xout + (size_t)n * D + c0 + c) =
+          make_float4(acc[c] / l[c], acc[c + 1] / l[c + 1], acc[c + 2] / l[c + 2], acc[c + 3] / l[c + 3]);
   }
 }
 
@@ -736,12 +690,15 @@ static int gnt_layer_tc(int i, int R, int S, int V, const float* ray_diff, const
   a.M = N; a.x = q; a.y0 = b0; a.w[0] = lp + L_V_Q; a.ln_w = lp + L_V_LN1_W; a.ln_b = lp + L_V_LN1_B;
   if ((rc = launch_lin<NPASS, LIN_PRE>(a, st, "k_gnt_lin_tc<pre>"))) return rc;
   a = LinArgs{};
-  a.M = (long long)rows; a.x = F; a.y0 = Kv; a.y1 = Vv; a.w[0] = lp + L_V_K; a.w[1] = lp + L_V_V;
+  a.M = (long long)rows; a.x = F; a.y0 = Vv; a.y1 = Kv; a.w[0] = lp + L_V_K; a.w[1] = lp + L_V_V;      // y0 = v + pos, y1 = a8
+  a.qq = b0; a.ray_diff = ray_diff; a.V = V;
+  a.p0_w = lp + L_V_POS0_W; a.p0_b = lp + L_V_POS0_B; a.p2_w = lp + L_V_POS2_W; a.p2_b = lp + L_V_POS2_B;
+  a.a0_w = lp + L_V_AT0_W; a.a0_b = lp + L_V_AT0_B;
   if ((rc = launch_lin<NPASS, LIN_KV>(a, st, "k_gnt_lin_tc<kv>"))) return rc;
   {
     int g = (N + 63) / 64;                      // 2 threads per sample
     if (g > sms * 8) g = sms * 8;
-    k_gnt_view_core<<<g, 128, 0, st>>>(N, V, b0, Kv, Vv, ray_diff, mask, lp, b1);
+    k_gnt_view_core<<<g, 128, 0, st>>>(N, V, Kv, Vv, mask, lp, b1);
     NFB_CHECK_LAUNCH("k_gnt_view_core");
   }
   a = LinArgs{};
@@ -752,10 +709,10 @@ static int gnt_layer_tc(int i, int R, int S, int V, const float* ray_diff, const
   a.ln_w = lp + L_V_LN2_W; a.ln_b = lp + L_V_LN2_B;
   if ((rc = launch_lin<NPASS, LIN_FFN>(a, st, "k_gnt_lin_tc<ffn>"))) return rc;
   if ((i & 1) == 0) {
-    int g = (N + 127) / 128;
-    if (g > sms * 3) g = sms * 3;
-    k_gnt_qfc<<<g, 128, (size_t)QS_TOTAL * sizeof(float), st>>>(N, S, pts, ray_d, lp, q);
-    NFB_CHECK_LAUNCH("k_gnt_qfc");
+    a = LinArgs{};
+    a.M = N; a.x = q; a.y0 = q; a.w[0] = lp + L_Q0_W; a.w[1] = lp + L_Q2_W; a.b0 = lp + L_Q0_B; a.b1 = lp + L_Q2_B;
+    a.pts = pts; a.ray_d = ray_d; a.S = S;
+    if ((rc = launch_lin<NPASS, LIN_QFC>(a, st, "k_gnt_lin_tc<qfc>"))) return rc;
   }
   // ---- ray transformer: Q, K, V = projections of LN(q); core; q = out_fc(o) + b + q; FFN
   a = LinArgs{};

@@ -10,10 +10,13 @@
 //
 // Modes (what one launch computes per row; every weight is a 64 x 64 tile, torch layout [out][in]):
 //   LIN_PRE   y0 = W0 LN(x)                                   view attention: qq = q_fc(attn_norm(q))
-//   LIN_KV    y0 = W0 x ; y1 = W1 y0                          view attention: k = k_fc(F), v = v_fc(k)   (per (sample, view) row)
+//   LIN_KV    k = W0 x ; v = W1 k ; pos = pos_fc(ray_diff) ;     view attention, per (sample, view) row: k = k_fc(F), v = v_fc(k);
+//             y0 = v + pos ; y1[8] = ReLU(attn_fc.0(k - qq + pos))   k never leaves the SM: the row hands on v + pos and the 8 hidden
+//                                                               units of attn_fc (288 B instead of 512 B per row)
 //   LIN_QKV   y0 = W0 LN(x) ; y1 = W1 LN(x) ; y2 = W2 LN(x)   ray attention:  q, k, v projections
 //   LIN_POST  y0 = W0 x + b + res                             out_fc + residual (view and ray attention)
 //   LIN_FFN   y0 = W2 ReLU(W1 LN(x) + b1) + b2 + x            feed-forward block: fc1 [256][64] = 4 N-chunks, fc2 [64][256] = 4 K-chunks
+//   LIN_QFC   y0 = W1 ReLU(W0 [x | posenc(pts) | posenc(dir)] + b0) + b1   q_fc of the even layers: fc.0 [64][190] = 3 K-rounds
 //   LIN_EMBED y0 = W1 ReLU(W0 x35 + b0) + b1                   rgbfeat_fc on the 35-channel rows (W0 [64][35] zero-padded to K = 64)
 #pragma once
 #include "nfb_common.cuh"
@@ -25,13 +28,17 @@ using namespace nfbtc;
 constexpr int GROUP = 128;
 constexpr int TD = 64;                           // tile edge = netwidth
 constexpr int TILE_BYTES = TD * TD * 2;          // one bf16 64 x 64 tile
-enum : int { LIN_PRE = 0, LIN_KV = 1, LIN_QKV = 2, LIN_POST = 3, LIN_FFN = 4, LIN_EMBED = 5 };
+enum : int { LIN_PRE = 0, LIN_KV = 1, LIN_QKV = 2, LIN_POST = 3, LIN_FFN = 4, LIN_EMBED = 5, LIN_QFC = 6 };
 
-__host__ __device__ constexpr int mode_tiles(int mode) { return mode == LIN_PRE || mode == LIN_POST ? 1 : (mode == LIN_KV || mode == LIN_EMBED) ? 2 : mode == LIN_QKV ? 3 : 8; }
+__host__ __device__ constexpr int mode_tiles(int mode) { return mode == LIN_PRE || mode == LIN_POST ? 1 : (mode == LIN_KV || mode == LIN_EMBED) ? 2 : mode == LIN_QKV ? 3 : mode == LIN_QFC ? 4 : 8; }
 __host__ __device__ constexpr int mode_groups(int mode) { return mode == LIN_FFN ? 2 : 4; }       // FFN needs 256 TMEM columns per group
 __host__ __device__ constexpr int mode_cols(int mode) { return mode == LIN_FFN ? 256 : 128; }
 // TMEM columns of a group: D0 [0,64) | A hi [64,96) | A lo [96,128) | FFN only: D1 [128,192) | A2 hi [192,224) | A2 lo [224,256)
 constexpr int C_D0 = 0, C_A = 64, C_ALO = 96, C_D1 = 128, C_A2 = 192, C_A2LO = 224;
+
+// fp32 side tables of LIN_KV (pos_fc and attn_fc.0 stay on the CUDA cores: 4 -> 8 -> 64 and 64 -> 8)
+enum : int { KV_P0 = 0 /*[4][8]*/, KV_P0_B = 32, KV_P2 = 40 /*[8][64]*/, KV_P2_B = KV_P2 + 8 * TD, KV_A0 = KV_P2_B + TD /*[64][8]*/,
+             KV_A0_B = KV_A0 + TD * 8, KV_TOTAL = KV_A0_B + 8 };
 
 struct LinArgs {
   long long M;                 // rows
@@ -42,11 +49,31 @@ struct LinArgs {
   const float* b0;             // LIN_POST: bias [64]; LIN_FFN: fc1 bias [256]
   const float* b1;             // LIN_FFN: fc2 bias [64]
   const float* ln_w; const float* ln_b;   // LayerNorm of the input (LIN_PRE, LIN_QKV, LIN_FFN), eps 1e-6
+  const float* pts; const float* ray_d; int S;   // LIN_QFC: sample positions [M][3], ray directions [M / S][3]
+  // LIN_KV: qq [M / V][64], ray_diff [M][4], pos_fc.0 (w [8][4], b), pos_fc.2 (w [64][8], b), attn_fc.0 (w [8][64], b)
+  const float* qq; const float* ray_diff; int V;
+  const float* p0_w; const float* p0_b; const float* p2_w; const float* p2_b; const float* a0_w; const float* a0_b;
 };
+
+// Embedder (transformer_network.py:6-37): [x, sin(x f0), cos(x f0), sin(x f1), ...], f_k = 2^k, k = 0..9 -> 63 values (+ 1 pad)
+__device__ __forceinline__ void posenc64(const float (&x3)[3], float (&e)[TD]) {
+  e[0] = x3[0]; e[1] = x3[1]; e[2] = x3[2];
+#pragma unroll
+  for (int f = 0; f < 10; ++f) {
+    const float fr = (float)(1 << f);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float ang = __fmul_rn(x3[i], fr);
+      e[3 + 6 * f + i] = sinf(ang);
+      e[3 + 6 * f + 3 + i] = cosf(ang);
+    }
+  }
+  e[63] = 0.f;
+}
 
 template <int NPASS, int MODE>
 __host__ __device__ constexpr size_t lin_smem_bytes() {
-  return (size_t)mode_tiles(MODE) * TILE_BYTES * (NPASS == 3 ? 2 : 1) + sizeof(float) * (256 + 64 + 128) + mode_groups(MODE) * 8 + 16;
+  return (size_t)mode_tiles(MODE) * TILE_BYTES * (NPASS == 3 ? 2 : 1) + sizeof(float) * (256 + 64 + 128 + KV_TOTAL) + mode_groups(MODE) * 8 + 16;
 }
 
 __host__ __device__ constexpr uint32_t canon_off(int n, int k) {      // element (n, k) of a [64][64] K-major tile
@@ -161,7 +188,8 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
   float* s_b0 = sf;            // 256
   float* s_b1 = sf + 256;      // 64
   float* s_ln = sf + 320;      // 64 + 64
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(sf + 448);
+  float* s_kv = sf + 448;      // KV_TOTAL
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(sf + 448 + KV_TOTAL);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + NG);
 
   const int tid = threadIdx.x, warp = tid >> 5, nt = blockDim.x;
@@ -182,6 +210,13 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
     }
     for (int i = tid; i < 256; i += nt) s_b0[i] = __ldg(a.b0 + i);
     for (int i = tid; i < 64; i += nt) s_b1[i] = __ldg(a.b1 + i);
+  } else if (MODE == LIN_QFC) {
+    // fc.0 [64][190]: columns [0,64) = q, [64,127) = posenc(pts), [127,190) = posenc(dir); the 63-wide blocks are zero-padded
+    load_tile64<NPASS>(sB, sB + NT * TILE_BYTES, a.w[0], 190, tid, nt);
+    load_tile64<NPASS>(sB + TILE_BYTES, sB + (NT + 1) * TILE_BYTES, a.w[0] + 64, 190, tid, nt, 63);
+    load_tile64<NPASS>(sB + 2 * TILE_BYTES, sB + (NT + 2) * TILE_BYTES, a.w[0] + 127, 190, tid, nt, 63);
+    load_tile64<NPASS>(sB + 3 * TILE_BYTES, sB + (NT + 3) * TILE_BYTES, a.w[1], TD, tid, nt);
+    for (int i = tid; i < 64; i += nt) { s_b0[i] = __ldg(a.b0 + i); s_b1[i] = __ldg(a.b1 + i); }
   } else if (MODE == LIN_EMBED) {
     load_tile64<NPASS>(sB, sB + NT * TILE_BYTES, a.w[0], NFB_ROW_CH, tid, nt, NFB_ROW_CH);
     load_tile64<NPASS>(sB + TILE_BYTES, sB + (NT + 1) * TILE_BYTES, a.w[1], TD, tid, nt);
@@ -191,6 +226,15 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
     for (int j = 0; j < NT; ++j) load_tile64<NPASS>(sB + j * TILE_BYTES, sB + (NT + j) * TILE_BYTES, a.w[j], TD, tid, nt);
     if (MODE == LIN_POST)
       for (int i = tid; i < 64; i += nt) s_b0[i] = __ldg(a.b0 + i);
+  }
+  if (MODE == LIN_KV) {
+    for (int i = tid; i < 32; i += nt) s_kv[KV_P0 + i] = __ldg(a.p0_w + (i & 7) * 4 + (i >> 3));          // [k][j] <- w[j][k]
+    for (int i = tid; i < 8; i += nt) { s_kv[KV_P0_B + i] = __ldg(a.p0_b + i); s_kv[KV_A0_B + i] = __ldg(a.a0_b + i); }
+    for (int i = tid; i < 8 * TD; i += nt) {
+      s_kv[KV_P2 + i] = __ldg(a.p2_w + (i & 63) * 8 + (i >> 6));                                             // [j][c] <- w[c][j]
+      s_kv[KV_A0 + i] = __ldg(a.a0_w + (i & 7) * TD + (i >> 3));                                             // [c][j] <- w[j][c]
+    }
+    for (int i = tid; i < TD; i += nt) s_kv[KV_P2_B + i] = __ldg(a.p2_b + i);
   }
   if (MODE == LIN_PRE || MODE == LIN_QKV || MODE == LIN_FFN)
     for (int i = tid; i < 64; i += nt) { s_ln[i] = __ldg(a.ln_w + i); s_ln[64 + i] = __ldg(a.ln_b + i); }
@@ -253,6 +297,38 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
 #pragma unroll
         for (int c = 0; c < TD; ++c) y[c] += s_b0[c] + (active ? r[c] : 0.f);
       }
+      if (MODE == LIN_QFC) {
+        // two more K-rounds into the same accumulator: the positional encodings of the point and of the view direction
+        const long long rs = active ? row : 0;
+        {
+          const float p3[3] = {__ldg(a.pts + rs * 3), __ldg(a.pts + rs * 3 + 1), __ldg(a.pts + rs * 3 + 2)};
+          float e[TD];
+          posenc64(p3, e);
+          a_store_row<NPASS>(tl, C_A, C_ALO, e);
+          GNT_TC_ISSUE(C_D0, C_A, C_ALO, 1, true);
+          GNT_TC_WAIT();
+        }
+        {
+          const long long r = rs / a.S;
+          const float dx = __ldg(a.ray_d + r * 3), dy = __ldg(a.ray_d + r * 3 + 1), dz = __ldg(a.ray_d + r * 3 + 2);
+          const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+          const float d3[3] = {__fdiv_rn(dx, nrm), __fdiv_rn(dy, nrm), __fdiv_rn(dz, nrm)};
+          float e[TD];
+          posenc64(d3, e);
+          a_store_row<NPASS>(tl, C_A, C_ALO, e);
+          GNT_TC_ISSUE(C_D0, C_A, C_ALO, 2, true);
+          GNT_TC_WAIT();
+        }
+        d_load_row(tl, C_D0, y);
+#pragma unroll
+        for (int c = 0; c < TD; ++c) y[c] = fmaxf(y[c] + s_b0[c], 0.f);
+        a_store_row<NPASS>(tl, C_A, C_ALO, y);
+        GNT_TC_ISSUE(C_D0, C_A, C_ALO, 3, false);
+        GNT_TC_WAIT();
+        d_load_row(tl, C_D0, y);
+#pragma unroll
+        for (int c = 0; c < TD; ++c) y[c] += s_b1[c];
+      }
       if (MODE == LIN_EMBED) {
 #pragma unroll
         for (int c = 0; c < TD; ++c) y[c] = fmaxf(y[c] + s_b0[c], 0.f);
@@ -263,13 +339,65 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
 #pragma unroll
         for (int c = 0; c < TD; ++c) y[c] += s_b1[c];
       }
-      if (active) row_store(a.y0 + row * TD, y);
+      if (MODE != LIN_KV && active) row_store(a.y0 + row * TD, y);
       if (MODE == LIN_KV) {
         a_store_row<NPASS>(tl, C_A, C_ALO, y);                     // v = v_fc(k): the projected k is the next input
         GNT_TC_ISSUE(C_D0, C_A, C_ALO, 1, false);
+        // while the MMA runs: pos = pos_fc(ray_diff) and the hidden units of attn_fc on k - qq + pos (CUDA cores)
+        const long long rs = active ? row : 0;
+        float pos[TD];
+        {
+          const float4 rd4 = __ldg(reinterpret_cast<const float4*>(a.ray_diff) + rs);
+          float p8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            p8[j] = fmaxf(s_kv[KV_P0_B + j] + rd4.x * s_kv[KV_P0 + j] + rd4.y * s_kv[KV_P0 + 8 + j] + rd4.z * s_kv[KV_P0 + 16 + j] +
+                          rd4.w * s_kv[KV_P0 + 24 + j], 0.f);
+#pragma unroll
+          for (int c = 0; c < TD; ++c) pos[c] = s_kv[KV_P2_B + c];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int c = 0; c < TD; c += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(s_kv + KV_P2 + j * TD + c);
+              pos[c] = fmaf(p8[j], w4.x, pos[c]); pos[c + 1] = fmaf(p8[j], w4.y, pos[c + 1]);
+              pos[c + 2] = fmaf(p8[j], w4.z, pos[c + 2]); pos[c + 3] = fmaf(p8[j], w4.w, pos[c + 3]);
+            }
+          }
+        }
+        float a8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a8[j] = s_kv[KV_A0_B + j];
+        {
+          const float4* qr = reinterpret_cast<const float4*>(a.qq + (rs / a.V) * TD);
+#pragma unroll
+          for (int c = 0; c < TD; c += 4) {
+            const float4 q4 = __ldg(qr + c / 4);
+            const float t0 = y[c] - q4.x + pos[c], t1 = y[c + 1] - q4.y + pos[c + 1], t2 = y[c + 2] - q4.z + pos[c + 2],
+                        t3 = y[c + 3] - q4.w + pos[c + 3];
+#pragma unroll
+            for (int j = 0; j < 8; j += 4) {
+              const float4 w0 = *reinterpret_cast<const float4*>(s_kv + KV_A0 + c * 8 + j);
+              const float4 w1 = *reinterpret_cast<const float4*>(s_kv + KV_A0 + (c + 1) * 8 + j);
+              const float4 w2 = *reinterpret_cast<const float4*>(s_kv + KV_A0 + (c + 2) * 8 + j);
+              const float4 w3 = *reinterpret_cast<const float4*>(s_kv + KV_A0 + (c + 3) * 8 + j);
+              a8[j] += t0 * w0.x + t1 * w1.x + t2 * w2.x + t3 * w3.x;
+              a8[j + 1] += t0 * w0.y + t1 * w1.y + t2 * w2.y + t3 * w3.y;
+              a8[j + 2] += t0 * w0.z + t1 * w1.z + t2 * w2.z + t3 * w3.z;
+              a8[j + 3] += t0 * w0.w + t1 * w1.w + t2 * w2.w + t3 * w3.w;
+            }
+          }
+        }
         GNT_TC_WAIT();
         d_load_row(tl, C_D0, y);
-        if (active) row_store(a.y1 + row * TD, y);
+        if (active) {
+#pragma unroll
+          for (int c = 0; c < TD; ++c) y[c] += pos[c];
+          row_store(a.y0 + row * TD, y);
+          float4* o8 = reinterpret_cast<float4*>(a.y1 + row * 8);
+          o8[0] = make_float4(fmaxf(a8[0], 0.f), fmaxf(a8[1], 0.f), fmaxf(a8[2], 0.f), fmaxf(a8[3], 0.f));
+          o8[1] = make_float4(fmaxf(a8[4], 0.f), fmaxf(a8[5], 0.f), fmaxf(a8[6], 0.f), fmaxf(a8[7], 0.f));
+        }
       }
       if (MODE == LIN_QKV) {
         GNT_TC_ISSUE(C_D0, C_A, C_ALO, 1, false);                  // A (LN(x)) is unchanged
