@@ -130,9 +130,10 @@ int nfb_ibrnet_view_bwd(int N, int S, int V, int anti_alias,
  * d_imgs / d_rgb_feat may be NULL when only the weights train) and, in addition, the gradient of every tensor of
  * the parameter blob, ACCUMULATED (+=) into d_params[NFB_IBRNET_PARAM_FLOATS] in the blob's layout -- the view
  * stage fills s, ray_dir_fc, base_fc, vis_fc, vis_fc2 and rgb_fc, the ray stage geometry_fc, ray_attention.* and
- * out_geometry_fc; pos_encoding is a buffer and has no gradient.  fp32 CUDA-core kernels that recompute the forward
- * per tile (no stash): per-row outer products are reduced over the 32 rows of a warp with an exchange butterfly,
- * summed per CTA in shared memory and added to d_params with one float atomic per weight and CTA.              */
+ * out_geometry_fc; pos_encoding is a buffer and has no gradient.  Kernels that recompute the forward per tile in fp32
+ * (no stash).  View stage: the weight gradients are GEMMs over the row index on the tensor cores (operands staged as
+ * bf16 in shared memory, fp32 accumulators resident in TMEM, flushed with one float atomic per weight and CTA);
+ * biases, s and the ray stage reduce per-row outer products with a warp exchange butterfly in fp32.             */
 int nfb_ibrnet_ray_wgrad(int R, int S, const float* ps, const float* params, const float* pos_enc,
                          const float* d_raw, float* d_ps, float* d_params, void* stream);
 int nfb_ibrnet_view_wgrad(int N, int S, int V, int anti_alias,

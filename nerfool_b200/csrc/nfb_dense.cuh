@@ -121,6 +121,30 @@ __device__ __forceinline__ void wgrad_vec(float* __restrict__ sg, const float (&
   wgrad_acc<1, NP>(sg, one, dy, scale);
 }
 
+// sg[n] += scale * (sum over the warp's rows of dy[n]), fully inlined with compile-time register indices (the caller's
+// array stays in registers): the same exchange butterfly, 31 shuffles per 32 values
+template <int NP>
+__device__ __forceinline__ void wgrad_rowsum(float* __restrict__ sg, const float (&dy)[NP], float scale) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int n0 = 0; n0 < NP; n0 += 32) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (n0 + i < NP) ? dy[(n0 + i < NP) ? n0 + i : 0] * scale : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < o; ++i) {
+        const float keep = up ? v[i + o] : v[i];
+        const float send = up ? v[i] : v[i + o];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    if (n0 + lane < NP) atomicAdd(sg + n0 + lane, v[0]);
+  }
+}
+
 // add a transposed [K][NP] shared-memory accumulator into the torch-layout [N][K] gradient blob
 __device__ __forceinline__ void flush_wt_transposed(float* __restrict__ dst, const float* __restrict__ sg, int N, int K,
                                                     int NP, int tid, int nthreads) {

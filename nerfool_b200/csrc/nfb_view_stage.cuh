@@ -10,6 +10,7 @@
 #pragma once
 #include "nfb_dense.cuh"
 #include "nfb_geom.cuh"
+#include "nfb_wgrad_tc.cuh"
 
 namespace nfbview {
 
@@ -72,31 +73,16 @@ static __device__ void load_view_weights(float* sw, const float* __restrict__ p,
   if (tid == 0) sw[W_S] = fabsf(__ldg(p + P_S));
 }
 
-// adds the per-CTA accumulators (shared-memory weight layout) into the torch-layout gradient blob
-static __device__ void flush_view_grads(float* __restrict__ dp, const float* sg, int tid, int nt) {
-  flush_wt_transposed(dp + P_DIR0_W, sg + W_DIR0, 16, 4, 16, tid, nt);
-  flush_vec(dp + P_DIR0_B, sg + B_DIR0, 16, tid, nt);
-  flush_wt_transposed(dp + P_DIR2_W, sg + W_DIR2, 35, 16, 36, tid, nt);
-  flush_vec(dp + P_DIR2_B, sg + B_DIR2, 35, tid, nt);
-  flush_wt_transposed(dp + P_BASE0_W, sg + W_BASE0, 64, 105, 64, tid, nt);
-  flush_vec(dp + P_BASE0_B, sg + B_BASE0, 64, tid, nt);
-  flush_wt_transposed(dp + P_BASE2_W, sg + W_BASE2, 32, 64, 32, tid, nt);
-  flush_vec(dp + P_BASE2_B, sg + B_BASE2, 32, tid, nt);
-  flush_wt_transposed(dp + P_VIS0_W, sg + W_VIS0, 32, 32, 32, tid, nt);
-  flush_vec(dp + P_VIS0_B, sg + B_VIS0, 32, tid, nt);
-  flush_wt_transposed(dp + P_VIS2_W, sg + W_VIS2, 33, 32, 36, tid, nt);
-  flush_vec(dp + P_VIS2_B, sg + B_VIS2, 33, tid, nt);
-  flush_wt_transposed(dp + P_VISB0_W, sg + W_VISB0, 32, 32, 32, tid, nt);
-  flush_vec(dp + P_VISB0_B, sg + B_VISB0, 32, tid, nt);
-  flush_vec(dp + P_VISB2_W, sg + W_VISB2, 32, tid, nt);
-  flush_vec(dp + P_VISB2_B, sg + B_VISB2, 1, tid, nt);
-  flush_wt_transposed(dp + P_RGB0_W, sg + W_RGB0, 16, 37, 16, tid, nt);
-  flush_vec(dp + P_RGB0_B, sg + B_RGB0, 16, tid, nt);
-  flush_wt_transposed(dp + P_RGB2_W, sg + W_RGB2, 8, 16, 8, tid, nt);
-  flush_vec(dp + P_RGB2_B, sg + B_RGB2, 8, tid, nt);
-  flush_vec(dp + P_RGB4_W, sg + W_RGB4, 8, tid, nt);
-  flush_vec(dp + P_RGB4_B, sg + B_RGB4, 1, tid, nt);
-}
+// WG (training) kernels: TMEM accumulator columns of the layers whose parameter gradient runs on the tensor cores
+// (nfb_wgrad_tc.cuh); the two single-output layers and s keep a small shared-memory accumulator (warp butterfly).
+enum : int { WC_DIR0 = 0, WC_DIR2 = 16, WC_BASE0 = 64, WC_BASE2 = 128, WC_VIS0 = 160, WC_VIS2 = 192, WC_VISB0 = 240,
+             WC_RGB0 = 272, WC_RGB2 = 288, WC_TOTAL = 304 };
+enum : int { SG_VISB2 = 0, SG_VISB2_B = 32, SG_RGB4 = 36, SG_RGB4_B = 44, SG_S = 48,
+             // bias gradients (plain row sums) stay exact fp32: warp butterfly into these slots
+             SG_DIR0_B = 52, SG_DIR2_B = SG_DIR0_B + 16, SG_BASE0_B = SG_DIR2_B + 36, SG_BASE2_B = SG_BASE0_B + 64,
+             SG_VIS0_B = SG_BASE2_B + 32, SG_VIS2_B = SG_VIS0_B + 32, SG_VISB0_B = SG_VIS2_B + 36, SG_RGB0_B = SG_VISB0_B + 32,
+             SG_RGB2_B = SG_RGB0_B + 16, SG_TOTAL = SG_RGB2_B + 8 };
+static_assert(SG_TOTAL % 4 == 0, "staging tiles behind the accumulators need 16-byte alignment");
 
 struct ViewArgs {
   int N, S, V, anti_alias;
@@ -132,16 +118,46 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
   float* ex = ex_all + (size_t)grp * GROUP * EXS;
   float* mv = ex_all + (size_t)NG * GROUP * EXS + (size_t)grp * TS_MAX * MVS;   // per-sample mean0 / var0
   const int bar_id = 1 + grp;
-  // WG: per-CTA parameter-gradient accumulators, same (transposed) layout as the weights
+  // WG: small shared accumulators (single-output layers, s), then the bf16 staging tiles of the tensor-core
+  // parameter-gradient GEMMs (one A and one B tile per group), mbarriers and the TMEM slot
   float* sg = ex_all + (size_t)NG * GROUP * EXS + (size_t)NG * TS_MAX * MVS;
+  uint8_t* s_tiles = reinterpret_cast<uint8_t*>(sg + SG_TOTAL);
+  uint64_t* s_wbar = reinterpret_cast<uint64_t*>(s_tiles + (size_t)NG * (nfbwg::A_TILE_BYTES + nfbwg::B_TILE_BYTES));
+  uint32_t* s_wtmem = reinterpret_cast<uint32_t*>(s_wbar + NG);
   float ds_acc = 0.f;                                          // d loss / d |s| of this thread's rows
-  if (WG)
-    for (int i = threadIdx.x; i < W_TOTAL; i += blockDim.x) sg[i] = 0.f;
+  nfbwg::WgTc wg{};
+  if (WG) {
+    for (int i = threadIdx.x; i < SG_TOTAL; i += blockDim.x) sg[i] = 0.f;
+    // stale bf16 patterns in never-written operand rows only reach unused accumulator lanes, but they must be finite
+    for (int i = threadIdx.x; i < NG * (nfbwg::A_TILE_BYTES + nfbwg::B_TILE_BYTES) / 4; i += blockDim.x)
+      reinterpret_cast<uint32_t*>(s_tiles)[i] = 0u;
+    if (threadIdx.x < 32) nfbtc::tmem_alloc(s_wtmem, 512);
+    if (threadIdx.x == 0) {
+      for (int g = 0; g < NG; ++g) nfbtc::mbar_init(s_wbar + g, 1);
+      nfbtc::mbar_init_fence();
+    }
+  }
 
   load_view_weights(sw, a.params, threadIdx.x, blockDim.x);
   if (FUSED)
     for (int i = threadIdx.x; i < 16 * a.V + 3; i += blockDim.x) s_cam[i] = __ldg(a.cam + i);
+  if (WG) nfbtc::fence_before_sync();
   __syncthreads();
+  if (WG) {
+    nfbtc::fence_after_sync();
+    wg.sA = s_tiles + (size_t)grp * nfbwg::A_TILE_BYTES;
+    wg.sB = s_tiles + (size_t)NG * nfbwg::A_TILE_BYTES + (size_t)grp * nfbwg::B_TILE_BYTES;
+    wg.mbar = s_wbar + grp;
+    wg.tmem = *s_wtmem;
+    wg.phase = 0;
+    wg.pending = false;
+    wg.tg = tg;
+    wg.bar_id = bar_id;
+    if (threadIdx.x < 128) nfbwg::wg_zero(wg.tmem, threadIdx.x >> 5, WC_TOTAL);     // warps 0..3 own TMEM lanes 0..127
+    nfbtc::fence_before_sync();
+    __syncthreads();
+    nfbtc::fence_after_sync();
+  }
 
   const int V = a.V;
   const int TS = (GROUP / V < TS_MAX) ? GROUP / V : TS_MAX;    // samples per tile
@@ -417,17 +433,17 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
         dense_T<32, 16>(sw + W_RGB0, dg1, d_x2);
         d_vis2 = dot_row<16>(dg1, sw + W_RGB0 + 32 * 16);
         if (WG) {
-          wgrad_vec<8>(sg + W_RGB4, g2, d_logit * gate);
+          wgrad_rowsum<8>(sg + SG_RGB4, g2, d_logit * gate);
           const float db4[4] = {d_logit, 0.f, 0.f, 0.f};
-          wgrad_vec<4>(sg + B_RGB4, db4, gate);
-          wgrad_acc<16, 8>(sg + W_RGB2, g1, dg2, gate);
-          wgrad_vec<8>(sg + B_RGB2, dg2, gate);
+          wgrad_rowsum<4>(sg + SG_RGB4_B, db4, gate);
+          nfbwg::wgrad_tc<16, 8>(wg, WC_RGB2, g1, dg2, gate);
+          wgrad_rowsum<8>(sg + SG_RGB2_B, dg2, gate);
           float xin[37];
 #pragma unroll
           for (int c = 0; c < 32; ++c) xin[c] = x2[c];
           xin[32] = vis2; xin[33] = rd[0]; xin[34] = rd[1]; xin[35] = rd[2]; xin[36] = rd[3];
-          wgrad_acc<37, 16>(sg + W_RGB0, xin, dg1, gate);
-          wgrad_vec<16>(sg + B_RGB0, dg1, gate);
+          nfbwg::wgrad_tc<37, 16>(wg, WC_RGB0, xin, dg1, gate);
+          wgrad_rowsum<16>(sg + SG_RGB0_B, dg1, gate);
         }
       }
 
@@ -461,14 +477,14 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
         float dt[32];
         dense_T<32, 32>(sw + W_VISB0, dh, dt);
         if (WG) {
-          wgrad_vec<32>(sg + W_VISB2, hv2, dz * gate);
+          wgrad_rowsum<32>(sg + SG_VISB2, hv2, dz * gate);
           const float dbz[4] = {dz, 0.f, 0.f, 0.f};
-          wgrad_vec<4>(sg + B_VISB2, dbz, gate);
+          wgrad_rowsum<4>(sg + SG_VISB2_B, dbz, gate);
           float t2[32];
 #pragma unroll
           for (int c = 0; c < 32; ++c) t2[c] = x2[c] * vis1;
-          wgrad_acc<32, 32>(sg + W_VISB0, t2, dh, gate);
-          wgrad_vec<32>(sg + B_VISB0, dh, gate);
+          nfbwg::wgrad_tc<32, 32>(wg, WC_VISB0, t2, dh, gate);
+          wgrad_rowsum<32>(sg + SG_VISB0_B, dh, gate);
         }
         d_vis1 = 0.f;
 #pragma unroll
@@ -495,16 +511,16 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) d_x1[c] = fmaf(dt[c], w, d_x2[c]);
         if (WG) {
-          wgrad_acc<32, 36>(sg + W_VIS2, hv, dxv, gate);
-          wgrad_vec<36>(sg + B_VIS2, dxv, gate);
+          nfbwg::wgrad_tc<32, 36>(wg, WC_VIS2, hv, dxv, gate);
+          wgrad_rowsum<36>(sg + SG_VIS2_B, dxv, gate);
           float t1[32];
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
             t1[c] = x1[c] * w;
             d_w = fmaf(dt[c], x1[c], d_w);         // vis_fc sees x * weight (:250)
           }
-          wgrad_acc<32, 32>(sg + W_VIS0, t1, dh, gate);
-          wgrad_vec<32>(sg + B_VIS0, dh, gate);
+          nfbwg::wgrad_tc<32, 32>(wg, WC_VIS0, t1, dh, gate);
+          wgrad_rowsum<32>(sg + SG_VIS0_B, dh, gate);
         }
       }
 
@@ -519,16 +535,16 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
       }
       float m0[NFB_ROW_CH];                        // WG: mean0 of this sample (the buffer is overwritten in (7))
       if (WG) {
-        wgrad_acc<64, 32>(sg + W_BASE2, h1, d_x1, gate);
-        wgrad_vec<32>(sg + B_BASE2, d_x1, gate);
+        nfbwg::wgrad_tc<64, 32>(wg, WC_BASE2, h1, d_x1, gate);
+        wgrad_rowsum<32>(sg + SG_BASE2_B, d_x1, gate);
         float xin[105];
 #pragma unroll
         for (int c = 0; c < NFB_ROW_CH; ++c) {
           m0[c] = mvs[c];
           xin[c] = mvs[c]; xin[35 + c] = mvs[36 + c]; xin[70 + c] = x[c];
         }
-        wgrad_acc<105, 64>(sg + W_BASE0, xin, d_h1, gate);
-        wgrad_vec<64>(sg + B_BASE0, d_h1, gate);
+        nfbwg::wgrad_tc<105, 64>(wg, WC_BASE0, xin, d_h1, gate);
+        wgrad_rowsum<64>(sg + SG_BASE0_B, d_h1, gate);
       }
 
       // (7) first pooling backward.  With Dm_c = sum_v d mean0_vc, Dv_c = sum_v d var0_vc:
@@ -582,14 +598,14 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
 #pragma unroll
           for (int c = 0; c < NFB_ROW_CH; ++c) ddf[c] = d_row[c] * elu_grad_from_out(elu_f(ddf[c]));
           ddf[35] = 0.f;
-          wgrad_acc<16, 36>(sg + W_DIR2, a1, ddf, gate);
-          wgrad_vec<36>(sg + B_DIR2, ddf, gate);
+          nfbwg::wgrad_tc<16, 36>(wg, WC_DIR2, a1, ddf, gate);
+          wgrad_rowsum<36>(sg + SG_DIR2_B, ddf, gate);
           float da1[16];
           dense_T<16, 36>(sw + W_DIR2, ddf, da1);
 #pragma unroll
           for (int k = 0; k < 16; ++k) da1[k] *= elu_grad_from_out(a1[k]);
-          wgrad_acc<4, 16>(sg + W_DIR0, rd, da1, gate);
-          wgrad_vec<16>(sg + B_DIR0, da1, gate);
+          nfbwg::wgrad_tc<4, 16>(wg, WC_DIR0, rd, da1, gate);
+          wgrad_rowsum<16>(sg + SG_DIR0_B, da1, gate);
         }
         // rgb_in enters the blend directly (:233,272)
         d_row[0] = fmaf(blend, d_r0, d_row[0]);
@@ -641,19 +657,51 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_stage(ViewArgs a) {
   if (WG) {
     if (a.anti_alias) {
       const float t = warp_sum(ds_acc);
-      if ((threadIdx.x & 31) == 0) atomicAdd(sg + W_S, t);
+      if ((threadIdx.x & 31) == 0) atomicAdd(sg + SG_S, t);
     }
+    nfbwg::wg_wait(wg);                                        // this group's last MMA batch has landed in TMEM
+    nfbtc::fence_before_sync();
     __syncthreads();
-    flush_view_grads(a.d_params, sg, threadIdx.x, blockDim.x);
+    nfbtc::fence_after_sync();
+    float* dp = a.d_params;
+    if (threadIdx.x < 128) {
+      const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+      nfbwg::wg_flush(wg.tmem, w, l, WC_DIR0, 4, 16, dp + P_DIR0_W);
+      nfbwg::wg_flush(wg.tmem, w, l, WC_DIR2, 16, 35, dp + P_DIR2_W);
+      nfbwg::wg_flush(wg.tmem, w, l, WC_BASE0, 105, 64, dp + P_BASE0_W);
+      nfbwg::wg_flush(wg.tmem, w, l, WC_BASE2, 64, 32, dp + P_BASE2_W);
+      nfbwg::wg_flush(wg.tmem, w, l, WC_VIS0, 32, 32, dp + P_VIS0_W);
+      nfbwg::wg_flush(wg.tmem, w, l, WC_VIS2, 32, 33, dp + P_VIS2_W);
+      nfbwg::wg_flush(wg.tmem, w, l, WC_VISB0, 32, 32, dp + P_VISB0_W);
+      nfbwg::wg_flush(wg.tmem, w, l, WC_RGB0, 37, 16, dp + P_RGB0_W);
+      nfbwg::wg_flush(wg.tmem, w, l, WC_RGB2, 16, 8, dp + P_RGB2_W);
+    }
+    flush_vec(dp + P_DIR0_B, sg + SG_DIR0_B, 16, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_DIR2_B, sg + SG_DIR2_B, 35, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_BASE0_B, sg + SG_BASE0_B, 64, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_BASE2_B, sg + SG_BASE2_B, 32, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_VIS0_B, sg + SG_VIS0_B, 32, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_VIS2_B, sg + SG_VIS2_B, 33, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_VISB0_B, sg + SG_VISB0_B, 32, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_RGB0_B, sg + SG_RGB0_B, 16, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_RGB2_B, sg + SG_RGB2_B, 8, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_VISB2_W, sg + SG_VISB2, 32, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_VISB2_B, sg + SG_VISB2_B, 1, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_RGB4_W, sg + SG_RGB4, 8, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_RGB4_B, sg + SG_RGB4_B, 1, threadIdx.x, blockDim.x);
     if (threadIdx.x == 0 && a.anti_alias) {
       const float sv = __ldg(a.params + P_S);
-      atomicAdd(a.d_params + P_S, (sv > 0.f ? 1.f : (sv < 0.f ? -1.f : 0.f)) * sg[W_S]);
+      atomicAdd(dp + P_S, (sv > 0.f ? 1.f : (sv < 0.f ? -1.f : 0.f)) * sg[SG_S]);
     }
+    nfbtc::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) nfbtc::tmem_dealloc(wg.tmem, 512);
   }
 }
 
 constexpr size_t view_smem_bytes(int ng, bool wg = false) {
-  return (size_t)(W_TOTAL * (wg ? 2 : 1) + 16 * NFB_MAX_VIEWS + 4 + ng * GROUP * EXS + ng * TS_MAX * MVS) * sizeof(float);
+  return (size_t)(W_TOTAL + 16 * NFB_MAX_VIEWS + 4 + ng * GROUP * EXS + ng * TS_MAX * MVS) * sizeof(float) +
+         (wg ? (size_t)SG_TOTAL * sizeof(float) + (size_t)ng * (nfbwg::A_TILE_BYTES + nfbwg::B_TILE_BYTES) + ng * 8 + 16 : 0);
 }
 
 template <bool FUSED, bool BWD, int NG, bool WG = false>

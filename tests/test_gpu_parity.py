@@ -167,9 +167,11 @@ def _grad_params(p, dtype):
     return q
 
 
-def _check_param_grads(net, p32, p64, what, floor=2e-3):
+def _check_param_grads(net, p32, p64, what, floor=6e-3):
     """every parameter gradient of our module within max(floor, 3 x the fp32 oracle's own distance) of the fp64 truth
-    (relative L2 per tensor; tensors whose true gradient is ~0 are compared absolutely)."""
+    (relative L2 per tensor; tensors whose true gradient is ~0 are compared absolutely).  The floor reflects the
+    arithmetic of the view-stage weight gradients: tensor-core GEMMs over the row index with bf16-rounded operands and
+    fp32 accumulation (nfb_wgrad_tc.cuh) -- the usual training precision, ~2^-9 per operand before averaging."""
     worst = {}
     for name, prm in net.named_parameters():
         assert prm.grad is not None, f'{what}: no gradient for {name}'
@@ -264,7 +266,7 @@ def test_render_rays_parameter_gradients(dev):
     for name, prm in nets[1].named_parameters():          # fine net: fp32 oracle at identical depths
         ref = runs[torch.float32][1][name].grad
         if ref.norm() > 1e-9:
-            assert relerr(prm.grad.cpu(), ref) < 5e-3, ('fine net', name, relerr(prm.grad.cpu(), ref))
+            assert relerr(prm.grad.cpu(), ref) < 8e-3, ('fine net', name, relerr(prm.grad.cpu(), ref))
     e_c = relerr(fm_g[0].grad.cpu(), runs[torch.float64][2][0].grad)
     e_r = relerr(runs[torch.float32][2][0].grad, runs[torch.float64][2][0].grad)
     assert e_c <= max(1e-3, 3 * e_r), (e_c, e_r)
