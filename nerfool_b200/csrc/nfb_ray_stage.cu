@@ -5,6 +5,7 @@
 // backward Q, dO and the softmax statistics) of the ray live in shared memory.
 #include "nfb_dense.cuh"
 #include "nfb_ray_tc.cuh"
+#include "nfb_wgrad_tc.cuh"
 
 namespace {
 
@@ -43,23 +44,11 @@ static __device__ void load_ray_weights(float* sw, const float* __restrict__ p, 
   load_vec_padded(sw + RB_OG2, p + P_OG2_B, 1, 4, tid, nt);
 }
 
-// adds the per-CTA accumulators (shared-memory weight layout) into the torch-layout gradient blob
-static __device__ void flush_ray_grads(float* __restrict__ dp, const float* sg, int tid, int nt) {
-  flush_wt_transposed(dp + P_GEO0_W, sg + R_GEO0, 64, 65, 64, tid, nt);
-  flush_vec(dp + P_GEO0_B, sg + RB_GEO0, 64, tid, nt);
-  flush_wt_transposed(dp + P_GEO2_W, sg + R_GEO2, 16, 64, 16, tid, nt);
-  flush_vec(dp + P_GEO2_B, sg + RB_GEO2, 16, tid, nt);
-  flush_wt_transposed(dp + P_ATT_Q, sg + R_Q, 16, 16, 16, tid, nt);
-  flush_wt_transposed(dp + P_ATT_K, sg + R_K, 16, 16, 16, tid, nt);
-  flush_wt_transposed(dp + P_ATT_V, sg + R_V, 16, 16, 16, tid, nt);
-  flush_wt_transposed(dp + P_ATT_FC, sg + R_FC, 16, 16, 16, tid, nt);
-  flush_vec(dp + P_LN_W, sg + R_LNW, 16, tid, nt);
-  flush_vec(dp + P_LN_B, sg + R_LNB, 16, tid, nt);
-  flush_wt_transposed(dp + P_OG0_W, sg + R_OG0, 16, 16, 16, tid, nt);
-  flush_vec(dp + P_OG0_B, sg + RB_OG0, 16, tid, nt);
-  flush_vec(dp + P_OG2_W, sg + R_OG2, 16, tid, nt);
-  flush_vec(dp + P_OG2_B, sg + RB_OG2, 1, tid, nt);
-}
+// WG (training) kernel: TMEM accumulator columns of the tensor-core parameter-gradient GEMMs (nfb_wgrad_tc.cuh; the
+// reduction runs over the samples of the ray = the threads of the CTA) and the small shared accumulators of the
+// vector-shaped tensors (biases, LayerNorm, the single-output layer), which stay exact fp32
+enum : int { RC_GEO0 = 0, RC_GEO2 = 64, RC_Q = 80, RC_K = 96, RC_V = 112, RC_FC = 128, RC_OG0 = 144, RC_TOTAL = 160, RC_ALLOC = 256 };
+enum : int { RG_GEO0_B = 0, RG_GEO2_B = 64, RG_LNW = 80, RG_LNB = 96, RG_OG0_B = 112, RG_OG2 = 128, RG_OG2_B = 144, RG_TOTAL = 148 };
 
 constexpr float INV_TEMP = 0.5f;   // 1 / sqrt(d_k), d_k = 4 (mlp_network.py:84)
 constexpr float LN_EPS = 1e-6f;    // mlp_network.py:87
@@ -122,7 +111,7 @@ __device__ __forceinline__ void attend(const float (&q)[16], bool row_valid, int
 }
 
 template <bool BWD, bool WG = false>
-__global__ void __launch_bounds__(256) k_ray_stage(int R, int S, const float* __restrict__ ps,
+__global__ void __launch_bounds__(256, 1) k_ray_stage(int R, int S, const float* __restrict__ ps,
                                                     const float* __restrict__ params,
                                                     const float* __restrict__ pos_enc, float* __restrict__ raw,
                                                     const float* __restrict__ d_raw, float* __restrict__ d_ps,
@@ -137,12 +126,35 @@ __global__ void __launch_bounds__(256) k_ray_stage(int R, int S, const float* __
   float* sdo = sq + (size_t)S * 16;    // [S][16] d(attention output)
   float* sst = sdo + (size_t)S * 16;   // [S][12]: m[4], 1/l[4], D[4]
   float* svalid = sst + (size_t)S * 12;  // [S]
-  float* sg = svalid + (((size_t)S + 3) & ~(size_t)3);   // WG: [R_TOTAL] parameter-gradient accumulators
-  if (WG)
-    for (int i = threadIdx.x; i < R_TOTAL; i += blockDim.x) sg[i] = 0.f;
+  float* sg = svalid + (((size_t)S + 3) & ~(size_t)3);   // WG: [RG_TOTAL] small accumulators, then the operand tiles
+  uint8_t* s_tiles = reinterpret_cast<uint8_t*>(sg + RG_TOTAL);
+  const int krows = blockDim.x;                           // rows of a tile = threads of the CTA (multiple of 32)
+  uint8_t* s_tb = s_tiles + (size_t)128 * krows * 2;      // B tile [64][krows] bf16 behind the A tile [128][krows]
+  uint64_t* s_wbar = reinterpret_cast<uint64_t*>(s_tb + (size_t)64 * krows * 2);
+  uint32_t* s_wtmem = reinterpret_cast<uint32_t*>(s_wbar + 1);
+  nfbwg::WgTc wg{};
+  if (WG) {
+    for (int i = threadIdx.x; i < RG_TOTAL; i += blockDim.x) sg[i] = 0.f;
+    for (int i = threadIdx.x; i < (128 + 64) * krows / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(s_tiles)[i] = 0u;
+    if (threadIdx.x < 32) nfbtc::tmem_alloc(s_wtmem, RC_ALLOC);
+    if (threadIdx.x == 0) {
+      nfbtc::mbar_init(s_wbar, 1);
+      nfbtc::mbar_init_fence();
+    }
+  }
 
   load_ray_weights(sw, params, threadIdx.x, blockDim.x);
+  if (WG) nfbtc::fence_before_sync();
   __syncthreads();
+  if (WG) {
+    nfbtc::fence_after_sync();
+    wg.sA = s_tiles; wg.sB = s_tb; wg.mbar = s_wbar; wg.tmem = *s_wtmem; wg.phase = 0; wg.pending = false;
+    wg.tg = threadIdx.x; wg.bar_id = 1; wg.nthreads = blockDim.x;
+    if (threadIdx.x < 128) nfbwg::wg_zero(wg.tmem, threadIdx.x >> 5, RC_TOTAL);
+    nfbtc::fence_before_sync();
+    __syncthreads();
+    nfbtc::fence_after_sync();
+  }
   const int s = threadIdx.x;
   const bool act = s < S;
 
@@ -225,16 +237,16 @@ __global__ void __launch_bounds__(256) k_ray_stage(int R, int S, const float* __
         for (int k = 0; k < 16; ++k) dh[k] = dz2 * sw[R_OG2 + k] * elu_grad_from_out(hh[k]);
         dense_T<16, 16>(sw + R_OG0, dh, dln);
         if (WG) {
-          wgrad_vec<16>(sg + R_OG2, hh, dz2 * gate);
+          wgrad_rowsum<16>(sg + RG_OG2, hh, dz2 * gate);
           const float dbz[4] = {dz2, 0.f, 0.f, 0.f};
-          wgrad_vec<4>(sg + RB_OG2, dbz, gate);
-          wgrad_acc<16, 16>(sg + R_OG0, ln, dh, gate);
-          wgrad_vec<16>(sg + RB_OG0, dh, gate);
+          wgrad_rowsum<4>(sg + RG_OG2_B, dbz, gate);
+          nfbwg::wgrad_tc<16, 16>(wg, RC_OG0, ln, dh, gate);
+          wgrad_rowsum<16>(sg + RG_OG0_B, dh, gate);
           float t[16];
 #pragma unroll
           for (int c = 0; c < 16; ++c) t[c] = dln[c] * xhat[c];
-          wgrad_vec<16>(sg + R_LNW, t, gate);
-          wgrad_vec<16>(sg + R_LNB, dln, gate);
+          wgrad_rowsum<16>(sg + RG_LNW, t, gate);
+          wgrad_rowsum<16>(sg + RG_LNB, dln, gate);
         }
       }
       // LayerNorm backward: dy = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dln * gamma
@@ -254,7 +266,7 @@ __global__ void __launch_bounds__(256) k_ray_stage(int R, int S, const float* __
       // y = fc(o) + xin
       float dO[16];
       dense_T<16, 16>(sw + R_FC, dy, dO);
-      if (WG) wgrad_acc<16, 16>(sg + R_FC, at.o, dy, gate);
+      if (WG) nfbwg::wgrad_tc<16, 16>(wg, RC_FC, at.o, dy, gate);
       // publish per-query quantities for the key-side pass
       if (act) {
 #pragma unroll
@@ -327,9 +339,9 @@ __global__ void __launch_bounds__(256) k_ray_stage(int R, int S, const float* __
         }
       }
       if (WG) {
-        wgrad_acc<16, 16>(sg + R_Q, xin, dq, gate);
-        wgrad_acc<16, 16>(sg + R_K, xin, dk, gate);
-        wgrad_acc<16, 16>(sg + R_V, xin, dv, gate);
+        nfbwg::wgrad_tc<16, 16>(wg, RC_Q, xin, dq, gate);
+        nfbwg::wgrad_tc<16, 16>(wg, RC_K, xin, dk, gate);
+        nfbwg::wgrad_tc<16, 16>(wg, RC_V, xin, dv, gate);
       }
       // d xin = dy (residual) + Wq^T dq + Wk^T dk + Wv^T dv ; pos_encoding is a constant
       float dx[16];
@@ -353,13 +365,13 @@ __global__ void __launch_bounds__(256) k_ray_stage(int R, int S, const float* __
 #pragma unroll
       for (int k = 0; k < 64; ++k) dh64[k] *= elu_grad_from_out(h64[k]);
       if (WG) {
-        wgrad_acc<64, 16>(sg + R_GEO2, h64, dx, gate);
-        wgrad_vec<16>(sg + RB_GEO2, dx, gate);
+        nfbwg::wgrad_tc<64, 16>(wg, RC_GEO2, h64, dx, gate);
+        wgrad_rowsum<16>(sg + RG_GEO2_B, dx, gate);
         float xin65[65];
 #pragma unroll
         for (int k = 0; k < 65; ++k) xin65[k] = __ldg(psrow + k);
-        wgrad_acc<65, 64>(sg + R_GEO0, xin65, dh64, gate);
-        wgrad_vec<64>(sg + RB_GEO0, dh64, gate);
+        nfbwg::wgrad_tc<65, 64>(wg, RC_GEO0, xin65, dh64, gate);
+        wgrad_rowsum<64>(sg + RG_GEO0_B, dh64, gate);
       }
       if (act) {
         float* out = d_ps + ((size_t)r * S + s) * NFB_PS_STRIDE;
@@ -380,8 +392,31 @@ __global__ void __launch_bounds__(256) k_ray_stage(int R, int S, const float* __
     }
   }
   if (WG) {
+    nfbwg::wg_wait(wg);
+    nfbtc::fence_before_sync();
     __syncthreads();
-    flush_ray_grads(d_params, sg, threadIdx.x, blockDim.x);
+    nfbtc::fence_after_sync();
+    float* dp = d_params;
+    if (threadIdx.x < 128) {
+      const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+      nfbwg::wg_flush(wg.tmem, w, l, RC_GEO0, 65, 64, dp + P_GEO0_W);
+      nfbwg::wg_flush(wg.tmem, w, l, RC_GEO2, 64, 16, dp + P_GEO2_W);
+      nfbwg::wg_flush(wg.tmem, w, l, RC_Q, 16, 16, dp + P_ATT_Q);
+      nfbwg::wg_flush(wg.tmem, w, l, RC_K, 16, 16, dp + P_ATT_K);
+      nfbwg::wg_flush(wg.tmem, w, l, RC_V, 16, 16, dp + P_ATT_V);
+      nfbwg::wg_flush(wg.tmem, w, l, RC_FC, 16, 16, dp + P_ATT_FC);
+      nfbwg::wg_flush(wg.tmem, w, l, RC_OG0, 16, 16, dp + P_OG0_W);
+    }
+    flush_vec(dp + P_GEO0_B, sg + RG_GEO0_B, 64, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_GEO2_B, sg + RG_GEO2_B, 16, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_LN_W, sg + RG_LNW, 16, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_LN_B, sg + RG_LNB, 16, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_OG0_B, sg + RG_OG0_B, 16, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_OG2_W, sg + RG_OG2, 16, threadIdx.x, blockDim.x);
+    flush_vec(dp + P_OG2_B, sg + RG_OG2_B, 1, threadIdx.x, blockDim.x);
+    nfbtc::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) nfbtc::tmem_dealloc(wg.tmem, RC_ALLOC);
   }
 }
 
@@ -461,11 +496,13 @@ extern "C" int nfb_ibrnet_ray_wgrad(int R, int S, const float* ps, const float* 
   NFB_REQUIRE(ps && params && pos_enc && d_raw && d_ps && d_params, NFB_EINVAL, "nfb_ibrnet_ray_wgrad: NULL buffer");
   NFB_REQUIRE(((uintptr_t)ps % 16) == 0 && ((uintptr_t)d_raw % 16) == 0 && ((uintptr_t)d_ps % 16) == 0, NFB_EINVAL,
               "nfb_ibrnet_ray_wgrad: ps/d_raw/d_ps must be 16-byte aligned");
-  const size_t smem = (size_t)(R_TOTAL * 2 + 4 * S * 16 + S * 12 + ((S + 3) & ~3)) * sizeof(float);
+  const int wblock = ray_block(S) < 128 ? 128 : ray_block(S);     // >= 4 warps: they own the 128 TMEM lanes of the accumulators
+  const size_t smem = (size_t)(R_TOTAL + 4 * S * 16 + S * 12 + ((S + 3) & ~3) + RG_TOTAL) * sizeof(float) +
+                      (size_t)(128 + 64) * wblock * 2 + 8 + 16;
   cudaError_t e = cudaFuncSetAttribute(k_ray_stage<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nfb_set_error(NFB_ECUDA, "nfb_ibrnet_ray_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  const int block = ray_block(S);
-  int per_sm = 2048 / block; if (per_sm > 2) per_sm = 2;
+  const int block = wblock;
+  int per_sm = 2;                                                  // 2 x 256 TMEM columns per SM
   int grid = nfb_num_sms() * per_sm; if (grid > R) grid = R;
   k_ray_stage<true, true><<<grid, block, smem, (cudaStream_t)stream>>>(R, S, ps, params, pos_enc, nullptr, d_raw, d_ps, d_params);
   NFB_CHECK_LAUNCH("k_ray_stage<bwd,wgrad>");

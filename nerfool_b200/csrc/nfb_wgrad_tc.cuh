@@ -23,6 +23,7 @@ struct WgTc {
   uint32_t phase;      // parity the next completion will have
   bool pending;        // an MMA batch of this group is still reading the staging tiles
   int tg, bar_id;
+  int nthreads;        // threads (= rows = MMA K extent, a multiple of 16) of the group; 0 means 128
 };
 
 __device__ __forceinline__ void st_bf16(uint8_t* p, float v) { *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(v); }
@@ -49,13 +50,13 @@ __device__ __forceinline__ void wgrad_tc(WgTc& c, int dcol, const float (&x)[K_I
 #pragma unroll
   for (int n = 0; n < NP; ++n) st_bf16(pb + (n >> 3) * 128 + (n & 7) * 16, n < N_ARR ? dy[n < N_ARR ? n : 0] * gate : 0.f);
   fence_proxy_async_smem();                                     // generic-proxy stores -> visible to the MMA (async proxy)
-  named_bar_sync(c.bar_id, 128);
+  const int rows = c.nthreads ? c.nthreads : 128;
+  named_bar_sync(c.bar_id, rows);
   if (c.tg == 0) {
     fence_after_sync();
     constexpr uint32_t idesc = idesc_bf16(128, NP);
     const uint32_t a_addr = smem_u32(c.sA), b_addr = smem_u32(c.sB);
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks)
+    for (int ks = 0; ks < rows / 16; ++ks)
       mma_ss(c.tmem + dcol, smem_desc(a_addr + ks * 4096, 2048, 128), smem_desc(b_addr + ks * 2 * NP * 16, NP * 16, 128), idesc, true);
     mma_commit(c.mbar);
   }
