@@ -288,6 +288,41 @@ def run_ours(a):
             except Exception as ex:
                 nrand[str(n)]['graph_error'] = f'{type(ex).__name__}: {ex}'[:160]
 
+    # ---------------- one TRAINING step (train.py:317-327): fwd + loss + backward incl. every IBRNet parameter gradient ----------------
+    train = None
+    if world == 1 and not a.no_nrand:
+        try:
+            from nerfool_b200.attack import rgb_loss
+            gen = torch.Generator(device='cpu').manual_seed(4)
+            sel = torch.randperm(R, generator=gen)[:4096].sort().values.to(device)
+            tb = dict(static)
+            for k in ('ray_o', 'ray_d', 'rgb'):
+                tb[k] = resident[k][sel].contiguous()
+            model.net_coarse.train(); model.net_fine.train()
+            tfm = tuple(f.detach().clone().requires_grad_(True) for f in featmaps)
+
+            def train_step():
+                for n in (model.net_coarse, model.net_fine):
+                    n.zero_grad(set_to_none=True)
+                out = render_rays(tb, model, tfm, projector, N_SAMPLES, inv_uniform=True, N_importance=N_IMPORTANCE, det=True)
+                rgb_loss(out, tb['rgb']).backward()
+            for _ in range(3):
+                train_step()
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(10):
+                train_step()
+            s1.record()
+            torch.cuda.synchronize()
+            train = {'rays': 4096, 'ms_per_step': s0.elapsed_time(s1) / 10, 'rays_per_s': 4096e4 / s0.elapsed_time(s1),
+                     'what': 'render_rays fwd + masked MSE + backward to the feature maps AND all 2 x 20,136 IBRNet parameters '
+                             '(weight gradients as tcgen05 GEMMs over the row index, bf16 operands, fp32 accumulate)'}
+        except Exception as ex:
+            train = {'error': f'{type(ex).__name__}: {ex}'[:200]}
+        finally:
+            model.net_coarse.eval(); model.net_fine.eval()
+
     # max over ranks
     t = torch.tensor([total_ms, e2e_total_ms, statistics.median(fwd_ms), bf16_ms or 0.0], device=device, dtype=torch.float64)
     if world > 1:
@@ -332,6 +367,21 @@ def run_ours(a):
                              'achieved_GBps': ach, 'hbm_frac': ach / hbm_peak,
                              'dense_TFLOPs': tfl, 'tensor_frac': tfl / tensor_peak if tensor_peak else None,
                              'traffic_bytes_per_launch': tr}
+        # the small HBM-bound kernels of the path: compositing and the importance sampler
+        s_c, s_f = N_SAMPLES, N_SAMPLES + N_IMPORTANCE
+        small = {'nfb_composite_fwd': (32, samples_per_step),        # raw 16 + z 4 + n_valid 4 in, weights 4 + alpha 4 out per sample
+                 'nfb_composite_bwd': (36, samples_per_step),        # raw 16 + z 4 in, d_raw 16 out per sample
+                 'nfb_fine_depths': (4 * (2 * s_c + s_f), R)}        # z, weights in, sorted z out per ray
+        for k, (bpu, units) in small.items():
+            if k in prof:
+                n_l = len(prof[k])
+                avg_ms = ktot[k] / n_l
+                per_launch_units = units * a.steps / n_l
+                ach = bpu * per_launch_units / (avg_ms * 1e-3) / 1e9
+                per_kernel[k] = {'ms_per_step': ktot[k] / a.steps, 'launches_per_step': n_l / a.steps, 'avg_launch_ms': avg_ms,
+                                 'algorithmic_bytes_per_unit': bpu, 'units_per_launch': per_launch_units,
+                                 'achieved_GBps': ach, 'hbm_frac': ach / hbm_peak, 'dense_TFLOPs': None, 'tensor_frac': None,
+                                 'traffic_bytes_per_launch': None}
         dom = max(per_kernel, key=lambda k: per_kernel[k]['ms_per_step'])
         d = per_kernel[dom]
         ms_per_step = total_ms / a.steps
@@ -353,6 +403,7 @@ def run_ours(a):
                              'the 2x6.3 MB feature maps are L2-resident by design'},
             'pgd_iters_per_s': 1e3 / ms_per_step,
             'pgd_iters_per_s_by_n_rand': nrand or None,
+            'training_step': train,
             'fwd_rays_per_s': rays_total / (fwd_med * 1e-3),
             'fwd_ms_per_frame': fwd_med,
             'encoder': 'not timed: the ResUNet stays on cuDNN in the reference and is outside this repo (north_star)',

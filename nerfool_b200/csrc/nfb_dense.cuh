@@ -76,51 +76,11 @@ __device__ __forceinline__ void load_vec_padded(float* __restrict__ dst, const f
 }
 
 // ---------------------------------------------------------------------------------------------------
-// parameter gradients (training): sg[e] += sum over the 32 rows of this warp of x[e / NP] * dy[e % NP],
-// e in [0, K*NP) -- the [K][NP] shared-memory accumulator mirrors the transposed weight layout.
-// 32 products per lane are reduced across the warp with a 5-stage exchange butterfly (31 shuffles per 32
-// weights, lane L ends up with the total of element e0 + L) and added with one shared-memory atomic.
-// The row copies are indexed dynamically (local memory); the caller's register arrays are untouched.
+// parameter gradients (training).  The weight gradients are GEMMs over the row index on the tensor cores
+// (nfb_wgrad_tc.cuh); vector-shaped gradients (biases, LayerNorm, single-output layers) are plain row sums:
+// 32 values per lane are reduced across the warp with a 5-stage exchange butterfly (31 shuffles per 32 values, lane
+// L ends up with the total of element n0 + L) and added with one shared-memory atomic.
 // ---------------------------------------------------------------------------------------------------
-template <int K, int NP>
-__device__ __noinline__ void wgrad_acc(float* __restrict__ sg, const float (&x)[K], const float (&dy)[NP], float gate) {
-  constexpr int E = K * NP;
-  const int lane = threadIdx.x & 31;
-  float xl[K], dl[NP];
-#pragma unroll
-  for (int k = 0; k < K; ++k) xl[k] = x[k] * gate;
-#pragma unroll
-  for (int n = 0; n < NP; ++n) dl[n] = dy[n];
-#pragma unroll 1
-  for (int e0 = 0; e0 < E; e0 += 32) {
-    float v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int e = e0 + i;
-      const int k = e / NP, n = e - k * NP;
-      v[i] = (e < E) ? xl[k] * dl[n] : 0.f;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const bool up = (lane & o) != 0;
-#pragma unroll
-      for (int i = 0; i < o; ++i) {
-        const float keep = up ? v[i + o] : v[i];
-        const float send = up ? v[i] : v[i + o];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-      }
-    }
-    if (e0 + lane < E) atomicAdd(sg + e0 + lane, v[0]);
-  }
-}
-
-// sg[n] += sum over the warp's rows of dy[n] * gate  (bias gradients, single-row weights scaled by a scalar)
-template <int NP>
-__device__ __forceinline__ void wgrad_vec(float* __restrict__ sg, const float (&dy)[NP], float scale) {
-  const float one[1] = {1.f};
-  wgrad_acc<1, NP>(sg, one, dy, scale);
-}
-
 // sg[n] += scale * (sum over the warp's rows of dy[n]), fully inlined with compile-time register indices (the caller's
 // array stays in registers): the same exchange butterfly, 31 shuffles per 32 values
 template <int NP>

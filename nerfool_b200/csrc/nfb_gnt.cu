@@ -482,12 +482,7 @@ __global__ void __launch_bounds__(256) k_gnt_head(int R, int S, const float* __r
 // ---------------------------------------------------------------------------------------------------
 // tensor-core form: the 64 x 64 projections run in k_gnt_lin_tc (nfb_gnt_tc.cuh); what stays on the CUDA cores is
 // the part of the two attentions that is not a dense contraction.
-// view core: per sample, given qq = q_fc(LN(q)) [N][64] and the per-row k, v [N*V][64]:
-//   pos = pos_fc(ray_diff), a = attn_fc(k - qq + pos) (masked), softmax over views per channel, x = sum_v (v + pos) a
 // ---------------------------------------------------------------------------------------------------
-enum : int { CS_P0 = 0 /*[4][8]*/, CS_P0_B = 32, CS_P2 = 40 /*[8][64]*/, CS_P2_B = CS_P2 + 8 * D, CS_A0 = CS_P2_B + D /*[64][8]*/,
-             CS_A0_B = CS_A0 + D * 8, CS_A2 = CS_A0_B + 8 /*[8][64]*/, CS_A2_B = CS_A2 + 8 * D, CS_TOTAL = CS_A2_B + D };
-
 // Input per (sample, view) row from k_gnt_lin_tc<LIN_KV>: a8 = ReLU(attn_fc.0(k - qq + pos)) [8] and vp = v + pos [64].
 // Two adjacent lanes share a sample, each owns 32 of the 64 channels: a = attn_fc.2(a8) (masked), softmax over the
 // views per channel (online), x = sum_v vp a.
