@@ -71,10 +71,21 @@ __device__ __forceinline__ void posenc64(const float (&x3)[3], float (&e)[TD]) {
   e[63] = 0.f;
 }
 
+// LIN_KV (the per-(sample, view) row kernel, the largest of the network) prefetches the input rows of a group's NEXT tile
+// into a shared-memory staging buffer with cp.async while the current tile is processed; row stride 272 B keeps the
+// 16-byte row reads of a warp conflict-free.
+constexpr int ROW_STAGE_STRIDE = 272;
+__host__ __device__ constexpr size_t stage_bytes(int mode) { return mode == LIN_KV ? (size_t)mode_groups(mode) * GROUP * ROW_STAGE_STRIDE : 0; }
+
 template <int NPASS, int MODE>
 __host__ __device__ constexpr size_t lin_smem_bytes() {
-  return (size_t)mode_tiles(MODE) * TILE_BYTES * (NPASS == 3 ? 2 : 1) + sizeof(float) * (256 + 64 + 128 + KV_TOTAL) + mode_groups(MODE) * 8 + 16;
+  return (size_t)mode_tiles(MODE) * TILE_BYTES * (NPASS == 3 ? 2 : 1) + sizeof(float) * (256 + 64 + 128 + KV_TOTAL) + stage_bytes(MODE) +
+         mode_groups(MODE) * 8 + 16;
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __host__ __device__ constexpr uint32_t canon_off(int n, int k) {      // element (n, k) of a [64][64] K-major tile
   return (uint32_t)((k >> 3) * (TD * 16) + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2);
@@ -189,7 +200,8 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
   float* s_b1 = sf + 256;      // 64
   float* s_ln = sf + 320;      // 64 + 64
   float* s_kv = sf + 448;      // KV_TOTAL
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(sf + 448 + KV_TOTAL);
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(sf + 448 + KV_TOTAL);          // LIN_KV: NG x [128 rows][272 B]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + stage_bytes(MODE));
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + NG);
 
   const int tid = threadIdx.x, warp = tid >> 5, nt = blockDim.x;
@@ -249,11 +261,25 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
   uint32_t phase = 0;
   const long long ntiles = (a.M + GROUP - 1) / GROUP;
 
+  uint8_t* my_stage = s_stage + ((size_t)(MODE == LIN_KV ? grp : 0) * GROUP + tg) * ROW_STAGE_STRIDE;
+  if (MODE == LIN_KV) {                      // prologue: this thread's row of the group's first tile
+    const long long r0 = ((long long)blockIdx.x * NG + grp) * GROUP + tg;
+    if (r0 < a.M)
+#pragma unroll
+      for (int c = 0; c < 16; ++c) cp_async16(my_stage + 16 * c, a.x + r0 * TD + 4 * c);
+  }
   for (long long tile = (long long)blockIdx.x * NG + grp; tile < ntiles; tile += (long long)gridDim.x * NG) {
     const long long row = tile * GROUP + tg;
     const bool active = row < a.M;
     float x[TD];
-    if (MODE == LIN_EMBED) {
+    if (MODE == LIN_KV) {
+      cp_async_wait_all();                   // own row only: no cross-thread dependence
+#pragma unroll
+      for (int c = 0; c < TD; c += 4) {
+        const float4 t4 = active ? *reinterpret_cast<const float4*>(my_stage + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[c] = t4.x; x[c + 1] = t4.y; x[c + 2] = t4.z; x[c + 3] = t4.w;
+      }
+    } else if (MODE == LIN_EMBED) {
 #pragma unroll
       for (int c = 0; c < TD; ++c) x[c] = (active && c < NFB_ROW_CH) ? __ldg(a.x + row * NFB_ROW_CH + c) : 0.f;
     } else if (active) row_load(a.x + row * TD, x);
@@ -288,6 +314,14 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
     } else {
       a_store_row<NPASS>(tl, C_A, C_ALO, x);
       GNT_TC_ISSUE(C_D0, C_A, C_ALO, 0, false);
+      if (MODE == LIN_KV) {
+        // x has been consumed (its TMEM stores completed before the barrier above), so the staging row is free: prefetch
+        // this thread's row of the group's next tile while the MMAs and the epilogue of this one run
+        const long long rn = row + (long long)gridDim.x * NG * GROUP;
+        if (rn < a.M)
+#pragma unroll
+          for (int c = 0; c < 16; ++c) cp_async16(my_stage + 16 * c, a.x + rn * TD + 4 * c);
+      }
       GNT_TC_WAIT();
       float y[TD];
       d_load_row(tl, C_D0, y);
