@@ -468,14 +468,53 @@ k_fine_depths(int R, int S, int n_imp, int inv_uniform, const float* __restrict_
       s_all[S + j] = smp;
     }
     __syncwarp();
-    for (int i = lane; i < T; i += 32) {
-      const float vi = s_all[i];
-      int rank = 0;
-      for (int j = 0; j < T; ++j) {
-        const float vj = s_all[j];
-        rank += (vj < vi || (vj == vi && j < i)) ? 1 : 0;
+    // torch.sort of cat(z_coarse, z_new) (render_ray.py:235-238), stable on ties (lower index first).  The coarse depths
+    // are non-decreasing and, for the deterministic sampler, the new samples are monotone (increasing u -> increasing
+    // inverse depth -> decreasing z with inv_uniform), so the sort is a merge of two monotone runs: the rank of an
+    // element is its position in its own run plus a binary search in the other one.  Checked per ray with a warp vote;
+    // anything else (stochastic u) takes the O(T^2) rank sort.
+    const float* A = s_all;            // [S]
+    const float* B = s_all + S;        // [n_imp]
+    bool okA = true, inc = true, dec = true;
+    for (int i = lane; i + 1 < S; i += 32) okA = okA && (A[i] <= A[i + 1]);
+    for (int j = lane; j + 1 < n_imp; j += 32) { inc = inc && (B[j] <= B[j + 1]); dec = dec && (B[j] >= B[j + 1]); }
+    okA = __all_sync(0xffffffffu, okA);
+    inc = __all_sync(0xffffffffu, inc);
+    dec = __all_sync(0xffffffffu, dec);
+    if (okA && (inc || dec)) {
+      for (int i = lane; i < T; i += 32) {
+        const float v = s_all[i];
+        int rank;
+        if (i < S) {
+          // coarse element: i earlier coarse elements + the new samples strictly below it (they lose ties)
+          int lo = 0, hi = n_imp;      // count of B < v
+          if (inc) { while (lo < hi) { const int mid = (lo + hi) >> 1; if (B[mid] < v) lo = mid + 1; else hi = mid; } rank = i + lo; }
+          else     { while (lo < hi) { const int mid = (lo + hi) >> 1; if (B[mid] >= v) lo = mid + 1; else hi = mid; } rank = i + (n_imp - lo); }
+        } else {
+          const int j = i - S;
+          int lo = 0, hi = S;          // coarse elements <= v come first (they win ties)
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (A[mid] <= v) lo = mid + 1; else hi = mid; }
+          if (inc) rank = lo + j;
+          else {
+            int l2 = 0, h2 = n_imp;    // #{B > v}: the equal run of v starts here
+            while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (B[mid] > v) l2 = mid + 1; else h2 = mid; }
+            int l3 = l2, h3 = n_imp;   // #{B >= v}
+            while (l3 < h3) { const int mid = (l3 + h3) >> 1; if (B[mid] >= v) l3 = mid + 1; else h3 = mid; }
+            rank = lo + (n_imp - l3) + (j - l2);
+          }
+        }
+        z_fine[(size_t)r * T + rank] = v;
       }
-      z_fine[(size_t)r * T + rank] = vi;
+    } else {
+      for (int i = lane; i < T; i += 32) {
+        const float vi = s_all[i];
+        int rank = 0;
+        for (int j = 0; j < T; ++j) {
+          const float vj = s_all[j];
+          rank += (vj < vi || (vj == vi && j < i)) ? 1 : 0;
+        }
+        z_fine[(size_t)r * T + rank] = vi;
+      }
     }
     __syncwarp();
   }
