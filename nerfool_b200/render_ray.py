@@ -97,7 +97,16 @@ def _fusable(model, projector):
         return False
     nc = _unwrap(model.net_coarse)
     nf = _unwrap(model.net_fine) if getattr(model, 'net_fine', None) is not None else None
-    return isinstance(projector, Projector) and isinstance(nc, IBRNet) and (nf is None or isinstance(nf, IBRNet))
+    if not (isinstance(projector, Projector) and isinstance(nc, IBRNet) and (nf is None or isinstance(nf, IBRNet))):
+        return False
+    # A DistributedDataParallel / DataParallel wrapper (model.py:78-110) must see its own forward() when the parameters
+    # train: its gradient-reduction hooks are armed there.  The fused path calls the unwrapped module, so in that case
+    # the composed path (Projector.compute -> wrapper(rgb_feat, ray_diff, mask) -> raw2outputs) is used instead.
+    for net, inner in ((model.net_coarse, nc), (getattr(model, 'net_fine', None), nf)):
+        if inner is not None and net is not inner and inner.training and torch.is_grad_enabled() and \
+                any(p.requires_grad for p in inner.parameters()):
+            return False
+    return True
 
 
 def render_rays(ray_batch, model, featmaps, projector, N_samples, inv_uniform=False, N_importance=0, det=False,

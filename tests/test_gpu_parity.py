@@ -167,7 +167,7 @@ def _grad_params(p, dtype):
     return q
 
 
-def _check_param_grads(net, p32, p64, what, floor=6e-3):
+def _check_param_grads(net, p32, p64, what, floor=1e-2):
     """every parameter gradient of our module within max(floor, 3 x the fp32 oracle's own distance) of the fp64 truth
     (relative L2 per tensor; tensors whose true gradient is ~0 are compared absolutely).  The floor reflects the
     arithmetic of the view-stage weight gradients: tensor-core GEMMs over the row index with bf16-rounded operands and
@@ -190,7 +190,8 @@ def _check_param_grads(net, p32, p64, what, floor=6e-3):
 
 
 @pytest.mark.parametrize('V,S,kind,H,W,R,aa', [(4, 64, 'llff', 378, 504, 100, 1), (10, 192, 'synthetic', 200, 200, 20, 1),
-                                               (5, 33, 'llff', 96, 128, 67, 1), (3, 40, 'llff', 96, 128, 50, 0)])
+                                               (5, 33, 'llff', 96, 128, 67, 1), (3, 40, 'llff', 96, 128, 50, 0),
+                                               (2, 256, 'llff', 96, 128, 5, 1)])
 def test_ibrnet_parameter_gradients(dev, V, S, kind, H, W, R, aa):
     """Training (train.py:317-327): d loss / d every IBRNet parameter through IBRNet.forward (tensor form) equals autograd
     of the oracle; the data gradient that comes out of the same kernels is checked too."""
@@ -828,3 +829,47 @@ def test_source_view_permutation_invariance_full_size(dev):
     assert relerr(f2[0].grad.cpu(), f1[0].grad[perm].cpu()) < 1e-4
     # the fine level re-samples from the coarse weights: identical up to samples that sit on a CDF tie
     assert (o1['outputs_fine']['rgb'] - o2['outputs_fine']['rgb']).abs().median().item() < 1e-5
+
+
+def test_wrapped_nets_train_through_the_wrapper(dev):
+    """model.py:78-110 wraps the nets in DistributedDataParallel / DataParallel.  In training the wrapper's own forward
+    must run (DDP arms its gradient hooks there), so render_rays takes the composed path through the wrapper; in eval /
+    attack mode it keeps the fused path.  Both give the same parameter gradients as the bare modules."""
+    from nerfool_b200.mlp_network import IBRNet
+    from nerfool_b200.projection import Projector
+    from nerfool_b200 import render_ray as RR
+    from nerfool_b200.attack import rgb_loss
+
+    class Wrap(torch.nn.Module):             # stands in for DDP / DataParallel: same `.module` attribute, counts forwards
+        def __init__(self, m):
+            super().__init__()
+            self.module, self.calls = m, 0
+
+        def forward(self, *a):
+            self.calls += 1
+            return self.module(*a)
+    V, R, S, NI = 3, 64, 16, 16
+    scene, batch = _scene(V, R, 96, 128, 'llff', seed=17)
+    gb = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    grads = {}
+    for wrapped in (False, True):
+        nets = []
+        for p, n in ((_params(S, 51), S), (_params(S + NI, 52), S + NI)):
+            net = IBRNet(types.SimpleNamespace(anti_alias_pooling=1), 32, n)
+            net.load_state_dict({k: v.clone() for k, v in p.items()})
+            nets.append(net.to(dev).train())
+        mods = [Wrap(n) for n in nets] if wrapped else nets
+        model = types.SimpleNamespace(net_coarse=mods[0], net_fine=mods[1])
+        fm = tuple(f.detach().to(dev).requires_grad_(True) for f in scene['featmaps'])
+        assert RR._fusable(model, Projector(dev)) == (not wrapped)
+        out = RR.render_rays(gb, model, fm, Projector(dev), S, inv_uniform=True, N_importance=NI, det=True)
+        rgb_loss(out, gb['rgb']).backward()
+        if wrapped:
+            assert mods[0].calls == 1 and mods[1].calls == 1
+            for m in mods:
+                m.eval()
+            assert RR._fusable(model, Projector(dev))          # attack / eval mode: fused path again
+        grads[wrapped] = [prm.grad.detach().clone() for n in nets for prm in n.parameters()]
+    for a, b in zip(grads[False], grads[True]):
+        if a.norm() > 1e-9:
+            assert relerr(b.cpu(), a.cpu()) < 2e-2        # two bf16-operand GEMM forms of the same sum (fused vs tensor-mode tiles)
