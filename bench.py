@@ -369,7 +369,7 @@ def run_ours(a):
                              'traffic_bytes_per_launch': tr}
         # the small HBM-bound kernels of the path: compositing and the importance sampler
         s_c, s_f = N_SAMPLES, N_SAMPLES + N_IMPORTANCE
-        small = {'nfb_composite_fwd': (32, samples_per_step),        # raw 16 + z 4 + n_valid 4 in, weights 4 + alpha 4 out per sample
+        small = {'nfb_composite_fwd': (29, samples_per_step),        # raw 16 + z 4 + pixel mask 1 in, weights 4 + alpha 4 out per sample
                  'nfb_composite_bwd': (36, samples_per_step),        # raw 16 + z 4 in, d_raw 16 out per sample
                  'nfb_fine_depths': (4 * (2 * s_c + s_f), R)}        # z, weights in, sorted z out per ray
         for k, (bpu, units) in small.items():

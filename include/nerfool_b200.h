@@ -111,8 +111,11 @@ int nfb_ibrnet_view_fwd(int N, int S, int V, int anti_alias,
 /* The ray stage has the same optional activation stash (tensor-core forms): 560 B per sample (q, k, v,
  * attention output and softmax statistics, LayerNorm xhat / rstd, ELU-derivative codes). */
 size_t nfb_ray_stash_bytes(int R, int S);
+/* pixel_mask (optional, may be NULL): uint8 [R][S] = (number of valid observations of the sample > 1), the `mask`
+ * argument of raw2outputs (render_ray.py:210), written compactly so that nfb_composite_fwd does not have to pick it out of
+ * the 288-byte interface rows. */
 int nfb_ibrnet_ray_fwd(int R, int S, const float* ps, const float* params, const float* pos_enc /*[S][16]*/,
-                       float* raw /*[R][S][4]*/, float* stash, int precision, void* stream);
+                       float* raw /*[R][S][4]*/, uint8_t* pixel_mask /*[R][S]*/, float* stash, int precision, void* stream);
 /* Backward (data gradients): d_raw[R][S][4] -> d_ps[N][72] -> d_rgb_feat[N][V][35] (tensor mode) or a
  * scatter into d_feat / d_imgs (fused mode, rgb_feat == NULL).                                         */
 int nfb_ibrnet_ray_bwd(int R, int S, const float* ps, const float* params, const float* pos_enc,

@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(256, 1) k_ray_stage(int R, int S, const float*
                                                     const float* __restrict__ params,
                                                     const float* __restrict__ pos_enc, float* __restrict__ raw,
                                                     const float* __restrict__ d_raw, float* __restrict__ d_ps,
-                                                    float* __restrict__ d_params = nullptr) {
+                                                    float* __restrict__ d_params = nullptr,
+                                                    uint8_t* __restrict__ pixel_mask = nullptr) {
   static_assert(!WG || BWD, "parameter gradients are part of the backward");
   extern __shared__ __align__(16) float smem[];
   float* sw = smem;
@@ -216,9 +217,11 @@ __global__ void __launch_bounds__(256, 1) k_ray_stage(int R, int S, const float*
     if (!BWD) {
       float sigma = fmaxf(z2, 0.f);
       if (nvalid < 1.f) sigma = 0.f;                     // mlp_network.py:265
-      if (act)
+      if (act) {
         reinterpret_cast<float4*>(raw)[(size_t)r * S + s] =
             make_float4(__ldg(psrow + PS_RGB), __ldg(psrow + PS_RGB + 1), __ldg(psrow + PS_RGB + 2), sigma);
+        if (pixel_mask) pixel_mask[(size_t)r * S + s] = nvalid > 1.f ? 1 : 0;
+      }
       __syncthreads();                                   // sk / sv are rewritten by the next ray
       continue;
     }
@@ -432,7 +435,7 @@ extern "C" size_t nfb_ray_stash_bytes(int R, int S) {
 }
 
 extern "C" int nfb_ibrnet_ray_fwd(int R, int S, const float* ps, const float* params, const float* pos_enc,
-                                  float* raw, float* stash, int precision, void* stream) {
+                                  float* raw, uint8_t* pixel_mask, float* stash, int precision, void* stream) {
   NFB_REQUIRE(R >= 0 && S >= 1, NFB_EINVAL, "nfb_ibrnet_ray_fwd: bad arguments (R=%d S=%d)", R, S);
   NFB_REQUIRE(S <= NFB_MAX_SAMPLES, NFB_EUNSUPPORTED, "nfb_ibrnet_ray_fwd: S=%d > %d samples per ray", S, NFB_MAX_SAMPLES);
   if (R == 0) return NFB_OK;
@@ -443,7 +446,7 @@ extern "C" int nfb_ibrnet_ray_fwd(int R, int S, const float* ps, const float* pa
     NFB_REQUIRE(precision != NFB_PREC_FP32 && ((uintptr_t)stash % 16) == 0, NFB_EUNSUPPORTED,
                 "nfb_ibrnet_ray_fwd: the activation stash exists for the tensor-core forms only, 16-byte aligned");
   if (precision != NFB_PREC_FP32) {
-    nfbrtc::RayArgs a{R, S, ps, params, pos_enc, raw, nullptr, nullptr, stash};
+    nfbrtc::RayArgs a{R, S, ps, params, pos_enc, raw, nullptr, nullptr, stash, pixel_mask};
     cudaStream_t st = (cudaStream_t)stream;
     if (stash) return precision == NFB_PREC_BF16 ? nfb_launch_ray_tc_fwd_p1_save(a, st) : nfb_launch_ray_tc_fwd_p3_save(a, st);
     return precision == NFB_PREC_BF16 ? nfb_launch_ray_tc_fwd_p1(a, st) : nfb_launch_ray_tc_fwd_p3(a, st);
@@ -454,7 +457,7 @@ extern "C" int nfb_ibrnet_ray_fwd(int R, int S, const float* ps, const float* pa
   const int block = ray_block(S);
   int per_sm = 2048 / block; if (per_sm > 4) per_sm = 4;
   int grid = nfb_num_sms() * per_sm; if (grid > R) grid = R;
-  k_ray_stage<false><<<grid, block, smem, (cudaStream_t)stream>>>(R, S, ps, params, pos_enc, raw, nullptr, nullptr);
+  k_ray_stage<false><<<grid, block, smem, (cudaStream_t)stream>>>(R, S, ps, params, pos_enc, raw, nullptr, nullptr, nullptr, pixel_mask);
   NFB_CHECK_LAUNCH("k_ray_stage<fwd>");
   return NFB_OK;
 }

@@ -169,6 +169,7 @@ struct RayArgs {
   const float* d_raw;   // backward input
   float* d_ps;          // backward output
   float* stash;         // forward (SAVE): out; stash backward: in
+  uint8_t* pixel_mask;  // forward, optional: [R][S] = (number of valid observations > 1), render_ray.py:210
 };
 
 // ---- activation stash of the ray stage (forward SAVE -> k_ray_tc_bwd_stash): per 128-sample tile RP_PLANES planes of
@@ -460,7 +461,10 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
     if (!BWD) {
       float sigma = fmaxf(z2, 0.f);
       if (nvalid < 1.f) sigma = 0.f;                     // mlp_network.py:265
-      if (act) reinterpret_cast<float4*>(a.raw)[smp] = make_float4(tail.y, tail.z, tail.w, sigma);
+      if (act) {
+        reinterpret_cast<float4*>(a.raw)[smp] = make_float4(tail.y, tail.z, tail.w, sigma);
+        if (a.pixel_mask) a.pixel_mask[smp] = nvalid > 1.f ? 1 : 0;
+      }
       named_bar_sync(att_bar, att_n);                    // K / V rows are rewritten by the next tile
       continue;
     }

@@ -161,7 +161,7 @@ class IBRNetAggregate(torch.autograd.Function):
             st = stream_ptr(dev)
             call('nfb_ibrnet_view_fwd', N, S, V, int(anti_alias), ptr(rf), ptr(rd), ptr(mk), 0, 0, 0, 0,
                  None, None, None, None, None, None, None, ptr(params), ptr(ps), None, _lib.precision_code(), st)
-            call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), None, _lib.precision_code(), st)
+            call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), None, None, _lib.precision_code(), st)
         ctx.save_for_backward(rf, rd, mk, params.detach(), pos_enc, ps)
         ctx.dims = (R, S, V, int(anti_alias))
         ctx.precision = _lib.precision_code()
@@ -303,6 +303,7 @@ class RenderLevel(torch.autograd.Function):
         weights = torch.empty(R, S, device=dev, dtype=torch.float32)
         alpha = torch.empty(R, S, device=dev, dtype=torch.float32)
         ray_mask = torch.empty(R, device=dev, dtype=torch.uint8)
+        pmask = torch.empty(R, S, device=dev, dtype=torch.uint8)      # per-sample pixel mask, written by the ray stage
         need_params = ctx.needs_input_grad[6]
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or need_params
         # activation stash for the backward (768 B per (sample, view) row): written only when a data gradient is
@@ -317,8 +318,8 @@ class RenderLevel(torch.autograd.Function):
             call('nfb_ibrnet_view_fwd', N, S, V, int(anti_alias), None, None, None, H, W, fh, fw,
                  None, ptr(o_c), ptr(d_c), ptr(z_c), ptr(cam), ptr(imgs_c), ptr(feat), ptr(params), ptr(ps),
                  ptr(stash), _lib.precision_code(), st)
-            call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), ptr(rstash), _lib.precision_code(), st)
-            call('nfb_composite_fwd', R, S, int(white_bkgd), ptr(raw), ptr(z_c), None, ptr(ps[:, 68:]), PS_STRIDE,
+            call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), ptr(pmask), ptr(rstash), _lib.precision_code(), st)
+            call('nfb_composite_fwd', R, S, int(white_bkgd), ptr(raw), ptr(z_c), ptr(pmask), None, 0,
                  ptr(rgb), ptr(depth), ptr(weights), ptr(alpha), ptr(ray_mask), st)
         ctx.stash = stash
         ctx.rstash = rstash

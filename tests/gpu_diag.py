@@ -119,7 +119,7 @@ def run(V, R, S_c, n_imp, H=378, W=504, kind='llff', inv_uniform=True, seed=0, t
     ps_og = ps_o.view(N, 72).to(dev).contiguous()
     raw_g = torch.zeros(R, S_c, 4, device=dev)
     pe = pc['pos_encoding'][0].to(dev).contiguous()
-    _lib.call('nfb_ibrnet_ray_fwd', R, S_c, _lib.ptr(ps_og), _lib.ptr(blob), _lib.ptr(pe), _lib.ptr(raw_g), None, _lib.precision_code(), st)
+    _lib.call('nfb_ibrnet_ray_fwd', R, S_c, _lib.ptr(ps_og), _lib.ptr(blob), _lib.ptr(pe), _lib.ptr(raw_g), None, None, _lib.precision_code(), st)
     torch.cuda.synchronize()
     rec(f'{tag}/ray.sigma(oracle ps)', raw_g[..., 3], raw[..., 3])
     # module forward + backward

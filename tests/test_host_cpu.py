@@ -61,7 +61,7 @@ def test_argument_validation_fails_loudly_without_touching_the_gpu(lib):
                   None, None, None, None, None, None)
     with pytest.raises(RuntimeError, match='> 256 samples'):
         _lib.call('nfb_ibrnet_ray_fwd', 1, 257, _lib.c_void_p(16), _lib.c_void_p(16), _lib.c_void_p(16),
-                  _lib.c_void_p(16), None, 0, None)
+                  _lib.c_void_p(16), None, None, 0, None)
     assert b'samples' in lib.nfb_last_error_string()
 
 
