@@ -569,33 +569,48 @@ __global__ void __launch_bounds__(256, 1) k_gnt_ray_core(int R, int S, int rpc, 
     __syncthreads();
     float o[D];
     const int Sr = (r < R) ? S : 0;
+    // one pass over the keys per head: online softmax (running max, rescale on the rare increase) and packed fp32x2
+    // arithmetic (FFMA2 issues at twice the scalar FFMA rate on sm_100: tests/probes/probe_ffma2.cu)
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
-      float mx = -3.4e38f;
+      float2 q2[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) q2[c] = make_float2(qv[16 * h + 2 * c], qv[16 * h + 2 * c + 1]);
+      float mx = -3.4e38f, l = 0.f;
+      float2 a2[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a2[c] = make_float2(0.f, 0.f);
       for (int j = 0; j < Sr; ++j) {
-        const float* kj = sk + (size_t)j * D + 16 * h;
-        float s = 0.f;
+        const float4* kj = reinterpret_cast<const float4*>(sk + (size_t)j * D + 16 * h);
+        const float4* vj = reinterpret_cast<const float4*>(sv + (size_t)j * D + 16 * h);
+        float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) s = fmaf(qv[16 * h + c], kj[c], s);
-        mx = fmaxf(mx, s);
-      }
-      float l = 0.f, a16[16];
+        for (int c = 0; c < 4; ++c) {
+          const float4 k4 = kj[c];
+          s2 = __ffma2_rn(q2[2 * c], make_float2(k4.x, k4.y), s2);
+          s2 = __ffma2_rn(q2[2 * c + 1], make_float2(k4.z, k4.w), s2);
+        }
+        const float sc = s2.x + s2.y;
+        if (sc > mx) {                                     // new maximum: rescale what has been accumulated
+          const float r = __expf(mx - sc);
+          l *= r;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) a16[c] = 0.f;
-      for (int j = 0; j < Sr; ++j) {
-        const float* kj = sk + (size_t)j * D + 16 * h;
-        const float* vj = sv + (size_t)j * D + 16 * h;
-        float s = 0.f;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) s = fmaf(qv[16 * h + c], kj[c], s);
-        const float p = __expf(s - mx);
+          for (int c = 0; c < 8; ++c) a2[c] = __fmul2_rn(a2[c], make_float2(r, r));
+          mx = sc;
+        }
+        const float p = __expf(sc - mx);
         l += p;
+        const float2 p2 = make_float2(p, p);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) a16[c] = fmaf(p, vj[c], a16[c]);
+        for (int c = 0; c < 4; ++c) {
+          const float4 v4 = vj[c];
+          a2[2 * c] = __ffma2_rn(p2, make_float2(v4.x, v4.y), a2[2 * c]);
+          a2[2 * c + 1] = __ffma2_rn(p2, make_float2(v4.z, v4.w), a2[2 * c + 1]);
+        }
       }
       const float il = 1.f / l;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) o[16 * h + c] = a16[c] * il;
+      for (int c = 0; c < 8; ++c) { o[16 * h + 2 * c] = a2[c].x * il; o[16 * h + 2 * c + 1] = a2[c].y * il; }
       if (t == 0) { sq0[RS_ST + h] = mx; sq0[RS_ST + 4 + h] = il; }
     }
     if (act) store_row64(O + n * D, o);
