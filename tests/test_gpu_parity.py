@@ -873,3 +873,27 @@ def test_wrapped_nets_train_through_the_wrapper(dev):
     for a, b in zip(grads[False], grads[True]):
         if a.norm() > 1e-9:
             assert relerr(b.cpu(), a.cpu()) < 2e-2        # two bf16-operand GEMM forms of the same sum (fused vs tensor-mode tiles)
+
+
+def test_parameter_gradients_with_fully_masked_rays(dev):
+    """Rays that see no source view at all (every sample masked: the blending softmax is uniform, sigma is forced to 0)
+    contribute exactly what the oracle says to the parameter gradients -- no NaN from the gated tensor-core operands."""
+    from nerfool_b200.mlp_network import IBRNet
+    V, S, R = 4, 32, 48
+    scene, batch = _scene(V, R, 96, 128, 'llff', seed=23)
+    pts, _ = O.coarse_depths(batch['ray_o'], batch['ray_d'], batch['depth_range'], S, inv_uniform=True, det=True)
+    rf, rd, mk = O.projector_compute(pts, batch['camera'], batch['src_rgbs'], batch['src_cameras'], scene['featmaps'][0])
+    mk = mk.clone()
+    mk[:16] = 0.            # 16 rays without any valid observation
+    mk[16:24, :, 1:] = 0.   # 8 rays with a single valid view
+    p = _params(S, 61)
+    cot = torch.randn(R, S, 4, generator=torch.Generator().manual_seed(9))
+    p32, p64 = _grad_params(p, torch.float32), _grad_params(p, torch.float64)
+    (O.ibrnet_forward(p32, p['pos_encoding'], rf, rd, mk) * cot).sum().backward()
+    (O.ibrnet_forward(p64, p['pos_encoding'].double(), rf.double(), rd.double(), mk.double()) * cot.double()).sum().backward()
+    net = IBRNet(types.SimpleNamespace(anti_alias_pooling=1), 32, S)
+    net.load_state_dict({k: v.clone() for k, v in p.items()})
+    net = net.to(dev).train()
+    (net(rf.to(dev), rd.to(dev), mk.to(dev)) * cot.to(dev)).sum().backward()
+    assert all(torch.isfinite(q.grad).all() for q in net.parameters())
+    _check_param_grads(net, p32, p64, 'masked rays')
