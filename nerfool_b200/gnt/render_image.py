@@ -3,6 +3,7 @@ signature and return value, device-resident -- chunks write into frame-sized dev
 the host once per frame instead of once per chunk (the reference synchronises the device for every chunk and key)."""
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 
 import torch
@@ -25,6 +26,11 @@ def render_single_image(ray_sampler, ray_batch, model, projector, chunk_size, N_
         raise NotImplementedError('nerfool_b200.gnt: the clean/adversarial mixing ablation (render_rays_hybrid, '
                                   'gnt/render_ray.py:281-390) is not built for the GNT path')
     N_rays = ray_batch['ray_o'].shape[0]
+    # Rays are independent, so the chunk size only bounds memory.  The reference's default (4096 rays, sized for eager
+    # PyTorch's saved tensors) leaves a B200 launch-bound; without autograd a chunk needs < 100 KB per ray, so render in
+    # chunks of at least NFB_RENDER_CHUNK rays (default 32768; identical output).
+    if not torch.is_grad_enabled():
+        chunk_size = max(int(chunk_size), int(os.environ.get('NFB_RENDER_CHUNK', '32768')))
     buf = {'outputs_coarse': None, 'outputs_fine': None}
     for i in range(0, N_rays, chunk_size):
         chunk = OrderedDict()

@@ -5,6 +5,7 @@ throttles a fast renderer.  Here the chunks write into preallocated device buffe
 the host once at the end (the callers expect CPU tensors: eval.py / eval_adv.py index them with numpy)."""
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 
 import torch
@@ -27,6 +28,11 @@ def render_single_image(ray_sampler, ray_batch, model, projector, chunk_size, N_
     :return: {'outputs_coarse': {'rgb': [H, W, 3], 'depth': [H, W], ...}, 'outputs_fine': {}}   (CPU tensors)
     '''
     N_rays = ray_batch['ray_o'].shape[0]
+    # Rays are independent, so the chunk size only bounds memory.  The reference's default (4096 rays, sized for eager
+    # PyTorch's saved tensors) leaves a B200 launch-bound; without autograd a chunk needs < 100 KB per ray, so render in
+    # chunks of at least NFB_RENDER_CHUNK rays (default 32768; identical output).
+    if not torch.is_grad_enabled():
+        chunk_size = max(int(chunk_size), int(os.environ.get('NFB_RENDER_CHUNK', '32768')))
     hybrid = args is not None and (getattr(args, 'use_clean_color', False) or getattr(args, 'use_clean_density', False))
     if hybrid:
         assert featmaps_clean is not None

@@ -631,10 +631,20 @@ def test_render_single_image_device_resident(dev):
     model = types.SimpleNamespace(net_coarse=_net(_params(S, 3), S, dev), net_fine=_net(_params(S + NI, 4), S + NI, dev))
     fm = tuple(f.to(dev) for f in scene['featmaps'])
     sampler = types.SimpleNamespace(H=Hh, W=Ww)
+    os.environ['NFB_RENDER_CHUNK'] = '1'          # keep the caller's 157-ray chunks (default: at least 32768 rays per chunk)
+    try:
+        with torch.no_grad():
+            img = render_single_image(sampler, gb, model, Projector(dev), 157, S, inv_uniform=True, N_importance=NI, det=True,
+                                      featmaps=fm)
+    finally:
+        del os.environ['NFB_RENDER_CHUNK']
     with torch.no_grad():
-        img = render_single_image(sampler, gb, model, Projector(dev), 157, S, inv_uniform=True, N_importance=NI, det=True,
-                                  featmaps=fm)
+        big = render_single_image(sampler, gb, model, Projector(dev), 157, S, inv_uniform=True, N_importance=NI, det=True,
+                                  featmaps=fm)     # internally one chunk: identical output
         full = render_rays(gb, model, fm, Projector(dev), S, inv_uniform=True, N_importance=NI, det=True)
+    for lvl in ('outputs_coarse', 'outputs_fine'):
+        for k in img[lvl]:
+            assert torch.equal(img[lvl][k], big[lvl][k]), (lvl, k)
     for lvl in ('outputs_coarse', 'outputs_fine'):
         assert list(img[lvl].keys()) == ['rgb', 'depth', 'weights', 'mask', 'alpha', 'z_vals']
         assert img[lvl]['rgb'].shape == (Hh, Ww, 3) and img[lvl]['depth'].shape == (Hh, Ww) and not img[lvl]['rgb'].is_cuda
