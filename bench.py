@@ -219,6 +219,27 @@ def run_ours(a):
             torch.cuda.synchronize()
             fwd_ms.append(s.elapsed_time(e))
 
+    # ---------------- the same frame through the reference-facing render_single_image (render_image.py:21-121): the caller's
+    # chunk size is the reference's default 4096; every output of the frame (rgb, depth, weights, alpha, z_vals, mask of both
+    # levels, ~230 MB) is copied to the host, as the reference's callers expect ----------------
+    rsi_ms = None
+    try:
+        from nerfool_b200.render_image import render_single_image
+        sampler = types.SimpleNamespace(H=H, W=W)
+        rb = dict(batch)
+        with torch.no_grad():
+            render_single_image(sampler, rb, model, projector, 4096, N_SAMPLES, inv_uniform=True, N_importance=N_IMPORTANCE, det=True,
+                                featmaps=featmaps)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                render_single_image(sampler, rb, model, projector, 4096, N_SAMPLES, inv_uniform=True, N_importance=N_IMPORTANCE,
+                                    det=True, featmaps=featmaps)
+            torch.cuda.synchronize()
+            rsi_ms = (time.perf_counter() - t0) * 500
+    except Exception as ex:
+        rsi_ms = f'{type(ex).__name__}: {ex}'[:160]
+
     # ---------------- e2e: host buffers in, loss out, inside the timed region ----------------
     barrier()
     e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
@@ -406,6 +427,7 @@ def run_ours(a):
             'training_step': train,
             'fwd_rays_per_s': rays_total / (fwd_med * 1e-3),
             'fwd_ms_per_frame': fwd_med,
+            'render_single_image_ms_per_frame': rsi_ms,
             'encoder': 'not timed: the ResUNet stays on cuDNN in the reference and is outside this repo (north_star)',
             'wall_s_timed_region': t_wall,
             'step_ms': step_ms,
