@@ -229,7 +229,7 @@ __device__ __forceinline__ void epi16_s(uint32_t tl, int col, const float* __res
   else epi16(tl, col, bias, y);
 }
 __device__ __forceinline__ void st_plane(float4* sp, int plane, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  sp[plane * GROUP] = make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d));
+  __stcs(sp + plane * GROUP, make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d)));   // streaming: written once, read once by the backward
 }
 __device__ __forceinline__ void st_codes8(float4* sp, int plane, const uint32_t (&q)[8]) {
   st_plane(sp, plane, q[0], q[1], q[2], q[3]);
@@ -458,8 +458,8 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
 
     if (save) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sp[(SP_X0 + j) * GROUP] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-      sp[(SP_X0 + 8) * GROUP] = make_float4(x[32], x[33], x[34], 0.f);
+      for (int j = 0; j < 8; ++j) __stcs(sp + (SP_X0 + j) * GROUP, make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
+      __stcs(sp + (SP_X0 + 8) * GROUP, make_float4(x[32], x[33], x[34], 0.f));
     }
     // ---------------- first pooling: weighted mean / variance over views ----------------
 #pragma unroll
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       if (save) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          sp[(SP_X2 + 4 * kc + j) * GROUP] = make_float4(x1[16 * kc + 4 * j], x1[16 * kc + 4 * j + 1], x1[16 * kc + 4 * j + 2], x1[16 * kc + 4 * j + 3]);
+          __stcs(sp + (SP_X2 + 4 * kc + j) * GROUP, make_float4(x1[16 * kc + 4 * j], x1[16 * kc + 4 * j + 1], x1[16 * kc + 4 * j + 2], x1[16 * kc + 4 * j + 3]));
       }
       a_store16<NPASS>(tl, kc, t);
     }
@@ -665,8 +665,8 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       logit = dot_row<8>(g2, sf + F_W_RGB4) + sf[F_B_RGB4];
       if (mk == 0.f) logit = -1e9f;
       if (save) {
-        sp[SP_SA * GROUP] = make_float4(w, mk, sg1, sg2);
-        sp[SP_SB * GROUP] = make_float4(logit, ggx, ggy, rgb_in0);
+        __stcs(sp + SP_SA * GROUP, make_float4(w, mk, sg1, sg2));
+        __stcs(sp + SP_SB * GROUP, make_float4(logit, ggx, ggy, rgb_in0));
         st_plane(sp, SP_SC, __float_as_uint(rgb_in1), __float_as_uint(rgb_in2), xvq16, 0u);
       }
     }
