@@ -178,3 +178,66 @@ __device__ __forceinline__ void scatter_row(const ViewGeom& g, int v, int H, int
     }
   }
 }
+
+// Scatter with pairwise de-duplication.  Consecutive samples of a ray fall into the same texel quad of a source view most
+// of the time (measured on the headline scene: 74 % at the coarse level, 87 % at the fine level).  The rows of a sample
+// pair (2k, 2k + 1) of one view are the lanes (l, l ^ V) of a warp when V is a power of two <= 16: if both hit the same
+// four texels, the even lane adds both weighted cotangents with ONE set of 8 x 4 RED.128 and the odd lane issues none --
+// ~40 % fewer vector atomics into the L2-resident gradient map for 41 shuffles per row.
+// Every lane of the warp must call (inactive rows pass active = false); V as described.
+__device__ __forceinline__ void scatter_row_paired(bool active, float gx, float gy, int v, int V, int H, int W, int fh, int fw,
+                                                   const float (&d_row)[NFB_ROW_CH], float* __restrict__ d_feat,
+                                                   float* __restrict__ d_imgs) {
+  if (active && d_imgs) {
+    const Taps t = bilinear_taps(gx, gy, W, H);
+    float* base = d_imgs + (size_t)v * H * W * 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (t.off[i] >= 0) {
+        float* p = base + (size_t)t.off[i] * 3;
+        atomicAdd(p + 0, d_row[0] * t.wt[i]);
+        atomicAdd(p + 1, d_row[1] * t.wt[i]);
+        atomicAdd(p + 2, d_row[2] * t.wt[i]);
+      }
+    }
+  }
+  if (!d_feat) return;                                   // kernel argument: uniform
+  Taps t = bilinear_taps(active ? gx : 0.f, active ? gy : 0.f, fw, fh);
+  if (!active) { t.off[0] = t.off[1] = t.off[2] = t.off[3] = -1; }
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int act_nb = __shfl_xor_sync(FULL, (int)active, V);
+  bool same = active && (act_nb != 0);
+  float wn[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int off_nb = __shfl_xor_sync(FULL, t.off[i], V);      // unconditionally: every lane must execute every shuffle
+    same = same && (off_nb == t.off[i]);
+    wn[i] = __shfl_xor_sync(FULL, t.wt[i], V);
+  }
+  const bool leader = (lane & V) == 0;
+  const bool emit = active && !(same && !leader);
+  float4* base = reinterpret_cast<float4*>(d_feat + (size_t)v * fh * fw * NFB_FEAT_CH);
+#pragma unroll
+  for (int j = 0; j < NFB_FEAT_CH / 4; ++j) {
+    const float m0 = d_row[3 + 4 * j], m1 = d_row[4 + 4 * j], m2 = d_row[5 + 4 * j], m3 = d_row[6 + 4 * j];
+    float n0 = __shfl_xor_sync(FULL, m0, V), n1 = __shfl_xor_sync(FULL, m1, V);
+    float n2 = __shfl_xor_sync(FULL, m2, V), n3 = __shfl_xor_sync(FULL, m3, V);
+    if (!same) { n0 = 0.f; n1 = 0.f; n2 = 0.f; n3 = 0.f; }       // the partner may be an inactive row holding anything
+    if (emit) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (t.off[i] >= 0) {
+          const float wm = t.wt[i], wp = same ? wn[i] : 0.f;
+          float4 q;
+          q.x = fmaf(n0, wp, m0 * wm);
+          q.y = fmaf(n1, wp, m1 * wm);
+          q.z = fmaf(n2, wp, m2 * wm);
+          q.w = fmaf(n3, wp, m3 * wm);
+          atomicAdd(base + (size_t)t.off[i] * (NFB_FEAT_CH / 4) + j, q);
+        }
+      }
+    }
+  }
+}
+

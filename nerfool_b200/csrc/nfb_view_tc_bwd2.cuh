@@ -509,7 +509,12 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       d_row[0] = fmaf(blend, d_r0, d_row[0]);
       d_row[1] = fmaf(blend, d_r1, d_row[1]);
       d_row[2] = fmaf(blend, d_r2, d_row[2]);
-      // (8) scatter (grid_sampler_2d backward w.r.t. the input)
+    }
+    // (8) scatter (grid_sampler_2d backward w.r.t. the input)
+    if (warp_local && V <= 16 && V > 0) {
+      // the rows of a sample pair of one view are lanes (l, l ^ V): same texel quad -> one set of atomics for both
+      scatter_row_paired(active, gx, gy, v, V, a.H, a.W, a.fh, a.fw, d_row, a.d_feat, a.d_imgs);
+    } else if (active) {
       ViewGeom g;
       g.gx = gx; g.gy = gy;
       scatter_row(g, v, a.H, a.W, a.fh, a.fw, d_row, a.d_feat, a.d_imgs);
