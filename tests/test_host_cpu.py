@@ -362,3 +362,10 @@ def test_gnt_module_interface_and_blob_layout():
         GNT(types.SimpleNamespace(netwidth=32, trans_depth=2), 32, 63, 63, True)
     with pytest.raises(RuntimeError, match='workspace'):
         _lib.call('nfb_gnt_fwd', 1, 4, 2, 2, 1, *[_lib.c_void_p(16)] * 8, _lib.ctypes.c_size_t(0), 1, None)
+
+
+def test_graphed_step_refuses_stochastic_sampling():
+    """A captured CUDA graph replays the same random numbers: GraphedPGDStep only accepts the deterministic sampler."""
+    from nerfool_b200.attack import GraphedPGDStep
+    with pytest.raises(ValueError, match='det=True'):
+        GraphedPGDStep(None, None, {}, [], 64, 64, det=False)
