@@ -1,26 +1,34 @@
 #!/usr/bin/env python
 """Benchmark of the NeRFool / IBRNet per-ray hot path (BASELINE.json: "rays/s fwd and PGD attack iters/s,
-378x504 view ...").
+378x504 view, 10 src views, 1/2/4/8 B200").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 1|2|3|4]
 
-Workload (config.workload): BASELINE.json configs[1] - the view-specific PGD attack on a synthetic
-378x504 LLFF-shaped scene, 4 source views, 64 coarse + 64 importance samples.  One *step* is one attack
-iteration of the hot path over ALL 190,512 rays of the target view: render_rays (coarse + fine) -> masked
-MSE -> backward to the two source feature maps (the cuDNN encoder that turns that gradient into
-delta.grad is out of scope and not timed here) -> sign-step on the feature maps (stand-in for the delta
-update, so consecutive steps depend on each other).  With N > 1 each rank renders its own target view
-(weak scaling, BASELINE configs[2] layout) and ONE NCCL allreduce sums the feature-map gradients.
+Workload (config.workload), default --config 2 = the shape BASELINE.json's metric is quoted on: a synthetic 378x504
+LLFF-shaped scene, 10 source views, 64 coarse + 64 importance samples (BASELINE configs[2]; one target view per GPU).
+One *step* is one attack iteration of the hot path over ALL 190,512 rays of the target view: render_rays (coarse + fine) ->
+masked MSE -> backward to the two source feature maps -> sign-step on the feature maps (so consecutive steps depend on
+each other).  With N > 1 each rank renders its own target view (weak scaling) and ONE NCCL allreduce combines the
+feature-map gradients.  --config 1 is the 4-source-view shape of configs[0]/[1]; it is also measured as an extra block
+("v4_block") in the default run.
 
 value       rays/s through forward + backward, inputs resident in HBM, CUDA-event timed, max over ranks
-e2e         the same step through the public API with the step's rays / target colours copied from pinned
-            host memory and the loss read back, inside the timed region
-roofline    the dominant kernel (largest share of the step) against the measured HBM peak, algorithmic
-            gather/scatter bytes (560 B per (sample, view) row gathered, 512 B scattered);
-            "kernels" carries the same for all four IBRNet kernels, with the dense-FLOP rate against the
-            measured bf16 tensor peak (roofline_tensor)
-cpu_baseline / --impl reference : the CPU oracle (oracle/ibrnet_oracle.py, a port of the reference path)
-            on a bounded ray sample with all host threads.
+e2e         the same step through the public API with the step's rays / target colours copied from pinned host memory
+            and the loss read back, inside the timed region
+roofline    the dominant kernel (largest share of the step) against the measured HBM peak, algorithmic gather/scatter
+            bytes (560 B per (sample, view) row gathered, 512 B scattered); "kernels" carries the same for
+            all four IBRNet kernels, with the dense-FLOP rate against the measured bf16 tensor peak (roofline_tensor)
+encoder / pgd_full_iteration
+            the reference's ResUNet (cuDNN; staged copy of the unmodified reference, oracle/stage_reference.py) timed
+            separately, and the COMPLETE PGD iteration of eval_adv.py:290-304,693-728 -- encoder(src + delta) ->
+            render_rays -> loss -> backward to delta -> Adam step + StepLR + clamps -- at N_rand = 512 / 4096 / 32768 /
+            all rays, next to the hot-path-only numbers
+strong_scaling (N > 1)
+            ONE view's 190,512 rays sharded over the N ranks, encoder sharded over the source views, global loss
+            normaliser, one allreduce: the full iteration (attack.delta_gradient_step)
+cpu_baseline / --impl reference
+            the reference's own render_rays (unmodified modules from the staged copy, kind "reference"; the oracle port
+            when no staged copy exists) on a bounded ray sample with all host threads, median of >= 3.
 """
 from __future__ import annotations
 
@@ -44,6 +52,35 @@ H, W = 378, 504
 SCENE_KIND = 'llff'
 N_SAMPLES, N_IMPORTANCE = 64, 64
 GATHER_B, SCATTER_B = 560, 512          # algorithmic bytes per (sample, view) row, SURVEY.md 8(d)
+REF_STAGED = os.path.join(REPO, 'baseline', '_ref')   # byte-for-byte staged copy of the unmodified reference (git-ignored)
+
+
+def workload_config(a, world=1):
+    """config of the JSON line -- built identically by our arm and by --impl reference."""
+    R = H * W
+    return {'workload': f'BASELINE configs[{a.config}]: IBRNet PGD hot-path step (render_rays fwd + masked-MSE + bwd to source feature '
+                        f'maps), {H}x{W} target view, all {R} rays per step, {a.views} source views, {N_SAMPLES} coarse + '
+                        f'{N_IMPORTANCE} importance samples, random-init weights',
+            'rays_per_step_per_gpu': R, 'source_views': a.views, 'image': [H, W], 'samples': [N_SAMPLES, N_IMPORTANCE]}
+
+
+def reference_root():
+    """Where the UNMODIFIED reference can be imported from at run time (bench.py never reads /root/reference: it does not
+    exist on the GPU box; the staged copy travels with the repo snapshot)."""
+    return REF_STAGED if os.path.isdir(os.path.join(REF_STAGED, 'ibrnet')) else None
+
+
+def load_reference_resunet():
+    """ibrnet/feature_network.py:ResUNet of the staged reference, loaded under a private module name (the encoder stays on
+    cuDNN and is out of scope for this repo -- north star -- but is part of every real PGD iteration)."""
+    root = reference_root()
+    if root is None:
+        return None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('nfb_ref_feature_network', os.path.join(root, 'ibrnet', 'feature_network.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.ResUNet
 
 
 def load_peaks():
@@ -65,10 +102,11 @@ def load_tensor_peak():
 
 def load_traffic_table():
     """DRAM bytes per unit measured ONCE with `ncu --set full` (profiles/traffic_r01.json, source named inside)."""
-    path = os.path.join(REPO, 'profiles', 'traffic_r01.json')
-    if os.path.exists(path):
-        with open(path) as f:
-            return json.load(f)
+    for name in ('traffic_r02.json', 'traffic_r01.json'):
+        path = os.path.join(REPO, 'profiles', name)
+        if os.path.exists(path):
+            with open(path) as f:
+                return json.load(f)
     return None
 
 
@@ -140,10 +178,184 @@ def build_workload(device, rank, V, seed=0):
     return scene, model, Projector(device), host, static, featmaps
 
 
+def _event_time(fn, iters, sync=True):
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(iters):
+        fn()
+    s1.record()
+    torch.cuda.synchronize()
+    return s0.elapsed_time(s1) / iters
+
+
+def make_hot_step(model, projector, featmaps, max_rays, group):
+    """The bench step: pgd_hot_step + sign-step on the feature maps + projection onto the eps-ball (eval_adv.py:711-728 form)."""
+    from nerfool_b200.attack import pgd_hot_step
+    eps, alpha = 8.0 / 255.0, 1.0 / 255.0
+    base_fm = [f.clone() for f in featmaps]
+
+    def step(batch):
+        loss, g_c, g_f = pgd_hot_step(model, projector, batch, featmaps, N_SAMPLES, N_IMPORTANCE, inv_uniform=True,
+                                      det=True, max_rays=max_rays, group=group)
+        with torch.no_grad():
+            for f, g, b in zip(featmaps, (g_c, g_f), base_fm):
+                f.add_(alpha * torch.sign(g))
+                torch.minimum(torch.maximum(f, b - eps), b + eps, out=f)
+        return loss
+    return step
+
+
+def chunk_rays_for(views):
+    """Bound the two activation stashes of a chunk to ~56 GB of the 180 GB."""
+    per_ray = (2 * N_SAMPLES + N_IMPORTANCE) * views * _stash_row_bytes() + (2 * N_SAMPLES + N_IMPORTANCE) * 560
+    return max(4096, min(65536, 1 << int(np.log2(56e9 / per_ray))))
+
+
+def _stash_row_bytes():
+    try:
+        from nerfool_b200 import _lib
+        return max(64, int(_lib.load().nfb_view_stash_bytes(128 * 1024, 4)) // (128 * 1024 * 4))
+    except Exception:
+        return 768
+
+
+def encoder_block(device, views):
+    """The reference's ResUNet on cuDNN, fwd and fwd+bwd (to the input image = what carries d featmaps on to delta.grad)."""
+    ResUNet = load_reference_resunet()
+    if ResUNet is None:
+        return None, {'unavailable': 'no staged reference (python oracle/stage_reference.py in the build container)'}
+    torch.manual_seed(0)
+    enc = ResUNet(coarse_out_ch=32, fine_out_ch=32, coarse_only=False).to(device).eval()
+    x = torch.rand(views, 3, H, W, device=device)
+    with torch.no_grad():
+        for _ in range(3):
+            enc(x)
+        fwd = _event_time(lambda: enc(x), 5)
+    xg = x.clone().requires_grad_(True)
+
+    def fb():
+        c, f = enc(xg)
+        torch.autograd.backward([c, f], [torch.ones_like(c), torch.ones_like(f)])
+        xg.grad = None
+    for _ in range(2):
+        fb()
+    fwdbwd = _event_time(fb, 5)
+    return enc, {'what': f'reference ResUNet (ibrnet/feature_network.py, staged unmodified copy) on {views}x3x{H}x{W}, cuDNN, torch default '
+                         f'precision flags (cudnn.allow_tf32={torch.backends.cudnn.allow_tf32})',
+                 'fwd_ms': fwd, 'fwd_bwd_ms': fwdbwd}
+
+
+def pgd_full_iteration_block(device, enc, model, projector, static, resident, R, max_rays):
+    """COMPLETE PGD iterations (eval_adv.py:290-304 + :693-728) through attack.PGDAttack: encoder(src + delta) -> render_rays on
+    N_rand rays (clean colours) -> masked MSE -> backward through the renderer and the encoder to delta -> Adam(-grad) + StepLR
+    + clamps."""
+    from nerfool_b200.attack import PGDAttack
+    out = {}
+    gen = torch.Generator(device='cpu').manual_seed(7)
+    for n in (512, 4096, 32768, R):
+        sel = torch.arange(R) if n == R else torch.randperm(R, generator=gen)[:n].sort().values
+        sel = sel.to(device)
+        tb = {'camera': static['camera'], 'depth_range': static['depth_range']}
+        for k in ('ray_o', 'ray_d', 'rgb'):
+            tb[k] = resident[k][sel].contiguous()
+        atk = PGDAttack(lambda x: enc(x), model, projector, static, N_SAMPLES, N_IMPORTANCE, epsilon=8.0, use_adam=True, adam_lr=1e-3,
+                        lr_step_size=100, lr_gamma=0.5, inv_uniform=True, det=True, max_rays=max_rays,
+                        generator=torch.Generator().manual_seed(11))
+        for _ in range(2):
+            atk.step(tb)
+        torch.cuda.synchronize()
+        iters = 3 if n == R else 8
+        ms = _event_time(lambda: atk.step(tb), iters)
+        out[str(n)] = {'ms_per_iter': ms, 'iters_per_s': 1e3 / ms}
+        del atk
+    return out
+
+
+def measure_core(a, device, rank, world, group, views, steps, warmup, extras):
+    """Build the workload for `views` source views and time the hot-path step.  Returns a dict of raw measurements."""
+    from nerfool_b200 import _lib
+    from nerfool_b200.render_ray import render_rays
+    import torch.distributed as dist
+    local = device.index
+    scene, model, projector, host, static, featmaps = build_workload(device, rank, views)
+    R = host['ray_o'].shape[0]
+    max_rays = a.max_rays if a.max_rays > 0 else chunk_rays_for(views)
+    resident = {k: v.to(device) for k, v in host.items()}
+    step = make_hot_step(model, projector, featmaps, max_rays, group)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    batch = dict(static)
+    batch.update(resident)
+    for _ in range(warmup):
+        step(batch)
+    barrier()
+    m = {'R': R, 'max_rays': max_rays, 'views': views}
+    # ---------------- timed region: K steps, inputs resident ----------------
+    sampler = ClockSampler(local) if (rank == 0 and extras) else None
+    launches0 = _lib.LAUNCHES
+    _lib.profile_start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for s, e in ev:
+        s.record()
+        step(batch)
+        e.record()
+    barrier()
+    m['t_wall'] = time.perf_counter() - t_wall
+    m['prof'] = _lib.profile_stop()
+    m['launches'] = _lib.LAUNCHES - launches0
+    m['clocks'] = sampler.stop() if sampler else None
+    m['step_ms'] = [s.elapsed_time(e) for s, e in ev]
+    m['total_ms'] = ev[0][0].elapsed_time(ev[-1][1])
+
+    # ---------------- the same K steps WITHOUT the per-call event pairs of the profiler ----------------
+    barrier()
+    m['unprofiled_ms_per_step'] = _event_time(lambda: step(batch), max(2, steps // 2))
+    barrier()
+
+    # ---------------- forward-only full-frame pass (rays/s fwd) ----------------
+    fwd_ms = []
+    with torch.no_grad():
+        for i in range(3):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for lo in range(0, R, max_rays):
+                chunk = dict(batch)
+                for k in ('ray_o', 'ray_d', 'rgb'):
+                    chunk[k] = batch[k][lo:lo + max_rays]
+                render_rays(chunk, model, featmaps, projector, N_SAMPLES, inv_uniform=True, N_importance=N_IMPORTANCE, det=True)
+            e.record()
+            torch.cuda.synchronize()
+            fwd_ms.append(s.elapsed_time(e))
+    m['fwd_ms'] = statistics.median(fwd_ms)
+
+    # ---------------- e2e: host buffers in, loss out, inside the timed region ----------------
+    barrier()
+    e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    m['h2d'] = sum(v.numel() * v.element_size() for v in host.values())
+    for s, e in e2e_ev:
+        s.record()
+        b2 = dict(static)
+        for k, v in host.items():
+            b2[k] = v.to(device, non_blocking=True)
+        loss = step(b2)
+        loss_host = loss.to('cpu', non_blocking=False)      # device -> host read of the step's result
+        e.record()
+    barrier()
+    m['e2e_total_ms'] = e2e_ev[0][0].elapsed_time(e2e_ev[-1][1])
+    m['loss_last'] = float(loss_host)
+    m['objects'] = (scene, model, projector, host, static, featmaps, resident, step, batch)
+    return m
+
+
 def run_ours(a):
     import torch.distributed as dist
     from nerfool_b200 import _lib
-    from nerfool_b200.attack import pgd_hot_step
     from nerfool_b200.render_ray import render_rays
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -159,101 +371,37 @@ def run_ours(a):
         dist.init_process_group('nccl', device_id=device)
         group = dist.group.WORLD
     _lib.load()
-    scene, model, projector, host, static, featmaps = build_workload(device, rank, a.views)
-    R = host['ray_o'].shape[0]
-    resident = {k: v.to(device) for k, v in host.items()}
-    eps, alpha = 8.0 / 255.0, 1.0 / 255.0
-    base_fm = [f.clone() for f in featmaps]
 
-    def step(batch):
-        loss, g_c, g_f = pgd_hot_step(model, projector, batch, featmaps, N_SAMPLES, N_IMPORTANCE, inv_uniform=True,
-                                      det=True, max_rays=a.max_rays, group=group)
-        with torch.no_grad():                      # sign-step + projection onto the eps-ball (eval_adv.py:824-839)
-            for f, g, b in zip(featmaps, (g_c, g_f), base_fm):
-                f.add_(alpha * torch.sign(g))
-                torch.minimum(torch.maximum(f, b - eps), b + eps, out=f)
-        return loss
+    m = measure_core(a, device, rank, world, group, a.views, a.steps, a.warmup, extras=True)
+    scene, model, projector, host, static, featmaps, resident, step, batch = m['objects']
+    R, max_rays = m['R'], m['max_rays']
+    prof, launches, clocks = m['prof'], m['launches'], m['clocks']
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    batch = dict(static)
-    batch.update(resident)
-    for _ in range(a.warmup):
-        step(batch)
-    barrier()
-
-    # ---------------- timed region: K steps, inputs resident ----------------
-    sampler = ClockSampler(local) if rank == 0 else None
-    launches0 = _lib.LAUNCHES
-    _lib.profile_start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-    barrier()
-    t_wall = time.perf_counter()
-    for s, e in ev:
-        s.record()
-        step(batch)
-        e.record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall
-    prof = _lib.profile_stop()
-    launches = _lib.LAUNCHES - launches0
-    clocks = sampler.stop() if sampler else None
-    step_ms = [s.elapsed_time(e) for s, e in ev]
-    total_ms = ev[0][0].elapsed_time(ev[-1][1])
-
-    # ---------------- forward-only full-frame pass (rays/s fwd) ----------------
-    fwd_ms = []
-    with torch.no_grad():
-        for i in range(3):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            for lo in range(0, R, a.max_rays):
-                chunk = dict(batch)
-                for k in ('ray_o', 'ray_d', 'rgb'):
-                    chunk[k] = batch[k][lo:lo + a.max_rays]
-                render_rays(chunk, model, featmaps, projector, N_SAMPLES, inv_uniform=True, N_importance=N_IMPORTANCE, det=True)
-            e.record()
-            torch.cuda.synchronize()
-            fwd_ms.append(s.elapsed_time(e))
-
     # ---------------- the same frame through the reference-facing render_single_image (render_image.py:21-121): the caller's
-    # chunk size is the reference's default 4096; every output of the frame (rgb, depth, weights, alpha, z_vals, mask of both
-    # levels, ~230 MB) is copied to the host, as the reference's callers expect ----------------
+    # chunk size is the reference's default 4096; every output of the frame is copied to the host, as the reference's callers expect
     rsi_ms = None
-    try:
-        from nerfool_b200.render_image import render_single_image
-        sampler = types.SimpleNamespace(H=H, W=W)
-        rb = dict(batch)
-        with torch.no_grad():
-            render_single_image(sampler, rb, model, projector, 4096, N_SAMPLES, inv_uniform=True, N_importance=N_IMPORTANCE, det=True,
-                                featmaps=featmaps)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(2):
-                render_single_image(sampler, rb, model, projector, 4096, N_SAMPLES, inv_uniform=True, N_importance=N_IMPORTANCE,
-                                    det=True, featmaps=featmaps)
-            torch.cuda.synchronize()
-            rsi_ms = (time.perf_counter() - t0) * 500
-    except Exception as ex:
-        rsi_ms = f'{type(ex).__name__}: {ex}'[:160]
-
-    # ---------------- e2e: host buffers in, loss out, inside the timed region ----------------
-    barrier()
-    e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    for s, e in e2e_ev:
-        s.record()
-        b2 = dict(static)
-        for k, v in host.items():
-            b2[k] = v.to(device, non_blocking=True)
-        loss = step(b2)
-        loss_host = loss.to('cpu', non_blocking=False)      # device -> host read of the step's result
-        e.record()
-    barrier()
-    e2e_total_ms = e2e_ev[0][0].elapsed_time(e2e_ev[-1][1])
+    if world == 1 and not a.no_nrand:
+        try:
+            from nerfool_b200.render_image import render_single_image
+            sampler = types.SimpleNamespace(H=H, W=W)
+            rb = dict(batch)
+            with torch.no_grad():
+                render_single_image(sampler, rb, model, projector, 4096, N_SAMPLES, inv_uniform=True, N_importance=N_IMPORTANCE, det=True,
+                                    featmaps=featmaps)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    render_single_image(sampler, rb, model, projector, 4096, N_SAMPLES, inv_uniform=True, N_importance=N_IMPORTANCE,
+                                        det=True, featmaps=featmaps)
+                torch.cuda.synchronize()
+                rsi_ms = (time.perf_counter() - t0) * 500
+        except Exception as ex:
+            rsi_ms = f'{type(ex).__name__}: {ex}'[:160]
 
     # ---------------- the same step in plain-bf16 tensor-core mode (reported beside the headline) ----------------
     bf16_ms = None
@@ -262,16 +410,11 @@ def run_ours(a):
         _lib.set_precision('bf16')
         step(batch)
         barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(2):
-            step(batch)
-        s1.record()
+        bf16_ms = _event_time(lambda: step(batch), 2)
         barrier()
-        bf16_ms = s0.elapsed_time(s1) / 2
         _lib.set_precision(saved_prec)
 
-    # ---------------- PGD iterations/s at the reference's ray-batch sizes (N_rand, config.py:55 default 512) ----------------
+    # ---------------- PGD iterations/s of the HOT PATH ONLY at the reference's ray-batch sizes (N_rand, config.py:55 default 512)
     nrand = {}
     if world == 1 and not a.no_nrand:
         gen = torch.Generator(device='cpu').manual_seed(3)
@@ -283,31 +426,42 @@ def run_ours(a):
             for _ in range(3):
                 step(nb)
             torch.cuda.synchronize()
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            for _ in range(10):
-                step(nb)
-            s1.record()
-            torch.cuda.synchronize()
-            nrand[str(n)] = {'ms_per_iter': s0.elapsed_time(s1) / 10, 'iters_per_s': 1e4 / s0.elapsed_time(s1)}
+            ms = _event_time(lambda: step(nb), 10)
+            nrand[str(n)] = {'ms_per_iter': ms, 'iters_per_s': 1e3 / ms}
             # the same step captured in a CUDA graph (attack.GraphedPGDStep): launch / host overhead removed
             try:
                 from nerfool_b200.attack import GraphedPGDStep
                 gstep = GraphedPGDStep(model, projector, nb, featmaps, N_SAMPLES, N_IMPORTANCE, inv_uniform=True, det=True,
-                                       max_rays=a.max_rays)
+                                       max_rays=max_rays)
                 for _ in range(3):
                     gstep(nb['ray_o'], nb['ray_d'], nb['rgb'], featmaps)
                 torch.cuda.synchronize()
-                s0.record()
-                for _ in range(20):
-                    gstep(nb['ray_o'], nb['ray_d'], nb['rgb'], featmaps)
-                s1.record()
-                torch.cuda.synchronize()
-                nrand[str(n)]['graph_ms_per_iter'] = s0.elapsed_time(s1) / 20
-                nrand[str(n)]['graph_iters_per_s'] = 2e4 / s0.elapsed_time(s1)
+                ms = _event_time(lambda: gstep(nb['ray_o'], nb['ray_d'], nb['rgb'], featmaps), 20)
+                nrand[str(n)]['graph_ms_per_iter'] = ms
+                nrand[str(n)]['graph_iters_per_s'] = 1e3 / ms
                 del gstep
             except Exception as ex:
                 nrand[str(n)]['graph_error'] = f'{type(ex).__name__}: {ex}'[:160]
+
+    # ---------------- the encoder (cuDNN, reference ResUNet) and the COMPLETE PGD iteration ----------------
+    encoder, pgd_full = None, None
+    if world == 1 and not a.no_nrand:
+        try:
+            enc, encoder = encoder_block(device, a.views)
+            if enc is not None:
+                pgd_full = pgd_full_iteration_block(device, enc, model, projector, static, resident, R, max_rays)
+                del enc
+        except Exception as ex:
+            encoder = encoder or {}
+            encoder['error'] = f'{type(ex).__name__}: {ex}'[:300]
+        torch.cuda.empty_cache()
+
+    # ---------------- strong scaling (N > 1): ONE view's rays sharded over the ranks, encoder sharded over the source views ----------------
+    strong = None
+    try:
+        strong = strong_scaling_block(a, device, rank, world, group, model, projector, static, resident, R, max_rays)
+    except Exception as ex:
+        strong = {'error': f'{type(ex).__name__}: {ex}'[:300]}
 
     # ---------------- one TRAINING step (train.py:317-327): fwd + loss + backward incl. every IBRNet parameter gradient ----------------
     train = None
@@ -330,13 +484,8 @@ def run_ours(a):
             for _ in range(3):
                 train_step()
             torch.cuda.synchronize()
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            for _ in range(10):
-                train_step()
-            s1.record()
-            torch.cuda.synchronize()
-            train = {'rays': 4096, 'ms_per_step': s0.elapsed_time(s1) / 10, 'rays_per_s': 4096e4 / s0.elapsed_time(s1),
+            ms = _event_time(train_step, 10)
+            train = {'rays': 4096, 'ms_per_step': ms, 'rays_per_s': 4096e3 / ms,
                      'what': 'render_rays fwd + masked MSE + backward to the feature maps AND all 2 x 20,136 IBRNet parameters '
                              '(weight gradients as tcgen05 GEMMs over the row index, bf16 operands, fp32 accumulate)'}
         except Exception as ex:
@@ -344,11 +493,30 @@ def run_ours(a):
         finally:
             model.net_coarse.eval(); model.net_fine.eval()
 
+    # ---------------- the 4-source-view shape (BASELINE configs[0]/[1]) as an extra block ----------------
+    v4 = None
+    if world == 1 and not a.no_nrand and a.views != 4 and a.config == 2:
+        del scene, model, projector, host, static, featmaps, resident, step, batch
+        m['objects'] = None
+        torch.cuda.empty_cache()
+        try:
+            m4 = measure_core(a, device, rank, world, group, 4, max(3, a.steps // 4), 3, extras=False)
+            ms4 = m4['total_ms'] / len(m4['step_ms'])
+            k4 = {k: sum(v) / len(m4['step_ms']) for k, v in m4['prof'].items()}
+            v4 = {'workload': f'BASELINE configs[1]: same step, 4 source views, all {m4["R"]} rays', 'ms_per_step': ms4,
+                  'rays_per_s': m4['R'] / (ms4 * 1e-3), 'pgd_iters_per_s': 1e3 / ms4, 'fwd_ms_per_frame': m4['fwd_ms'],
+                  'fwd_rays_per_s': m4['R'] / (m4['fwd_ms'] * 1e-3), 'e2e_rays_per_s': m4['R'] / (m4['e2e_total_ms'] / len(m4['step_ms']) * 1e-3),
+                  'kernel_ms_per_step': k4, 'max_rays_per_launch': m4['max_rays']}
+            m4['objects'] = None
+        except Exception as ex:
+            v4 = {'error': f'{type(ex).__name__}: {ex}'[:200]}
+
     # max over ranks
-    t = torch.tensor([total_ms, e2e_total_ms, statistics.median(fwd_ms), bf16_ms or 0.0], device=device, dtype=torch.float64)
+    total_ms, e2e_total_ms, fwd_med = m['total_ms'], m['e2e_total_ms'], m['fwd_ms']
+    t = torch.tensor([total_ms, e2e_total_ms, fwd_med, bf16_ms or 0.0, m['unprofiled_ms_per_step']], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_total_ms, fwd_med, bf16_max = t.tolist()
+    total_ms, e2e_total_ms, fwd_med, bf16_max, unprof = t.tolist()
     bf16_ms = bf16_max if bf16_ms is not None else None
 
     if rank == 0:
@@ -361,8 +529,8 @@ def run_ours(a):
         samples_per_step = R * (N_SAMPLES + N_SAMPLES + N_IMPORTANCE)
         rows_per_step = samples_per_step * a.views
         # ALGORITHMIC bytes per unit (SURVEY.md 8d / DESIGN.md 3): gather 560 B and scatter 512 B per (sample, view) row;
-        # the view backward is charged the gather it replaces by reading the activation stash (which actually moves
-        # 768 B/row); ray stage: the 288-byte interface row in (fwd) / in + out (bwd) per sample
+        # the view backward is charged the gather it replaces by reading the activation stash; ray stage: the 288-byte
+        # interface row in (fwd) / in + out (bwd) per sample
         alg = {'nfb_ibrnet_view_fwd': (GATHER_B, rows_per_step), 'nfb_ibrnet_view_bwd': (GATHER_B + SCATTER_B, rows_per_step),
                'nfb_ibrnet_ray_fwd': (288 + 16, samples_per_step), 'nfb_ibrnet_ray_bwd': (288 * 2 + 16, samples_per_step)}
         # dense MACs per unit (SURVEY.md 8a FLOP model): 13,256 per row in the view stage, 6,480 + 32 S per sample in the
@@ -407,30 +575,34 @@ def run_ours(a):
         d = per_kernel[dom]
         ms_per_step = total_ms / a.steps
         rays_total = R * world
-        from nerfool_b200 import _lib as _l
+        cfg = workload_config(a, world)
+        cfg.update({'max_rays_per_launch': max_rays,
+                    'arithmetic': f'{_lib.get_precision()}: fp32 data, dense layers on tcgen05 with bf16 hi+lo split operands '
+                                  '(3 MMA passes, fp32 accumulate) = fp32-equivalent results' if _lib.get_precision() == 'bf16x3'
+                                  else _lib.get_precision(),
+                    'parallelism': f'one target view per GPU x{world}, 1 NCCL allreduce of d(featmaps)/step' if world > 1 else 'single GPU',
+                    'l2': 'per-step working set (per-sample workspaces + activation stash, tens of GB) >> 126 MB L2; '
+                          'the 2 x 15.7 MB feature maps are L2-resident by design'})
         out = {
             'metric': 'rays/s', 'value': rays_total / (ms_per_step * 1e-3), 'unit': 'rays/s',
             'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'BASELINE configs[{a.config}]: IBRNet PGD hot-path step (render_rays fwd + masked-MSE + '
-                                   f'bwd to source feature maps), {H}x{W} target view, all {R} rays per step, '
-                                   f'{a.views} source views, {N_SAMPLES} coarse + {N_IMPORTANCE} importance samples, random-init weights',
-                       'rays_per_step_per_gpu': R, 'source_views': a.views, 'max_rays_per_launch': a.max_rays,
-                       'arithmetic': f'{_l.get_precision()}: fp32 data, dense layers on tcgen05 with bf16 hi+lo split operands '
-                                     '(3 MMA passes, fp32 accumulate) = fp32-equivalent results' if _l.get_precision() == 'bf16x3'
-                                     else _l.get_precision(),
-                       'parallelism': f'one target view per GPU x{world}, 1 NCCL allreduce of d(featmaps)/step' if world > 1 else 'single GPU',
-                       'l2': 'per-step working set (per-sample workspaces + activation stash, tens of GB) >> 126 MB L2; '
-                             'the 2x6.3 MB feature maps are L2-resident by design'},
+            'config': cfg,
             'pgd_iters_per_s': 1e3 / ms_per_step,
-            'pgd_iters_per_s_by_n_rand': nrand or None,
+            'pgd_iters_per_s_note': 'hot path only (render_rays fwd + loss + bwd to the feature maps), all rays of the view per '
+                                    'iteration; the complete iteration incl. the cuDNN encoder and the optimiser is pgd_full_iteration',
+            'pgd_iters_per_s_by_n_rand_hot_path_only': nrand or None,
+            'encoder': encoder,
+            'pgd_full_iteration': pgd_full,
+            'strong_scaling': strong,
             'training_step': train,
+            'v4_block': v4,
             'fwd_rays_per_s': rays_total / (fwd_med * 1e-3),
             'fwd_ms_per_frame': fwd_med,
             'render_single_image_ms_per_frame': rsi_ms,
-            'encoder': 'not timed: the ResUNet stays on cuDNN in the reference and is outside this repo (north_star)',
-            'wall_s_timed_region': t_wall,
-            'step_ms': step_ms,
+            'wall_s_timed_region': m['t_wall'],
+            'ms_per_step_without_event_pairs': unprof,
+            'step_ms': m['step_ms'],
             'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': d['achieved_GBps'], 'peak': hbm_peak, 'unit': 'GB/s',
                          'frac': d['hbm_frac'], 'traffic': d['traffic_bytes_per_launch'], 'peak_source': peak_src,
                          'avg_launch_ms': d['avg_launch_ms'],
@@ -445,16 +617,16 @@ def run_ours(a):
             'kernel_share': {k: round(v, 4) for k, v in sorted(kshare.items(), key=lambda kv: -kv[1])},
             'kernel_ms_per_step': {k: v / a.steps for k, v in ktot.items()},
             'e2e': {'value': rays_total / (e2e_total_ms / a.steps * 1e-3), 'unit': 'rays/s',
-                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'ms_per_step': e2e_total_ms / a.steps},
+                    'h2d_bytes_per_step': m['h2d'], 'd2h_bytes_per_step': 4, 'ms_per_step': e2e_total_ms / a.steps},
             'gpu_launches': launches,
             'clocks': clocks,
-            'loss_last': float(loss_host),
+            'loss_last': m['loss_last'],
         }
         if bf16_ms is not None:
             out['bf16_mode'] = {'ms_per_step': bf16_ms, 'rays_per_s': rays_total / (bf16_ms * 1e-3),
                                 'note': 'same step with NFB_PREC_BF16 (single bf16 MMA pass; PSNR-parity mode, tests/test_gpu_parity.py::test_precision_modes)'}
         if world == 1 and not a.no_cpu_baseline:
-            out['cpu_baseline'] = cpu_reference(a, sample_rays=a.cpu_rays, steps=1, warmup=1)
+            out['cpu_baseline'] = cpu_reference(a, sample_rays=a.cpu_rays, steps=3, warmup=1)
             out['torch_eager_b200'] = eager_gpu_reference(a, device)
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -462,32 +634,118 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def strong_scaling_block(a, device, rank, world, group, model, projector, static, resident, R, max_rays):
+    """SURVEY.md 8(d) "fixed global batch": ONE target view's R rays sharded over the ranks (contiguous slices), the global
+    mask count as loss normaliser, the reference encoder sharded over the source views, one packed allreduce, delta-gradient
+    slices all-gathered (attack.delta_gradient_step).  Reported at every N (N = 1 is the same program without collectives)."""
+    import torch.distributed as dist
+    from nerfool_b200.attack import delta_gradient_step, shard_slice
+    ResUNet = load_reference_resunet()
+    if ResUNet is None or a.no_nrand:
+        return None
+    torch.manual_seed(0)
+    enc = ResUNet(coarse_out_ch=32, fine_out_ch=32, coarse_only=False).to(device).eval()
+    if world > 1:                       # every rank works on RANK 0's target view
+        for k in ('ray_o', 'ray_d', 'rgb'):
+            dist.broadcast(resident[k], src=0)
+        cam = static['camera'].clone()
+        dist.broadcast(cam, src=0)
+    else:
+        cam = static['camera']
+    lo, hi = shard_slice(R, rank, world)
+    shard = {'camera': cam, 'depth_range': static['depth_range'], 'src_rgbs': static['src_rgbs'], 'src_cameras': static['src_cameras']}
+    for k in ('ray_o', 'ray_d', 'rgb'):
+        shard[k] = resident[k][lo:hi].contiguous()
+    delta = ((torch.rand(static['src_rgbs'].shape, generator=torch.Generator().manual_seed(5)) * 2 - 1) * (8. / 255.)).to(device)
+
+    def it():
+        return delta_gradient_step(lambda x: enc(x), model, projector, shard, delta, N_SAMPLES, N_IMPORTANCE, inv_uniform=True, det=True,
+                                   max_rays=max_rays, group=group, global_norm=True, shard_encoder=True)
+    for _ in range(2):
+        it()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    iters = 4
+    ms = _event_time(it, iters)
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    del enc
+    torch.cuda.empty_cache()
+    return {'what': f'one {H}x{W} view ({R} rays) sharded over {world} rank(s), encoder sharded over the {a.views} source views, full '
+                    'iteration to d delta (encoder fwd + render fwd/bwd + encoder bwd + collectives)', 'ms_per_iter': ms,
+            'iters_per_s': 1e3 / ms, 'rays_per_s': R / (ms * 1e-3), 'n_gpus': world}
+
+
 # ----------------------------------------------------------------------------------------------------
+def _reference_modules():
+    """The UNMODIFIED reference modules of the path, imported from the staged copy (None when it is absent)."""
+    root = reference_root()
+    if root is None:
+        return None
+    if root not in sys.path:
+        sys.path.append(root)
+    from ibrnet.projection import Projector as RefProjector
+    from ibrnet.mlp_network import IBRNet as RefIBRNet
+    from ibrnet import render_ray as ref_rr
+    assert os.path.samefile(os.path.dirname(ref_rr.__file__), os.path.join(root, 'ibrnet')), 'ibrnet resolved to something other than the staged reference'
+    return RefProjector, RefIBRNet, ref_rr
+
+
 def cpu_reference(a, sample_rays, steps, warmup):
-    """The CPU port of the reference path (oracle/) on a bounded sample of the same workload: the same step
-    (render_rays fwd + masked MSE + backward to the feature maps) on `sample_rays` rays of the view."""
-    from oracle import ibrnet_oracle as O
+    """The reference's own CPU implementation of the path on a bounded sample of the same workload: the same step
+    (render_rays fwd + masked MSE + backward to the feature maps) on `sample_rays` rays of the view, all host threads.
+    kind "reference": the unmodified ibrnet.{projection, mlp_network, render_ray} from the staged copy; kind "port": the
+    oracle restatement (only when no staged copy exists)."""
     from nerfool_b200.synthetic import make_scene, ray_batch_for
     torch.set_num_threads(os.cpu_count() or 1)
     scene = make_scene(H, W, a.views, seed=0, kind=SCENE_KIND)
     ids = np.sort(np.random.RandomState(1).choice(H * W, sample_rays, replace=False))
     batch = ray_batch_for(scene, ids)
-    pc = O.random_ibrnet_params(N_SAMPLES, 1, sigma_bias=0.3)
-    pf = O.random_ibrnet_params(N_SAMPLES + N_IMPORTANCE, 2, sigma_bias=0.3)
+    mods = _reference_modules()
+    if mods is not None:
+        RefProjector, RefIBRNet, ref_rr = mods
+        args = types.SimpleNamespace(anti_alias_pooling=1, local_rank=0)
+        torch.manual_seed(0)
+        nc, nf = RefIBRNet(args, in_feat_ch=32, n_samples=N_SAMPLES).eval(), RefIBRNet(args, in_feat_ch=32, n_samples=N_SAMPLES + N_IMPORTANCE).eval()
+        with torch.no_grad():
+            for n in (nc, nf):
+                n.out_geometry_fc[2].bias += 0.3
+        model, proj = types.SimpleNamespace(net_coarse=nc, net_fine=nf), RefProjector(device='cpu')
+
+        def one(fm):
+            ret = ref_rr.render_rays(batch, model, fm, proj, N_samples=N_SAMPLES, inv_uniform=True, N_importance=N_IMPORTANCE, det=True)
+            loss = 0.
+            for lvl in ('outputs_coarse', 'outputs_fine'):
+                mk = ret[lvl]['mask'].float()
+                loss = loss + torch.sum((ret[lvl]['rgb'] - batch['rgb']) ** 2 * mk[:, None]) / (torch.sum(mk) * 3 + 1e-6)   # utils.img2mse
+            loss.backward()
+        kind = 'reference'
+    else:
+        from oracle import ibrnet_oracle as O
+        pc = O.random_ibrnet_params(N_SAMPLES, 1, sigma_bias=0.3)
+        pf = O.random_ibrnet_params(N_SAMPLES + N_IMPORTANCE, 2, sigma_bias=0.3)
+
+        def one(fm):
+            out = O.render_rays(batch, pc, pf, fm, N_SAMPLES, inv_uniform=True, n_importance=N_IMPORTANCE, det=True)
+            O.attack_loss(out, batch['rgb']).backward()
+        kind = 'port'
     times = []
     for i in range(warmup + steps):
         fm = tuple(f.clone().requires_grad_(True) for f in scene['featmaps'])
         t0 = time.perf_counter()
-        out = O.render_rays(batch, pc, pf, fm, N_SAMPLES, inv_uniform=True, n_importance=N_IMPORTANCE, det=True)
-        loss = O.attack_loss(out, batch['rgb'])
-        loss.backward()
+        one(fm)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    sec = sum(times) / len(times)
-    return {'value': sample_rays / sec, 'unit': 'rays/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': f'{sample_rays} random rays of the {H}x{W} view, same step (fwd + loss + bwd to feature maps), '
-                      f'{warmup} warm-up + mean of {steps}', 'ms_per_step': sec * 1e3}
+    sec = statistics.median(times)
+    return {'value': sample_rays / sec, 'unit': 'rays/s', 'cores': torch.get_num_threads(), 'kind': kind,
+            'sample': f'{sample_rays} random rays of the {H}x{W} view ({a.views} source views), same step (fwd + loss + bwd to feature maps), '
+                      f'{warmup} warm-up + median of {steps}' + ('; unmodified reference modules (staged copy)' if kind == 'reference'
+                                                                   else '; oracle port (no staged reference present)'),
+            'ms_per_step': sec * 1e3, 'step_s': times}
 
 
 def eager_gpu_reference(a, device, rays=4096, steps=3):
@@ -705,9 +963,7 @@ def run_reference(a):
     out = {'impl': 'reference', 'metric': 'rays/s', 'value': cb['value'], 'unit': 'rays/s', 'n_gpus': world,
            'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': cb['ms_per_step'], 'higher_is_better': True,
            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': f'BASELINE configs[{a.config}]: IBRNet PGD hot-path step, {H}x{W} target view, '
-                                  f'{a.views} source views, {N_SAMPLES} + {N_IMPORTANCE} samples; CPU port of the reference path on a bounded sample',
-                      'rays_per_step': a.cpu_rays, 'source_views': a.views},
+           'config': workload_config(a, world),
            'cpu_baseline': cb,
            'e2e': {'value': cb['value'], 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(out), flush=True)
@@ -719,28 +975,24 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--views', type=int, default=4)
+    ap.add_argument('--views', type=int, default=0, help='source views (0 = what --config names)')
     ap.add_argument('--max-rays', dest='max_rays', type=int, default=0, help='rays per launch (0 = sized from the stash budget)')
-    ap.add_argument('--cpu-rays', dest='cpu_rays', type=int, default=2048)
+    ap.add_argument('--cpu-rays', dest='cpu_rays', type=int, default=0, help='rays of the bounded CPU sample per step (0 = 512 at 10 views, 2048 at 4)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-nrand', dest='no_nrand', action='store_true', help='skip the N_rand = 512/4096/32768 PGD iteration timings')
     ap.add_argument('--no-bf16', dest='no_bf16', action='store_true', help='skip the extra plain-bf16 measurement')
-    ap.add_argument('--config', type=int, default=1, choices=[1, 2, 3, 4],
-                    help='BASELINE.json configs index: 1 = headline (378x504, 4 views, 64+64); 2 = universal-attack shape '
-                         '(378x504, 10 views, one target view per GPU); 3 = NeRF-Synthetic shape (800x800, 10 views, 64+128); '
-                         '4 = GNT forward render (378x504, 8 views, 64 samples, depth 4)')
+    ap.add_argument('--config', type=int, default=2, choices=[1, 2, 3, 4],
+                    help='BASELINE.json configs index: 2 (default) = the shape the metric is quoted on (378x504, 10 source views, '
+                         '64+64, one target view per GPU); 1 = the 4-source-view shape of configs[0]/[1]; 3 = NeRF-Synthetic '
+                         'shape (800x800, 10 views, 64+128); 4 = GNT forward render (378x504, 8 views, 64 samples, depth 4)')
     a = ap.parse_args()
     global H, W, N_SAMPLES, N_IMPORTANCE, SCENE_KIND
-    if a.config == 2:
-        a.views = 10
-    elif a.config == 3:
+    if a.config == 3:
         H, W, N_IMPORTANCE, SCENE_KIND = 800, 800, 128, 'synthetic'
-        a.views = 10
-    if a.max_rays <= 0:
-        # bound the two activation stashes of a chunk (768 B per (sample, view) row) to ~56 GB of the 180 GB: 65,536-ray chunks for
-        # the headline config (measured: 32,768-ray chunks 167.7 ms/step, 65,536: 164.3, 98,304: 163.9)
-        per_ray = (2 * N_SAMPLES + N_IMPORTANCE) * a.views * 768 + (2 * N_SAMPLES + N_IMPORTANCE) * 560
-        a.max_rays = max(4096, min(65536, 1 << int(np.log2(56e9 / per_ray))))
+    if a.views <= 0:
+        a.views = {1: 4, 2: 10, 3: 10, 4: GNT_VIEWS}[a.config]
+    if a.cpu_rays <= 0:
+        a.cpu_rays = 2048 if a.views <= 4 else 512
     a.warmup = max(a.warmup, 3) if a.impl == 'ours' else a.warmup
     if a.impl == 'reference':
         run_reference(a)

@@ -355,7 +355,11 @@ extern "C" int nfb_composite_bwd(int R, int S, int white_bkgd, const float* raw,
   NFB_REQUIRE(S <= 4096, NFB_EUNSUPPORTED, "nfb_composite_bwd: S=%d > 4096", S);
   if (R == 0) return NFB_OK;
   const int grid = tiles_grid((size_t)R, CMP_WARPS, 16);
-  const size_t smem = (size_t)CMP_WARPS * 2 * S * sizeof(float);
+  const size_t smem = (size_t)CMP_WARPS * 2 * S * sizeof(float);   // 32 S bytes: S = 4096 -> 128 KB (limit 227 KB)
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_composite_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return nfb_set_error(NFB_ECUDA, "nfb_composite_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
   k_composite_bwd<<<grid, CMP_WARPS * 32, smem, (cudaStream_t)stream>>>(R, S, white_bkgd, raw, z, d_rgb, d_depth,
                                                                      d_weights, d_alpha, d_raw);
   NFB_CHECK_LAUNCH("k_composite_bwd");

@@ -30,10 +30,13 @@ def _tensor_key(t: torch.Tensor):
     return (t.untyped_storage().data_ptr(), t.storage_offset(), tuple(t.shape), tuple(t.stride()), t._version, str(t.device))
 
 
-def camera_block(train_cameras: torch.Tensor, query_camera: torch.Tensor, device) -> torch.Tensor:
+def camera_block(train_cameras: torch.Tensor, query_camera: torch.Tensor, device, H=None, W=None) -> torch.Tensor:
     """train_cameras [V,34], query_camera [34] (any device) -> device float32 [16*V+4].
-    Cached per (storage, view geometry, version); the cache keeps the key tensors alive so addresses cannot be reused."""
-    key = (_tensor_key(train_cameras), _tensor_key(query_camera), str(device))
+    Cached per (storage, view geometry, version); the cache keeps the key tensors alive so addresses cannot be reused.
+    H, W: size of the source images the kernels will normalise / bounds-check with.  The reference reads them from the
+    camera vector (``h, w = train_cameras[0][:2]``, projection.py:112); the kernels take them from the image tensor, so
+    the two must agree -- checked here, once per cached camera tensor."""
+    key = (_tensor_key(train_cameras), _tensor_key(query_camera), str(device), H, W)
     hit = _cam_cache.get(key)
     if hit is not None:
         _cam_cache.move_to_end(key)
@@ -41,6 +44,10 @@ def camera_block(train_cameras: torch.Tensor, query_camera: torch.Tensor, device
     tc = train_cameras.detach().float().cpu()
     qc = query_camera.detach().float().cpu()
     V = tc.shape[0]
+    if H is not None and (float(tc[0, 0]) != float(H) or float(tc[0, 1]) != float(W)):
+        raise RuntimeError(f'source camera vector says h, w = {float(tc[0, 0]):g}, {float(tc[0, 1]):g} but the source images are '
+                           f'{H} x {W}: the reference normalises projections with the camera\'s h, w (projection.py:112); '
+                           'resized source images need matching camera vectors')
     K = tc[:, 2:18].reshape(-1, 4, 4)
     c2w = tc[:, -16:].reshape(-1, 4, 4)
     P = K.bmm(torch.inverse(c2w))                              # [V,4,4], same ops as the reference
@@ -286,7 +293,7 @@ class RenderLevel(torch.autograd.Function):
     params, pos_enc).  Differentiable w.r.t. featmaps and imgs."""
 
     @staticmethod
-    def forward(ctx, featmaps, imgs, ray_o, ray_d, z, cam, params, pos_enc, H, W, anti_alias, white_bkgd):
+    def forward(ctx, featmaps, imgs, ray_o, ray_d, z, cam, params, pos_enc, H, W, anti_alias, white_bkgd, geo_noise=0.0):
         _lib.require_cuda(featmaps, imgs, ray_o, ray_d, z, cam, params, pos_enc)
         feat = channels_last_feat(featmaps)
         imgs_c, o_c, d_c, z_c = f32c(imgs), f32c(ray_o), f32c(ray_d), f32c(z)
@@ -319,6 +326,10 @@ class RenderLevel(torch.autograd.Function):
                  None, ptr(o_c), ptr(d_c), ptr(z_c), ptr(cam), ptr(imgs_c), ptr(feat), ptr(params), ptr(ps),
                  ptr(stash), _lib.precision_code(), st)
             call('nfb_ibrnet_ray_fwd', R, S, ptr(ps), ptr(params), ptr(pos_enc), ptr(raw), ptr(pmask), ptr(rstash), _lib.precision_code(), st)
+            if geo_noise:
+                # sigma += N(0, geo_noise) (render_ray.py:133-134); additive, so every backward kernel is unchanged (the
+                # compositing backward reads this noisy `raw`, the ray stage differentiates its own pre-noise sigma)
+                raw[..., 3].add_(torch.randn(R, S, device=dev, dtype=torch.float32), alpha=float(geo_noise))
             call('nfb_composite_fwd', R, S, int(white_bkgd), ptr(raw), ptr(z_c), ptr(pmask), None, 0,
                  ptr(rgb), ptr(depth), ptr(weights), ptr(alpha), ptr(ray_mask), st)
         ctx.stash = stash
@@ -362,4 +373,4 @@ class RenderLevel(torch.autograd.Function):
         ctx.stash = None
         ctx.rstash = None
         return (d_feat.permute(0, 3, 1, 2) if need_feat else None, d_imgs,
-                None, None, None, None, d_params, None, None, None, None, None)
+                None, None, None, None, d_params, None, None, None, None, None, None)

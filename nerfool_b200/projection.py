@@ -28,7 +28,7 @@ class Projector:
             'only support batch_size=1 for now'
         H, W = int(train_imgs.shape[2]), int(train_imgs.shape[3])
         cams = train_cameras[0]
-        # the reference normalises with h, w read from the camera vector (projection.py:112); they equal the
-        # image size for every loader in the repo -- checked here once per camera tensor via the cached block
-        cam = ops.camera_block(cams, query_camera[0], xyz.device)
+        # the reference normalises with h, w read from the camera vector (projection.py:112); camera_block checks (once per
+        # cached camera tensor) that they equal the image size the kernels use
+        cam = ops.camera_block(cams, query_camera[0], xyz.device, H, W)
         return ops.ProjectGather.apply(xyz, train_imgs[0], featmaps, cam, H, W)

@@ -124,22 +124,28 @@ def render_rays(ray_batch, model, featmaps, projector, N_samples, inv_uniform=Fa
     assert near > 0 and far > 0 and far > near
     R = ray_d.shape[0]
     dev = ray_d.device
-    t_rand = None if det else torch.rand(R, N_samples, device=dev)
-    z_vals = ops.coarse_depths(R, N_samples, near, far, inv_uniform, t_rand, dev)
+    if 'nfb_coarse_z' in ray_batch and det:
+        z_vals = ray_batch['nfb_coarse_z']        # caller-owned static buffer (attack.GraphedPGDStep)
+    else:
+        t_rand = None if det else torch.rand(R, N_samples, device=dev)
+        z_vals = ops.coarse_depths(R, N_samples, near, far, inv_uniform, t_rand, dev)
 
-    fused = _fusable(model, projector) and not (geo_noise is not None and geo_noise > 0)
+    fused = _fusable(model, projector)
+    noise = float(geo_noise) if (geo_noise is not None and geo_noise > 0) else 0.0
     if fused:
         src_rgbs, src_cams = src['src_rgbs'], src['src_cameras']
         assert src_rgbs.shape[0] == 1 and src_cams.shape[0] == 1 and ray_batch['camera'].shape[0] == 1, \
             'only support batch_size=1 for now'
         H, W = int(src_rgbs.shape[2]), int(src_rgbs.shape[3])
-        cam = ops.camera_block(src_cams[0], ray_batch['camera'][0], dev)
+        cam = ray_batch.get('nfb_camera_block')     # caller-owned static block (attack.GraphedPGDStep)
+        if cam is None:
+            cam = ops.camera_block(src_cams[0], ray_batch['camera'][0], dev, H, W)
 
         def level(net, fmap, z):
             net = _unwrap(net)
             rgb, depth, weights, alpha, mask = ops.RenderLevel.apply(
                 fmap, src_rgbs[0], ray_o, ray_d, z, cam, net.param_blob(), net.pos_encoding[0], H, W,
-                bool(net.anti_alias_pooling), bool(white_bkgd))
+                bool(net.anti_alias_pooling), bool(white_bkgd), noise)
             return OrderedDict([('rgb', rgb), ('depth', depth), ('weights', weights), ('mask', mask),
                                 ('alpha', alpha), ('z_vals', z)])
     else:

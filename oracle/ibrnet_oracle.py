@@ -13,11 +13,13 @@ algorithm on the path
     sample_pdf                   /root/reference/ibrnet/render_ray.py:24-70
     raw2outputs                  /root/reference/ibrnet/render_ray.py:123-170
     render_rays                  /root/reference/ibrnet/render_ray.py:173-256
+    render_rays_hybrid           /root/reference/ibrnet/render_ray.py:261-390
+    render_single_image          /root/reference/ibrnet/render_image.py:21-123
     img2mse (masked MSE)         /root/reference/utils.py:48-58
 
 Parity pinning: the reference ships no tests / golden vectors, so the oracle is pinned
-against outputs of the reference itself, generated in the build container by ``oracle/make_golden.py``
-(which imports /root/reference) and committed under ``tests/golden/``.  ``tests/test_oracle_golden.py``
+against outputs of the reference itself, generated in the build container by ``oracle/make_golden.py`` and
+``oracle/make_golden_baseline.py`` (BASELINE-shaped scenes, render_single_image, render_rays_hybrid; both import /root/reference) and committed under ``tests/golden/``.  ``tests/test_oracle_golden.py``
 checks every function here against those vectors.
 
 One deliberate, documented deviation: the normaliser of ``sample_pdf`` (render_ray.py:36, a 62-term
@@ -325,8 +327,10 @@ def composite(raw, z_vals, pixel_mask, white_bkgd=False):
 
 def render_rays(ray_batch, params_coarse, params_fine, featmaps, n_samples, inv_uniform=False,
                 n_importance=0, det=False, white_bkgd=False, anti_alias_pooling=True, src_ray_batch=None,
-                u=None, t_rand=None):
-    """render_ray.py:173-256.  ``params_*`` are state_dict-like mappings that also hold 'pos_encoding'."""
+                u=None, t_rand=None, fine_z=None):
+    """render_ray.py:173-256.  ``params_*`` are state_dict-like mappings that also hold 'pos_encoding'.
+    ``fine_z`` (test hook, not in the reference): evaluate the fine level at these depths instead of sampling them -- used
+    to compare two precisions of the same arithmetic at IDENTICAL sample positions."""
     src = ray_batch if src_ray_batch is None else src_ray_batch
     pts, z = coarse_depths(ray_batch['ray_o'], ray_batch['ray_d'], ray_batch['depth_range'],
                            n_samples, inv_uniform=inv_uniform, det=det, t_rand=t_rand)
@@ -337,7 +341,7 @@ def render_rays(ray_batch, params_coarse, params_fine, featmaps, n_samples, inv_
                          anti_alias_pooling)
     out = {'outputs_coarse': composite(raw, z, pixel_mask, white_bkgd), 'outputs_fine': None}
     if n_importance > 0:
-        z = fine_depths(z, out['outputs_coarse']['weights'], n_importance, inv_uniform, det, u=u)
+        z = fine_depths(z, out['outputs_coarse']['weights'], n_importance, inv_uniform, det, u=u) if fine_z is None else fine_z
         pts = z.unsqueeze(2) * ray_batch['ray_d'].unsqueeze(1) + ray_batch['ray_o'].unsqueeze(1)
         rgb_feat, ray_diff, mask = projector_compute(pts, ray_batch['camera'], src['src_rgbs'],
                                                      src['src_cameras'], featmaps[1])
@@ -346,6 +350,69 @@ def render_rays(ray_batch, params_coarse, params_fine, featmaps, n_samples, inv_
                              anti_alias_pooling)
         out['outputs_fine'] = composite(raw, z, pixel_mask, white_bkgd)
     return out
+
+
+def render_rays_hybrid(ray_batch, params_coarse, params_fine, featmaps, featmaps_clean, n_samples, use_clean_color,
+                       use_clean_density, inv_uniform=False, n_importance=0, det=False, white_bkgd=False,
+                       anti_alias_pooling=True, src_ray_batch=None):
+    """render_ray.py:261-390: both feature-map sets at the same points; colour and density each from the clean or the
+    adversarial pass; composited with the ADVERSARIAL pass's pixel mask (:320-321, :386-387)."""
+    src = ray_batch if src_ray_batch is None else src_ray_batch
+
+    def level(params, fm_adv, fm_clean, z):
+        pts = z.unsqueeze(2) * ray_batch['ray_d'].unsqueeze(1) + ray_batch['ray_o'].unsqueeze(1)
+        raws, pixel_mask = [], None
+        for fm in (fm_adv, fm_clean):
+            rgb_feat, ray_diff, mask = projector_compute(pts, ray_batch['camera'], src['src_rgbs'], src['src_cameras'], fm)
+            if pixel_mask is None:
+                pixel_mask = mask[..., 0].sum(dim=2) > 1
+            raws.append(ibrnet_forward(params, params['pos_encoding'], rgb_feat, ray_diff, mask, anti_alias_pooling))
+        color = raws[1][:, :, :3] if use_clean_color else raws[0][:, :, :3]
+        sigma = raws[1][:, :, 3:4] if use_clean_density else raws[0][:, :, 3:4]
+        return composite(torch.cat([color, sigma], dim=2), z, pixel_mask, white_bkgd)
+
+    _, z = coarse_depths(ray_batch['ray_o'], ray_batch['ray_d'], ray_batch['depth_range'], n_samples,
+                         inv_uniform=inv_uniform, det=det)
+    out = {'outputs_coarse': level(params_coarse, featmaps[0], featmaps_clean[0], z), 'outputs_fine': None}
+    if n_importance > 0:
+        z = fine_depths(z, out['outputs_coarse']['weights'], n_importance, inv_uniform, det)
+        out['outputs_fine'] = level(params_fine, featmaps[1], featmaps_clean[1], z)
+    return out
+
+
+def render_single_image(H, W, ray_batch, params_coarse, params_fine, featmaps, chunk_size, n_samples, inv_uniform=False,
+                        n_importance=0, det=False, white_bkgd=False):
+    """render_image.py:21-123 (render_stride 1, plain render_rays branch): chunk loop over the rays of a view, outputs
+    concatenated and reshaped to [H, W, ...] (squeezed), masked-out pixels of the COARSE image painted white (:109)."""
+    shared = ('camera', 'depth_range', 'src_rgbs', 'src_cameras')
+    acc = {'outputs_coarse': {}, 'outputs_fine': {}}
+    n_rays = ray_batch['ray_o'].shape[0]
+    for i in range(0, n_rays, chunk_size):
+        chunk = {k: (v if k in shared or v is None else v[i:i + chunk_size]) for k, v in ray_batch.items()}
+        ret = render_rays(chunk, params_coarse, params_fine, featmaps, n_samples, inv_uniform, n_importance, det, white_bkgd)
+        for lvl in acc:
+            if ret[lvl] is None:
+                acc[lvl] = None
+                continue
+            for k, v in ret[lvl].items():
+                acc[lvl].setdefault(k, []).append(v)
+    out = {}
+    for lvl, d in acc.items():
+        out[lvl] = None if d is None else OrderedDict((k, torch.cat(v, dim=0).reshape(H, W, -1).squeeze()) for k, v in d.items())
+    out['outputs_coarse']['rgb'][out['outputs_coarse']['mask'] == 0] = 1.
+    return out
+
+
+def fine_depth_report(z_ours, z_ref, n_coarse_sorted=None):
+    """How two fine-depth tensors [R, S] differ, for the end-to-end z_vals parity statement (render_ray.py:216-238): the
+    importance samples are CONTINUOUS piecewise-linear functions of the coarse weights (inverse CDF), so a relative
+    weight error e moves a sample by <= e x (bin width) -- except that merge-sort ranks swap when two depths cross, which
+    is harmless (same multiset up to e).  Returns max |dz|, max |dz| / bin-scale, and the number of rays whose sorted
+    sequences differ by more than `n ulp` anywhere."""
+    dz = (z_ours.double() - z_ref.double()).abs()
+    scale = (z_ref[:, -1] - z_ref[:, 0]).double().clamp_min(1e-12).unsqueeze(1)
+    return {'max_abs': dz.max().item(), 'max_rel_range': (dz / scale).max().item(),
+            'n_exact': int((dz == 0).sum().item()), 'n': dz.numel()}
 
 
 def masked_mse(x, y, mask=None):

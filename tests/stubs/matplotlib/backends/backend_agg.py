@@ -1,0 +1,3 @@
+class FigureCanvasAgg:
+    def __init__(self, *a, **k):
+        raise RuntimeError('matplotlib stub: plotting is not available in the test harness')

@@ -275,26 +275,39 @@ def test_delta_gradient_step_with_view_sharded_encoder_gloo():
     delta = _delta_for(g)
     pc = {k[3:]: t(v) for k, v in g.items() if k.startswith('nc.')}
     pf = {k[3:]: t(v) for k, v in g.items() if k.startswith('nf.')}
-    # plain autograd through encoder + oracle renderer: the truth for d loss / d delta
+    # plain autograd through encoder + oracle renderer: the truth for d loss / d delta.  As in the reference
+    # (eval_adv.py:290-304, train.py:129-143) delta reaches the loss ONLY through the feature maps: render_rays gets the
+    # CLEAN source colours.
     enc = _tiny_encoder()
     adv = (batch['src_rgbs'] + delta).requires_grad_(True)
     fc, ff = enc(adv[0].permute(0, 3, 1, 2))
-    b2 = dict(batch)
-    b2['src_rgbs'] = adv
-    out = O.render_rays(b2, pc, pf, (fc, ff), int(g['S_c']), inv_uniform=bool(g['inv_uniform']), n_importance=int(g['N_imp']), det=True)
+    out = O.render_rays(batch, pc, pf, (fc, ff), int(g['S_c']), inv_uniform=bool(g['inv_uniform']), n_importance=int(g['N_imp']), det=True)
     loss0 = O.attack_loss(out, batch['rgb'])
     loss0.backward()
     truth = adv.grad
+    # the non-reference variant that also perturbs the blended colours (explicit flag)
+    adv2 = (batch['src_rgbs'] + delta).requires_grad_(True)
+    fc2, ff2 = _tiny_encoder()(adv2[0].permute(0, 3, 1, 2))
+    b2 = dict(batch)
+    b2['src_rgbs'] = adv2
+    out2 = O.render_rays(b2, pc, pf, (fc2, ff2), int(g['S_c']), inv_uniform=bool(g['inv_uniform']), n_importance=int(g['N_imp']), det=True)
+    loss2 = O.attack_loss(out2, batch['rgb'])
+    loss2.backward()
+    assert ((adv2.grad - truth).norm() / truth.norm()) > 1e-3, 'the two variants must differ for this test to mean anything'
     # single process through delta_gradient_step (chunked)
     saved = attack.render_rays
     attack.render_rays = _oracle_render(g)
     try:
         loss1, dd1 = attack.delta_gradient_step(_tiny_encoder(), None, None, batch, delta, int(g['S_c']), int(g['N_imp']),
                                                 inv_uniform=bool(g['inv_uniform']), det=True, max_rays=13)
+        loss3, dd3 = attack.delta_gradient_step(_tiny_encoder(), None, None, batch, delta, int(g['S_c']), int(g['N_imp']),
+                                                inv_uniform=bool(g['inv_uniform']), det=True, max_rays=13, perturb_colours=True)
     finally:
         attack.render_rays = saved
     assert abs(loss1.item() - loss0.item()) < 1e-6
     assert ((dd1 - truth).norm() / truth.norm()) < 1e-5
+    assert abs(loss3.item() - loss2.item()) < 1e-6
+    assert ((dd3 - adv2.grad).norm() / adv2.grad.norm()) < 1e-5
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = 31500 + (os.getpid() % 2000)

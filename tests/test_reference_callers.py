@@ -1,0 +1,211 @@
+"""The reference's own DRIVERS, unmodified, on top of dropin/ (north star: "eval_adv.py and train.py run unmodified").
+
+``eval/ibrnet/eval_adv.py:optimize_adv_perturb`` (:258-510) and ``train.py:train`` (:47-236) are imported from the reference
+checkout (or its byte-for-byte staged copy, oracle/stage_reference.py) with only the absent third-party packages stubbed
+(tests/stubs) and a synthetic dataset registered in the reference's ``dataset_dict`` (tests/ref_harness.py).  Everything they
+call on the hot path -- ``Projector``, ``IBRNet`` (inside the reference's ``IBRNetModel``), ``render_rays``,
+``render_single_image`` -- resolves to nerfool_b200 and runs on the CUDA library; the encoder is the reference's ResUNet on cuDNN.
+The resulting ``delta`` gradient / parameter gradients are compared with autograd of the CPU oracle on the inputs the
+drivers actually passed to ``render_rays`` (captured by wrapping the name the driver module imported)."""
+import copy
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import ref_harness as RH
+from helpers import relerr, report
+
+needs_ref = pytest.mark.skipif(not RH.reference_available(), reason='no reference checkout / staged copy (oracle/stage_reference.py)')
+
+
+@pytest.fixture()
+def ref_env(tmp_path):
+    saved_path, saved_mods, saved_cwd = list(sys.path), dict(sys.modules), os.getcwd()
+    root = RH.setup_paths('ibrnet')
+    try:
+        yield root, tmp_path
+    finally:
+        os.chdir(saved_cwd)
+        sys.path[:] = saved_path
+        for name in list(sys.modules):
+            if name.split('.')[0] in RH._GENERIC:
+                del sys.modules[name]
+        for name, mod in saved_mods.items():
+            if name.split('.')[0] in RH._GENERIC:
+                sys.modules[name] = mod
+
+
+def _args(root, tmp_path, extra=()):
+    RH.register_dataset('synthetic_b200')
+    return RH.parse_args(root, ['--expname', 'nfb_callers', '--rootdir', str(tmp_path), '--eval_dataset', 'synthetic_b200',
+                                '--train_dataset', 'synthetic_b200', '--num_source_views', '4', '--N_rand', '192', '--workers', '0',
+                                '--no_reload', '--chunk_size', '2048', *extra])
+
+
+@needs_ref
+def test_reference_drivers_import_through_dropin(ref_env):
+    """CPU: the unmodified driver modules import, their hot-path names are nerfool_b200's, the rest is the reference's."""
+    root, tmp = ref_env
+    import train as T
+    import eval_adv as E
+    import ibrnet.model as M
+    from nerfool_b200.projection import Projector
+    from nerfool_b200.render_ray import render_rays
+    from nerfool_b200.mlp_network import IBRNet
+    from nerfool_b200.render_image import render_single_image
+    assert os.path.samefile(T.__file__, os.path.join(root, 'train.py'))
+    assert os.path.samefile(E.__file__, os.path.join(root, 'eval', 'ibrnet', 'eval_adv.py'))
+    assert T.render_rays is render_rays and E.render_rays is render_rays and E.Projector is Projector and T.Projector is Projector
+    assert E.render_single_image is render_single_image and M.IBRNet is IBRNet
+    assert M.ResUNet.__module__ == 'ibrnet.feature_network' and os.path.samefile(sys.modules['ibrnet.feature_network'].__file__,
+                                                                                os.path.join(root, 'ibrnet', 'feature_network.py'))
+    a = _args(root, tmp)
+    assert (a.N_samples, a.N_importance, a.inv_uniform, a.chunk_size) == (64, 64, True, 2048)   # configs/ibrnet/eval_llff.txt
+    from torch.utils.data import DataLoader
+    from ibrnet.data_loaders import dataset_dict
+    data = next(iter(DataLoader(dataset_dict['synthetic_b200'](a, 'test', scenes=a.eval_scenes), batch_size=1)))
+    assert data['src_rgbs'].shape == (1, 4, 96, 128, 3) and data['camera'].shape == (1, 34) and data['depth_range'].shape == (1, 2)
+
+
+def _oracle_params(net):
+    return {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+
+
+def _capture(module):
+    """Wrap the ``render_rays`` name the driver module imported: same call, inputs recorded."""
+    calls = []
+    inner = module.render_rays
+
+    def recording(*a, **k):
+        calls.append((a, dict(k)))
+        return inner(*a, **k)
+    module.render_rays = recording
+    return calls
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_reference_optimize_adv_perturb_unmodified(ref_env):
+    """eval_adv.py:258-310 as shipped: RaySamplerSingleImage -> feature_net(src + delta) -> render_rays(clean src_ray_batch) ->
+    Criterion -> torch.autograd.grad(loss, delta).  Gradient vs the CPU oracle + the same ResUNet on the CPU."""
+    root, tmp = ref_env
+    from oracle import ibrnet_oracle as O
+    import eval_adv as E
+    from ibrnet.model import IBRNetModel
+    from ibrnet.sample_ray import RaySamplerSingleImage
+    from ibrnet.data_loaders import dataset_dict
+    from torch.utils.data import DataLoader
+    a = _args(root, tmp)
+    a.distributed, a.det = False, True                       # as eval_adv.py's __main__ does (:515-517)
+    RH.seed_everything(0)
+    model = IBRNetModel(a, load_scheduler=False, load_opt=False)
+    with torch.no_grad():
+        for n in (model.net_coarse, model.net_fine):
+            n.out_geometry_fc[2].bias += 0.3                  # non-trivial compositing weights
+    model.switch_to_eval()
+    projector = E.Projector(device='cuda:0')
+    E.criterion = E.Criterion()                               # eval_adv.py sets this module global in its __main__ block
+    data = next(iter(DataLoader(dataset_dict['synthetic_b200'](a, 'test', scenes=a.eval_scenes), batch_size=1)))
+    src_ray_batch = RaySamplerSingleImage(data, device='cuda:0').get_all()
+    epsilon = torch.tensor(a.epsilon / 255.).cuda()
+    delta = E.init_adv_perturb(a, src_ray_batch, epsilon, 1, 0)
+    calls = _capture(E)
+    grad = E.optimize_adv_perturb(a, delta, model, projector, src_ray_batch, data, return_loss=False)
+    loss, loss_dict = E.optimize_adv_perturb(a, delta, model, projector, src_ray_batch, data, return_loss=True)
+    assert grad.shape == delta.shape and torch.isfinite(grad).all() and float(grad.abs().max()) > 0
+    assert set(loss_dict) == {'rgb'} and len(calls) == 2
+    # --- the oracle on what the driver passed to render_rays in the first call ---
+    (_, kw) = calls[0]
+    rb = {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in kw['ray_batch'].items()}
+    srb = {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in kw['src_ray_batch'].items()}
+    assert torch.equal(srb['src_rgbs'], data['src_rgbs']), 'the reference renders with the CLEAN source colours'
+    enc = copy.deepcopy(model.feature_net).cpu().eval()
+    d_cpu = delta.detach().cpu().clone().requires_grad_(True)
+    fm = enc((srb['src_rgbs'] + d_cpu).squeeze(0).permute(0, 3, 1, 2))
+    pc, pf = _oracle_params(model.net_coarse), _oracle_params(model.net_fine)
+    out = O.render_rays(rb, pc, pf, fm, a.N_samples, inv_uniform=a.inv_uniform, n_importance=a.N_importance, det=True,
+                        white_bkgd=a.white_bkgd, src_ray_batch=srb)
+    loss_o = O.attack_loss(out, rb['rgb'])
+    g_o = torch.autograd.grad(loss_o, d_cpu)[0]
+    e = relerr(grad.cpu(), g_o)
+    cos = float(torch.dot(grad.cpu().flatten().double(), g_o.flatten().double()) / (grad.cpu().double().norm() * g_o.double().norm()))
+    report(f'reference optimize_adv_perturb through dropin: d delta relerr vs oracle {e:.2e}, cosine {cos:.6f}; '
+           f'loss (2nd call, new rays) {loss.item():.6f}')
+    assert e < 3e-3 and cos > 0.99999, (e, cos)
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize('adv_train', [False, True])
+def test_reference_train_loop_unmodified(ref_env, adv_train):
+    """train.py:47-236 as shipped, two iterations on the synthetic dataset: IBRNetModel (our IBRNet inside), the reference's
+    RaySamplerSingleImage, Criterion, Adam + StepLR; with --use_adv_train also the inner PGD loop (:120-148).  The IBRNet
+    parameter gradients the first optimiser step sees are compared with autograd of the oracle on the captured inputs."""
+    root, tmp = ref_env
+    from oracle import ibrnet_oracle as O
+    import train as T
+    extra = ['--n_iters', '2', '--det', '--i_img', '100000', '--i_weights', '100000', '--i_print', '100000']
+    if adv_train:
+        extra += ['--use_adv_train', '--adv_iters', '2']
+    a = _args(root, tmp, extra)
+    a.distributed = False
+    RH.seed_everything(1)
+    calls = _capture(T)
+    seen = {}
+    real_step = torch.optim.Adam.step
+
+    def spy_step(self, *aa, **kk):
+        if 'grads' not in seen:
+            seen['grads'] = [[None if p.grad is None else p.grad.detach().clone() for p in grp['params']] for grp in self.param_groups]
+            seen['params'] = [[p.detach().clone() for p in grp['params']] for grp in self.param_groups]
+        return real_step(self, *aa, **kk)
+    torch.optim.Adam.step = spy_step
+    real_model = T.IBRNetModel
+    made = {}
+
+    def model_spy(*aa, **kk):
+        made['model'] = real_model(*aa, **kk)
+        made['state0'] = (_oracle_params(made['model'].net_coarse), _oracle_params(made['model'].net_fine))
+        return made['model']
+    T.IBRNetModel = model_spy
+    try:
+        T.train(a)
+    finally:
+        torch.optim.Adam.step = real_step
+        T.IBRNetModel = real_model
+    n_render = (3 if adv_train else 1) * 2
+    assert len(calls) == n_render, len(calls)
+    model = made['model']
+    names = [n for n, _ in model.net_coarse.named_parameters()]
+    # the LAST render of iteration 1 is the training render (after the inner PGD loop when adv_train)
+    (_, kw) = calls[n_render // 2 - 1]
+    rb = {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in kw['ray_batch'].items()}
+    fm = tuple(f.detach().cpu().clone() for f in kw['featmaps'])
+    pc, pf = made['state0']
+    for p in (pc, pf):
+        for k in p:
+            if p[k].is_floating_point() and k != 'pos_encoding':
+                p[k].requires_grad_(True)
+    out = O.render_rays(rb, pc, pf, fm, a.N_samples, inv_uniform=a.inv_uniform, n_importance=a.N_importance, det=True,
+                        white_bkgd=a.white_bkgd)
+    O.attack_loss(out, rb['rgb']).backward()
+    worst = 0.0
+    for gi, p in ((0, pc), (1, pf)):                       # optimiser groups 0 / 1 = net_coarse / net_fine (model.py:54-58)
+        for name, g in zip(names, seen['grads'][gi]):
+            assert g is not None, name
+            ref = p[name].grad
+            if float(ref.abs().max()) < 1e-12:             # rgb_fc.4.bias: the blending softmax is shift invariant
+                assert float(g.abs().max()) < 1e-6, name
+                continue
+            e = relerr(g.cpu(), ref)
+            worst = max(worst, e)
+            assert e < 2e-2, (gi, name, e)
+    report(f'reference train.py through dropin (adv_train={adv_train}): worst IBRNet parameter-gradient relerr vs oracle {worst:.2e}')
+    # the optimiser really stepped our parameters, and the run stayed finite
+    moved = sum(float((p.detach() - q).abs().max()) > 0 for p, q in zip(model.net_coarse.parameters(), seen['params'][0]))
+    assert moved > 30
+    assert all(torch.isfinite(p).all() for p in model.net_coarse.parameters())
