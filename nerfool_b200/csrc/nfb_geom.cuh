@@ -184,8 +184,11 @@ __device__ __forceinline__ void scatter_row(const ViewGeom& g, int v, int H, int
 // pair (2k, 2k + 1) of one view are the lanes (l, l ^ V) of a warp when V is a power of two <= 16: if both hit the same
 // four texels, the even lane adds both weighted cotangents with ONE set of 8 x 4 RED.128 and the odd lane issues none --
 // ~40 % fewer vector atomics into the L2-resident gradient map for 41 shuffles per row.
-// Every lane of the warp must call (inactive rows pass active = false); V as described.
-__device__ __forceinline__ void scatter_row_paired(bool active, float gx, float gy, int v, int V, int H, int W, int fh, int fw,
+// Every lane of the warp must call (inactive rows pass active = false).  `partner` = lane of the same view of the paired
+// sample (own lane when the row has no partner), `leader` = true for the lane that emits for a merged pair.  (For V a power
+// of two that divides 32 the pairs are the lanes (l, l ^ V); the packed row mapping of nfb_view_tc.cuh pairs the samples
+// (2k, 2k + 1) of a warp for any V <= 16.)
+__device__ __forceinline__ void scatter_row_paired(bool active, float gx, float gy, int v, int partner, bool leader, int H, int W, int fh, int fw,
                                                    const float (&d_row)[NFB_ROW_CH], float* __restrict__ d_feat,
                                                    float* __restrict__ d_imgs) {
   if (active && d_imgs) {
@@ -206,23 +209,22 @@ __device__ __forceinline__ void scatter_row_paired(bool active, float gx, float 
   if (!active) { t.off[0] = t.off[1] = t.off[2] = t.off[3] = -1; }
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const int act_nb = __shfl_xor_sync(FULL, (int)active, V);
-  bool same = active && (act_nb != 0);
+  const int act_nb = __shfl_sync(FULL, (int)active, partner);
+  bool same = active && (act_nb != 0) && (partner != lane);
   float wn[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int off_nb = __shfl_xor_sync(FULL, t.off[i], V);      // unconditionally: every lane must execute every shuffle
+    const int off_nb = __shfl_sync(FULL, t.off[i], partner);    // unconditionally: every lane must execute every shuffle
     same = same && (off_nb == t.off[i]);
-    wn[i] = __shfl_xor_sync(FULL, t.wt[i], V);
+    wn[i] = __shfl_sync(FULL, t.wt[i], partner);
   }
-  const bool leader = (lane & V) == 0;
   const bool emit = active && !(same && !leader);
   float4* base = reinterpret_cast<float4*>(d_feat + (size_t)v * fh * fw * NFB_FEAT_CH);
 #pragma unroll
   for (int j = 0; j < NFB_FEAT_CH / 4; ++j) {
     const float m0 = d_row[3 + 4 * j], m1 = d_row[4 + 4 * j], m2 = d_row[5 + 4 * j], m3 = d_row[6 + 4 * j];
-    float n0 = __shfl_xor_sync(FULL, m0, V), n1 = __shfl_xor_sync(FULL, m1, V);
-    float n2 = __shfl_xor_sync(FULL, m2, V), n3 = __shfl_xor_sync(FULL, m3, V);
+    float n0 = __shfl_sync(FULL, m0, partner), n1 = __shfl_sync(FULL, m1, partner);
+    float n2 = __shfl_sync(FULL, m2, partner), n3 = __shfl_sync(FULL, m3, partner);
     if (!same) { n0 = 0.f; n1 = 0.f; n2 = 0.f; n3 = 0.f; }       // the partner may be an inactive row holding anything
     if (emit) {
 #pragma unroll

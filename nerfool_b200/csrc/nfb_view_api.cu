@@ -29,7 +29,7 @@ static int check_view_args(const char* who, int N, int S, int V, const float* rg
 
 extern "C" size_t nfb_view_stash_bytes(int N, int V) {
   if (N <= 0 || V < 1 || V > NFB_MAX_VIEWS) return 0;
-  const int TS = (nfbvtc::GROUP / V < nfbvtc::TS_MAX) ? nfbvtc::GROUP / V : nfbvtc::TS_MAX;
+  const int TS = nfbvtc::row_map(V).TS;      // the forward (SAVE) and the stash backward use the same tile mapping
   return (size_t)((N + TS - 1) / TS) * nfbvtc::ST_TILE_BYTES;
 }
 

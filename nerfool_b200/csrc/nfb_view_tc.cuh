@@ -36,6 +36,38 @@ constexpr int MVP = 72;      // 32-bit words per sample of the packed copy: bf16
                              // 35 words) at 0, lo halves at 36 -- already in base_fc.0 operand order
 constexpr int GC = 128;      // TMEM columns per group
 constexpr int C_D = 0, C_A = 64, C_ALO = 96;
+constexpr int EXQ = 36;      // exchange-buffer row stride of the forward / stash-backward kernels (floats): 144 B rows are 16-byte
+                             // aligned and 8 consecutive rows start in 8 different 16-byte bank groups -> the float4 loads /
+                             // stores of the cross-view poolings are conflict-free
+constexpr int SIDE = 4;      // per-row side slots (rgb_in[3] for the blending, 1 spare)
+
+// ---- thread -> (sample, view) mapping of a 128-row tile ------------------------------------------------------------
+// contiguous: row r of the tile = thread r = (sample r / V, view r % V); a sample's rows straddle warps unless V | 32.
+// packed:     every warp holds spw = floor(32 / V) whole samples in its first spw * V lanes (the rest idle), so the V rows
+//             of a sample always share a warp: the cross-view exchanges need __syncwarp() only and may use shuffles.
+//             Chosen when it keeps >= 90 % of the samples per tile of the contiguous form (V = 10: 12 samples either way).
+struct RowMap {
+  int TS;        // samples per tile
+  int spw;       // samples per warp (packed form)
+  bool packed;
+};
+__host__ __device__ inline RowMap row_map(int V) {
+  RowMap m;
+  const int ts_c = (GROUP / V < TS_MAX) ? GROUP / V : TS_MAX;
+  int spw = V <= 32 ? 32 / V : 0;
+  if (spw > TS_MAX / 4) spw = TS_MAX / 4;
+  const int ts_w = 4 * spw;
+  m.packed = spw >= 1 && ts_w * 10 >= ts_c * 9;
+  m.TS = m.packed ? ts_w : ts_c;
+  m.spw = spw;
+  return m;
+}
+// exchange-buffer slot (= thread index within the group) of row rr = sample * V + view of the tile
+__device__ __forceinline__ int row_slot(const RowMap& m, int V, int rr) {
+  if (!m.packed) return rr;
+  const int s = rr / V, vv = rr - s * V;
+  return (s / m.spw) * 32 + (s % m.spw) * V + vv;
+}
 
 // ---- weight tiles ---------------------------------------------------------------------------------
 enum : int { L_DIR2 = 0, L_BASE0, L_BASE2, L_VIS0, L_VIS2, L_VISB0, L_RGB0, L_COUNT };
@@ -82,7 +114,7 @@ enum : int {
 template <int NPASS>
 __host__ __device__ constexpr size_t smem_bytes() {
   return (size_t)B_SET_BYTES * (NPASS == 3 ? 2 : 1) +
-         sizeof(float) * (F_TOTAL + 16 * NFB_MAX_VIEWS + 4 + NG * GROUP * EXS + NG * TS_MAX * (MVS + MVP)) + NG * 8 + 16;
+         sizeof(float) * (F_TOTAL + 16 * NFB_MAX_VIEWS + 4 + NG * GROUP * (EXQ + SIDE) + NG * TS_MAX * MVP) + NG * 8 + 16;
 }
 
 template <int NPASS>
@@ -276,6 +308,41 @@ __device__ __forceinline__ void pool_var(const float* __restrict__ row0, int V, 
   }
 }
 
+// ---- cross-view pooling on float4 quads (forward / stash-backward kernels, row stride EXQ) ---------------------------------
+// The V rows of a sample sit in consecutive exchange rows (row0 = view 0).  Thread v of the sample owns the channel quads
+// q = v, v + V, ... < NQ; per quad and view one LDS.128 + one LDS.32 (the weight) instead of four guarded scalar loads.
+// Same operation order as pool_sum / pool_var: mean = fma(x_u, w_u, mean) over u, var = fma(w_u * d, d, var), d = x_u - mean.
+enum : int { POOL_SUM = 0, POOL_MEAN = 1, POOL_MEAN_VAR = 2 };
+template <int NQ, int MODE, typename EMIT>
+__device__ __forceinline__ void pool4(const float* __restrict__ row0, int V, int v, int wslot, float scale, EMIT&& emit) {
+  for (int q = v; q < NQ; q += V) {
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int u = 0; u < V; ++u) {
+      const float* r = row0 + u * EXQ;
+      const float4 x = *reinterpret_cast<const float4*>(r + 4 * q);
+      if (MODE != POOL_SUM) {
+        const float wu = r[wslot] * scale;
+        m.x = fmaf(x.x, wu, m.x); m.y = fmaf(x.y, wu, m.y); m.z = fmaf(x.z, wu, m.z); m.w = fmaf(x.w, wu, m.w);
+      } else {
+        m.x += x.x; m.y += x.y; m.z += x.z; m.w += x.w;
+      }
+    }
+    float4 s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE == POOL_MEAN_VAR) {
+#pragma unroll 2
+      for (int u = 0; u < V; ++u) {
+        const float* r = row0 + u * EXQ;
+        const float4 x = *reinterpret_cast<const float4*>(r + 4 * q);
+        const float wu = r[wslot] * scale;
+        const float dx = x.x - m.x, dy = x.y - m.y, dz = x.z - m.z, dw = x.w - m.w;
+        s2.x = fmaf(wu * dx, dx, s2.x); s2.y = fmaf(wu * dy, dy, s2.y); s2.z = fmaf(wu * dz, dz, s2.z); s2.w = fmaf(wu * dw, dw, s2.w);
+      }
+    }
+    emit(q, m, s2);
+  }
+}
+
 // all threads of the group: publish the A stores, let thread 0 issue + commit
 #define NFB_TC_ISSUE(LAYER, KS0, KS1, ACC0)                                   \
   do {                                                                        \
@@ -313,15 +380,15 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
   float* sf = reinterpret_cast<float*>(smem_raw + (size_t)B_SET_BYTES * (NPASS == 3 ? 2 : 1));
   float* s_cam = sf + F_TOTAL;
   float* ex_all = s_cam + (16 * NFB_MAX_VIEWS + 4);
-  float* mv_all = ex_all + NG * GROUP * EXS;
-  uint32_t* mvp_all = reinterpret_cast<uint32_t*>(mv_all + NG * TS_MAX * MVS);
+  float* side_all = ex_all + NG * GROUP * EXQ;
+  uint32_t* mvp_all = reinterpret_cast<uint32_t*>(side_all + NG * GROUP * SIDE);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(mvp_all + NG * TS_MAX * MVP);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + NG);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int grp = tid / GROUP, tg = tid % GROUP;
-  float* ex = ex_all + (size_t)grp * GROUP * EXS;
-  float* mv = mv_all + (size_t)grp * TS_MAX * MVS;
+  float* ex = ex_all + (size_t)grp * GROUP * EXQ;
+  float* side = side_all + (size_t)grp * GROUP * SIDE;
   uint32_t* mvp = mvp_all + (size_t)grp * TS_MAX * MVP;
   const int bar_id = 1 + grp;
   uint64_t* mbar = s_bar + grp;
@@ -355,18 +422,25 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
   uint32_t phase = 0;
 
   const int V = a.V;
-  const bool warp_local = (32 % V) == 0;
-  const int TS = (GROUP / V < TS_MAX) ? GROUP / V : TS_MAX;
-  const int sl = tg / V, v = tg - sl * V;
+  const RowMap rm = row_map(V);
+  const bool warp_local = rm.packed;
+  const int TS = rm.TS;
+  int sl, v;
+  bool lane_ok;
+  if (rm.packed) {
+    const int wq = tg >> 5, l = tg & 31, si = l / V;
+    v = l - si * V; sl = wq * rm.spw + si; lane_ok = si < rm.spw;
+  } else {
+    sl = tg / V; v = tg - sl * V; lane_ok = sl < TS;
+  }
   const int ntiles = (a.N + TS - 1) / TS;
   const float Wm1 = (float)a.W - 1.f, Hm1 = (float)a.H - 1.f;
   const float s_abs = sf[F_S];
 
   for (int tile = blockIdx.x * NG + grp; tile < ntiles; tile += gridDim.x * NG) {
     const int p = tile * TS + sl;
-    const bool active = (sl < TS) && (p < a.N);
-    const int base = active ? sl * V : 0;
-    float* mvs = mv + (active ? sl : 0) * MVS;
+    const bool active = lane_ok && (p < a.N);
+    const int base = active ? tg - v : 0;
     uint32_t* mvps = mvp + (active ? sl : 0) * MVP;
     float4* sp = reinterpret_cast<float4*>(a.stash) + (size_t)tile * (ST_PLANES * GROUP) + tg;
     const bool save = SAVE && active;
@@ -397,11 +471,11 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       const float* src = a.rgb_feat + row0 * NFB_ROW_CH;
       for (int i = tg; i < rows_here * NFB_ROW_CH; i += GROUP) {
         const int rr = i / NFB_ROW_CH, cc = i - rr * NFB_ROW_CH;
-        ex[rr * EXS + cc] = __ldg(src + i);
+        ex[row_slot(rm, V, rr) * EXQ + cc] = __ldg(src + i);
       }
       named_bar_sync(bar_id, GROUP);
 #pragma unroll
-      for (int c = 0; c < NFB_ROW_CH; ++c) x[c] = active ? ex[tg * EXS + c] : 0.f;
+      for (int c = 0; c < NFB_ROW_CH; ++c) x[c] = active ? ex[tg * EXQ + c] : 0.f;
       if (active) {
         const size_t row = (size_t)p * V + v;
         const float4 q = __ldg(reinterpret_cast<const float4*>(a.ray_diff) + row);
@@ -429,17 +503,20 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
     float w, n_valid;
     {
       const float e = a.anti_alias ? (float)exp((double)__fmul_rn(s_abs, __fsub_rn(rd[3], 1.f))) : 1.f;
-      ex[tg * EXS + 35] = e;
-      ex[tg * EXS + 36] = mk;
+      *reinterpret_cast<float2*>(ex + tg * EXQ) = make_float2(e, mk);
       NFB_EX_SYNC();
       float mn = 3.4e38f, nv = 0.f;
       for (int u = 0; u < V; ++u) {
-        mn = fminf(mn, ex[(base + u) * EXS + 35]);
-        nv += ex[(base + u) * EXS + 36];
+        const float2 q = *reinterpret_cast<const float2*>(ex + (base + u) * EXQ);
+        mn = fminf(mn, q.x);
+        nv += q.y;
       }
       if (!a.anti_alias) mn = 0.f;
       float sum = 0.f;
-      for (int u = 0; u < V; ++u) sum += (ex[(base + u) * EXS + 35] - mn) * ex[(base + u) * EXS + 36];
+      for (int u = 0; u < V; ++u) {
+        const float2 q = *reinterpret_cast<const float2*>(ex + (base + u) * EXQ);
+        sum += (q.x - mn) * q.y;
+      }
       w = (e - mn) * mk / (sum + 1e-8f);
       n_valid = nv;
       NFB_EX_SYNC();
@@ -463,35 +540,29 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
     }
     // ---------------- first pooling: weighted mean / variance over views ----------------
 #pragma unroll
-    for (int c = 0; c < NFB_ROW_CH; ++c) ex[tg * EXS + c] = x[c];
-    ex[tg * EXS + 35] = w;
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(ex + tg * EXQ + 4 * j) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+    *reinterpret_cast<float4*>(ex + tg * EXQ + 32) = make_float4(x[32], x[33], x[34], w);
     NFB_EX_SYNC();
     if (active) {
-      const float* row0 = ex + base * EXS;
-      for (int c0 = v; c0 < NFB_ROW_CH; c0 += POOL_K * V) {
-        float mk9[POOL_K], vk9[POOL_K];
-        pool_sum<true>(row0, V, c0, NFB_ROW_CH, 35, 1.f, mk9);
-        pool_var(row0, V, c0, NFB_ROW_CH, 35, 1.f, mk9, vk9);
-        __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(mvps);
-        __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(mvps + 36);
+      __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(mvps);
+      __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(mvps + 36);
+      pool4<9, POOL_MEAN_VAR>(ex + base * EXQ, V, v, 35, 1.f, [&](int q, const float4& m4, const float4& v4) {
+        const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-        for (int k = 0; k < POOL_K; ++k) {
-          const int c = c0 + k * V;
+        for (int i = 0; i < 4; ++i) {
+          const int c = 4 * q + i;
           if (c < NFB_ROW_CH) {
-            const float m = mk9[k], vr = vk9[k];
-            mvs[c] = m;
-            mvs[36 + c] = vr;
             // the operand halves of this statistic, split once per sample instead of once per row
-            const __nv_bfloat16 mh = __float2bfloat16_rn(m), vh = __float2bfloat16_rn(vr);
+            const __nv_bfloat16 mh = __float2bfloat16_rn(mm[i]), vh = __float2bfloat16_rn(vv[i]);
             ph[c] = mh;
             ph[35 + c] = vh;
             if (NPASS == 3) {
-              pl[c] = __float2bfloat16_rn(m - __bfloat162float(mh));
-              pl[35 + c] = __float2bfloat16_rn(vr - __bfloat162float(vh));
+              pl[c] = __float2bfloat16_rn(mm[i] - __bfloat162float(mh));
+              pl[35 + c] = __float2bfloat16_rn(vv[i] - __bfloat162float(vh));
             }
           }
         }
-      }
+      });
     }
     NFB_EX_SYNC();
 
@@ -673,50 +744,37 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
 
     // ---------------- second pooling, blending, output ----------------
 #pragma unroll
-    for (int c = 0; c < 32; ++c) ex[tg * EXS + c] = x1[c];
-    ex[tg * EXS + 32] = vis2;
-    ex[tg * EXS + 33] = logit;
-    ex[tg * EXS + 34] = rgb_in0;
-    ex[tg * EXS + 35] = rgb_in1;
-    ex[tg * EXS + 36] = rgb_in2;
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(ex + tg * EXQ + 4 * j) = make_float4(x1[4 * j], x1[4 * j + 1], x1[4 * j + 2], x1[4 * j + 3]);
+    *reinterpret_cast<float2*>(ex + tg * EXQ + 32) = make_float2(vis2, logit);
+    *reinterpret_cast<float4*>(side + tg * SIDE) = make_float4(rgb_in0, rgb_in1, rgb_in2, 0.f);
     NFB_EX_SYNC();
     if (active) {
       float D = 1e-8f;
-      for (int u = 0; u < V; ++u) D += ex[(base + u) * EXS + 32];
+      for (int u = 0; u < V; ++u) D += ex[(base + u) * EXQ + 32];
       const float invD = 1.f / D;
       float* out = a.ps + (size_t)p * NFB_PS_STRIDE;
-      const float* row0 = ex + base * EXS;
-      for (int c0 = v; c0 < 32; c0 += POOL_K * V) {
-        float mk9[POOL_K], vk9[POOL_K];
-        pool_sum<true>(row0, V, c0, 32, 32, invD, mk9);
-        pool_var(row0, V, c0, 32, 32, invD, mk9, vk9);
-#pragma unroll
-        for (int k = 0; k < POOL_K; ++k) {
-          const int c = c0 + k * V;
-          if (c < 32) {
-            out[PS_MEAN + c] = mk9[k];
-            out[PS_VAR + c] = vk9[k];
-          }
-        }
-      }
+      pool4<8, POOL_MEAN_VAR>(ex + base * EXQ, V, v, 32, invD, [&](int q, const float4& m4, const float4& v4) {
+        *reinterpret_cast<float4*>(out + PS_MEAN + 4 * q) = m4;
+        *reinterpret_cast<float4*>(out + PS_VAR + 4 * q) = v4;
+      });
       if (v == 0) {
         float mx = -3.4e38f;
-        for (int u = 0; u < V; ++u) mx = fmaxf(mx, ex[(base + u) * EXS + 33]);
+        for (int u = 0; u < V; ++u) mx = fmaxf(mx, ex[(base + u) * EXQ + 33]);
         float se = 0.f;
-        for (int u = 0; u < V; ++u) se += __expf(ex[(base + u) * EXS + 33] - mx);
+        for (int u = 0; u < V; ++u) se += __expf(ex[(base + u) * EXQ + 33] - mx);
         const float inv_se = 1.f / se;
         float wsum = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
         for (int u = 0; u < V; ++u) {
-          wsum += ex[(base + u) * EXS + 32] * invD;
-          const float b = __expf(ex[(base + u) * EXS + 33] - mx) * inv_se;
-          r0 = fmaf(b, ex[(base + u) * EXS + 34], r0);
-          r1 = fmaf(b, ex[(base + u) * EXS + 35], r1);
-          r2 = fmaf(b, ex[(base + u) * EXS + 36], r2);
+          const float2 vl = *reinterpret_cast<const float2*>(ex + (base + u) * EXQ + 32);
+          const float4 c4 = *reinterpret_cast<const float4*>(side + (base + u) * SIDE);
+          wsum += vl.x * invD;
+          const float b = __expf(vl.y - mx) * inv_se;
+          r0 = fmaf(b, c4.x, r0);
+          r1 = fmaf(b, c4.y, r1);
+          r2 = fmaf(b, c4.z, r2);
         }
-        out[PS_WMEAN] = wsum / (float)V;
-        out[PS_RGB + 0] = r0; out[PS_RGB + 1] = r1; out[PS_RGB + 2] = r2;
-        out[PS_NVALID] = n_valid;
-        out[69] = 0.f; out[70] = 0.f; out[71] = 0.f;
+        *reinterpret_cast<float4*>(out + 64) = make_float4(wsum / (float)V, r0, r1, r2);   // PS_WMEAN, PS_RGB
+        *reinterpret_cast<float4*>(out + 68) = make_float4(n_valid, 0.f, 0.f, 0.f);        // PS_NVALID
       }
     }
     if (FUSED) NFB_EX_SYNC(); else named_bar_sync(bar_id, GROUP);            // exchange buffer is reused by the next tile
@@ -732,7 +790,7 @@ int launch_view_tc_fwd(const ViewArgs& a, cudaStream_t st) {
   constexpr size_t smem = smem_bytes<NPASS>();
   cudaError_t e = cudaFuncSetAttribute(k_view_tc_fwd<NPASS, FUSED, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nfb_set_error(NFB_ECUDA, "k_view_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  const int TS = (GROUP / a.V < TS_MAX) ? GROUP / a.V : TS_MAX;
+  const int TS = row_map(a.V).TS;
   const int ntiles = (a.N + TS - 1) / TS;
   int grid = (ntiles + NG - 1) / NG;
   const int cap = nfb_num_sms();

@@ -25,7 +25,7 @@ constexpr int DPS = 100;     // staged cotangent row: d_mean[32] d_var[32] d_wme
 template <int NPASS>
 __host__ __device__ constexpr size_t smem_bytes_bwd2() {
   return (size_t)B_SET_BYTES * (NPASS == 3 ? 2 : 1) +
-         sizeof(float) * (F_TOTAL + NG * GROUP * EXS + NG * TS_MAX * MVS + NG * TS_MAX * DPS) + NG * 8 + 16;
+         sizeof(float) * (F_TOTAL + NG * GROUP * EXQ + NG * TS_MAX * MVS + NG * TS_MAX * DPS) + NG * 8 + 16;
 }
 
 __device__ __forceinline__ void d_raw16(uint32_t tl, int col, float (&y)[16]) {
@@ -97,14 +97,14 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
   uint8_t* sB = smem_raw;
   float* sf = reinterpret_cast<float*>(smem_raw + (size_t)B_SET_BYTES * (NPASS == 3 ? 2 : 1));
   float* ex_all = sf + F_TOTAL;
-  float* mv_all = ex_all + NG * GROUP * EXS;
+  float* mv_all = ex_all + NG * GROUP * EXQ;
   float* dp_all = mv_all + NG * TS_MAX * MVS;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(dp_all + NG * TS_MAX * DPS);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + NG);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int grp = tid / GROUP, tg = tid % GROUP;
-  float* ex = ex_all + (size_t)grp * GROUP * EXS;
+  float* ex = ex_all + (size_t)grp * GROUP * EXQ;
   float* mv = mv_all + (size_t)grp * TS_MAX * MVS;
   float* dpb = dp_all + (size_t)grp * TS_MAX * DPS;
   const int bar_id = 1 + grp;
@@ -137,15 +137,28 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
   uint32_t phase = 0;
 
   const int V = a.V;
-  const bool warp_local = (32 % V) == 0;       // NFB_EX_SYNC (nfb_view_tc.cuh): warp barrier when a sample's rows share a warp
-  const int TS = (GROUP / V < TS_MAX) ? GROUP / V : TS_MAX;
-  const int sl = tg / V, v = tg - sl * V;
+  const RowMap rm = row_map(V);                // the forward's tile mapping (the stash is indexed by tile and thread)
+  const bool warp_local = rm.packed;           // NFB_EX_SYNC (nfb_view_tc.cuh): warp barrier when a sample's rows share a warp
+  const int TS = rm.TS;
+  int sl, v, partner = tid & 31;
+  bool lane_ok, pair_leader = true;
+  if (rm.packed) {
+    const int wq = tg >> 5, l = tg & 31, si = l / V;
+    v = l - si * V; sl = wq * rm.spw + si; lane_ok = si < rm.spw;
+    if (lane_ok) {                             // scatter pairs: samples (2k, 2k + 1) of the warp, same view
+      pair_leader = (si & 1) == 0;
+      if (!pair_leader) partner = l - V;
+      else if (si + 1 < rm.spw) partner = l + V;
+    }
+  } else {
+    sl = tg / V; v = tg - sl * V; lane_ok = sl < TS;
+  }
   const int ntiles = (a.N + TS - 1) / TS;
 
   for (int tile = blockIdx.x * NG + grp; tile < ntiles; tile += gridDim.x * NG) {
     const int p = tile * TS + sl;
-    const bool active = (sl < TS) && (p < a.N);
-    const int base = active ? sl * V : 0;
+    const bool active = lane_ok && (p < a.N);
+    const int base = active ? tg - v : 0;
     float* mvs = mv + (active ? sl : 0) * MVS;
     const float* dp = dpb + (active ? sl : 0) * DPS;
     const float4* sp = reinterpret_cast<const float4*>(a.stash) + (size_t)tile * (ST_PLANES * GROUP) + tg;
@@ -198,49 +211,45 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       if (active) {
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
-          const float4 q = __ldcs(sp + (SP_X0 + j) * GROUP);
-          ex[tg * EXS + 4 * j] = q.x;
-          ex[tg * EXS + 4 * j + 1] = q.y;
-          ex[tg * EXS + 4 * j + 2] = q.z;
-          if (j < 8) ex[tg * EXS + 4 * j + 3] = q.w;
+          float4 q = __ldcs(sp + (SP_X0 + j) * GROUP);
+          if (j == 8) q.w = w;                              // slot 35: the pooling weight
+          *reinterpret_cast<float4*>(ex + tg * EXQ + 4 * j) = q;
         }
+      } else {
+        ex[tg * EXQ + 35] = 0.f;
       }
-      ex[tg * EXS + 35] = w;
       NFB_EX_SYNC();
     }
     float wsum0 = 0.f;
-    for (int u = 0; u < V; ++u) wsum0 += ex[(base + u) * EXS + 35];
+    for (int u = 0; u < V; ++u) wsum0 += ex[(base + u) * EXQ + 35];
     if (active) {
-      const float* row0 = ex + base * EXS;
-      for (int c0 = v; c0 < NFB_ROW_CH; c0 += POOL_K * V) {
-        float mk9[POOL_K];
-        pool_sum<true>(row0, V, c0, NFB_ROW_CH, 35, 1.f, mk9);
-#pragma unroll
-        for (int k = 0; k < POOL_K; ++k)
-          if (c0 + k * V < NFB_ROW_CH) mvs[c0 + k * V] = mk9[k];
-      }
+      pool4<9, POOL_MEAN>(ex + base * EXQ, V, v, 35, 1.f, [&](int q, const float4& m4, const float4&) {
+        *reinterpret_cast<float4*>(mvs + 4 * q) = m4;       // mvs[35] (quad 8, lane 3) is a pad slot
+      });
     }
     NFB_EX_SYNC();
 
     // ---------------- exchange vis2 / logit / rgb_in ; blending softmax ----------------
-    ex[tg * EXS + 32] = vis2;
-    ex[tg * EXS + 33] = logit;
-    ex[tg * EXS + 34] = rgb_in0;
-    ex[tg * EXS + 35] = rgb_in1;
-    ex[tg * EXS + 36] = rgb_in2;
+    // slots 0..4 of the row: vis2, logit, rgb_in[3]  (the x0 rows above are dead: mean0 sits in mvs)
+    *reinterpret_cast<float4*>(ex + tg * EXQ) = make_float4(vis2, logit, rgb_in0, rgb_in1);
+    ex[tg * EXQ + 4] = rgb_in2;
     cp_async_wait_all();                    // the staged cotangent rows are read after this barrier
     named_bar_sync(bar_id, GROUP);
-    float Dsum = 1e-8f;
-    for (int u = 0; u < V; ++u) Dsum += ex[(base + u) * EXS + 32];
+    float Dsum = 1e-8f, mx = -3.4e38f;
+    for (int u = 0; u < V; ++u) {
+      const float2 q = *reinterpret_cast<const float2*>(ex + (base + u) * EXQ);
+      Dsum += q.x;
+      mx = fmaxf(mx, q.y);
+    }
     const float invD = 1.f / Dsum;
-    float mx = -3.4e38f;
-    for (int u = 0; u < V; ++u) mx = fmaxf(mx, ex[(base + u) * EXS + 33]);
-    float se = 0.f;
-    for (int u = 0; u < V; ++u) se += __expf(ex[(base + u) * EXS + 33] - mx);
+    float se = 0.f, w2sum = 0.f;
+    for (int u = 0; u < V; ++u) {
+      const float2 q = *reinterpret_cast<const float2*>(ex + (base + u) * EXQ);
+      se += __expf(q.y - mx);
+      w2sum += q.x * invD;
+    }
     const float inv_se = 1.f / se;
     const float w2 = vis2 * invD;
-    float w2sum = 0.f;
-    for (int u = 0; u < V; ++u) w2sum += ex[(base + u) * EXS + 32] * invD;
     const float d_r0 = dp[65], d_r1 = dp[66], d_r2 = dp[67];
     const float d_wmean = dp[64];
 
@@ -250,8 +259,9 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
     {
       float bt = 0.f;
       for (int u = 0; u < V; ++u) {
-        const float b = __expf(ex[(base + u) * EXS + 33] - mx) * inv_se;
-        const float tu = ex[(base + u) * EXS + 34] * d_r0 + ex[(base + u) * EXS + 35] * d_r1 + ex[(base + u) * EXS + 36] * d_r2;
+        const float4 q = *reinterpret_cast<const float4*>(ex + (base + u) * EXQ);
+        const float b = __expf(q.y - mx) * inv_se;
+        const float tu = q.z * d_r0 + q.w * d_r1 + ex[(base + u) * EXQ + 4] * d_r2;
         bt = fmaf(b, tu, bt);
       }
       const float tv = rgb_in0 * d_r0 + rgb_in1 * d_r1 + rgb_in2 * d_r2;
@@ -300,13 +310,13 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
         d_x2[c] = w2 * (dm - 2.f * dv * mean * (1.f - w2sum)) + 2.f * w2 * diff * dv;
       }
     }
-    NFB_EX_SYNC();          // all reads of slots 33..36 above are done
-    ex[tg * EXS + 33] = d_w2 * vis2;
+    NFB_EX_SYNC();          // all reads of slots 0..4 above are done
+    ex[tg * EXQ + 1] = d_w2 * vis2;
     NFB_EX_SYNC();
     float d_vis2;
     {
       float sdv = 0.f;
-      for (int u = 0; u < V; ++u) sdv += ex[(base + u) * EXS + 33];
+      for (int u = 0; u < V; ++u) sdv += ex[(base + u) * EXQ + 1];
       d_vis2 = d_w2 * invD - sdv * invD * invD;
     }
     uint32_t cq[16];                        // ELU' codes of the next layer, loaded ahead of the MMA wait
@@ -440,7 +450,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
         d_raw16(tl, c0, t);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          if (c0 + j < 35) ex[tg * EXS + c0 + j] = t[j];
+          if (c0 + j < 35) ex[tg * EXQ + c0 + j] = t[j];
           else dvar_lo[c0 + j - 35] = t[j];
         }
       }
@@ -450,14 +460,9 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
     // exchange round 1 (overlaps the MMA): per-sample sums of d mean0, parked in the (now dead) cotangent staging row
     float* dpw = dpb + (active ? sl : 0) * DPS;
     if (active) {
-      const float* row0 = ex + base * EXS;
-      for (int c0 = v; c0 < NFB_ROW_CH; c0 += POOL_K * V) {
-        float s9[POOL_K];
-        pool_sum<false>(row0, V, c0, NFB_ROW_CH, 0, 1.f, s9);
-#pragma unroll
-        for (int k = 0; k < POOL_K; ++k)
-          if (c0 + k * V < NFB_ROW_CH) dpw[c0 + k * V] = s9[k];
-      }
+      pool4<9, POOL_SUM>(ex + base * EXQ, V, v, 0, 1.f, [&](int q, const float4& s4, const float4&) {
+        *reinterpret_cast<float4*>(dpw + 4 * q) = s4;       // dpw[35] is a pad slot (d_var[3] of the dead cotangent row)
+      });
     }
     NFB_EX_SYNC();
     float x0[36];
@@ -471,11 +476,11 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
     {
       // d var0: 29 values kept from the first MMA + 6 from the second
 #pragma unroll
-      for (int c = 0; c < 29; ++c) ex[tg * EXS + c] = dvar_lo[c];
+      for (int c = 0; c < 29; ++c) ex[tg * EXQ + c] = dvar_lo[c];
       float t[16];
       d_raw16(tl, 0, t);
 #pragma unroll
-      for (int j = 0; j < 6; ++j) ex[tg * EXS + 29 + j] = t[j];
+      for (int j = 0; j < 6; ++j) ex[tg * EXQ + 29 + j] = t[j];
 #pragma unroll
       for (int j = 6; j < 16; ++j) d_row[j - 6] = t[j];
       d_raw16(tl, 16, t);
@@ -487,20 +492,13 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
     }
     NFB_EX_SYNC();
     if (active) {
-      const float* row0 = ex + base * EXS;
-      for (int c0 = v; c0 < NFB_ROW_CH; c0 += POOL_K * V) {
-        float s9[POOL_K];
-        pool_sum<false>(row0, V, c0, NFB_ROW_CH, 0, 1.f, s9);
-#pragma unroll
-        for (int k = 0; k < POOL_K; ++k) {
-          const int c = c0 + k * V;
-          if (c < NFB_ROW_CH) {
-            const float dv = s9[k], m0 = mvs[c];
-            mvs[c] = dpw[c] - 2.f * dv * m0 * (2.f - wsum0);
-            mvs[36 + c] = 2.f * dv;
-          }
-        }
-      }
+      pool4<9, POOL_SUM>(ex + base * EXQ, V, v, 0, 1.f, [&](int q, const float4& s4, const float4&) {
+        const float4 m0 = *reinterpret_cast<const float4*>(mvs + 4 * q), dm = *reinterpret_cast<const float4*>(dpw + 4 * q);
+        const float k2 = 2.f - wsum0;
+        *reinterpret_cast<float4*>(mvs + 4 * q) = make_float4(dm.x - 2.f * s4.x * m0.x * k2, dm.y - 2.f * s4.y * m0.y * k2,
+                                                             dm.z - 2.f * s4.z * m0.z * k2, dm.w - 2.f * s4.w * m0.w * k2);
+        *reinterpret_cast<float4*>(mvs + 36 + 4 * q) = make_float4(2.f * s4.x, 2.f * s4.y, 2.f * s4.z, 2.f * s4.w);
+      });
     }
     NFB_EX_SYNC();
     if (active) {
@@ -511,9 +509,9 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       d_row[2] = fmaf(blend, d_r2, d_row[2]);
     }
     // (8) scatter (grid_sampler_2d backward w.r.t. the input)
-    if (warp_local && V <= 16 && V > 0) {
-      // the rows of a sample pair of one view are lanes (l, l ^ V): same texel quad -> one set of atomics for both
-      scatter_row_paired(active, gx, gy, v, V, a.H, a.W, a.fh, a.fw, d_row, a.d_feat, a.d_imgs);
+    if (warp_local && rm.spw >= 2) {
+      // sample pairs (2k, 2k + 1) of a warp, same view: same texel quad -> one set of atomics for both
+      scatter_row_paired(active, gx, gy, v, partner, pair_leader, a.H, a.W, a.fh, a.fw, d_row, a.d_feat, a.d_imgs);
     } else if (active) {
       ViewGeom g;
       g.gx = gx; g.gy = gy;
@@ -532,7 +530,7 @@ int launch_view_tc_bwd_stash(const ViewArgs& a, cudaStream_t st) {
   constexpr size_t smem = smem_bytes_bwd2<NPASS>();
   cudaError_t e = cudaFuncSetAttribute(k_view_tc_bwd_stash<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return nfb_set_error(NFB_ECUDA, "k_view_tc_bwd_stash: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  const int TS = (GROUP / a.V < TS_MAX) ? GROUP / a.V : TS_MAX;
+  const int TS = row_map(a.V).TS;
   const int ntiles = (a.N + TS - 1) / TS;
   int grid = (ntiles + NG - 1) / NG;
   const int cap = nfb_num_sms();

@@ -1,7 +1,9 @@
 """Join an ncu SASS source-page CSV (`ncu -i x.ncu-rep --page source --csv --print-source sass`, one block per
 captured launch) with the nvdisasm line info of the same kernel, and aggregate instruction counts, stall samples and
 stall reasons by CUDA source line.
-usage: python profiles/sass_lines.py <ncu_source.csv> <object.o> <kernel-name-substring> [occurrence=0] [top=50]"""
+usage: python profiles/sass_lines.py <ncu_source.csv> <object.o> <kernel-name-substring> [occurrence=0] [top=50] [csv-kernel-substring]
+(the object's section names are mangled, the CSV's kernel names demangled: pass the demangled form as the last argument when a
+plain substring does not select one instantiation in both)"""
 import collections
 import csv
 import glob
@@ -14,6 +16,7 @@ import tempfile
 src_csv, obj, kname = sys.argv[1:4]
 occ = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 50
+csv_kname = sys.argv[6] if len(sys.argv) > 6 else kname
 
 tmp = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(obj)], cwd=tmp, capture_output=True)
@@ -39,7 +42,7 @@ for l in dis[start + 1:]:
 
 csv.field_size_limit(1 << 30)
 rows = list(csv.reader(open(src_csv)))
-blocks = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name' and kname in r[1]]
+blocks = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name' and csv_kname in r[1]]
 b = blocks[occ]
 hdr = rows[b + 1]
 end = next((i for i in range(b + 2, len(rows)) if rows[i] and rows[i][0] == 'Kernel Name'), len(rows))
