@@ -51,8 +51,9 @@ template <int NPASS, bool BWD>
 struct Cfg {
   static constexpr int NG = BWD ? 2 : 4;
   static constexpr int GC = BWD ? 256 : 128;
-  // per-group shared memory (floats): K, V [128][16]; backward: Q, dO [128][16] and statistics [128][4] float4
-  static constexpr int GROUP_FLOATS = BWD ? (4 * GROUP * 16 + GROUP * 16) : (2 * GROUP * 16);
+  // per-group shared memory (floats): K, V [128][16]; backward: Q, dO [128][16] and statistics [128][4] float4;
+  // forward: Q [128][16], the pair exchange [128][24] and the per-warp key norms [4][4] of the two-query attention
+  static constexpr int GROUP_FLOATS = BWD ? (4 * GROUP * 16 + GROUP * 16) : (3 * GROUP * 16 + GROUP * 24 + 16);
   static size_t smem(int S) {
     return (size_t)R_SET_BYTES * (NPASS == 3 ? 2 : 1) + sizeof(float) * (RF_TOTAL + (size_t)S * 16 + (size_t)NG * GROUP_FLOATS) +
            NG * 8 + 16;
@@ -217,9 +218,11 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
   float* abase = s_grp + (size_t)(pair_mode ? 2 * pair : grp) * C::GROUP_FLOATS;
   float* sk = abase;                                                  // [AR][16]
   float* sv = sk + AR * 16;
-  float* sq = sv + AR * 16;                                           // backward only
-  float* sdo = sq + AR * 16;
+  float* sq = sv + AR * 16;                                           // [AR][16]
+  float* sdo = sq + AR * 16;                                          // backward only
   float* sst = sdo + AR * 16;                                         // [AR][16]: -m | 1/l | -D | valid
+  float* sx = sq + AR * 16;                                           // forward only: [AR][24] partial (l, o) of the partner's query
+  float* skm = sx + AR * 24;                                          // forward only: [AR / 32][4] per-warp max |k_h|^2
   const int row = pair_mode ? gp * GROUP + tg : tg;                   // this thread's row in those buffers
   const int bar_id = 1 + grp;
   const int att_bar = pair_mode ? 9 + pair : bar_id, att_n = pair_mode ? 2 * GROUP : GROUP;
@@ -337,7 +340,208 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
     // the scalar fp32 instructions issue at half the packed rate).  Masked query rows (<= 1 valid view:
     // masked_fill(mask == 0, -1e9) on the whole row = uniform attention) carry q = 0, so their scores, maxima and
     // probabilities come out as 0, 0 and 1 without a branch.
+    // TWO-QUERY form (forward kernel, S a multiple of 64): the broadcast K / V row loads are the bound of the loop above (12
+    // LDS.128 per key and query over two passes: ncu shows the shared-memory pipe at 70 %).  Warps w and w ^ 1 of a ray split
+    // its keys in halves; every thread runs its OWN query and the query of the same lane of the partner warp over its half,
+    // so a K / V row is loaded once per TWO (query, key) pairs, and the partial (l, o) of the partner's query is handed over
+    // through shared memory.  The max pass disappears: softmax is shift invariant, and |q_h| max_j |k_jh| >= max_j q_h.k_jh
+    // (Cauchy-Schwarz) is a valid shift that needs no pass over the keys; 2^(s - shift) cannot underflow the whole row while
+    // the shift is < 60 (log2 units) -- beyond that (never seen; scores of +-40 nats) the warp pair falls back to the exact
+    // two-pass loop for its own queries.  4 LDS.128 per (query, key) instead of 12, 28 instructions instead of 48.
+    const bool fast = !BWD && (S % 64 == 0);
     float2 q01[4], q23[4];
+    float o[16], m2[4], il[4];
+    if (fast) {
+      float kn[4];
+      {
+        float qq[16], kk[16], vv[16];
+        r_ld16(tl, 0, qq);
+        r_ld16(tl, 16, kk);
+        r_ld16(tl, 32, vv);
+        const float qs = row_valid ? INV_TEMP * LOG2E : 0.f;          // scores in the log2 domain
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          q01[d] = make_float2(qq[d] * qs, qq[4 + d] * qs);
+          q23[d] = make_float2(qq[8 + d] * qs, qq[12 + d] * qs);
+          *reinterpret_cast<float4*>(sk + row * 16 + 4 * d) = make_float4(kk[d], kk[4 + d], kk[8 + d], kk[12 + d]);
+          *reinterpret_cast<float4*>(sv + row * 16 + 4 * d) = make_float4(vv[d], vv[4 + d], vv[8 + d], vv[12 + d]);
+          *reinterpret_cast<float4*>(sq + row * 16 + 4 * d) = make_float4(q01[d].x, q01[d].y, q23[d].x, q23[d].y);
+          if (save) {
+            rp_st(sp, RP_Q + d, q01[d].x, q01[d].y, q23[d].x, q23[d].y);
+            rp_st(sp, RP_K + d, kk[d], kk[4 + d], kk[8 + d], kk[12 + d]);
+            rp_st(sp, RP_V + d, vv[d], vv[4 + d], vv[8 + d], vv[12 + d]);
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+          kn[h] = fmaf(kk[4 * h + 3], kk[4 * h + 3], fmaf(kk[4 * h + 2], kk[4 * h + 2], fmaf(kk[4 * h + 1], kk[4 * h + 1], kk[4 * h] * kk[4 * h])));
+      }
+      {                                               // residual input parked in the free D columns while the loop runs
+        uint32_t park[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) park[c] = __float_as_uint(xin[c]);
+        tmem_st16(tl + RC_D + 48, park);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) kn[h] = fmaxf(kn[h], __shfl_xor_sync(0xffffffffu, kn[h], off));
+      }
+      if ((tid & 31) == 0) *reinterpret_cast<float4*>(skm + (row >> 5) * 4) = make_float4(kn[0], kn[1], kn[2], kn[3]);
+      named_bar_sync(att_bar, att_n);
+      float4 km = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int wv = kb >> 5; wv < ((kb + S) >> 5); ++wv) {
+        const float4 t4 = *reinterpret_cast<const float4*>(skm + wv * 4);
+        km.x = fmaxf(km.x, t4.x); km.y = fmaxf(km.y, t4.y); km.z = fmaxf(km.z, t4.z); km.w = fmaxf(km.w, t4.w);
+      }
+      const int prow = row ^ 32;                       // same lane of the partner warp (same ray: S is a multiple of 64)
+      float2 qb01[4], qb23[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const float4 t4 = *reinterpret_cast<const float4*>(sq + prow * 16 + 4 * d);
+        qb01[d] = make_float2(t4.x, t4.y);
+        qb23[d] = make_float2(t4.z, t4.w);
+      }
+      // shift of a query: sqrt(|q_h|^2 max_j |k_jh|^2), inflated by 1e-4 relative + 1e-6 so that rounding cannot put a score above it.
+      // Both threads of a pair evaluate this expression on the same numbers in the same order: bit-identical shifts.
+      float shA[4], shB[4];
+      {
+        const float kmx[4] = {km.x, km.y, km.z, km.w};
+        float qa[4] = {0.f, 0.f, 0.f, 0.f}, qb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          qa[0] = fmaf(q01[d].x, q01[d].x, qa[0]); qa[1] = fmaf(q01[d].y, q01[d].y, qa[1]);
+          qa[2] = fmaf(q23[d].x, q23[d].x, qa[2]); qa[3] = fmaf(q23[d].y, q23[d].y, qa[3]);
+          qb[0] = fmaf(qb01[d].x, qb01[d].x, qb[0]); qb[1] = fmaf(qb01[d].y, qb01[d].y, qb[1]);
+          qb[2] = fmaf(qb23[d].x, qb23[d].x, qb[2]); qb[3] = fmaf(qb23[d].y, qb23[d].y, qb[3]);
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          shA[h] = fmaf(sqrtf(qa[h] * kmx[h]), 1.0001f, 1e-6f);
+          shB[h] = fmaf(sqrtf(qb[h] * kmx[h]), 1.0001f, 1e-6f);
+        }
+      }
+      bool big = false;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) big = big || !(shA[h] < 60.f) || !(shB[h] < 60.f);
+      float2 lB01 = make_float2(0.f, 0.f), lB23 = lB01;
+      float2 oB01[4], oB23[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) oB01[d] = oB23[d] = make_float2(0.f, 0.f);
+      float2 l01 = make_float2(0.f, 0.f), l23 = l01;
+      float2 o01[4], o23[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) o01[d] = o23[d] = make_float2(0.f, 0.f);
+      if (__any_sync(0xffffffffu, big)) {
+        // exact form for this warp pair (the partner warp takes the same branch: it sees the same two shift sets): own query
+        // over ALL keys with the true row maximum; the partner's partial stays zero
+        const float4* kr = reinterpret_cast<const float4*>(sk + kb * 16);
+        const float4* vr = reinterpret_cast<const float4*>(sv + kb * 16);
+        float2 mx01 = make_float2(-3.4e38f, -3.4e38f), mx23 = mx01;
+        for (int j = 0; j < S; ++j) {
+          float2 s01, s23;
+          attn_scores(kr + 4 * j, q01, q23, s01, s23);
+          mx01.x = fmaxf(mx01.x, s01.x); mx01.y = fmaxf(mx01.y, s01.y);
+          mx23.x = fmaxf(mx23.x, s23.x); mx23.y = fmaxf(mx23.y, s23.y);
+        }
+        shA[0] = mx01.x; shA[1] = mx01.y; shA[2] = mx23.x; shA[3] = mx23.y;
+        const float2 nm01 = make_float2(-mx01.x, -mx01.y), nm23 = make_float2(-mx23.x, -mx23.y);
+        for (int j = 0; j < S; ++j) {
+          float2 s01, s23;
+          attn_scores(kr + 4 * j, q01, q23, s01, s23);
+          s01 = __fadd2_rn(s01, nm01);
+          s23 = __fadd2_rn(s23, nm23);
+          const float2 p01 = make_float2(ex2_approx(s01.x), ex2_approx(s01.y));
+          const float2 p23 = make_float2(ex2_approx(s23.x), ex2_approx(s23.y));
+          l01 = __fadd2_rn(l01, p01);
+          l23 = __fadd2_rn(l23, p23);
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            const float4 vj = vr[4 * j + d];
+            o01[d] = __ffma2_rn(p01, make_float2(vj.x, vj.y), o01[d]);
+            o23[d] = __ffma2_rn(p23, make_float2(vj.z, vj.w), o23[d]);
+          }
+        }
+      } else {
+        const int j0 = kb + ((row >> 5) & 1) * (S >> 1);
+        const float4* kr = reinterpret_cast<const float4*>(sk + j0 * 16);
+        const float4* vr = reinterpret_cast<const float4*>(sv + j0 * 16);
+        const float2 nA01 = make_float2(-shA[0], -shA[1]), nA23 = make_float2(-shA[2], -shA[3]);
+        const float2 nB01 = make_float2(-shB[0], -shB[1]), nB23 = make_float2(-shB[2], -shB[3]);
+        const int half = S >> 1;
+#pragma unroll 2
+        for (int j = 0; j < half; ++j) {
+          float2 sa01, sa23, sb01, sb23;
+          {
+            const float4 ka = kr[4 * j], kb4 = kr[4 * j + 1], kc = kr[4 * j + 2], kd = kr[4 * j + 3];
+            const float2 a01 = make_float2(ka.x, ka.y), a23 = make_float2(ka.z, ka.w);
+            const float2 b01 = make_float2(kb4.x, kb4.y), b23 = make_float2(kb4.z, kb4.w);
+            const float2 c01 = make_float2(kc.x, kc.y), c23 = make_float2(kc.z, kc.w);
+            const float2 d01 = make_float2(kd.x, kd.y), d23 = make_float2(kd.z, kd.w);
+            sa01 = __ffma2_rn(q01[0], a01, nA01); sa23 = __ffma2_rn(q23[0], a23, nA23);
+            sb01 = __ffma2_rn(qb01[0], a01, nB01); sb23 = __ffma2_rn(qb23[0], a23, nB23);
+            sa01 = __ffma2_rn(q01[1], b01, sa01); sa23 = __ffma2_rn(q23[1], b23, sa23);
+            sb01 = __ffma2_rn(qb01[1], b01, sb01); sb23 = __ffma2_rn(qb23[1], b23, sb23);
+            sa01 = __ffma2_rn(q01[2], c01, sa01); sa23 = __ffma2_rn(q23[2], c23, sa23);
+            sb01 = __ffma2_rn(qb01[2], c01, sb01); sb23 = __ffma2_rn(qb23[2], c23, sb23);
+            sa01 = __ffma2_rn(q01[3], d01, sa01); sa23 = __ffma2_rn(q23[3], d23, sa23);
+            sb01 = __ffma2_rn(qb01[3], d01, sb01); sb23 = __ffma2_rn(qb23[3], d23, sb23);
+          }
+          const float2 pa01 = make_float2(ex2_approx(sa01.x), ex2_approx(sa01.y));
+          const float2 pa23 = make_float2(ex2_approx(sa23.x), ex2_approx(sa23.y));
+          const float2 pb01 = make_float2(ex2_approx(sb01.x), ex2_approx(sb01.y));
+          const float2 pb23 = make_float2(ex2_approx(sb23.x), ex2_approx(sb23.y));
+          l01 = __fadd2_rn(l01, pa01); l23 = __fadd2_rn(l23, pa23);
+          lB01 = __fadd2_rn(lB01, pb01); lB23 = __fadd2_rn(lB23, pb23);
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            const float4 vj = vr[4 * j + d];
+            const float2 v01 = make_float2(vj.x, vj.y), v23 = make_float2(vj.z, vj.w);
+            o01[d] = __ffma2_rn(pa01, v01, o01[d]);
+            o23[d] = __ffma2_rn(pa23, v23, o23[d]);
+            oB01[d] = __ffma2_rn(pb01, v01, oB01[d]);
+            oB23[d] = __ffma2_rn(pb23, v23, oB23[d]);
+          }
+        }
+      }
+      // hand the partner's partial over, collect mine
+      {
+        float4* xo = reinterpret_cast<float4*>(sx + prow * 24);
+        xo[0] = make_float4(lB01.x, lB01.y, lB23.x, lB23.y);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) xo[1 + d] = make_float4(oB01[d].x, oB01[d].y, oB23[d].x, oB23[d].y);
+      }
+      named_bar_sync(att_bar, att_n);
+      {
+        const float4* xi = reinterpret_cast<const float4*>(sx + row * 24);
+        const float4 lp = xi[0];
+        l01 = __fadd2_rn(l01, make_float2(lp.x, lp.y));
+        l23 = __fadd2_rn(l23, make_float2(lp.z, lp.w));
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const float4 op = xi[1 + d];
+          o01[d] = __fadd2_rn(o01[d], make_float2(op.x, op.y));
+          o23[d] = __fadd2_rn(o23[d], make_float2(op.z, op.w));
+        }
+      }
+      il[0] = 1.f / l01.x; il[1] = 1.f / l01.y; il[2] = 1.f / l23.x; il[3] = 1.f / l23.y;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) m2[h] = shA[h];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        o[d] = o01[d].x * il[0];
+        o[4 + d] = o01[d].y * il[1];
+        o[8 + d] = o23[d].x * il[2];
+        o[12 + d] = o23[d].y * il[3];
+      }
+      {
+        uint32_t park[16];
+        tmem_ld16u(tl + RC_D + 48, park);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) xin[c] = __uint_as_float(park[c]);
+      }
+    } else {
     {
       float qq[16], kk[16], vv[16];
       r_ld16(tl, 0, qq);
@@ -358,7 +562,6 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
       }
     }
     named_bar_sync(att_bar, att_n);
-    float o[16], m2[4], il[4];
     {
       const float4* kr = reinterpret_cast<const float4*>(sk + kb * 16);
       const float4* vr = reinterpret_cast<const float4*>(sv + kb * 16);
@@ -399,6 +602,7 @@ __global__ void __launch_bounds__(GROUP * Cfg<NPASS, BWD>::NG, 1) k_ray_tc(RayAr
         o[8 + d] = o23[d].x * il[2];
         o[12 + d] = o23[d].y * il[3];
       }
+    }
     }
 
     if (save) {
@@ -905,11 +1109,8 @@ __global__ void __launch_bounds__(GROUP * BS_NG, 1) k_ray_tc_bwd_stash(RayArgs a
         nD[h] = -(dO[4 * h] * o[4 * h] + dO[4 * h + 1] * o[4 * h + 1] + dO[4 * h + 2] * o[4 * h + 2] + dO[4 * h + 3] * o[4 * h + 3]);
       const float vf = row_valid ? 1.f : 0.f;
 #pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        dO01[d] = make_float2(dO[d], dO[4 + d]);
-        dO23[d] = make_float2(dO[8 + d], dO[12 + d]);
+      for (int d = 0; d < 4; ++d)
         *reinterpret_cast<float4*>(sdo + row * 16 + 4 * d) = make_float4(dO[d], dO[4 + d], dO[8 + d], dO[12 + d]);
-      }
       *reinterpret_cast<float4*>(sst + row * 16) = nm4;
       *reinterpret_cast<float4*>(sst + row * 16 + 4) = il4;
       *reinterpret_cast<float4*>(sst + row * 16 + 8) = make_float4(nD[0], nD[1], nD[2], nD[3]);
@@ -926,6 +1127,12 @@ __global__ void __launch_bounds__(GROUP * BS_NG, 1) k_ray_tc_bwd_stash(RayArgs a
         const float4 q4 = *reinterpret_cast<const float4*>(sq + row * 16 + 4 * d);
         q01[d] = make_float2(q4.x, q4.y);
         q23[d] = make_float2(q4.z, q4.w);
+        // dO pairs re-read from the row just published: LDS.128 delivers (head 0, head 1) / (head 2, head 3) in ALIGNED register
+        // pairs.  Built from the TMEM read-back (head-major registers) the compiler re-packed all eight pairs with IMAD.MOV
+        // in every iteration of the loop below (11.5 % of the kernel's instructions, ncu r02d).
+        const float4 g4 = *reinterpret_cast<const float4*>(sdo + row * 16 + 4 * d);
+        dO01[d] = make_float2(g4.x, g4.y);
+        dO23[d] = make_float2(g4.z, g4.w);
       }
       const float4* kr = reinterpret_cast<const float4*>(sk + kb * 16);
       const float4* vr = reinterpret_cast<const float4*>(sv + kb * 16);

@@ -218,14 +218,17 @@ __device__ __forceinline__ float2 elu_fast2(float2 x) {
   const float2 em = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(-1.f, -1.f));
   return make_float2(fmaxf(x.x, fminf(em.x, 0.f)), fmaxf(x.y, fminf(em.y, 0.f)));
 }
-// ELU of a pair and the 16-bit derivative codes of both (ELU' = min(e, 1) = 2 - t, t = max(1.9999999 - e, 1))
+// ELU of a pair and the 16-bit derivative codes of both.  The exponent argument is clamped to <= 0, so e = exp(min(x, 0)) lies in
+// (0, 1]: y = max(x, e - 1) is ELU for either sign, ELU' = e needs no clamp, and the code word t = 1.9999999 - e (1 - 2^-22)
+// stays inside [1, 2) by construction (4 FMNMX per pair instead of 6).
 __device__ __forceinline__ float2 elu_code2(float2 x, uint32_t& code) {
-  const float2 t = __fmul2_rn(x, make_float2(1.4426950408889634f, 1.4426950408889634f));
+  float2 t = __fmul2_rn(x, make_float2(1.4426950408889634f, 1.4426950408889634f));
+  t.x = fminf(t.x, 0.f); t.y = fminf(t.y, 0.f);
   const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
   const float2 em = __fadd2_rn(e, make_float2(-1.f, -1.f));
-  const float2 c = __ffma2_rn(e, make_float2(-1.f, -1.f), make_float2(1.9999999f, 1.9999999f));
-  code = __byte_perm(__float_as_uint(fmaxf(c.x, 1.f)), __float_as_uint(fmaxf(c.y, 1.f)), 0x6521);
-  return make_float2(fmaxf(x.x, fminf(em.x, 0.f)), fmaxf(x.y, fminf(em.y, 0.f)));
+  const float2 c = __ffma2_rn(e, make_float2(-0.99999976f, -0.99999976f), make_float2(1.9999999f, 1.9999999f));
+  code = __byte_perm(__float_as_uint(c.x), __float_as_uint(c.y), 0x6521);
+  return make_float2(fmaxf(x.x, em.x), fmaxf(x.y, em.y));
 }
 // derivative pair of a code word: (ELU'_lo, ELU'_hi) = 2 - (t_lo, t_hi)
 __device__ __forceinline__ float2 elu_stash2(uint32_t w) {

@@ -344,12 +344,15 @@ __device__ __forceinline__ void pool4(const float* __restrict__ row0, int V, int
 }
 
 // all threads of the group: publish the A stores, let thread 0 issue + commit
-#define NFB_TC_ISSUE(LAYER, KS0, KS1, ACC0)                                   \
+// ISSUER (0..3): which warp of the group issues this layer.  Issuing an MMA batch costs its thread ~15 instructions per
+// tcgen05.mma (descriptors, R2UR); rotating the issuer over the four warps keeps them in step (measured: with one fixed issuer
+// that warp runs ~15 % more instructions per tile than the other three, and they wait for it at every barrier).
+#define NFB_TC_ISSUE(LAYER, KS0, KS1, ACC0, ISSUER)                           \
   do {                                                                        \
     tmem_st_wait();                                                           \
     fence_before_sync();                                                      \
     named_bar_sync(bar_id, GROUP);                                            \
-    if (tg == 0) {                                                            \
+    if (tg == 32 * (ISSUER)) {                                                \
       fence_after_sync();                                                     \
       issue_mma<NPASS, LAYER, KS0, KS1>(tb, sB_addr, ACC0);                   \
       mma_commit(mbar);                                                       \
@@ -497,7 +500,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       for (int j = 0; j < 16; ++j) a1[j] = elu_fast(a1[j]);
       a_store16<NPASS>(tl, 0, a1);
     }
-    NFB_TC_ISSUE(L_DIR2, 0, 1, false);
+    NFB_TC_ISSUE(L_DIR2, 0, 1, false, 0);
 
     // ---------------- pooling weights (overlaps the MMA) ----------------
     float w, n_valid;
@@ -582,7 +585,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
         a_store_words<NPASS>(tl, kc, hi, lo);
       }
       if (NPASS == 3) {               // A region holds K = 64 per round: issue the first round now
-        NFB_TC_ISSUE(L_BASE0, 0, 4, false);
+        NFB_TC_ISSUE(L_BASE0, 0, 4, false, 0);
         NFB_TC_WAIT();
       }
       constexpr int KC0 = (NPASS == 3) ? 4 : 0;   // chunk index offset of the second round
@@ -603,8 +606,8 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
         lo[5] = lo[6] = lo[7] = 0u;
         a_store_words<NPASS>(tl, 6 - KC0, hi, lo);
       }
-      if (NPASS == 3) NFB_TC_ISSUE(L_BASE0, 4, 7, true);
-      else NFB_TC_ISSUE(L_BASE0, 0, 7, false);
+      if (NPASS == 3) NFB_TC_ISSUE(L_BASE0, 4, 7, true, 1);
+      else NFB_TC_ISSUE(L_BASE0, 0, 7, false, 1);
       NFB_TC_WAIT();
     }
 
@@ -617,7 +620,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       if (save) st_codes8(sp, SP_H1 + 2 * kc, q);
       a_store16<NPASS>(tl, kc, h);
     }
-    NFB_TC_ISSUE(L_BASE2, 0, 4, false);
+    NFB_TC_ISSUE(L_BASE2, 0, 4, false, 2);
     NFB_TC_WAIT();
 
     // ---------------- vis_fc (32 -> 32 -> 33) on x1 * w ----------------
@@ -636,7 +639,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       }
       a_store16<NPASS>(tl, kc, t);
     }
-    NFB_TC_ISSUE(L_VIS0, 0, 2, false);
+    NFB_TC_ISSUE(L_VIS0, 0, 2, false, 1);
     NFB_TC_WAIT();
 #pragma unroll
     for (int kc = 0; kc < 2; ++kc) {
@@ -646,7 +649,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       if (save) st_codes8(sp, SP_HV + 2 * kc, q);
       a_store16<NPASS>(tl, kc, h);
     }
-    NFB_TC_ISSUE(L_VIS2, 0, 2, false);
+    NFB_TC_ISSUE(L_VIS2, 0, 2, false, 2);
     NFB_TC_WAIT();
 
     // x2 = x1 + x_res ; vis1 = sigmoid(xv[32]) * mask ; vis_fc2 on x2 * vis1
@@ -679,7 +682,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       }
       a_store16<NPASS>(tl, kc, t);
     }
-    NFB_TC_ISSUE(L_VISB0, 0, 2, false);
+    NFB_TC_ISSUE(L_VISB0, 0, 2, false, 3);
     NFB_TC_WAIT();
     float vis2, sg2;
     {
@@ -711,7 +714,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       t[0] = vis2; t[1] = rd[0]; t[2] = rd[1]; t[3] = rd[2]; t[4] = rd[3];
       a_store16<NPASS>(tl, 2, t);
     }
-    NFB_TC_ISSUE(L_RGB0, 0, 3, false);
+    NFB_TC_ISSUE(L_RGB0, 0, 3, false, 3);
     NFB_TC_WAIT();
     float logit;
     {

@@ -53,12 +53,12 @@ __device__ __forceinline__ void issue_bwd(uint32_t tb, uint32_t sB_addr) {
   }
 }
 
-#define NFB_TCS_BWD(LAYER, N0, NW)                                            \
+#define NFB_TCS_BWD(LAYER, N0, NW, ISSUER)                                    \
   do {                                                                        \
     tmem_st_wait();                                                           \
     fence_before_sync();                                                      \
     named_bar_sync(bar_id, GROUP);                                            \
-    if (tg == 0) {                                                            \
+    if (tg == 32 * (ISSUER)) {      /* issuer rotates over the group's warps: see NFB_TC_ISSUE */ \
       fence_after_sync();                                                     \
       issue_bwd<NPASS, LAYER, N0, NW>(tb, sB_addr);                           \
       mma_commit(mbar);                                                       \
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       }
       a_store16<NPASS>(tl, 0, dg1);
     }
-    NFB_TCS_BWD(L_RGB0, 0, 48);
+    NFB_TCS_BWD(L_RGB0, 0, 48, 0);
 
     // (3) second pooling backward (overlaps the MMA)
     float x2[32];
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
         }
         a_store16<NPASS>(tl, kc, dh);
       }
-      NFB_TCS_BWD(L_VISB0, 0, 32);
+      NFB_TCS_BWD(L_VISB0, 0, 32, 1);
       ld_codes16(sp, SP_XV, cq);
       NFB_TCS_WAIT();
       d_vis1 = 0.f;
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       dxv[0] = d_vis1 * mk * sg1 * (1.f - sg1) * elu_stash_lo(xvq16);
       a_store16<NPASS>(tl, 2, dxv);
     }
-    NFB_TCS_BWD(L_VIS2, 0, 32);
+    NFB_TCS_BWD(L_VIS2, 0, 32, 2);
     ld_codes16(sp, SP_HV, cq);
     NFB_TCS_WAIT();
 #pragma unroll
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       }
       a_store16<NPASS>(tl, kc, dh);
     }
-    NFB_TCS_BWD(L_VIS0, 0, 32);
+    NFB_TCS_BWD(L_VIS0, 0, 32, 3);
     ld_codes16(sp, SP_X1, cq);
     NFB_TCS_WAIT();
 
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       }
       a_store16<NPASS>(tl, kc, dt);
     }
-    NFB_TCS_BWD(L_BASE2, 0, 64);
+    NFB_TCS_BWD(L_BASE2, 0, 64, 0);
     uint32_t hq[32];
     ld_codes16(sp, SP_H1, cq);
     {
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       a_store16<NPASS>(tl, kc, dh);
     }
     // base_fc.0 inputs [mean0 (35) | var0 (35) | x0 (35) | pad]: first MMA = input columns [0,64)
-    NFB_TCS_BWD(L_BASE0, 0, 64);
+    NFB_TCS_BWD(L_BASE0, 0, 64, 1);
     NFB_TCS_WAIT();
 
     // (7) first pooling backward.  With Dm_c = sum_v d mean0_vc, Dv_c = sum_v d var0_vc:
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       }
     }
     // second MMA: input columns [64,112) -> D columns [0,48): d var0[29..35) then d x0[0..35)
-    NFB_TCS_BWD(L_BASE0, 64, 48);            // (its barrier also publishes the d mean0 rows written above)
+    NFB_TCS_BWD(L_BASE0, 64, 48, 2);            // (its barrier also publishes the d mean0 rows written above)
     // exchange round 1 (overlaps the MMA): per-sample sums of d mean0, parked in the (now dead) cotangent staging row
     float* dpw = dpb + (active ? sl : 0) * DPS;
     if (active) {

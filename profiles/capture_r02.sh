@@ -13,12 +13,12 @@ ncu --set full --clock-control none --import-source on -k regex:'k_view_tc|k_ray
 ncu -i /tmp/prof.ncu-rep --page raw --csv > $out/${tag}_ncu_full_raw.csv 2>/dev/null
 ncu -i /tmp/prof.ncu-rep --page details --csv > $out/${tag}_ncu_full_details.csv 2>/dev/null
 ncu -i /tmp/prof.ncu-rep --page source --csv --print-source sass > /tmp/${tag}_ncu_source_sass.csv 2>/dev/null
-if [ -n "${ONLY_LINES:-}" ]; then :; fi
+grep -a "^\"Kernel Name\"" /tmp/${tag}_ncu_source_sass.csv | cut -c1-160 > $out/${tag}_source_kernels.txt
 B=nerfool_b200/csrc/build
-python profiles/sass_lines.py /tmp/${tag}_ncu_source_sass.csv $B/nfb_view_tc_bwd2_inst1.o k_view_tc_fwdILi3ELb1ELb1 1 70 'k_view_tc_fwd<3, 1, 1>' > $out/${tag}_lines_view_fwd.txt 2>&1
-python profiles/sass_lines.py /tmp/${tag}_ncu_source_sass.csv $B/nfb_view_tc_bwd2_inst3.o k_view_tc_bwd_stashILi3 1 70 'k_view_tc_bwd_stash<3>' > $out/${tag}_lines_view_bwd.txt 2>&1
-python profiles/sass_lines.py /tmp/${tag}_ncu_source_sass.csv $B/nfb_ray_tc_inst5.o k_ray_tcILi3ELb0ELb1 1 50 'k_ray_tc<3, 0, 1>' > $out/${tag}_lines_ray_fwd.txt 2>&1
-python profiles/sass_lines.py /tmp/${tag}_ncu_source_sass.csv $B/nfb_ray_tc_inst7.o k_ray_tc_bwd_stashILi3 1 50 'k_ray_tc_bwd_stash<3>' > $out/${tag}_lines_ray_bwd.txt 2>&1
+python profiles/sass_lines.py /tmp/${tag}_ncu_source_sass.csv $B/nfb_view_tc_bwd2_inst1.o k_view_tc_fwdILi3ELb1ELb1 1 70 'k_view_tc_fwd' > $out/${tag}_lines_view_fwd.txt 2>&1
+python profiles/sass_lines.py /tmp/${tag}_ncu_source_sass.csv $B/nfb_view_tc_bwd2_inst3.o k_view_tc_bwd_stashILi3 1 70 'k_view_tc_bwd_stash' > $out/${tag}_lines_view_bwd.txt 2>&1
+python profiles/sass_lines.py /tmp/${tag}_ncu_source_sass.csv $B/nfb_ray_tc_inst5.o k_ray_tcILi3ELb0ELb1 1 50 'k_ray_tc' > $out/${tag}_lines_ray_fwd.txt 2>&1
+python profiles/sass_lines.py /tmp/${tag}_ncu_source_sass.csv $B/nfb_ray_tc_inst7.o k_ray_tc_bwd_stashILi3 1 50 'k_ray_tc_bwd_stash' > $out/${tag}_lines_ray_bwd.txt 2>&1
 ls -la /tmp/prof.ncu-rep | tail -2
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-bf16 --no-nrand "$@" > $out/${tag}_launches_bench.log 2>&1

@@ -42,7 +42,9 @@ for l in dis[start + 1:]:
 
 csv.field_size_limit(1 << 30)
 rows = list(csv.reader(open(src_csv)))
-blocks = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name' and csv_kname in r[1]]
+blocks = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name' and csv_kname in r[1] and not (csv_kname + '_') in r[1]]
+if len(blocks) <= occ:
+    print('kernels in the CSV:', [r[1][:80] for r in rows if r and r[0] == 'Kernel Name'])
 b = blocks[occ]
 hdr = rows[b + 1]
 end = next((i for i in range(b + 2, len(rows)) if rows[i] and rows[i][0] == 'Kernel Name'), len(rows))
