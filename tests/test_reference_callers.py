@@ -232,8 +232,8 @@ def test_reference_train_loop_unmodified(ref_env, adv_train):
         for name, g in zip(names, seen['grads'][gi]):
             assert g is not None, name
             ref, truth = p[name].grad, p64[name].grad
-            if float(ref.abs().max()) < 1e-12:             # rgb_fc.4.bias: the blending softmax is shift invariant
-                assert float(g.abs().max()) < 1e-6, name
+            if float(truth.abs().max()) < 1e-9:            # rgb_fc.4.bias: the blending softmax is shift invariant, the true
+                assert float(g.abs().max()) < 1e-5, name  # gradient is exactly 0 (fp32 runs leave rounding noise)
                 continue
             e, e_ref = relerr(g.cpu(), truth), relerr(ref, truth)
             worst = max(worst, e)
