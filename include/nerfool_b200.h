@@ -194,6 +194,17 @@ int nfb_sample_pdf(int R, int M, int n, const float* bins, const float* weights,
 int nfb_fine_depths(int R, int S, int n_imp, int inv_uniform, const float* z_coarse,
                     const float* weights_coarse, const float* u, int u_rows, float* z_fine, void* stream);
 
+/* ---- forward_warp  (eval/ibrnet/eval_adv.py:97-197, the Python z-buffer loop of the depth / camera consistency losses) ----
+ * x_res, y_res: int32 [H*W] destination pixel of every source pixel (clamped and truncated as eval_adv.py:131-136 does);
+ * depth_src float [H*W], rgb_ref float [H*W][3]; allowed: uint8 [H*W] destination pixels that accept writes (the
+ * `if inds in selected_inds` test of the src2tar branch, :142) or NULL; sources: int32 [n_src] source pixels in loop order (the
+ * tar2src branch iterates selected_inds, :160) or NULL = all pixels in raster order.  Outputs new_rgb [H*W][3], new_depth [H*W]
+ * (initialised by the call); keys: uint64 [H*W] workspace; flag: int32, set to 1 when a depth <= 0 / NaN was met, in which case
+ * the outputs are NOT valid and the caller repeats the call with sequential = 1 (the reference loop in one thread).          */
+int nfb_forward_warp(int H, int W, const int* x_res, const int* y_res, const float* depth_src, const float* rgb_ref,
+                     const uint8_t* allowed, const int* sources, int n_src, float* new_rgb, float* new_depth,
+                     unsigned long long* keys, int* flag, int sequential, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,8 +35,16 @@ def shard_slice(n_items: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def _has_reduce_scatter(group):
+    """reduce_scatter exists on NCCL; gloo (the CPU test backend) has none."""
+    try:
+        return torch.distributed.get_backend(group) == 'nccl'
+    except Exception:
+        return False
+
+
 def pgd_hot_step(model, projector, ray_batch, featmaps, N_samples, N_importance, inv_uniform=True, det=True,
-                 white_bkgd=False, max_rays=65536, group=None, global_norm=False, want_img_grad=False):
+                 white_bkgd=False, max_rays=65536, group=None, global_norm=False, want_img_grad=False, scatter_views=None):
     """One attack step on the rays of `ray_batch` (already this rank's shard).
     Returns (loss, d_feat_coarse, d_feat_fine); with a process group ONE allreduce (both levels + the loss packed in
     one buffer) combines the ranks: the SUM when one view's rays are sharded (``global_norm``: every term already carries
@@ -44,6 +52,9 @@ def pgd_hot_step(model, projector, ray_batch, featmaps, N_samples, N_importance,
     renders its own target view (the universal attack's minibatch of views).
     Rays are processed in chunks of `max_rays` to bound the size of the per-sample workspaces; the loss of
     each chunk is normalised by the global mask count so the result equals the un-chunked step.
+    scatter_views: per-rank source-view counts of a view-sharded encoder (delta_gradient_step): every rank then needs the
+    summed gradient of ITS views only, so the exchange is ONE reduce-scatter (NCCL; padded to the largest shard, the loss rides
+    in each shard) instead of an allreduce; the returned gradients hold valid data in the rank's own view slice only.
     want_img_grad: also return d loss / d ray_batch['src_rgbs'] (4th value).  The gathered source colours enter the
     blending directly (mlp_network.py:233,272); NOTE that the reference's attacks never perturb them (eval_adv.py:292-304
     and train.py:131-143 pass the CLEAN ray batch to render_rays), so this is off unless a caller asks for it."""
@@ -105,7 +116,33 @@ def pgd_hot_step(model, projector, ray_batch, featmaps, N_samples, N_importance,
         g_i = g_img[0] * scale[0]
         if g_img[1] is not None:
             g_i = g_i + g_img[1] * scale[1]
-    if multi:
+    if multi and scatter_views is not None and not want_img_grad and _has_reduce_scatter(group):
+        # view-sharded encoder: reduce-scatter.  Shard r = [d feat_c | d feat_f] of rank r's views (zero-padded to the largest
+        # shard) + the loss; every rank receives the sum over ranks of its own shard.
+        dist = torch.distributed
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        per_view = g_c[0].numel()
+        m = max(scatter_views)
+        width = 2 * m * per_view + 1
+        send = g_c.new_zeros(world, width)
+        lo = 0
+        for r, c in enumerate(scatter_views):
+            if c:
+                send[r, :c * per_view] = g_c[lo:lo + c].reshape(-1)
+                send[r, m * per_view:(m + c) * per_view] = g_f[lo:lo + c].reshape(-1)
+            send[r, -1] = loss
+            lo += c
+        recv = g_c.new_empty(width)
+        dist.reduce_scatter_tensor(recv, send.reshape(-1), op=dist.ReduceOp.SUM, group=group)
+        if not global_norm:
+            recv = recv / world
+        mine, lo = scatter_views[rank], sum(scatter_views[:rank])
+        g_c, g_f = torch.zeros_like(g_c), torch.zeros_like(g_f)
+        if mine:
+            g_c[lo:lo + mine] = recv[:mine * per_view].view(mine, *g_c.shape[1:])
+            g_f[lo:lo + mine] = recv[m * per_view:(m + mine) * per_view].view(mine, *g_f.shape[1:])
+        total = loss if global_norm else recv[-1]
+    elif multi:
         world = torch.distributed.get_world_size(group)
         parts = [g_c.reshape(-1), g_f.reshape(-1), loss.reshape(1)] + ([g_i.reshape(-1)] if want_img_grad else [])
         packed = torch.cat(parts)
@@ -155,7 +192,8 @@ def delta_gradient_step(encoder, model, projector, ray_batch, delta, N_samples, 
     With a process group and ``shard_encoder`` the ENCODER is sharded over the source views (exact,
     the encoder normalises per image): rank g encodes views shard_slice(V, g, world), the feature maps are
     all-gathered, every rank renders its rays against all V views, the feature-map gradients are combined over
-    ranks (one packed allreduce -- the reduce-scatter of f2 plus the loss, in one collective), each rank back-propagates
+    ranks (ONE reduce-scatter on NCCL: each rank receives the summed gradient of its own views plus the loss; an allreduce on
+    backends without reduce-scatter), each rank back-propagates
     its own views through its encoder shard, and the delta-gradient slices are all-gathered.  Without ``shard_encoder``
     every rank encodes all views (redundant cuDNN work, no all-gathers).  Returns (loss, d_delta [1,V,H,W,3])."""
     dist = torch.distributed
@@ -189,7 +227,8 @@ def delta_gradient_step(encoder, model, projector, ray_batch, delta, N_samples, 
         batch['src_rgbs'] = adv
     out = pgd_hot_step(model, projector, batch, (full_c, full_f), N_samples, N_importance,
                        inv_uniform=inv_uniform, det=det, white_bkgd=white_bkgd, max_rays=max_rays,
-                       group=group, global_norm=global_norm, want_img_grad=perturb_colours)
+                       group=group, global_norm=global_norm, want_img_grad=perturb_colours,
+                       scatter_views=counts if sharded else None)
     loss, g_c, g_f = out[:3]
     d_local = out[3][0, lo:hi].clone() if perturb_colours else None
     if hi > lo:

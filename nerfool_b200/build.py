@@ -21,6 +21,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
 UNITS = [
     ('nfb_api', 'nfb_api.cu', []),
     ('nfb_geom', 'nfb_geom.cu', []),
+    ('nfb_warp', 'nfb_warp.cu', []),
     ('nfb_ray_stage', 'nfb_ray_stage.cu', []),
     ('nfb_gnt', 'nfb_gnt.cu', []),
     ('nfb_view_api', 'nfb_view_api.cu', []),

@@ -8,6 +8,7 @@
   base_synth_v10.npz   200x200, V=10, 64+128  (configs[3] sampling, reduced image),  96 rays
   render_image.npz     ibrnet/render_image.py:21-123 on a 40x56 view (V=4, 24+24, chunk 500) -- every output map
   hybrid.npz           ibrnet/render_ray.py:261-390 for the three (use_clean_color, use_clean_density) settings
+  forward_warp.npz     eval/ibrnet/eval_adv.py:97-197 (three modes, with and without zero depths) + depth-smooth / depth-var losses
 
 The BASELINE-shaped scenes are too large to commit (9 MB of source images + 12.6 MB of feature maps at V=4), so those
 fixtures hold the scene SEED plus a sha256 of every regenerated input tensor: the tests rebuild the inputs with
@@ -166,11 +167,65 @@ def golden_hybrid(H=40, W=56, V=4, R=60, s_c=24, n_imp=24, seed=6):
     print('hybrid', os.path.getsize(path) // 1024, 'KiB')
 
 
+def golden_forward_warp(H=40, W=56, seed=9, n_sel=300):
+    """forward_warp (eval/ibrnet/eval_adv.py:97-197), the reference's Python z-buffer loop, in its three modes (src2tar with
+    the selected-ray filter, tar2src over the selected rays, full image) and on a depth map holding zeros (the "empty" marker
+    doubles as a value).  eval_adv.py is imported unmodified through tests/ref_harness.py (stub modules for absent packages)."""
+    sys.path.insert(0, os.path.join(REPO, 'tests'))
+    import ref_harness
+    ref_harness.setup_paths('ibrnet')
+    import eval_adv
+    scene = make_scene(H, W, 2, seed=seed, kind='llff')
+    cams = scene['src_cameras'][0]
+    K = [c[2:18].reshape(4, 4)[:3, :3].clone() for c in cams]
+    E = [c[18:34].reshape(4, 4).clone() for c in cams]
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing='ij')
+    depth = 2.5 + 0.8 * torch.sin(xx / 7.0) * torch.cos(yy / 5.0) + 0.6 * (xx > W / 2).float()      # smooth + an occluding step
+    depth_z = depth.clone()
+    depth_z[torch.rand(H, W, generator=g) < 0.03] = 0.0
+    rgb = torch.rand(H, W, 3, generator=g)
+    sel = np.sort(np.random.RandomState(seed).choice(H * W, n_sel, replace=False))
+    arrs = dict(H=H, W=W, depth=depth.numpy(), depth_zeros=depth_z.numpy(), rgb=rgb.numpy(), sel=sel,
+                K0=K[0].numpy(), K1=K[1].numpy(), E0=E[0].numpy(), E1=E[1].numpy())
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for tag, d in (('pos', depth), ('zero', depth_z)):
+            for mode, kw in (('s2t', dict(src2tar=True)), ('t2s', dict(src2tar=False)), ('full', dict(derive_full_image=True))):
+                out = eval_adv.forward_warp(sel, rgb, d[None], K[0], E[0], K[1], E[1], **kw)
+                arrs[f'{tag}_{mode}_new'] = out[0].numpy()
+                arrs[f'{tag}_{mode}_new_depth'] = out[1].numpy()
+                arrs[f'{tag}_{mode}_rgb_proj'] = out[2].numpy()
+                arrs[f'{tag}_{mode}_depth_proj'] = out[3].numpy()
+                if mode == 't2s':
+                    arrs[f'{tag}_{mode}_inds_new'] = np.asarray(out[4], dtype=np.int64)
+    # depth-smooth / depth-variance losses on fixed inputs (eval_adv.py:32-48, train.py:329-340)
+    import train as ref_train
+    dm = torch.rand(4 * 8 * 8, generator=g) * 3 + 2
+    wts = torch.rand(50, 24, generator=g) ** 3
+    wts[:3] = 0                                            # zero total weight -> NaN rays, dropped
+    zs = torch.sort(torch.rand(50, 24, generator=g) * 10 + 2, dim=1)[0]
+    dep = (wts * zs).sum(1)
+    arrs.update(ds_depth=dm.numpy(), ds_l2=eval_adv.calc_depth_smooth_loss({'depth': dm}, 8).numpy(),
+                ds_l1=eval_adv.calc_depth_smooth_loss({'depth': dm}, 8, 'l1').numpy(),
+                dv_weights=wts.numpy(), dv_z=zs.numpy(), dv_depth=dep.numpy(),
+                dv=ref_train.calc_depth_var({'depth': dep, 'weights': wts, 'z_vals': zs}).numpy())
+    path = os.path.join(OUT, 'forward_warp.npz')
+    np.savez_compressed(path, **arrs)
+    print('forward_warp', 'filled px (s2t/t2s/full):', int((arrs['pos_s2t_new_depth'] > 0).sum()), int((arrs['pos_t2s_new_depth'] > 0).sum()),
+          int((arrs['pos_full_new_depth'] > 0).sum()), os.path.getsize(path) // 1024, 'KiB')
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == 'warp':
+        golden_forward_warp()
+        sys.exit(0)
     torch.set_num_threads(os.cpu_count() or 1)
     golden_baseline('base_llff_v4', 378, 504, 4, 192, 64, 64, seed=41, kind='llff')
     golden_baseline('base_llff_v10', 378, 504, 10, 128, 64, 64, seed=42, kind='llff')
     golden_baseline('base_synth_v10', 200, 200, 10, 96, 64, 128, seed=43, kind='synthetic')
     golden_render_image()
     golden_hybrid()
+    golden_forward_warp()

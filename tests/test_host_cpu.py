@@ -324,6 +324,106 @@ def test_delta_gradient_step_with_view_sharded_encoder_gloo():
             assert np.abs(dd - truth.numpy()).max() <= 2e-5 * np.abs(truth.numpy()).max(), (rank, shard_enc)
 
 
+# ----------------------------------------------------------------------------------------------------
+# SURVEY 8 row f2, second half: the universal-attack loop (eval_adv.py:609-740) with one target view per rank
+# ----------------------------------------------------------------------------------------------------
+def _universal_batches(g, world):
+    """`world` pseudo target views: disjoint ray subsets of the golden scene (same camera; the host logic under test does not care)."""
+    from helpers import batch_from_golden
+    from nerfool_b200 import attack
+    batch = batch_from_golden(g)
+    out = []
+    for r in range(world):
+        lo, hi = attack.shard_slice(batch['ray_o'].shape[0], r, world)
+        out.append({'ray_o': batch['ray_o'][lo:hi], 'ray_d': batch['ray_d'][lo:hi], 'rgb': batch['rgb'][lo:hi],
+                    'camera': batch['camera'], 'depth_range': batch['depth_range']})
+    return batch, out
+
+
+def _universal_worker(rank, world, port, q, use_adam):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(REPO, 'tests'))
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from nerfool_b200 import attack
+    from helpers import load_golden
+    g = load_golden('render_llff_v3')
+    attack.render_rays = _oracle_render(g)
+    batch, views = _universal_batches(g, world)
+    atk = attack.UniversalAttack(_tiny_encoder(), None, None, batch, int(g['S_c']), int(g['N_imp']), use_adam=use_adam, adam_lr=1e-2,
+                                 lr_step_size=1, lr_gamma=0.5, inv_uniform=bool(g['inv_uniform']), group=dist.group.WORLD,
+                                 generator=torch.Generator().manual_seed(3))
+    losses = [atk.step(views[rank]).item() for _ in range(2)]
+    q.put((rank, losses, atk.delta.detach().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('use_adam', [True, False])
+def test_universal_attack_one_view_per_rank_gloo(use_adam):
+    """Two ranks, one target view each == the single-process loop fed the MEAN of the two views' losses / gradients, followed by
+    the reference's update: Adam on -grad + StepLR (eval_adv.py:693-709) or alpha * sign(grad) (:711-716), then the two clamps
+    (:727-728)."""
+    import torch.multiprocessing as mp
+    from nerfool_b200 import attack
+    g = load_golden('render_llff_v3')
+    batch, views = _universal_batches(g, 2)
+    saved = attack.render_rays
+    attack.render_rays = _oracle_render(g)
+    try:
+        gen = torch.Generator().manual_seed(3)
+        eps = 8. / 255.
+        src = batch['src_rgbs']
+        delta = torch.empty(src.shape).uniform_(-eps, eps, generator=gen)
+        delta = torch.max(torch.min(delta, 1 - src), 0 - src).requires_grad_(True)
+        opt = torch.optim.Adam([delta], lr=1e-2)
+        sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=0.5)
+        want_losses = []
+        for _ in range(2):
+            parts = []
+            for v in views:
+                b = dict(v)
+                b['src_rgbs'], b['src_cameras'] = batch['src_rgbs'], batch['src_cameras']
+                parts.append(attack.delta_gradient_step(_tiny_encoder(), None, None, b, delta.detach(), int(g['S_c']), int(g['N_imp']),
+                                                        inv_uniform=bool(g['inv_uniform']), det=True))
+            loss = sum(p[0] for p in parts) / 2
+            grad = sum(p[1] for p in parts) / 2
+            want_losses.append(loss.item())
+            with torch.no_grad():
+                if use_adam:
+                    opt.zero_grad()
+                    delta.grad = -grad
+                    opt.step()
+                    sched.step()
+                else:
+                    delta.add_((2. / 255.) * torch.sign(grad))
+                d = torch.max(torch.min(delta, torch.tensor(eps)), torch.tensor(-eps))
+                delta.copy_(torch.max(torch.min(d, 1 - src), 0 - src))
+    finally:
+        attack.render_rays = saved
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000) + (1 if use_adam else 0)
+    procs = [ctx.Process(target=_universal_worker, args=(r, 2, port, q, use_adam)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(res[0][2], res[1][2]), 'the replicas of delta must stay in lock-step'
+    for rank, losses, d in res:
+        assert np.allclose(losses, want_losses, atol=1e-6), (losses, want_losses)
+        # the view-sharded encoder back-propagates batches of 2 + 1 images instead of 3: gradients equal to ~1e-9, which Adam's
+        # g / sqrt(v) (and sign()) turn into visible differences only where the gradient itself is rounding noise
+        diff = np.abs(d - delta.detach().numpy())
+        assert (diff > 2e-6).mean() < 2e-3 and diff.max() < (1e-4 if use_adam else 5. / 255.), (diff.max(), (diff > 2e-6).mean())
+        assert np.abs(d).max() <= eps + 1e-7
+        adv = d + src.numpy()
+        assert adv.min() >= -1e-7 and adv.max() <= 1 + 1e-7
+
+
 def test_dropin_overlay_resolves_hot_path_modules_and_falls_through(tmp_path, monkeypatch):
     """The overlay package shadows the three hot-path modules and leaves the rest of ``ibrnet`` to the
     reference checkout (simulated here with a stub checkout: the real one does not travel to the GPU box)."""
