@@ -443,8 +443,10 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
   for (int tile = blockIdx.x * NG + grp; tile < ntiles; tile += gridDim.x * NG) {
     const int p = tile * TS + sl;
     const bool active = lane_ok && (p < a.N);
-    const int base = active ? tg - v : 0;
-    uint32_t* mvps = mvp + (active ? sl : 0) * MVP;
+    // rows without a sample (idle lanes, tile tail) still execute the exchange reads; they are pointed at rows / slots of their
+    // OWN warp so that the warp-level fences of the packed mapping cover every shared-memory read (racecheck-clean)
+    const int base = active ? tg - v : (tg & ~31);
+    uint32_t* mvps = mvp + (active ? sl : (rm.packed ? (tg >> 5) * rm.spw : 0)) * MVP;
     float4* sp = reinterpret_cast<float4*>(a.stash) + (size_t)tile * (ST_PLANES * GROUP) + tg;
     const bool save = SAVE && active;
 

@@ -158,9 +158,11 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
   for (int tile = blockIdx.x * NG + grp; tile < ntiles; tile += gridDim.x * NG) {
     const int p = tile * TS + sl;
     const bool active = lane_ok && (p < a.N);
-    const int base = active ? tg - v : 0;
-    float* mvs = mv + (active ? sl : 0) * MVS;
-    const float* dp = dpb + (active ? sl : 0) * DPS;
+    // rows without a sample read rows / slots of their OWN warp (see the forward kernel): covered by the warp-level fences
+    const int base = active ? tg - v : (tg & ~31);
+    const int sl_safe = active ? sl : (rm.packed ? (tg >> 5) * rm.spw : 0);
+    float* mvs = mv + sl_safe * MVS;
+    const float* dp = dpb + sl_safe * DPS;
     const float4* sp = reinterpret_cast<const float4*>(a.stash) + (size_t)tile * (ST_PLANES * GROUP) + tg;
 
     // ---------------- stage the cotangents / forward means of the tile's samples (asynchronous copies) ----------------
@@ -458,7 +460,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
     // second MMA: input columns [64,112) -> D columns [0,48): d var0[29..35) then d x0[0..35)
     NFB_TCS_BWD(L_BASE0, 64, 48, 2);            // (its barrier also publishes the d mean0 rows written above)
     // exchange round 1 (overlaps the MMA): per-sample sums of d mean0, parked in the (now dead) cotangent staging row
-    float* dpw = dpb + (active ? sl : 0) * DPS;
+    float* dpw = dpb + sl_safe * DPS;
     if (active) {
       pool4<9, POOL_SUM>(ex + base * EXQ, V, v, 0, 1.f, [&](int q, const float4& s4, const float4&) {
         *reinterpret_cast<float4*>(dpw + 4 * q) = s4;       // dpw[35] is a pad slot (d_var[3] of the dead cotangent row)
