@@ -352,8 +352,8 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
         }
         a_store16<NPASS>(tl, kc, dh);
       }
+      ld_codes16(sp, SP_XV, cq);            // stash loads of the NEXT layer issued before the group barrier: in flight while it waits
       NFB_TCS_BWD(L_VISB0, 0, 32, 1);
-      ld_codes16(sp, SP_XV, cq);
       NFB_TCS_WAIT();
       d_vis1 = 0.f;
 #pragma unroll
@@ -386,8 +386,8 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       dxv[0] = d_vis1 * mk * sg1 * (1.f - sg1) * elu_stash_lo(xvq16);
       a_store16<NPASS>(tl, 2, dxv);
     }
-    NFB_TCS_BWD(L_VIS2, 0, 32, 2);
     ld_codes16(sp, SP_HV, cq);
+    NFB_TCS_BWD(L_VIS2, 0, 32, 2);
     NFB_TCS_WAIT();
 #pragma unroll
     for (int kc = 0; kc < 2; ++kc) {
@@ -399,8 +399,8 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       }
       a_store16<NPASS>(tl, kc, dh);
     }
-    NFB_TCS_BWD(L_VIS0, 0, 32, 3);
     ld_codes16(sp, SP_X1, cq);
+    NFB_TCS_BWD(L_VIS0, 0, 32, 3);
     NFB_TCS_WAIT();
 
     // (6) base_fc backward
