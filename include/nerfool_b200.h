@@ -171,6 +171,20 @@ int nfb_gnt_fwd(int R, int S, int V, int depth, int ret_alpha,
                 const float* rgb_feat, const float* ray_diff, const float* mask, const float* pts, const float* ray_d,
                 const float* params, float* out, void* workspace, size_t workspace_bytes, int precision, void* stream);
 
+/* ---- GNT data gradient  (autograd of gnt/transformer_network.py:270-309 w.r.t. its sampled inputs; what
+ * eval/gnt/eval_adv.py:282-545 back-propagates through Projector.compute to the source-image perturbation)
+ * d_out: cotangent of nfb_gnt_fwd's `out` ([R][3] or [R][3+S]; the alpha columns are differentiated too).
+ * d_rgb_feat[R][S][V][35] (written) and, if not NULL, d_ray_diff[R][S][V][4] (written; feeds the camera gradients of
+ * gnt/projection.py:64-87, which does not detach the source cameras).  The call re-runs the forward in fp32 on the CUDA
+ * cores with the running query checkpointed after every block and sweeps back block by block (ReLU masks are those of
+ * the fp32 forward, i.e. the reference's to ~1e-7).  workspace: nfb_gnt_bwd_workspace_bytes(R, S, V, depth) bytes, 16-byte
+ * aligned; no parameter gradients (the attack optimises the perturbation, the network is frozen: eval_adv.py:959).      */
+size_t nfb_gnt_bwd_workspace_bytes(int R, int S, int V, int depth);
+int nfb_gnt_bwd(int R, int S, int V, int depth, int ret_alpha,
+                const float* rgb_feat, const float* ray_diff, const float* mask, const float* pts, const float* ray_d,
+                const float* params, const float* d_out, float* d_rgb_feat, float* d_ray_diff,
+                void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- raw2outputs  (render_ray.py:123-170) ------------------------------------------------------------
  * pixel_mask: uint8 [R][S] (the `mask` argument), or NULL with n_valid (stride n_valid_stride floats per
  * sample) from which pixel_mask = n_valid > 1 (render_ray.py:210).  Outputs rgb[R][3], depth[R],

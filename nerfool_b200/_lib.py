@@ -33,10 +33,11 @@ _SIGNATURES = {
     'nfb_sample_pdf': [_I, _I, _I, _P, _P, _P, _I, _P, _P, _P],
     'nfb_fine_depths': [_I, _I, _I, _I, _P, _P, _P, _I, _P, _P],
     'nfb_gnt_fwd': [_I] * 5 + [_P] * 8 + [ctypes.c_size_t, _I, _P],
+    'nfb_gnt_bwd': [_I] * 5 + [_P] * 10 + [ctypes.c_size_t, _P],
     'nfb_forward_warp': [_I, _I] + [_P] * 6 + [_I] + [_P] * 4 + [_I, _P],
 }
 EXPORTS = ['nfb_version', 'nfb_last_error_string', 'nfb_ibrnet_param_offset', 'nfb_view_stash_bytes', 'nfb_ray_stash_bytes',
-           'nfb_gnt_param_floats', 'nfb_gnt_param_offset', 'nfb_gnt_workspace_bytes'] + list(_SIGNATURES)
+           'nfb_gnt_param_floats', 'nfb_gnt_param_offset', 'nfb_gnt_workspace_bytes', 'nfb_gnt_bwd_workspace_bytes'] + list(_SIGNATURES)
 
 _lib = None
 
@@ -108,6 +109,8 @@ def load():
     lib.nfb_gnt_param_offset.argtypes = [c_int, c_char_p]
     lib.nfb_gnt_workspace_bytes.restype = ctypes.c_size_t
     lib.nfb_gnt_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.nfb_gnt_bwd_workspace_bytes.restype = ctypes.c_size_t
+    lib.nfb_gnt_bwd_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int

@@ -24,6 +24,7 @@ UNITS = [
     ('nfb_warp', 'nfb_warp.cu', []),
     ('nfb_ray_stage', 'nfb_ray_stage.cu', []),
     ('nfb_gnt', 'nfb_gnt.cu', []),
+    ('nfb_gnt_bwd', 'nfb_gnt_bwd.cu', []),
     ('nfb_view_api', 'nfb_view_api.cu', []),
     ('nfb_view_inst0', 'nfb_view_inst.cu', ['-DNFB_VIEW_INST=0']),
     ('nfb_view_inst1', 'nfb_view_inst.cu', ['-DNFB_VIEW_INST=1']),

@@ -8,98 +8,12 @@
 // Launch sequence of nfb_gnt_fwd: embed (rgbfeat_fc + max over views) -> per layer { view attention, FFN,
 // [q_fc with positional encodings on even layers], ray attention, FFN } -> head (LayerNorm, mean over samples,
 // rgb_fc).  Dropout is the identity (eval mode, transformer_network.py:45,72,136).
-#include "nfb_dense.cuh"
+#include "nfb_gnt_common.cuh"
 #include "nfb_gnt_tc.cuh"
 
+using namespace nfbgnt;
+
 namespace {
-
-constexpr int D = 64;          // netwidth (eval/gnt/config.py:111)
-constexpr int DH = 256;        // feed-forward hidden width (4 x netwidth)
-constexpr int PE = 63;         // 3 + 3 * 2 * 10 positional-encoding width (transformer_network.py:253-268)
-constexpr int QIN = D + 2 * PE;  // 190
-
-// ---- parameter blob layout (floats; every tensor in torch's [out][in] layout) ------------------------------
-enum : int {
-  G_RF0_W = 0,                       // rgbfeat_fc.0.weight [64][35]
-  G_RF0_B = G_RF0_W + D * 35,
-  G_RF2_W = G_RF0_B + D,             // rgbfeat_fc.2.weight [64][64]
-  G_RF2_B = G_RF2_W + D * D,
-  G_HEAD = G_RF2_B + D               // end of the header block
-};
-// per-layer block
-enum : int {
-  L_V_LN1_W = 0,                     // view_crosstrans.i.attn_norm
-  L_V_LN1_B = L_V_LN1_W + D,
-  L_V_Q = L_V_LN1_B + D,             // attn.q_fc / k_fc / v_fc .weight [64][64]
-  L_V_K = L_V_Q + D * D,
-  L_V_V = L_V_K + D * D,
-  L_V_POS0_W = L_V_V + D * D,        // attn.pos_fc.0 [8][4]
-  L_V_POS0_B = L_V_POS0_W + 32,
-  L_V_POS2_W = L_V_POS0_B + 8,       // attn.pos_fc.2 [64][8]
-  L_V_POS2_B = L_V_POS2_W + D * 8,
-  L_V_AT0_W = L_V_POS2_B + D,        // attn.attn_fc.0 [8][64]
-  L_V_AT0_B = L_V_AT0_W + 8 * D,
-  L_V_AT2_W = L_V_AT0_B + 8,         // attn.attn_fc.2 [64][8]
-  L_V_AT2_B = L_V_AT2_W + D * 8,
-  L_V_O_W = L_V_AT2_B + D,           // attn.out_fc [64][64] + bias
-  L_V_O_B = L_V_O_W + D * D,
-  L_V_LN2_W = L_V_O_B + D,           // ff_norm
-  L_V_LN2_B = L_V_LN2_W + D,
-  L_V_FF1_W = L_V_LN2_B + D,         // ff.fc1 [256][64]
-  L_V_FF1_B = L_V_FF1_W + DH * D,
-  L_V_FF2_W = L_V_FF1_B + DH,        // ff.fc2 [64][256]
-  L_V_FF2_B = L_V_FF2_W + D * DH,
-  L_Q0_W = L_V_FF2_B + D,            // q_fcs.i.0 [64][190]   (even layers; the slot is unused on odd layers)
-  L_Q0_B = L_Q0_W + D * QIN,
-  L_Q2_W = L_Q0_B + D,               // q_fcs.i.2 [64][64]
-  L_Q2_B = L_Q2_W + D * D,
-  L_R_LN1_W = L_Q2_B + D,            // view_selftrans.i.attn_norm
-  L_R_LN1_B = L_R_LN1_W + D,
-  L_R_Q = L_R_LN1_B + D,             // attn.q_fc / k_fc / v_fc [64][64]
-  L_R_K = L_R_Q + D * D,
-  L_R_V = L_R_K + D * D,
-  L_R_O_W = L_R_V + D * D,           // attn.out_fc + bias
-  L_R_O_B = L_R_O_W + D * D,
-  L_R_LN2_W = L_R_O_B + D,           // ff_norm
-  L_R_LN2_B = L_R_LN2_W + D,
-  L_R_FF1_W = L_R_LN2_B + D,
-  L_R_FF1_B = L_R_FF1_W + DH * D,
-  L_R_FF2_W = L_R_FF1_B + DH,
-  L_R_FF2_B = L_R_FF2_W + D * DH,
-  L_SIZE = L_R_FF2_B + D
-};
-// tail block (after depth layers): norm.weight, norm.bias, rgb_fc.weight [3][64], rgb_fc.bias [3]
-enum : int { T_LN_W = 0, T_LN_B = D, T_RGB_W = 2 * D, T_RGB_B = 2 * D + 3 * D, T_SIZE = 2 * D + 3 * D + 3 };
-
-constexpr float LN_EPS_T = 1e-6f;   // Transformer / Transformer2D norms (transformer_network.py:96-97,182-183)
-constexpr float LN_EPS_HEAD = 1e-5f;  // GNT.norm = nn.LayerNorm default (:250)
-
-__device__ __forceinline__ void layer_norm64(const float (&x)[D], const float* __restrict__ w, const float* __restrict__ b,
-                                             float eps, float (&y)[D]) {
-  float mu = 0.f;
-#pragma unroll
-  for (int c = 0; c < D; ++c) mu += x[c];
-  mu *= (1.f / D);
-  float var = 0.f;
-#pragma unroll
-  for (int c = 0; c < D; ++c) var = fmaf(x[c] - mu, x[c] - mu, var);
-  var *= (1.f / D);
-  const float rstd = 1.f / sqrtf(var + eps);
-#pragma unroll
-  for (int c = 0; c < D; ++c) y[c] = fmaf((x[c] - mu) * rstd, w[c], b[c]);
-}
-
-__device__ __forceinline__ void load_row64(const float* __restrict__ p, float (&x)[D]) {
-#pragma unroll
-  for (int c = 0; c < D; c += 4) {
-    const float4 t = *reinterpret_cast<const float4*>(p + c);
-    x[c] = t.x; x[c + 1] = t.y; x[c + 2] = t.z; x[c + 3] = t.w;
-  }
-}
-__device__ __forceinline__ void store_row64(float* __restrict__ p, const float (&x)[D]) {
-#pragma unroll
-  for (int c = 0; c < D; c += 4) *reinterpret_cast<float4*>(p + c) = make_float4(x[c], x[c + 1], x[c + 2], x[c + 3]);
-}
 
 // ---------------------------------------------------------------------------------------------------
 // embed: F[row] = rgbfeat_fc(rgb_feat[row])  (35 -> 64 ReLU -> 64), one thread per (sample, view) row
@@ -148,16 +62,10 @@ __global__ void __launch_bounds__(256) k_gnt_qinit(size_t n_elems, int V, const 
 //   a = attn_fc(k - qq + pos) (masked_fill -1e9), softmax over views PER CHANNEL, out = sum_v (v + pos) a;
 //   q <- out_fc(out) + q.   The softmax over views runs online (running max / sum / weighted accumulator).
 // ---------------------------------------------------------------------------------------------------
-enum : int {
-  VS_LN_W = 0, VS_LN_B = D, VS_Q = 2 * D, VS_K = VS_Q + D * D, VS_V = VS_K + D * D, VS_O = VS_V + D * D,
-  VS_O_B = VS_O + D * D, VS_P0 = VS_O_B + D /*[4][8]*/, VS_P0_B = VS_P0 + 32, VS_P2 = VS_P0_B + 8 /*[8][64]*/,
-  VS_P2_B = VS_P2 + 8 * D, VS_A0 = VS_P2_B + D /*[64][8]*/, VS_A0_B = VS_A0 + D * 8, VS_A2 = VS_A0_B + 8 /*[8][64]*/,
-  VS_A2_B = VS_A2 + 8 * D, VS_TOTAL = VS_A2_B + D
-};
 
 __global__ void __launch_bounds__(128) k_gnt_view_attn(int N, int V, const float* __restrict__ F,
                                                         const float* __restrict__ ray_diff, const float* __restrict__ mask,
-                                                        const float* __restrict__ lp, float* __restrict__ q) {
+                                                        const float* __restrict__ lp, const float* q_in, float* q) {
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, nt = blockDim.x;
   load_vec_padded(sm + VS_LN_W, lp + L_V_LN1_W, D, D, t, nt);
@@ -179,7 +87,7 @@ __global__ void __launch_bounds__(128) k_gnt_view_attn(int N, int V, const float
 
   for (int n = blockIdx.x * blockDim.x + t; n < N; n += gridDim.x * blockDim.x) {
     float q0[D];
-    load_row64(q + (size_t)n * D, q0);
+    load_row64(q_in + (size_t)n * D, q0);
     float qq[D];
     {
       float x[D];
@@ -250,10 +158,8 @@ __global__ void __launch_bounds__(128) k_gnt_view_attn(int N, int V, const float
 // feed-forward block (second half of Transformer2D / Transformer): q <- fc2(ReLU(fc1(LN(q)))) + q
 // lp points at the block's {ff_norm.w, ff_norm.b, fc1.w, fc1.b, fc2.w, fc2.b} (contiguous in the blob)
 // ---------------------------------------------------------------------------------------------------
-enum : int { FS_LN_W = 0, FS_LN_B = D, FS_W1 = 2 * D /*[64][256]*/, FS_B1 = FS_W1 + D * DH, FS_W2 = FS_B1 + DH /*[256][64]*/,
-             FS_B2 = FS_W2 + DH * D, FS_TOTAL = FS_B2 + D };
 
-__global__ void __launch_bounds__(256, 1) k_gnt_ffn(int N, const float* __restrict__ lp, float* __restrict__ q) {
+__global__ void __launch_bounds__(256, 1) k_gnt_ffn(int N, const float* __restrict__ lp, const float* q_in, float* q) {
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, nt = blockDim.x;
   load_vec_padded(sm + FS_LN_W, lp, D, D, t, nt);
@@ -265,7 +171,7 @@ __global__ void __launch_bounds__(256, 1) k_gnt_ffn(int N, const float* __restri
   __syncthreads();
   for (int n = blockIdx.x * blockDim.x + t; n < N; n += gridDim.x * blockDim.x) {
     float q0[D], x[D], y[D];
-    load_row64(q + (size_t)n * D, q0);
+    load_row64(q_in + (size_t)n * D, q0);
     layer_norm64(q0, sm + FS_LN_W, sm + FS_LN_B, LN_EPS_T, x);
     load_bias<D>(y, sm + FS_B2);
 #pragma unroll 1
@@ -287,25 +193,10 @@ __global__ void __launch_bounds__(256, 1) k_gnt_ffn(int N, const float* __restri
 // q_fc on even layers (:295-297): q <- fc2(ReLU(fc1([q, posenc(pts), posenc(ray_d / |ray_d|)])))
 // Embedder order (:12-37): [x, sin(x f0), cos(x f0), sin(x f1), ...], f_k = 2^k, k = 0..9, 3 components each.
 // ---------------------------------------------------------------------------------------------------
-enum : int { QS_W0 = 0 /*[190][64]*/, QS_B0 = QIN * D, QS_W2 = QS_B0 + D, QS_B2 = QS_W2 + D * D, QS_TOTAL = QS_B2 + D };
 
-__device__ __forceinline__ void posenc_axpy(float (&h)[D], const float (&x3)[3], const float* __restrict__ w /*[63][64]*/) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i) axpy_row<D>(h, x3[i], w + i * D);
-#pragma unroll 1
-  for (int f = 0; f < 10; ++f) {
-    const float fr = (float)(1 << f);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const float ang = __fmul_rn(x3[i], fr);
-      axpy_row<D>(h, sinf(ang), w + (3 + 6 * f + i) * D);
-      axpy_row<D>(h, cosf(ang), w + (3 + 6 * f + 3 + i) * D);
-    }
-  }
-}
 
 __global__ void __launch_bounds__(128) k_gnt_qfc(int N, int S, const float* __restrict__ pts, const float* __restrict__ ray_d,
-                                                  const float* __restrict__ lp, float* __restrict__ q) {
+                                                  const float* __restrict__ lp, const float* q_in, float* q) {
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, nt = blockDim.x;
   load_wt_transposed(sm + QS_W0, lp + L_Q0_W, D, QIN, D, t, nt);
@@ -318,7 +209,7 @@ __global__ void __launch_bounds__(128) k_gnt_qfc(int N, int S, const float* __re
     load_bias<D>(h, sm + QS_B0);
     {
       float q0[D];
-      load_row64(q + (size_t)n * D, q0);
+      load_row64(q_in + (size_t)n * D, q0);
       dense_acc<D, D>(sm + QS_W0, q0, h);
     }
     const float p3[3] = {__ldg(pts + (size_t)n * 3), __ldg(pts + (size_t)n * 3 + 1), __ldg(pts + (size_t)n * 3 + 2)};
@@ -342,12 +233,8 @@ __global__ void __launch_bounds__(128) k_gnt_qfc(int N, int S, const float* __re
 // sample; K / V rows of the ray in shared memory; 4 heads x 16, scores / sqrt(16), softmax over the samples, no mask.
 // q <- out_fc(attn) + q.   attn_out (optional): mean over heads of the probabilities of QUERY 0 (:200) -> [R][S].
 // ---------------------------------------------------------------------------------------------------
-enum : int { RS_LN_W = 0, RS_LN_B = D, RS_Q = 2 * D, RS_K = RS_Q + D * D, RS_V = RS_K + D * D, RS_O = RS_V + D * D,
-             RS_O_B = RS_O + D * D, RS_W_TOTAL = RS_O_B + D,
-             // per ray of the CTA: query 0 (scaled) [64], its softmax statistics m[4], 1/l[4]; then K [S][64], V [S][64]
-             RS_Q0 = 0, RS_ST = D, RS_PER_RAY = D + 8 };
 
-__global__ void __launch_bounds__(256, 1) k_gnt_ray_attn(int R, int S, int rpc, const float* __restrict__ lp, float* __restrict__ q,
+__global__ void __launch_bounds__(256, 1) k_gnt_ray_attn(int R, int S, int rpc, const float* __restrict__ lp, const float* q_in, float* q,
                                                           float* __restrict__ attn_out, int attn_stride) {
   extern __shared__ __align__(16) float sm[];
   const int nt = blockDim.x;
@@ -368,9 +255,10 @@ __global__ void __launch_bounds__(256, 1) k_gnt_ray_attn(int R, int S, int rpc, 
   for (int r0 = blockIdx.x * rpc; r0 < R; r0 += gridDim.x * rpc) {
     const int r = r0 + lr;
     const bool act = (t < S) && (r < R);
-    float* qrow = q + ((size_t)(r < R ? r : 0) * S + (t < S ? t : 0)) * D;
+    const size_t qoff = ((size_t)(r < R ? r : 0) * S + (t < S ? t : 0)) * D;
+    float* qrow = q + qoff;
     float q0[D], qv[D];
-    load_row64(qrow, q0);
+    load_row64(q_in + qoff, q0);
     {
       float x[D], kk[D];
       layer_norm64(q0, sm + RS_LN_W, sm + RS_LN_B, LN_EPS_T, x);
@@ -821,22 +709,75 @@ extern "C" int nfb_gnt_fwd(int R, int S, int V, int depth, int ret_alpha, const 
       if (rc) return rc;
       continue;
     }
-    k_gnt_view_attn<<<grid_for(3), 128, sm_view, st>>>(N, V, F, ray_diff, mask, lp, q);
+    k_gnt_view_attn<<<grid_for(3), 128, sm_view, st>>>(N, V, F, ray_diff, mask, lp, q, q);
     NFB_CHECK_LAUNCH("k_gnt_view_attn");
-    k_gnt_ffn<<<ffn_grid, 256, sm_ffn, st>>>(N, lp + L_V_LN2_W, q);
+    k_gnt_ffn<<<ffn_grid, 256, sm_ffn, st>>>(N, lp + L_V_LN2_W, q, q);
     NFB_CHECK_LAUNCH("k_gnt_ffn<view>");
     if ((i & 1) == 0) {
-      k_gnt_qfc<<<grid_for(3), 128, sm_qfc, st>>>(N, S, pts, ray_d, lp, q);
+      k_gnt_qfc<<<grid_for(3), 128, sm_qfc, st>>>(N, S, pts, ray_d, lp, q, q);
       NFB_CHECK_LAUNCH("k_gnt_qfc");
     }
     const bool last = ret_alpha && i == depth - 1;
     k_gnt_ray_attn<<<ray_grid, ray_block * rpc, (size_t)(RS_W_TOTAL + (size_t)rpc * (2 * S * D + RS_PER_RAY)) * sizeof(float), st>>>(
-        R, S, rpc, lp, q, last ? out + 3 : nullptr, out_stride);
+        R, S, rpc, lp, q, q, last ? out + 3 : nullptr, out_stride);
     NFB_CHECK_LAUNCH("k_gnt_ray_attn");
-    k_gnt_ffn<<<ffn_grid, 256, sm_ffn, st>>>(N, lp + L_R_LN2_W, q);
+    k_gnt_ffn<<<ffn_grid, 256, sm_ffn, st>>>(N, lp + L_R_LN2_W, q, q);
     NFB_CHECK_LAUNCH("k_gnt_ffn<ray>");
   }
   k_gnt_head<<<head_grid, ray_block < 64 ? 64 : ray_block, sm_head, st>>>(R, S, params + G_HEAD + (size_t)depth * L_SIZE, q, out, out_stride);
   NFB_CHECK_LAUNCH("k_gnt_head");
+  return NFB_OK;
+}
+
+
+// fp32 forward with checkpoints (the first half of nfb_gnt_bwd, nfb_gnt_bwd.cu)
+int nfbgnt::gnt_forward_checkpoints(int R, int S, int V, int depth, const float* rgb_feat, const float* ray_diff, const float* mask,
+                                    const float* pts, const float* ray_d, const float* params, float* F, float* CK, cudaStream_t st) {
+  const int N = R * S;
+  const size_t rows = (size_t)N * V, NB = (size_t)N * D;
+  auto ck = [&](int i, int j) { return CK + NB * (size_t)(5 * i + j); };
+  const int sms = nfb_num_sms();
+  int rc;
+  const size_t sm_embed = (size_t)(35 * D + D + D * D + D) * sizeof(float), sm_view = (size_t)VS_TOTAL * sizeof(float),
+               sm_ffn = (size_t)FS_TOTAL * sizeof(float), sm_qfc = (size_t)QS_TOTAL * sizeof(float);
+  const int ray_block = ((S + 31) / 32) * 32;
+  int rpc = 256 / ray_block;
+  const int rpc_smem = (int)((200 * 1024 - (size_t)RS_W_TOTAL * sizeof(float)) / ((size_t)(2 * S * D + RS_PER_RAY) * sizeof(float)));
+  if (rpc > rpc_smem) rpc = rpc_smem;
+  if (rpc < 1) rpc = 1;
+  const size_t sm_ray = (size_t)(RS_W_TOTAL + (size_t)rpc * (2 * S * D + RS_PER_RAY)) * sizeof(float);
+  if ((rc = set_smem(k_gnt_embed, sm_embed, "k_gnt_embed"))) return rc;
+  if ((rc = set_smem(k_gnt_view_attn, sm_view, "k_gnt_view_attn"))) return rc;
+  if ((rc = set_smem(k_gnt_ffn, sm_ffn, "k_gnt_ffn"))) return rc;
+  if ((rc = set_smem(k_gnt_qfc, sm_qfc, "k_gnt_qfc"))) return rc;
+  if ((rc = set_smem(k_gnt_ray_attn, sm_ray, "k_gnt_ray_attn"))) return rc;
+  auto grid_n = [&](size_t n, int block, int per_sm) {
+    size_t g = (n + block - 1) / block;
+    if (g > (size_t)sms * per_sm) g = (size_t)sms * per_sm;
+    return (int)(g < 1 ? 1 : g);
+  };
+  const int ffn_grid = grid_n(N, 256, 1);
+  const int ray_ctas = (R + rpc - 1) / rpc, ray_grid = ray_ctas < sms ? ray_ctas : sms;
+  k_gnt_embed<<<grid_n(rows, 128, 8), 128, sm_embed, st>>>(rows, rgb_feat, params, F);
+  NFB_CHECK_LAUNCH("k_gnt_embed");
+  k_gnt_qinit<<<grid_n(NB, 256, 16), 256, 0, st>>>(NB, V, F, ck(0, 0));
+  NFB_CHECK_LAUNCH("k_gnt_qinit");
+  for (int i = 0; i < depth; ++i) {
+    const float* lp = params + G_HEAD + (size_t)i * L_SIZE;
+    k_gnt_view_attn<<<grid_n(N, 128, 3), 128, sm_view, st>>>(N, V, F, ray_diff, mask, lp, ck(i, 0), ck(i, 1));
+    NFB_CHECK_LAUNCH("k_gnt_view_attn");
+    k_gnt_ffn<<<ffn_grid, 256, sm_ffn, st>>>(N, lp + L_V_LN2_W, ck(i, 1), ck(i, 2));
+    NFB_CHECK_LAUNCH("k_gnt_ffn<view>");
+    const float* qd = ck(i, 2);
+    if ((i & 1) == 0) {
+      k_gnt_qfc<<<grid_n(N, 128, 3), 128, sm_qfc, st>>>(N, S, pts, ray_d, lp, ck(i, 2), ck(i, 3));
+      NFB_CHECK_LAUNCH("k_gnt_qfc");
+      qd = ck(i, 3);
+    }
+    k_gnt_ray_attn<<<ray_grid, ray_block * rpc, sm_ray, st>>>(R, S, rpc, lp, qd, ck(i, 4), nullptr, 3);
+    NFB_CHECK_LAUNCH("k_gnt_ray_attn");
+    k_gnt_ffn<<<ffn_grid, 256, sm_ffn, st>>>(N, lp + L_R_LN2_W, ck(i, 4), ck(i, 5));
+    NFB_CHECK_LAUNCH("k_gnt_ffn<ray>");
+  }
   return NFB_OK;
 }

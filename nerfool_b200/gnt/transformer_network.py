@@ -2,7 +2,9 @@
 
 An ``nn.Module`` with the reference's parameter names, shapes and construction order (checkpoints load strictly, the
 same torch seed gives the same initial weights) whose ``forward`` runs ``nfb_gnt_fwd``.  The sub-modules are parameter
-containers; their ``forward`` is never called.  Forward only: asking for a gradient raises (no silent fallback)."""
+containers; their ``forward`` is never called.  Differentiable w.r.t. its sampled inputs ``rgb_feat`` and ``ray_diff``
+(``nfb_gnt_bwd``: what eval/gnt/eval_adv.py:282-545 back-propagates to the perturbation and, with ``--perturb_camera``, to the
+source poses); parameter gradients (training) are not built and asking for them raises (no silent fallback)."""
 from __future__ import annotations
 
 import ctypes
@@ -91,6 +93,51 @@ def pack_params(tensors: dict, depth: int, device=None) -> torch.Tensor:
     return blob
 
 
+# rays per nfb_gnt_bwd call: the backward's workspace (checkpoints + per-row buffers) is ~ 0.9 MB per ray at S = 64, V = 8, depth 4
+BWD_WORKSPACE_GIB = float(__import__('os').environ.get('NFB_GNT_BWD_WS_GIB', '24'))
+
+
+class _GNTFn(torch.autograd.Function):
+    """out = nfb_gnt_fwd(...);  backward = nfb_gnt_bwd in ray chunks (rays are independent)."""
+
+    @staticmethod
+    def forward(ctx, rgb_feat, ray_diff, mask, pts, ray_d, blob, depth, ret_alpha):
+        rf, rd, mk, pt, dd = f32c(rgb_feat.detach()), f32c(ray_diff.detach()), f32c(mask.detach()), f32c(pts.detach()), f32c(ray_d.detach())
+        R, S, V = rf.shape[:3]
+        dev = rf.device
+        out = torch.empty(R, 3 + S if ret_alpha else 3, device=dev, dtype=torch.float32)
+        nbytes = int(_lib.load().nfb_gnt_workspace_bytes(R, S, V))
+        ws = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            call('nfb_gnt_fwd', R, S, V, depth, int(bool(ret_alpha)), ptr(rf), ptr(rd), ptr(mk), ptr(pt), ptr(dd),
+                 ptr(blob), ptr(out), ptr(ws), ctypes.c_size_t(nbytes), _lib.precision_code(), stream_ptr(dev))
+        ctx.save_for_backward(rf, rd, mk, pt, dd, blob)
+        ctx.meta = (depth, bool(ret_alpha), ray_diff.requires_grad)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        rf, rd, mk, pt, dd, blob = ctx.saved_tensors
+        depth, ret_alpha, want_rd = ctx.meta
+        R, S, V = rf.shape[:3]
+        dev = rf.device
+        g = f32c(d_out)
+        d_rf = torch.empty_like(rf)
+        d_rd = torch.empty_like(rd) if want_rd else None
+        lib = _lib.load()
+        per_ray = max(int(lib.nfb_gnt_bwd_workspace_bytes(1, S, V, depth)), 1)
+        chunk = max(1, min(R, int(BWD_WORKSPACE_GIB * 2 ** 30) // per_ray, (2 ** 31 - 1) // (S * V)))
+        nbytes = int(lib.nfb_gnt_bwd_workspace_bytes(min(chunk, max(R, 1)), S, V, depth))
+        ws = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            for r0 in range(0, R, chunk):
+                r1 = min(R, r0 + chunk)
+                call('nfb_gnt_bwd', r1 - r0, S, V, depth, int(ret_alpha), ptr(rf[r0:r1]), ptr(rd[r0:r1]), ptr(mk[r0:r1]), ptr(pt[r0:r1]),
+                     ptr(dd[r0:r1]), ptr(blob), ptr(g[r0:r1]), ptr(d_rf[r0:r1]), ptr(d_rd[r0:r1]) if want_rd else None,
+                     ptr(ws), ctypes.c_size_t(nbytes), stream_ptr(dev))
+        return d_rf, d_rd, None, None, None, None, None, None
+
+
 class GNT(nn.Module):
     def __init__(self, args, in_feat_ch=32, posenc_dim=3, viewenc_dim=3, ret_alpha=False):
         super().__init__()
@@ -137,20 +184,11 @@ class GNT(nn.Module):
         :return: [n_rays, 3] or, with ret_alpha, [n_rays, 3 + n_samples]
         """
         _lib.require_cuda(rgb_feat, ray_diff, mask, pts, ray_d)
-        if torch.is_grad_enabled() and (rgb_feat.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
-            raise NotImplementedError('nerfool_b200.gnt.GNT: only the forward (render) path is implemented in this round; '
-                                      'wrap the call in torch.no_grad() (gradients of the GNT path are listed as next in DESIGN.md)')
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError('nerfool_b200.gnt.GNT: parameter gradients (training) are not built; the data gradient '
+                                      '(rgb_feat, ray_diff) is -- freeze the parameters or call .eval()')
         if self.training:
             raise NotImplementedError('nerfool_b200.gnt.GNT runs in eval mode only (dropout is the identity); call .eval()')
         if rgb_feat.shape[-1] != 35:
             raise RuntimeError(f'GNT kernels are built for 35-channel rows, got {rgb_feat.shape[-1]}')
-        R, S, V = rgb_feat.shape[:3]
-        rf, rd, mk, pt, dd = f32c(rgb_feat.detach()), f32c(ray_diff.detach()), f32c(mask.detach()), f32c(pts.detach()), f32c(ray_d.detach())
-        dev = rf.device
-        out = torch.empty(R, 3 + S if self.ret_alpha else 3, device=dev, dtype=torch.float32)
-        nbytes = int(_lib.load().nfb_gnt_workspace_bytes(R, S, V))
-        ws = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
-        with torch.cuda.device(dev):
-            call('nfb_gnt_fwd', R, S, V, self.depth, int(bool(self.ret_alpha)), ptr(rf), ptr(rd), ptr(mk), ptr(pt), ptr(dd),
-                 ptr(self.param_blob()), ptr(out), ptr(ws), ctypes.c_size_t(nbytes), _lib.precision_code(), stream_ptr(dev))
-        return out
+        return _GNTFn.apply(rgb_feat, ray_diff, mask, pts, ray_d, self.param_blob(), self.depth, bool(self.ret_alpha))
