@@ -898,6 +898,32 @@ def run_gnt(a):
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    # GNT attack step (eval/gnt/eval_adv.py:282-545 below the encoder): render N_rand rays -> MSE -> backward to the feature maps
+    attack = None
+    if world == 1 and not a.no_nrand:
+        attack = {}
+        for nr in (512, 4096):
+            idx = torch.arange(0, R, max(R // nr, 1), device=device)[:nr]
+            b = dict(static)
+            b['ray_o'], b['ray_d'] = resident['ray_o'][idx].contiguous(), resident['ray_d'][idx].contiguous()
+            tgt = torch.rand(idx.numel(), 3, device=device)
+            fm = [f.clone().requires_grad_(True) for f in featmaps]
+
+            def astep():
+                out = gnt_render_rays(b, model, fm, projector, GNT_SAMPLES, inv_uniform=True, N_importance=0, det=True,
+                                      ret_alpha=True, single_net=True)
+                loss = ((out['outputs_coarse']['rgb'] - tgt) ** 2).mean()
+                return torch.autograd.grad(loss, fm[0])[0]
+            astep(); astep()
+            torch.cuda.synchronize()
+            ms = _event_time(astep, 5)
+            _lib.profile_start()
+            astep()
+            torch.cuda.synchronize()
+            kp = {k: sum(v) for k, v in _lib.profile_stop().items()}
+            attack[f'N_rand_{nr}'] = {'ms_per_iter': ms, 'iters_per_s': 1e3 / ms, 'rays_per_s': idx.numel() / (ms * 1e-3), 'kernel_ms': kp}
+        attack['note'] = ('hot path only (no encoder): gnt.render_rays -> MSE -> d featmaps; nfb_gnt_bwd = fp32 checkpointing forward + '
+                          'block-wise reverse sweep on the CUDA cores (ReLU masks of the fp32 forward), scatter by nfb_project_gather_bwd')
     t = torch.tensor([total_ms, e2e_ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -931,7 +957,7 @@ def run_gnt(a):
                             'traffic': None, 'avg_launch_ms': net_ms / max(n_calls / a.steps, 1),
                             'note': 'algorithmic FLOPs = SURVEY.md Appendix B formula (101 MFLOP/ray at depth 4, S 64, V 8), useful FLOPs only '
                                     '(not the 3x of the split passes); the unfused linear kernels are HBM-bound (rows in / out per layer)'},
-               'kernel_ms_per_step': ktot,
+               'kernel_ms_per_step': ktot, 'attack_step': attack,
                'e2e': {'value': R * world / (e2e_ms / a.steps * 1e-3), 'unit': 'rays/s',
                        'h2d_bytes_per_step': sum(v.numel() * v.element_size() for v in host.values()), 'd2h_bytes_per_step': 4,
                        'ms_per_step': e2e_ms / a.steps},

@@ -1,2 +1,2 @@
-"""``from gnt.projection import Projector`` -> nerfool_b200 (gnt/projection.py equals ibrnet/projection.py up to formatting)."""
-from nerfool_b200.projection import Projector  # noqa: F401
+"""``from gnt.projection import Projector`` -> nerfool_b200 (gnt/projection.py: the source cameras stay differentiable)."""
+from nerfool_b200.gnt.projection import Projector  # noqa: F401

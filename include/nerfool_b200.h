@@ -88,6 +88,13 @@ int nfb_project_gather_bwd(int N, int S, int V, int H, int W, int fh, int fw,
                            const float* xyz, const float* ray_o, const float* ray_d, const float* z,
                            const float* cam, const float* d_rgb_feat, float* d_feat, float* d_imgs,
                            void* stream);
+/* grid_sampler_2d backward w.r.t. the sampling grid: d_grid[N][V][2] = d loss / d (normalised x, y) of both gathers.
+ * gnt/projection.py:84-132 keeps the source cameras in the graph (eval/gnt/eval_adv.py:749-869, --perturb_camera); the chain
+ * from the grid to the camera vectors is host-side torch (nerfool_b200/ops.py: ProjectGatherCam).                          */
+int nfb_project_grid_bwd(int N, int S, int V, int H, int W, int fh, int fw,
+                         const float* xyz, const float* ray_o, const float* ray_d, const float* z,
+                         const float* cam, const float* imgs, const float* feat, const float* d_rgb_feat,
+                         float* d_grid, void* stream);
 
 /* ---- IBRNet.forward  (mlp_network.py:222-274) --------------------------------------------------------
  * Two kernels: the view stage (per (sample,view) rows: ray_dir_fc, pooling, base_fc, vis_fc, vis_fc2,

@@ -22,6 +22,7 @@ _SIGNATURES = {
     'nfb_coarse_depths': [_I, _I, c_float, c_float, _I, _P, _P, _P],
     'nfb_project_gather_fwd': [_I] * 7 + [_P] * 11,
     'nfb_project_gather_bwd': [_I] * 7 + [_P] * 9,
+    'nfb_project_grid_bwd': [_I] * 7 + [_P] * 10,
     'nfb_ibrnet_view_fwd': [_I] * 4 + [_P] * 3 + [_I] * 4 + [_P] * 10 + [_I, _P],
     'nfb_ibrnet_ray_fwd': [_I, _I, _P, _P, _P, _P, _P, _P, _I, _P],
     'nfb_ibrnet_ray_bwd': [_I, _I, _P, _P, _P, _P, _P, _P, _I, _P],

@@ -183,6 +183,76 @@ extern "C" int nfb_project_gather_bwd(int N, int S, int V, int H, int W, int fh,
   return NFB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// grid_sampler_2d backward w.r.t. the GRID, per (point, view) row: d loss / d (gx, gy) of both bilinear gathers.
+// gnt/projection.py:84-132 does not detach the source cameras, so eval/gnt/eval_adv.py --perturb_camera differentiates the
+// sampling positions; the chain from (gx, gy) to the 34-float camera vectors is a handful of torch ops on the host side
+// (ops.ProjectGatherCam).  Same tap set / weights as the forward (ATen: t = x - floor(x), zero padding per tap).
+// ---------------------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void grid_grad_accum(float gx, float gy, int w, int h, const float* __restrict__ base /*[h][w][C]*/,
+                                                const float* __restrict__ g /*[C]*/, float& dgx, float& dgy) {
+  const float ix = __fmul_rn(__fadd_rn(gx, 1.f), 0.5f * (float)(w - 1));
+  const float iy = __fmul_rn(__fadd_rn(gy, 1.f), 0.5f * (float)(h - 1));
+  const float fx = floorf(ix), fy = floorf(iy);
+  const float tw = ix - fx, te = 1.f - tw, tn = iy - fy, ts = 1.f - tn;
+  const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+  const bool xw = (x0 >= 0) && (x0 < w), xe = (x1 >= 0) && (x1 < w);
+  const bool yn = (y0 >= 0) && (y0 < h), ys = (y1 >= 0) && (y1 < h);
+  const float* pnw = (xw && yn) ? base + ((size_t)y0 * w + x0) * C : nullptr;
+  const float* pne = (xe && yn) ? base + ((size_t)y0 * w + x1) * C : nullptr;
+  const float* psw = (xw && ys) ? base + ((size_t)y1 * w + x0) * C : nullptr;
+  const float* pse = (xe && ys) ? base + ((size_t)y1 * w + x1) * C : nullptr;
+  float ax = 0.f, ay = 0.f;
+#pragma unroll 4
+  for (int c = 0; c < C; ++c) {
+    const float nw = pnw ? __ldg(pnw + c) : 0.f, ne = pne ? __ldg(pne + c) : 0.f;
+    const float sw = psw ? __ldg(psw + c) : 0.f, se = pse ? __ldg(pse + c) : 0.f;
+    ax = fmaf(g[c], ts * (ne - nw) + tn * (se - sw), ax);
+    ay = fmaf(g[c], te * (sw - nw) + tw * (se - ne), ay);
+  }
+  dgx = fmaf(ax, 0.5f * (float)(w - 1), dgx);
+  dgy = fmaf(ay, 0.5f * (float)(h - 1), dgy);
+}
+
+__global__ void __launch_bounds__(128)
+k_project_grid_bwd(int N, int V, int H, int W, int fh, int fw, PointSrc psrc, const float* __restrict__ cam,
+                   const float* __restrict__ imgs, const float* __restrict__ feat, const float* __restrict__ d_rgb_feat,
+                   float* __restrict__ d_grid) {
+  __shared__ float s_cam[16 * NFB_MAX_VIEWS + 4];
+  for (int i = threadIdx.x; i < 16 * V + 3; i += blockDim.x) s_cam[i] = cam[i];
+  __syncthreads();
+  const float Wm1 = (float)W - 1.f, Hm1 = (float)H - 1.f;
+  const size_t total = (size_t)N * V;
+  for (size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x; row < total; row += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(row / V), v = (int)(row % V);
+    float x, y, z;
+    load_point(psrc, p, x, y, z);
+    const ViewGeom g = view_geometry(x, y, z, s_cam + 16 * v, s_cam + 16 * V, Wm1, Hm1);
+    const float* gr = d_rgb_feat + row * NFB_ROW_CH;
+    float dgx = 0.f, dgy = 0.f;
+    grid_grad_accum<3>(g.gx, g.gy, W, H, imgs + (size_t)v * H * W * 3, gr, dgx, dgy);
+    grid_grad_accum<NFB_FEAT_CH>(g.gx, g.gy, fw, fh, feat + (size_t)v * fh * fw * NFB_FEAT_CH, gr + 3, dgx, dgy);
+    d_grid[row * 2] = dgx;
+    d_grid[row * 2 + 1] = dgy;
+  }
+}
+
+extern "C" int nfb_project_grid_bwd(int N, int S, int V, int H, int W, int fh, int fw,
+                                    const float* xyz, const float* ray_o, const float* ray_d, const float* z,
+                                    const float* cam, const float* imgs, const float* feat, const float* d_rgb_feat,
+                                    float* d_grid, void* stream) {
+  int rc = check_geometry_args("nfb_project_grid_bwd", N, S, V, H, W, fh, fw, xyz, ray_o, ray_d, z, cam);
+  if (rc) return rc;
+  if (N == 0) return NFB_OK;
+  NFB_REQUIRE(imgs && feat && d_rgb_feat && d_grid, NFB_EINVAL, "nfb_project_grid_bwd: NULL buffer");
+  PointSrc ps{xyz, ray_o, ray_d, z, S};
+  k_project_grid_bwd<<<tiles_grid((size_t)N * V, 128, 16), 128, 0, (cudaStream_t)stream>>>(N, V, H, W, fh, fw, ps, cam, imgs, feat,
+                                                                                        d_rgb_feat, d_grid);
+  NFB_CHECK_LAUNCH("k_project_grid_bwd");
+  return NFB_OK;
+}
+
 // =====================================================================================================
 // raw2outputs (render_ray.py:123-170): one warp per ray, lanes stride the samples (coalesced), the
 // transmittance is a warp scan.  The running product is kept in fp64 like torch's CPU cumprod.

@@ -144,6 +144,83 @@ class ProjectGather(torch.autograd.Function):
         return (None, d_imgs, d_feat.permute(0, 3, 1, 2) if need_feat else None, None, None, None)
 
 
+class ProjectGatherCam(torch.autograd.Function):
+    """Projector.compute with the source cameras in the graph (gnt/projection.py:84-132 does not detach them; eval/gnt/eval_adv.py
+    --perturb_camera optimises source rotations / translations): rgb_feat, ray_diff, mask = f(xyz, imgs, featmaps, train_cameras
+    [V,34], query_camera [34]).  Forward = the same kernel as ProjectGather.  Backward: d featmaps / d imgs by the scatter kernel;
+    d train_cameras = the grid gradient of both gathers (``nfb_project_grid_bwd``) and the incoming d ray_diff chained through the
+    reference's own camera arithmetic (projection.py:42-87: K inverse(c2w), perspective divide, clamps, unit-vector differences)
+    replayed with torch autograd -- 34 floats per view, not on the hot path."""
+
+    @staticmethod
+    def forward(ctx, xyz, imgs, featmaps, train_cameras, query_camera, H, W):
+        _lib.require_cuda(xyz, imgs, featmaps)
+        cam = camera_block(train_cameras, query_camera, xyz.device, H, W)
+        xyz_c, imgs_c, feat = f32c(xyz), f32c(imgs), channels_last_feat(featmaps)
+        R, S = xyz.shape[:2]
+        V, fh, fw = feat.shape[0], feat.shape[1], feat.shape[2]
+        N, dev = R * S, xyz.device
+        rgb_feat = torch.empty(R, S, V, ROW_CH, device=dev, dtype=torch.float32)
+        ray_diff = torch.empty(R, S, V, 4, device=dev, dtype=torch.float32)
+        mask = torch.empty(R, S, V, 1, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            call('nfb_project_gather_fwd', N, S, V, H, W, fh, fw, ptr(xyz_c), None, None, None, ptr(cam),
+                 ptr(imgs_c), ptr(feat), ptr(rgb_feat), ptr(ray_diff), ptr(mask), stream_ptr(dev))
+        ctx.save_for_backward(xyz_c, cam, imgs_c, feat, train_cameras.detach(), query_camera.detach())
+        ctx.dims = (N, S, V, H, W, fh, fw)
+        ctx.imgs_shape = imgs.shape
+        ctx.mark_non_differentiable(mask)
+        return rgb_feat, ray_diff, mask
+
+    @staticmethod
+    def backward(ctx, d_rgb_feat, d_ray_diff, _d_mask):
+        xyz_c, cam, imgs_c, feat, cams, qcam = ctx.saved_tensors
+        N, S, V, H, W, fh, fw = ctx.dims
+        dev = xyz_c.device
+        need_imgs, need_feat, need_cam = ctx.needs_input_grad[1], ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        d_feat = torch.zeros(V, fh, fw, FEAT_CH, device=dev, dtype=torch.float32) if need_feat else None
+        d_imgs = torch.zeros(ctx.imgs_shape, device=dev, dtype=torch.float32) if need_imgs else None
+        g = f32c(d_rgb_feat) if d_rgb_feat is not None else None
+        if g is not None and (need_feat or need_imgs):
+            with torch.cuda.device(dev):
+                call('nfb_project_gather_bwd', N, S, V, H, W, fh, fw, ptr(xyz_c), None, None, None, ptr(cam),
+                     ptr(g), ptr(d_feat), ptr(d_imgs), stream_ptr(dev))
+        d_cams = None
+        if need_cam:
+            outs, cots = [], []
+            with torch.enable_grad():
+                c = cams.to(dev).float().requires_grad_(True)
+                flat = xyz_c.reshape(-1, 3)
+                c2w = c[:, -16:].reshape(-1, 4, 4)
+                if g is not None:
+                    d_grid = torch.empty(N, V, 2, device=dev, dtype=torch.float32)
+                    with torch.cuda.device(dev):
+                        call('nfb_project_grid_bwd', N, S, V, H, W, fh, fw, ptr(xyz_c), None, None, None, ptr(cam),
+                             ptr(imgs_c), ptr(feat), ptr(g), ptr(d_grid), stream_ptr(dev))
+                    P = c[:, 2:18].reshape(-1, 4, 4).bmm(torch.inverse(c2w))
+                    homog = torch.cat([flat, torch.ones_like(flat[:, :1])], dim=-1)
+                    proj = P.bmm(homog.t()[None].repeat(V, 1, 1)).permute(0, 2, 1)                     # [V,N,4]
+                    pix = torch.clamp(proj[..., :2] / torch.clamp(proj[..., 2:3], min=1e-8), min=-1e6, max=1e6)
+                    grid = 2 * pix / torch.tensor([W - 1., H - 1.], device=dev)[None, None, :] - 1.
+                    outs.append(grid)
+                    cots.append(d_grid.permute(1, 0, 2))
+                if d_ray_diff is not None:
+                    tgt = qcam.to(dev).float()[-16:].reshape(4, 4)[:3, 3]
+                    a = tgt[None, None, :] - flat[None]
+                    a = a / (torch.norm(a, dim=-1, keepdim=True) + 1e-6)
+                    b = c2w[:, :3, 3].unsqueeze(1) - flat[None]
+                    b = b / (torch.norm(b, dim=-1, keepdim=True) + 1e-6)
+                    d = a - b
+                    rd = torch.cat([d / torch.clamp(torch.norm(d, dim=-1, keepdim=True), min=1e-6), torch.sum(a * b, dim=-1, keepdim=True)], dim=-1)
+                    outs.append(rd)                                                                     # [V,N,4]
+                    cots.append(f32c(d_ray_diff).reshape(N, V, 4).permute(1, 0, 2))
+                if outs:
+                    (d_cams,) = torch.autograd.grad(outs, c, cots)
+            if d_cams is not None:
+                d_cams = d_cams.to(cams.device)
+        return (None, d_imgs, d_feat.permute(0, 3, 1, 2) if need_feat else None, d_cams, None, None, None)
+
+
 # --------------------------------------------------------------------------------------------------
 # IBRNet.forward
 # --------------------------------------------------------------------------------------------------

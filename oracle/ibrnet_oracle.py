@@ -99,12 +99,13 @@ def view_angle_features(xyz: torch.Tensor, tgt_cam: torch.Tensor, src_cams: torc
     return out.reshape(V, *lead, 4)
 
 
-def projector_compute(xyz, query_camera, train_imgs, train_cameras, featmaps):
-    """projection.py:89-132.  Same argument shapes as ``Projector.compute``:
+def projector_compute(xyz, query_camera, train_imgs, train_cameras, featmaps, detach_cameras=True):
+    """projection.py:89-132 (``detach_cameras=False``: gnt/projection.py:84-132, which keeps the source cameras in the
+    graph).  Same argument shapes as ``Projector.compute``:
     xyz [R,S,3]; query_camera [1,34]; train_imgs [1,V,H,W,3]; train_cameras [1,V,34]; featmaps [V,C,h',w'].
     Returns rgb_feat [R,S,V,3+C], ray_diff [R,S,V,4], mask [R,S,V,1]."""
     assert train_imgs.shape[0] == 1 and train_cameras.shape[0] == 1 and query_camera.shape[0] == 1
-    cams = train_cameras.detach()[0]
+    cams = (train_cameras.detach() if detach_cameras else train_cameras)[0]
     imgs = train_imgs[0].permute(0, 3, 1, 2)                                   # [V,3,H,W]
     tgt = query_camera[0]
     h, w = cams[0][:2]

@@ -38,7 +38,8 @@ def setup_paths(kind: str = 'ibrnet') -> str:
     for name in list(sys.modules):
         if name.split('.')[0] in _GENERIC:
             del sys.modules[name]
-    want = [os.path.join(REPO, 'tests', 'stubs'), os.path.join(REPO, 'dropin'), REPO, root, os.path.join(root, 'eval', kind)]
+    # the driver's own directory first, as when it is run from there (eval/gnt/ holds the GNT path's own config.py / train.py / utils.py)
+    want = [os.path.join(REPO, 'tests', 'stubs'), os.path.join(REPO, 'dropin'), REPO, os.path.join(root, 'eval', kind), root]
     sys.path[:] = want + [p for p in sys.path if p not in want]
     importlib.invalidate_caches()
     return root
@@ -68,7 +69,8 @@ class SyntheticSceneDataset(torch.utils.data.Dataset):
 
 def register_dataset(name: str = 'synthetic_b200', **shape):
     """Add the synthetic dataset to the reference's own ``dataset_dict`` (ibrnet/data_loaders/__init__.py:28-37)."""
-    from ibrnet.data_loaders import dataset_dict
+    kind = shape.pop('kind', 'ibrnet')
+    dataset_dict = importlib.import_module(kind + '.data_loaders').dataset_dict
     cls = type('SyntheticSceneDataset_' + name, (SyntheticSceneDataset,), dict(shape))
     dataset_dict[name] = cls
     return cls
@@ -82,8 +84,8 @@ def parse_args(root: str, extra: list[str], config: str = 'configs/ibrnet/eval_l
     return parser.parse_args(argv)
 
 
-def seed_everything(seed: int = 0):
+def seed_everything(seed: int = 0, kind: str = 'ibrnet'):
     torch.manual_seed(seed)
     np.random.seed(seed)
-    from ibrnet import sample_ray
+    sample_ray = importlib.import_module(kind + '.sample_ray')
     sample_ray.rng.seed(234)          # the module-level RandomState(234) of sample_ray.py:20

@@ -23,9 +23,9 @@ needs_ref = pytest.mark.skipif(not RH.reference_available(), reason='no referenc
 
 
 @pytest.fixture()
-def ref_env(tmp_path):
+def ref_env(tmp_path, request):
     saved_path, saved_mods, saved_cwd = list(sys.path), dict(sys.modules), os.getcwd()
-    root = RH.setup_paths('ibrnet')
+    root = RH.setup_paths(getattr(request, 'param', 'ibrnet'))
     try:
         yield root, tmp_path
     finally:
@@ -243,3 +243,91 @@ def test_reference_train_loop_unmodified(ref_env, adv_train):
     moved = sum(float((p.detach() - q).abs().max()) > 0 for p, q in zip(model.net_coarse.parameters(), seen['params'][0]))
     assert moved > 30
     assert all(torch.isfinite(p).all() for p in model.net_coarse.parameters())
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GNT path: eval/gnt/eval_adv.py
+# ----------------------------------------------------------------------------------------------------------------------
+def _gnt_args(root, tmp_path, extra=()):
+    RH.register_dataset('synthetic_b200', kind='gnt')
+    return RH.parse_args(root, ['--expname', 'nfb_gnt_callers', '--rootdir', str(tmp_path), '--eval_dataset', 'synthetic_b200',
+                                '--train_dataset', 'synthetic_b200', '--num_source_views', '4', '--N_rand', '96', '--workers', '0',
+                                '--no_reload', '--chunk_size', '2048', '--ret_alpha', *extra], config='configs/gnt/gnt_llff.txt')
+
+
+@needs_ref
+@pytest.mark.parametrize('ref_env', ['gnt'], indirect=True)
+def test_reference_gnt_drivers_import_through_dropin(ref_env):
+    """CPU: eval/gnt/eval_adv.py imports unmodified (its own config.py / utils.py / train.py next to it), the hot-path names are
+    nerfool_b200's, GNTModel / ResUNet / RaySamplerSingleImage / Criterion the reference's."""
+    root, tmp = ref_env
+    import eval_adv as E
+    import gnt.model as M
+    from nerfool_b200.gnt import GNT, Projector, render_rays
+    assert os.path.samefile(E.__file__, os.path.join(root, 'eval', 'gnt', 'eval_adv.py'))
+    assert E.render_rays is render_rays and E.Projector is Projector and M.GNT is GNT
+    assert M.ResUNet.__module__ == 'gnt.feature_network' and E.GNTModel.__module__ == 'gnt.model' and E.Criterion.__module__ == 'gnt.criterion'
+    a = _gnt_args(root, tmp)
+    assert (a.N_samples, a.N_importance, a.single_net, a.trans_depth, a.netwidth, a.ret_alpha) == (64, 0, True, 4, 64, True)
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize('ref_env', ['gnt'], indirect=True)
+def test_reference_gnt_optimize_adv_perturb_unmodified(ref_env):
+    """eval/gnt/eval_adv.py:282-545 as shipped: RaySamplerSingleImage -> feature_net(src + delta) -> gnt render_rays (clean
+    src_ray_batch) -> Criterion -> torch.autograd.grad(loss, delta), the reference's GNTModel holding our GNT.  d delta against
+    autograd of the CPU oracle behind the same ResUNet on the inputs the driver passed to render_rays."""
+    root, tmp = ref_env
+    from oracle import ibrnet_oracle as O
+    from oracle import gnt_oracle as G
+    import eval_adv as E
+    from gnt.model import GNTModel
+    from gnt.sample_ray import RaySamplerSingleImage
+    from gnt.data_loaders import dataset_dict
+    from torch.utils.data import DataLoader
+    a = _gnt_args(root, tmp)
+    a.distributed, a.det, a.local_rank = False, True, 0
+    RH.seed_everything(0, kind='gnt')
+    saved_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                  # the oracle side runs the same ResUNet in fp32 (see the IBRNet test)
+    try:
+        model = GNTModel(a, load_scheduler=False, load_opt=False)
+        model.switch_to_eval()                               # eval_adv.py:959 (view-specific attack); dropout is the identity
+        projector = E.Projector(device='cuda:0')
+        data = next(iter(DataLoader(dataset_dict['synthetic_b200'](a, 'test', scenes=a.eval_scenes), batch_size=1)))
+        src_ray_batch = RaySamplerSingleImage(data, device='cuda:0').get_all()
+        epsilon = torch.tensor(a.epsilon / 255.).cuda()
+        delta = E.init_adv_perturb(a, src_ray_batch, epsilon, 1, 0)
+        calls = _capture(E)
+        crit = E.Criterion()
+        grad = E.optimize_adv_perturb(a, delta, model, projector, src_ray_batch, data, return_loss=False, criterion=crit)
+        assert grad.shape == delta.shape and torch.isfinite(grad).all() and float(grad.abs().max()) > 0 and len(calls) == 1
+        (_, kw) = calls[0]
+        rb = {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in kw['ray_batch'].items()}
+        srb = {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in kw['src_ray_batch'].items()}
+        assert torch.equal(srb['src_rgbs'], data['src_rgbs']), 'the reference renders with the CLEAN source colours'
+        p = _oracle_params(model.net_coarse)
+
+        def oracle_grad(dev, dtype):
+            enc = copy.deepcopy(model.feature_net).to(dev).to(dtype).eval()
+            c = lambda v: v.to(dev).to(dtype)
+            d_ = delta.detach().to(dev).to(dtype).clone().requires_grad_(True)
+            fm = enc((c(srb['src_rgbs']) + d_).squeeze(0).permute(0, 3, 1, 2))
+            pts, z = O.coarse_depths(c(rb['ray_o']), c(rb['ray_d']), c(rb['depth_range']), a.N_samples, inv_uniform=a.inv_uniform, det=True)
+            rf, rd, mk = O.projector_compute(pts, c(rb['camera']), c(srb['src_rgbs']), c(srb['src_cameras']), fm[0], detach_cameras=False)
+            out = G.gnt_forward({k: c(v) for k, v in p.items()}, a.trans_depth, rf, rd, mk, pts, c(rb['ray_d']), ret_alpha=True)
+            loss = torch.mean((out[:, :3] - c(rb['rgb'])) ** 2)            # utils.img2mse without a mask (gnt/criterion.py:14-21)
+            return torch.autograd.grad(loss, d_)[0].cpu()
+
+        def cosine(x, y):
+            return float(torch.dot(x.flatten().double(), y.flatten().double()) / (x.double().norm() * y.double().norm()))
+        g_gpu32, g_cpu32, g_cpu64 = oracle_grad('cuda:0', torch.float32), oracle_grad('cpu', torch.float32), oracle_grad('cpu', torch.float64)
+        ours = grad.cpu()
+        e_ours, e_gpu, e_cpu = relerr(ours, g_cpu64), relerr(g_gpu32, g_cpu64), relerr(g_cpu32, g_cpu64)
+        report(f'reference GNT optimize_adv_perturb through dropin: d delta vs fp64 truth: ours {e_ours:.2e}, eager fp32 oracle on the GPU {e_gpu:.2e}, '
+               f'fp32 oracle on the CPU {e_cpu:.2e}; ours vs eager-GPU oracle {relerr(ours, g_gpu32):.2e}; cosine to truth {cosine(ours, g_cpu64):.6f}')
+        assert e_ours <= max(1e-3, 3 * max(e_gpu, e_cpu)), (e_ours, e_gpu, e_cpu)
+        assert cosine(ours, g_cpu64) > 0.999
+    finally:
+        torch.backends.cudnn.allow_tf32 = saved_tf32
