@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libnerfool_b200.so')
+LIB_PATH = os.environ.get('NFB_LIB_PATH') or os.path.join(_HERE, 'libnerfool_b200.so')     # NFB_LIB_PATH: experiment builds (build.py)
 
 _P = c_void_p
 _I = c_int

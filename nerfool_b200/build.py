@@ -11,11 +11,14 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-OBJ = os.path.join(CSRC, 'build')
-LIB = os.path.join(HERE, 'libnerfool_b200.so')
+# experiment hooks: NFB_BUILD_TAG=<tag> builds csrc/build_<tag>/ -> libnerfool_b200_<tag>.so with NFB_EXTRA_DEFS (e.g. "-DNFB_VTC_NG=3");
+# NFB_LIB_PATH=<that .so> makes _lib.py load it.  The default build is untouched.
+_TAG = os.environ.get('NFB_BUILD_TAG', '')
+OBJ = os.path.join(CSRC, 'build' + ('_' + _TAG if _TAG else ''))
+LIB = os.path.join(HERE, 'libnerfool_b200' + ('_' + _TAG if _TAG else '') + '.so')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-Xptxas', '-v']
+              '-Xcompiler', '-fPIC', '-Xptxas', '-v'] + os.environ.get('NFB_EXTRA_DEFS', '').split()
 
 # (object name, source, extra defines)
 UNITS = [
@@ -93,8 +96,33 @@ def _sources_digest(src, extra):
     return h.hexdigest()
 
 
+_EXTRA = os.environ.get('NFB_EXTRA_DEFS', '').split()
+_BASE_FLAGS = [f for f in NVCC_FLAGS if f not in _EXTRA]
+
+
+def _affected(src):
+    """Does any -D macro of NFB_EXTRA_DEFS occur in the unit's sources?  (experiment builds reuse the default objects otherwise)"""
+    names = [d[2:].split('=')[0] for d in _EXTRA if d.startswith('-D')]
+    if not _TAG or not names or len(names) != len(_EXTRA):
+        return True
+    seen = set()
+    _deps(os.path.join(CSRC, src), seen)
+    for n in seen:
+        with open(n) as f:
+            text = f.read()
+        if any(nm in text for nm in names):
+            return True
+    return False
+
+
 def _compile(unit):
     name, src, defs = unit
+    if not _affected(src):
+        base = os.path.join(CSRC, 'build', name + '.o')
+        if os.path.exists(base):
+            import shutil
+            shutil.copyfile(base, os.path.join(OBJ, name + '.o'))
+            return name, 'reused', ''
     obj = os.path.join(OBJ, name + '.o')
     stamp = obj + '.sha'
     digest = _sources_digest(src, defs)
@@ -120,7 +148,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
                 os.remove(os.path.join(OBJ, f))
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
         results = list(ex.map(_compile, UNITS))
-    rebuilt = [n for n, st, _ in results if st == 'built']
+    rebuilt = [n for n, st, _ in results if st in ('built', 'reused')]
     if verbose:
         for n, st, _ in results:
             print(f'[nerfool_b200.build] {n}: {st}')

@@ -28,7 +28,11 @@ using namespace nfbtc;
 using nfbview::ViewArgs;
 
 constexpr int GROUP = 128;
-constexpr int NG = 4;
+#ifndef NFB_VTC_NG
+#define NFB_VTC_NG 4          // 128-row groups per CTA (4 x 128 TMEM columns = the whole TMEM of the SM)
+#endif
+constexpr int NG = NFB_VTC_NG;
+constexpr int TMEM_ALLOC = NG * 128 > 256 ? 512 : (NG * 128 > 128 ? 256 : 128);   // tcgen05.alloc takes powers of two
 constexpr int EXS = 37;      // exchange-buffer row stride (floats)
 constexpr int TS_MAX = 32;   // samples per tile cap (V < 4 leaves part of a 128-row tile idle)
 constexpr int MVS = 72;      // per-sample pooled statistics: mean0[35] at 0, var0[35] at 36
@@ -260,6 +264,34 @@ __device__ __forceinline__ void epi16_s(uint32_t tl, int col, const float* __res
   if (SAVE) epi16_code(tl, col, bias, y, q);
   else epi16(tl, col, bias, y);
 }
+// Two 16-column chunks with ONE tcgen05.wait::ld (the asm statements are volatile: two epi16 calls in a row serialise
+// load -> wait -> compute -> load -> wait; here both loads are in flight before the wait).  NFB_VTC_PAIR selects it.
+#ifndef NFB_VTC_PAIR
+#define NFB_VTC_PAIR 0
+#endif
+template <bool SAVE>
+__device__ __forceinline__ void epi16_pair(uint32_t tl, int col, const float* __restrict__ bias, float (&y0)[16], float (&y1)[16],
+                                           uint32_t (&q0)[8], uint32_t (&q1)[8]) {
+  tmem_ld16(tl + C_D + col, y0);
+  tmem_ld16(tl + C_D + col + 16, y1);
+  tmem_ld_wait();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float (&y)[16] = h ? y1 : y0;
+    uint32_t (&q)[8] = h ? q1 : q0;
+    const float* b_ = bias + 16 * h;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(b_ + j);
+      const float2 s0 = __fadd2_rn(make_float2(y[j + 0], y[j + 1]), make_float2(b.x, b.y));
+      const float2 s1 = __fadd2_rn(make_float2(y[j + 2], y[j + 3]), make_float2(b.z, b.w));
+      float2 r0, r1;
+      if (SAVE) { r0 = elu_code2(s0, q[j / 2]); r1 = elu_code2(s1, q[j / 2 + 1]); }
+      else { r0 = elu_fast2(s0); r1 = elu_fast2(s1); }
+      y[j + 0] = r0.x; y[j + 1] = r0.y; y[j + 2] = r1.x; y[j + 3] = r1.y;
+    }
+  }
+}
 __device__ __forceinline__ void st_plane(float4* sp, int plane, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   __stcs(sp + plane * GROUP, make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d)));   // streaming: written once, read once by the backward
 }
@@ -396,7 +428,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
   const int bar_id = 1 + grp;
   uint64_t* mbar = s_bar + grp;
 
-  if (warp == 0) tmem_alloc(s_tmem, NG * GC);
+  if (warp == 0) tmem_alloc(s_tmem, TMEM_ALLOC);
   if (tid == 0) {
     for (int g = 0; g < NG; ++g) mbar_init(s_bar + g, 1);
     mbar_init_fence();
@@ -614,6 +646,17 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
     }
 
     // ---------------- base_fc.2 (64 -> 32) ----------------
+#if NFB_VTC_PAIR
+#pragma unroll
+    for (int kc = 0; kc < 4; kc += 2) {
+      float h[16], h2[16];
+      uint32_t q[8], q2[8];
+      epi16_pair<SAVE>(tl, 16 * kc, sf + F_B_BASE0 + 16 * kc, h, h2, q, q2);
+      if (save) { st_codes8(sp, SP_H1 + 2 * kc, q); st_codes8(sp, SP_H1 + 2 * kc + 2, q2); }
+      a_store16<NPASS>(tl, kc, h);
+      a_store16<NPASS>(tl, kc + 1, h2);
+    }
+#else
 #pragma unroll
     for (int kc = 0; kc < 4; ++kc) {
       float h[16];
@@ -622,11 +665,27 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       if (save) st_codes8(sp, SP_H1 + 2 * kc, q);
       a_store16<NPASS>(tl, kc, h);
     }
+#endif
     NFB_TC_ISSUE(L_BASE2, 0, 4, false, 2);
     NFB_TC_WAIT();
 
     // ---------------- vis_fc (32 -> 32 -> 33) on x1 * w ----------------
     float x1[32];
+#if NFB_VTC_PAIR
+    {
+      float h[16], h2[16];
+      uint32_t q[8], q2[8];
+      epi16_pair<SAVE>(tl, 0, sf + F_B_BASE2, h, h2, q, q2);
+      if (save) { st_codes8(sp, SP_X1, q); st_codes8(sp, SP_X1 + 2, q2); }
+      float t[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { x1[j] = h[j]; t[j] = h[j] * w; }
+      a_store16<NPASS>(tl, 0, t);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { x1[16 + j] = h2[j]; t[j] = h2[j] * w; }
+      a_store16<NPASS>(tl, 1, t);
+    }
+#else
 #pragma unroll
     for (int kc = 0; kc < 2; ++kc) {
       float h[16];
@@ -641,8 +700,19 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       }
       a_store16<NPASS>(tl, kc, t);
     }
+#endif
     NFB_TC_ISSUE(L_VIS0, 0, 2, false, 1);
     NFB_TC_WAIT();
+#if NFB_VTC_PAIR
+    {
+      float h[16], h2[16];
+      uint32_t q[8], q2[8];
+      epi16_pair<SAVE>(tl, 0, sf + F_B_VIS0, h, h2, q, q2);
+      if (save) { st_codes8(sp, SP_HV, q); st_codes8(sp, SP_HV + 2, q2); }
+      a_store16<NPASS>(tl, 0, h);
+      a_store16<NPASS>(tl, 1, h2);
+    }
+#else
 #pragma unroll
     for (int kc = 0; kc < 2; ++kc) {
       float h[16];
@@ -651,6 +721,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       if (save) st_codes8(sp, SP_HV + 2 * kc, q);
       a_store16<NPASS>(tl, kc, h);
     }
+#endif
     NFB_TC_ISSUE(L_VIS2, 0, 2, false, 2);
     NFB_TC_WAIT();
 
@@ -689,6 +760,18 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
     float vis2, sg2;
     {
       float z = sf[F_B_VISB2];
+#if NFB_VTC_PAIR
+      {
+        float h[16], h2[16];
+        uint32_t q[8], q2[8];
+        epi16_pair<SAVE>(tl, 0, sf + F_B_VISB0, h, h2, q, q2);
+        if (save) { st_codes8(sp, SP_HV2, q); st_codes8(sp, SP_HV2 + 2, q2); }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z = fmaf(h[j], sf[F_W_VISB2 + j], z);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z = fmaf(h2[j], sf[F_W_VISB2 + 16 + j], z);
+      }
+#else
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
         float h[16];
@@ -698,6 +781,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) z = fmaf(h[j], sf[F_W_VISB2 + 16 * kc + j], z);
       }
+#endif
       sg2 = sigmoid_f(z);
       vis2 = sg2 * mk;
     }
@@ -787,7 +871,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
 
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(*s_tmem, NG * GC);
+  if (warp == 0) tmem_dealloc(*s_tmem, TMEM_ALLOC);
 }
 
 template <int NPASS, bool FUSED, bool SAVE = false>

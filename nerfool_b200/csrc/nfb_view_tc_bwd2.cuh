@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
   const int bar_id = 1 + grp;
   uint64_t* mbar = s_bar + grp;
 
-  if (warp == 0) tmem_alloc(s_tmem, NG * GC);
+  if (warp == 0) tmem_alloc(s_tmem, TMEM_ALLOC);
   if (tid == 0) {
     for (int g = 0; g < NG; ++g) mbar_init(s_bar + g, 1);
     mbar_init_fence();
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
 
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(*s_tmem, NG * GC);
+  if (warp == 0) tmem_dealloc(*s_tmem, TMEM_ALLOC);
 }
 
 template <int NPASS>
