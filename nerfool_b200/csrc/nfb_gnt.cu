@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(256) k_gnt_qinit(size_t n_elems, int V, const 
 
 __global__ void __launch_bounds__(128) k_gnt_view_attn(int N, int V, const float* __restrict__ F,
                                                         const float* __restrict__ ray_diff, const float* __restrict__ mask,
-                                                        const float* __restrict__ lp, const float* q_in, float* q) {
+                                                        const float* __restrict__ lp, const float* q_in, float* q,
+                                                        float* __restrict__ vp_out = nullptr, float* __restrict__ a8_out = nullptr) {
+  // vp_out / a8_out (nfb_gnt_bwd's checkpointing forward): per (sample, view) row v + pos [64] and ReLU(attn_fc.0(k - qq + pos)) [8]
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, nt = blockDim.x;
   load_vec_padded(sm + VS_LN_W, lp + L_V_LN1_W, D, D, t, nt);
@@ -129,6 +131,15 @@ __global__ void __launch_bounds__(128) k_gnt_view_attn(int N, int V, const float
       for (int c = 0; c < D; ++c) axpy_row<8>(a8, k[c] - qq[c] + pos[c], sm + VS_A0 + c * 8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) a8[j] = fmaxf(a8[j], 0.f);
+      if (vp_out) {
+        float vp[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) vp[c] = vv[c] + pos[c];
+        store_row64(vp_out + row * D, vp);
+        float4* o8 = reinterpret_cast<float4*>(a8_out + row * 8);
+        o8[0] = make_float4(a8[0], a8[1], a8[2], a8[3]);
+        o8[1] = make_float4(a8[4], a8[5], a8[6], a8[7]);
+      }
       const bool valid = __ldg(mask + row) != 0.f;
       float a[D];
       load_bias<D>(a, sm + VS_A2_B);
@@ -732,7 +743,8 @@ extern "C" int nfb_gnt_fwd(int R, int S, int V, int depth, int ret_alpha, const 
 
 // fp32 forward with checkpoints (the first half of nfb_gnt_bwd, nfb_gnt_bwd.cu)
 int nfbgnt::gnt_forward_checkpoints(int R, int S, int V, int depth, const float* rgb_feat, const float* ray_diff, const float* mask,
-                                    const float* pts, const float* ray_d, const float* params, float* F, float* CK, cudaStream_t st) {
+                                    const float* pts, const float* ray_d, const float* params, float* F, float* CK, float* VPA,
+                                    cudaStream_t st) {
   const int N = R * S;
   const size_t rows = (size_t)N * V, NB = (size_t)N * D;
   auto ck = [&](int i, int j) { return CK + NB * (size_t)(5 * i + j); };
@@ -764,7 +776,8 @@ int nfbgnt::gnt_forward_checkpoints(int R, int S, int V, int depth, const float*
   NFB_CHECK_LAUNCH("k_gnt_qinit");
   for (int i = 0; i < depth; ++i) {
     const float* lp = params + G_HEAD + (size_t)i * L_SIZE;
-    k_gnt_view_attn<<<grid_n(N, 128, 3), 128, sm_view, st>>>(N, V, F, ray_diff, mask, lp, ck(i, 0), ck(i, 1));
+    float* vp_i = VPA + (size_t)i * rows * (D + 8);           // layer i: VP [rows][64] then A8 [rows][8]
+    k_gnt_view_attn<<<grid_n(N, 128, 3), 128, sm_view, st>>>(N, V, F, ray_diff, mask, lp, ck(i, 0), ck(i, 1), vp_i, vp_i + rows * D);
     NFB_CHECK_LAUNCH("k_gnt_view_attn");
     k_gnt_ffn<<<ffn_grid, 256, sm_ffn, st>>>(N, lp + L_V_LN2_W, ck(i, 1), ck(i, 2));
     NFB_CHECK_LAUNCH("k_gnt_ffn<view>");

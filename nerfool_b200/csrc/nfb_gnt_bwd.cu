@@ -18,10 +18,10 @@ int set_smem(K kern, size_t bytes, const char* name) {
 // data gradient (nfb_gnt_bwd.cuh)
 // ---------------------------------------------------------------------------------------------------
 extern "C" size_t nfb_gnt_bwd_workspace_bytes(int R, int S, int V, int depth) {
-  // F, dF, VP [rows][64], A8 [rows][8]  |  5 * depth + 1 checkpoints, dq and seven per-sample buffers [N][64]
+  // F, dF [rows][64], per layer VP [rows][64] + A8 [rows][8]  |  5 * depth + 1 checkpoints, dq and seven per-sample buffers [N][64]
   if (R <= 0 || S < 1 || V < 1 || depth < 1) return 0;
   const size_t N = (size_t)R * S, rows = N * V;
-  return (rows * (3 * D + 8) + N * D * (size_t)(5 * depth + 1 + 1 + 7)) * sizeof(float);
+  return (rows * (2 * D + (size_t)depth * (D + 8)) + N * D * (size_t)(5 * depth + 1 + 1 + 7)) * sizeof(float);
 }
 
 extern "C" int nfb_gnt_bwd(int R, int S, int V, int depth, int ret_alpha, const float* rgb_feat, const float* ray_diff,
@@ -42,9 +42,8 @@ extern "C" int nfb_gnt_bwd(int R, int S, int V, int depth, int ret_alpha, const 
   const size_t rows = (size_t)N * V, NB = (size_t)N * D;
   float* F = reinterpret_cast<float*>(workspace);
   float* dF = F + rows * D;
-  float* VP = dF + rows * D;
-  float* A8 = VP + rows * D;
-  float* CK = A8 + rows * 8;
+  float* VPA = dF + rows * D;                     // depth x { VP [rows][64], A8 [rows][8] }, written by the checkpointing forward
+  float* CK = VPA + (size_t)depth * rows * (D + 8);
   float* dq = CK + NB * (size_t)(5 * depth + 1);
   float* B = dq + NB;                              // B[0..6]
   auto ck = [&](int i, int j) { return CK + NB * (size_t)(5 * i + j); };
@@ -55,7 +54,7 @@ extern "C" int nfb_gnt_bwd(int R, int S, int V, int depth, int ret_alpha, const 
 
   const int ray_block = ((S + 31) / 32) * 32;
   const size_t sm_proj = (size_t)(2 * D + 4 * D * D) * sizeof(float), sm_post = (size_t)(D + 3 * D * D) * sizeof(float),
-               sm_vrow = (size_t)VS_TOTAL * sizeof(float), sm_vbwd = (size_t)VB_TOTAL * sizeof(float),
+               sm_vbwd = (size_t)VB_TOTAL * sizeof(float),
                sm_qb = (size_t)QB_TOTAL * sizeof(float), sm_eb = (size_t)EB_TOTAL * sizeof(float),
                sm_ffn = (size_t)(FS_B2 + 256 * D) * sizeof(float);     // k_gnt_ffn_bwd: weights + the per-thread dx columns
   int rpc_b = 256 / ray_block;
@@ -64,7 +63,6 @@ extern "C" int nfb_gnt_bwd(int R, int S, int V, int depth, int ret_alpha, const 
   if ((rc = set_smem(k_gnt_ffn_bwd, sm_ffn, "k_gnt_ffn_bwd"))) return rc;
   if ((rc = set_smem(k_gnt_proj, sm_proj, "k_gnt_proj"))) return rc;
   if ((rc = set_smem(k_gnt_post, sm_post, "k_gnt_post"))) return rc;
-  if ((rc = set_smem(k_gnt_view_row_fwd, sm_vrow, "k_gnt_view_row_fwd"))) return rc;
   if ((rc = set_smem(k_gnt_view_row_bwd, sm_vbwd, "k_gnt_view_row_bwd"))) return rc;
   if ((rc = set_smem(k_gnt_qfc_bwd, sm_qb, "k_gnt_qfc_bwd"))) return rc;
   if ((rc = set_smem(k_gnt_ray_core_bwd, sm_rcore, "k_gnt_ray_core_bwd"))) return rc;
@@ -79,7 +77,7 @@ extern "C" int nfb_gnt_bwd(int R, int S, int V, int depth, int ret_alpha, const 
   const int rcore_ctas = (R + rpc_b - 1) / rpc_b, rcore_grid = rcore_ctas < sms * 2 ? rcore_ctas : sms * 2;
 
   // ---------------- checkpointing forward (fp32 kernels of nfb_gnt.cu) ----------------
-  if ((rc = gnt_forward_checkpoints(R, S, V, depth, rgb_feat, ray_diff, mask, pts, ray_d, params, F, CK, st))) return rc;
+  if ((rc = gnt_forward_checkpoints(R, S, V, depth, rgb_feat, ray_diff, mask, pts, ray_d, params, F, CK, VPA, st))) return rc;
 
   // ---------------- reverse sweep ----------------
   cudaError_t e = cudaMemsetAsync(dF, 0, rows * D * sizeof(float), st);
@@ -118,12 +116,12 @@ extern "C" int nfb_gnt_bwd(int R, int S, int V, int depth, int ret_alpha, const 
     NFB_CHECK_LAUNCH("k_gnt_ffn_bwd<view>");
     {
       ProjArgs a{};
-      a.N = N; a.nw = 1; a.q_in = ck(i, 0); a.dy = dq; a.ln_w = lp + L_V_LN1_W; a.ln_b = lp + L_V_LN1_B;
-      a.w[0] = lp + L_V_Q; a.s0 = 1.f; a.wo = lp + L_V_O_W; a.y[0] = buf(0); a.g = buf(3);
+      a.N = N; a.nw = 0; a.q_in = ck(i, 0); a.dy = dq; a.ln_w = lp + L_V_LN1_W; a.ln_b = lp + L_V_LN1_B;     // only g = out_fc^T dq
+      a.s0 = 1.f; a.wo = lp + L_V_O_W; a.g = buf(3);
       k_gnt_proj<<<grid_n(N, 128, 3), 128, sm_proj, st>>>(a);
       NFB_CHECK_LAUNCH("k_gnt_proj<view>");
-      k_gnt_view_row_fwd<<<grid_n(rows, 128, 4), 128, sm_vrow, st>>>(rows, V, F, buf(0), ray_diff, lp, VP, A8);
-      NFB_CHECK_LAUNCH("k_gnt_view_row_fwd");
+      float* VP = VPA + (size_t)i * rows * (D + 8);           // this layer's rows, saved by the forward (consumed in place below)
+      float* A8 = VP + rows * D;
       k_gnt_view_core_bwd<<<grid_n((size_t)N * 2, 128, 8), 128, 0, st>>>(N, V, A8, VP, mask, buf(3), lp);
       NFB_CHECK_LAUNCH("k_gnt_view_core_bwd");
       k_gnt_view_row_bwd<<<grid_n(rows, 128, 4), 128, sm_vbwd, st>>>(rows, A8, VP, ray_diff, lp, dF, d_ray_diff);

@@ -9,7 +9,7 @@
 //      ReLUs, and a gradient is only comparable with the reference's if the ReLU masks are the reference's -- a
 //      pre-activation that differs by 1e-5 relative flips ~1e-5 of the masks, fp32 arithmetic ~1e-7.
 //   2. reverse sweep, every block re-computing its internals from its checkpoint with the SAME code as the forward
-//      (bit-identical masks):  head -> { FFN, ray attention, [q_fc], FFN, view attention } x depth -> max over views ->
+//      (bit-identical masks; the view attention's per-row products are saved by the forward instead, 288 B per row and layer):  head -> { FFN, ray attention, [q_fc], FFN, view attention } x depth -> max over views ->
 //      rgbfeat_fc.  One thread per sample (or per (sample, view) row), weights in shared memory, like the forward.
 //   The projected view features F are shared by all layers, so d F accumulates over the sweep (each row is owned by one
 //   thread: plain read-modify-write, no atomics).
@@ -233,69 +233,11 @@ __global__ void __launch_bounds__(128) k_gnt_post(PostArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// view attention, per (sample, view) row, forward re-computation in the arithmetic of k_gnt_view_attn:
-//   k = k_fc(F), v = v_fc(k), pos = pos_fc(ray_diff)  ->  VP = v + pos [64],  A8 = ReLU(attn_fc.0(k - qq + pos)) [8]
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_gnt_view_row_fwd(size_t rows, int V, const float* __restrict__ F, const float* __restrict__ QQ,
-                                                           const float* __restrict__ ray_diff, const float* __restrict__ lp,
-                                                           float* __restrict__ VP, float* __restrict__ A8) {
-  extern __shared__ __align__(16) float sm[];
-  const int t = threadIdx.x, nt = blockDim.x;
-  load_wt_transposed(sm + VS_K, lp + L_V_K, D, D, D, t, nt);
-  load_wt_transposed(sm + VS_V, lp + L_V_V, D, D, D, t, nt);
-  load_wt_transposed(sm + VS_P0, lp + L_V_POS0_W, 8, 4, 8, t, nt);
-  load_vec_padded(sm + VS_P0_B, lp + L_V_POS0_B, 8, 8, t, nt);
-  load_wt_transposed(sm + VS_P2, lp + L_V_POS2_W, D, 8, D, t, nt);
-  load_vec_padded(sm + VS_P2_B, lp + L_V_POS2_B, D, D, t, nt);
-  load_wt_transposed(sm + VS_A0, lp + L_V_AT0_W, 8, D, 8, t, nt);
-  load_vec_padded(sm + VS_A0_B, lp + L_V_AT0_B, 8, 8, t, nt);
-  __syncthreads();
-  for (size_t row = (size_t)blockIdx.x * blockDim.x + t; row < rows; row += (size_t)gridDim.x * blockDim.x) {
-    float k[D], vv[D], pos[D];
-    {
-      float f[D];
-      load_row64(F + row * D, f);
-#pragma unroll
-      for (int c = 0; c < D; ++c) k[c] = 0.f;
-      dense_acc<D, D>(sm + VS_K, f, k);
-    }
-#pragma unroll
-    for (int c = 0; c < D; ++c) vv[c] = 0.f;
-    dense_acc<D, D>(sm + VS_V, k, vv);
-    {
-      const float4 rd4 = __ldg(reinterpret_cast<const float4*>(ray_diff) + row);
-      const float rd[4] = {rd4.x, rd4.y, rd4.z, rd4.w};
-      float p8[8];
-      load_bias<8>(p8, sm + VS_P0_B);
-      dense_acc<4, 8>(sm + VS_P0, rd, p8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) p8[j] = fmaxf(p8[j], 0.f);
-      load_bias<D>(pos, sm + VS_P2_B);
-      dense_acc<8, D>(sm + VS_P2, p8, pos);
-    }
-    float a8[8];
-    load_bias<8>(a8, sm + VS_A0_B);
-    {
-      float qq[D];
-      load_row64(QQ + (row / V) * D, qq);
-#pragma unroll
-      for (int c = 0; c < D; ++c) axpy_row<8>(a8, k[c] - qq[c] + pos[c], sm + VS_A0 + c * 8);
-    }
-#pragma unroll
-    for (int c = 0; c < D; ++c) vv[c] += pos[c];
-    store_row64(VP + row * D, vv);
-    float4* o8 = reinterpret_cast<float4*>(A8 + row * 8);
-    o8[0] = make_float4(fmaxf(a8[0], 0.f), fmaxf(a8[1], 0.f), fmaxf(a8[2], 0.f), fmaxf(a8[3], 0.f));
-    o8[1] = make_float4(fmaxf(a8[4], 0.f), fmaxf(a8[5], 0.f), fmaxf(a8[6], 0.f), fmaxf(a8[7], 0.f));
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
 // view attention core backward.  Two adjacent lanes share a sample, each owns 32 of the 64 channels (as k_gnt_view_core).
 //   forward:  a_v = attn_fc.2(A8_v) (masked_fill -1e9), w_v = softmax_v(a_v) per channel, out = sum_v VP_v w_v
 //   backward: dVP_v = g w_v ;  d a_v = w_v g (VP_v - out)  (0 for a masked row: masked_fill blocks it) ;
 //             dA8_v = (attn_fc.2^T d a_v) . [A8_v > 0]          g = out_fc^T dy (from k_gnt_proj)
-// dVP / dA8 overwrite VP / A8 in place.
+// VP / A8 are the rows the checkpointing forward (k_gnt_view_attn) saved for this layer; dVP / dA8 overwrite them in place.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_gnt_view_core_bwd(int N, int V, float* __restrict__ A8, float* __restrict__ VP,
                                                             const float* __restrict__ mask, const float* __restrict__ G,
