@@ -331,3 +331,70 @@ def test_reference_gnt_optimize_adv_perturb_unmodified(ref_env):
         assert cosine(ours, g_cpu64) > 0.999
     finally:
         torch.backends.cudnn.allow_tf32 = saved_tf32
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize('ref_env', ['gnt'], indirect=True)
+def test_reference_gnt_perturb_camera_unmodified(ref_env):
+    """--perturb_camera (eval/gnt/eval_adv.py:749-869) as shipped: rot_param / trans_param -> transform_src_cameras -> src_cameras (in the
+    graph) -> optimize_adv_perturb(return_loss=True) -> loss.backward().  d rot_param, d trans_param and d delta against autograd of the CPU
+    oracle (gnt/projection.py semantics: cameras not detached) behind the same ResUNet and the driver's own transform_src_cameras."""
+    root, tmp = ref_env
+    from oracle import ibrnet_oracle as O
+    from oracle import gnt_oracle as G
+    import eval_adv as E
+    from gnt.model import GNTModel
+    from gnt.sample_ray import RaySamplerSingleImage
+    from gnt.data_loaders import dataset_dict
+    from torch.utils.data import DataLoader
+    a = _gnt_args(root, tmp, ['--perturb_camera'])
+    a.distributed, a.det, a.local_rank = False, True, 0
+    RH.seed_everything(0, kind='gnt')
+    saved_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        model = GNTModel(a, load_scheduler=False, load_opt=False)
+        model.switch_to_eval()
+        projector = E.Projector(device='cuda:0')
+        data = next(iter(DataLoader(dataset_dict['synthetic_b200'](a, 'test', scenes=a.eval_scenes), batch_size=1)))
+        src_ray_batch = RaySamplerSingleImage(data, device='cuda:0').get_all()
+        delta = E.init_adv_perturb(a, src_ray_batch, torch.tensor(a.epsilon / 255.).cuda(), 1, 0)
+        g = torch.Generator().manual_seed(3)
+        rot0 = (torch.rand(a.num_source_views, 3, generator=g) * 2 - 1) * (2.0 / 180 * np.pi)
+        trans0 = (torch.rand(a.num_source_views, 3, generator=g) * 2 - 1) * 0.02
+        rot_param, trans_param = rot0.clone().cuda().requires_grad_(True), trans0.clone().cuda().requires_grad_(True)
+        src_cameras_orig = src_ray_batch['src_cameras'].clone()
+        rot_trans = E.transform_src_cameras(src_cameras_orig, rot_param, trans_param, a.num_source_views).reshape(-1, 12)
+        src_ray_batch['src_cameras'] = torch.cat([src_cameras_orig[:, :, :-16], rot_trans.unsqueeze(0), src_cameras_orig[:, :, -4:]], dim=2)
+        calls = _capture(E)
+        loss, loss_dict = E.optimize_adv_perturb(a, delta, model, projector, src_ray_batch, data, return_loss=True, criterion=E.Criterion())
+        loss.backward()
+        assert rot_param.grad is not None and trans_param.grad is not None and delta.grad is not None
+        (_, kw) = calls[0]
+        rb = {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in kw['ray_batch'].items()}
+        p = _oracle_params(model.net_coarse)
+        src_rgbs, cams_orig = data['src_rgbs'], src_cameras_orig.detach().cpu()
+
+        def oracle_grads(dtype):
+            enc = copy.deepcopy(model.feature_net).cpu().to(dtype).eval()
+            c = lambda v: v.cpu().to(dtype)
+            d_ = delta.detach().cpu().to(dtype).clone().requires_grad_(True)
+            r_, t_ = rot0.to(dtype).clone().requires_grad_(True), trans0.to(dtype).clone().requires_grad_(True)
+            rt = E.transform_src_cameras(c(cams_orig), r_, t_, a.num_source_views).reshape(-1, 12)
+            cams = torch.cat([c(cams_orig)[:, :, :-16], rt.unsqueeze(0), c(cams_orig)[:, :, -4:]], dim=2)
+            fm = enc((c(src_rgbs) + d_).squeeze(0).permute(0, 3, 1, 2))
+            pts, z = O.coarse_depths(c(rb['ray_o']), c(rb['ray_d']), c(rb['depth_range']), a.N_samples, inv_uniform=a.inv_uniform, det=True)
+            rf, rd, mk = O.projector_compute(pts, c(rb['camera']), c(src_rgbs), cams, fm[0], detach_cameras=False)
+            out = G.gnt_forward({k: c(v) for k, v in p.items()}, a.trans_depth, rf, rd, mk, pts, c(rb['ray_d']), ret_alpha=True)
+            l = torch.mean((out[:, :3] - c(rb['rgb'])) ** 2)
+            return [x.cpu() for x in torch.autograd.grad(l, (r_, t_, d_))]
+
+        g32, g64 = oracle_grads(torch.float32), oracle_grads(torch.float64)
+        for name, ours, o32, o64 in (('d rot_param', rot_param.grad, g32[0], g64[0]), ('d trans_param', trans_param.grad, g32[1], g64[1]),
+                                     ('d delta', delta.grad, g32[2], g64[2])):
+            e_ours, e_ref = relerr(ours.cpu(), o64), relerr(o32, o64)
+            report(f'reference GNT --perturb_camera through dropin: {name} vs fp64 truth: ours {e_ours:.2e}, fp32 oracle on the CPU {e_ref:.2e}')
+            assert e_ours <= max(1e-3, 3 * e_ref), (name, e_ours, e_ref)
+    finally:
+        torch.backends.cudnn.allow_tf32 = saved_tf32
