@@ -24,6 +24,21 @@ int nfb_set_error(int code, const char* fmt, ...);
 
 int nfb_num_sms();
 
+// First use of the library's device code in a process: resolve a kernel through cudaFuncGetAttributes before the first <<<>>>
+// launch.  Launching first makes cudart probe cuKernelGetFunction on a module it has not loaded into the context yet; it
+// recovers, but compute-sanitizer reports the probe as "CUDA_ERROR_INVALID_HANDLE ... cuKernelGetFunction" (the one API error of
+// the round-1 memcheck log).  Used by the entry points that launch without a preceding cudaFuncSetAttribute.
+#define NFB_RESOLVE_ONCE(kernel, who)                                                                      \
+  do {                                                                                                     \
+    static bool resolved__ = false;                                                                        \
+    if (!resolved__) {                                                                                     \
+      cudaFuncAttributes fa__;                                                                             \
+      cudaError_t e__ = cudaFuncGetAttributes(&fa__, kernel);                                              \
+      if (e__ != cudaSuccess) return nfb_set_error(NFB_ECUDA, "%s: cudaFuncGetAttributes: %s", (who), cudaGetErrorString(e__)); \
+      resolved__ = true;                                                                                   \
+    }                                                                                                      \
+  } while (0)
+
 // ---------------------------------------------------------------------------------------------------
 // IBRNet parameter blob layout (torch-native [out][in] tensors, mlp_network.py:153-208)
 // ---------------------------------------------------------------------------------------------------

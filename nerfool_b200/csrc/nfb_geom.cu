@@ -43,6 +43,7 @@ extern "C" int nfb_coarse_depths(int R, int S, float near_depth, float far_depth
               "nfb_coarse_depths: need 0 < near < far (render_ray.py:87)");
   if (R == 0) return NFB_OK;   // empty ray batch: nothing to do, pointers may be NULL
   NFB_REQUIRE(z_out, NFB_EINVAL, "nfb_coarse_depths: bad arguments (z_out is NULL)");
+  NFB_RESOLVE_ONCE(k_coarse_depths, "nfb_coarse_depths");
   const size_t n = (size_t)R * S;
   const int block = 256;
   const int grid = (int)((n + block - 1) / block < (size_t)nfb_num_sms() * 8 ? (n + block - 1) / block
@@ -159,6 +160,7 @@ extern "C" int nfb_project_gather_fwd(int N, int S, int V, int H, int W, int fh,
   NFB_REQUIRE(((uintptr_t)feat % 16) == 0 && ((uintptr_t)ray_diff % 16) == 0, NFB_EINVAL,
               "nfb_project_gather_fwd: feat / ray_diff must be 16-byte aligned");
   if (N == 0) return NFB_OK;
+  NFB_RESOLVE_ONCE(k_project_gather_fwd, "nfb_project_gather_fwd");
   PointSrc ps{xyz, ray_o, ray_d, z, S};
   k_project_gather_fwd<<<tiles_grid((size_t)N * V, PG_ROWS, 8), PG_ROWS, 0, (cudaStream_t)stream>>>(
       N, V, H, W, fh, fw, ps, cam, imgs, feat, rgb_feat, ray_diff, mask);
@@ -407,6 +409,7 @@ extern "C" int nfb_composite_fwd(int R, int S, int white_bkgd, const float* raw,
   NFB_REQUIRE(pixel_mask || n_valid, NFB_EINVAL, "nfb_composite_fwd: need pixel_mask or n_valid");
   NFB_REQUIRE(((uintptr_t)raw % 16) == 0, NFB_EINVAL, "nfb_composite_fwd: raw must be 16-byte aligned");
   if (R == 0) return NFB_OK;
+  NFB_RESOLVE_ONCE(k_composite_fwd, "nfb_composite_fwd");
   const int grid = tiles_grid((size_t)R, CMP_WARPS, 16);
   k_composite_fwd<<<grid, CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(R, S, white_bkgd, raw, z, pixel_mask, n_valid,
                                                                   n_valid_stride, rgb, depth, weights, alpha, ray_mask);

@@ -84,6 +84,7 @@ extern "C" int nfb_forward_warp(int H, int W, const int* x_res, const int* y_res
   const int n = H * W;
   cudaStream_t st = (cudaStream_t)stream;
   const int ns = sources ? n_src : n;
+  NFB_RESOLVE_ONCE(k_warp_init, "nfb_forward_warp");
   if (sequential) {
     k_warp_sequential<<<1, 32, 0, st>>>(n, W, ns, sources, x_res, y_res, depth_src, rgb_ref, allowed, new_rgb, new_depth);
     NFB_CHECK_LAUNCH("k_warp_sequential");

@@ -177,7 +177,7 @@ def _grad_params(p, dtype):
 
 
 def _check_param_grads(net, p32, p64, what, floor=1e-2):
-    """every parameter gradient of our module within max(floor, 3 x the fp32 oracle's own distance) of the fp64 truth
+    """every parameter gradient of our module within max(floor, 3 x the fp32 oracle's own distance) of the fp64 truth (10 x for the scalar `s`)
     (relative L2 per tensor; tensors whose true gradient is ~0 are compared absolutely).  The floor reflects the
     arithmetic of the view-stage weight gradients: tensor-core GEMMs over the row index with bf16-rounded operands and
     fp32 accumulation (nfb_wgrad_tc.cuh) -- the usual training precision, ~2^-9 per operand before averaging."""
@@ -194,7 +194,10 @@ def _check_param_grads(net, p32, p64, what, floor=1e-2):
         e_ours = ((g - g64).norm() / scale).item()
         e_ref = ((g32 - g64).norm() / scale).item()
         worst[name] = (e_ours, e_ref)
-        assert e_ours <= max(floor, 3 * e_ref), f'{what}: d {name}: ours {e_ours:.3e}, fp32 oracle {e_ref:.3e}'
+        # the scalar `s` (one cancelling sum over all rows, fp32 atomics in a run-dependent order) gets 10x, see
+        # tests/test_reference_callers.py::test_reference_train_loop_unmodified; tensor-valued gradients keep 3x
+        k_ref = 10 if name == 's' else 3
+        assert e_ours <= max(floor, k_ref * e_ref), f'{what}: d {name}: ours {e_ours:.3e}, fp32 oracle {e_ref:.3e}'
     return worst
 
 
