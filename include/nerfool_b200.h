@@ -191,6 +191,16 @@ int nfb_gnt_bwd(int R, int S, int V, int depth, int ret_alpha,
                 const float* rgb_feat, const float* ray_diff, const float* mask, const float* pts, const float* ray_d,
                 const float* params, const float* d_out, float* d_rgb_feat, float* d_ray_diff,
                 void* workspace, size_t workspace_bytes, void* stream);
+/* The same in two calls, for callers that know at forward time that a gradient will be asked for (PyTorch autograd): nfb_gnt_fwd_save
+ * is the fp32 checkpointing forward (writes `out` and fills the workspace), nfb_gnt_bwd_saved the reverse sweep on that workspace -- the
+ * forward is not run twice.  Same workspace size; the workspace must stay untouched between the two calls.                          */
+int nfb_gnt_fwd_save(int R, int S, int V, int depth, int ret_alpha,
+                     const float* rgb_feat, const float* ray_diff, const float* mask, const float* pts, const float* ray_d,
+                     const float* params, float* out, void* workspace, size_t workspace_bytes, void* stream);
+int nfb_gnt_bwd_saved(int R, int S, int V, int depth, int ret_alpha,
+                      const float* rgb_feat, const float* ray_diff, const float* mask, const float* pts, const float* ray_d,
+                      const float* params, const float* d_out, float* d_rgb_feat, float* d_ray_diff,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- raw2outputs  (render_ray.py:123-170) ------------------------------------------------------------
  * pixel_mask: uint8 [R][S] (the `mask` argument), or NULL with n_valid (stride n_valid_stride floats per

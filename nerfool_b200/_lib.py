@@ -35,6 +35,8 @@ _SIGNATURES = {
     'nfb_fine_depths': [_I, _I, _I, _I, _P, _P, _P, _I, _P, _P],
     'nfb_gnt_fwd': [_I] * 5 + [_P] * 8 + [ctypes.c_size_t, _I, _P],
     'nfb_gnt_bwd': [_I] * 5 + [_P] * 10 + [ctypes.c_size_t, _P],
+    'nfb_gnt_fwd_save': [_I] * 5 + [_P] * 8 + [ctypes.c_size_t, _P],
+    'nfb_gnt_bwd_saved': [_I] * 5 + [_P] * 10 + [ctypes.c_size_t, _P],
     'nfb_forward_warp': [_I, _I] + [_P] * 6 + [_I] + [_P] * 4 + [_I, _P],
 }
 EXPORTS = ['nfb_version', 'nfb_last_error_string', 'nfb_ibrnet_param_offset', 'nfb_view_stash_bytes', 'nfb_ray_stash_bytes',

@@ -744,7 +744,7 @@ extern "C" int nfb_gnt_fwd(int R, int S, int V, int depth, int ret_alpha, const 
 // fp32 forward with checkpoints (the first half of nfb_gnt_bwd, nfb_gnt_bwd.cu)
 int nfbgnt::gnt_forward_checkpoints(int R, int S, int V, int depth, const float* rgb_feat, const float* ray_diff, const float* mask,
                                     const float* pts, const float* ray_d, const float* params, float* F, float* CK, float* VPA,
-                                    cudaStream_t st) {
+                                    float* out, int ret_alpha, cudaStream_t st) {
   const int N = R * S;
   const size_t rows = (size_t)N * V, NB = (size_t)N * D;
   auto ck = [&](int i, int j) { return CK + NB * (size_t)(5 * i + j); };
@@ -787,10 +787,20 @@ int nfbgnt::gnt_forward_checkpoints(int R, int S, int V, int depth, const float*
       NFB_CHECK_LAUNCH("k_gnt_qfc");
       qd = ck(i, 3);
     }
-    k_gnt_ray_attn<<<ray_grid, ray_block * rpc, sm_ray, st>>>(R, S, rpc, lp, qd, ck(i, 4), nullptr, 3);
+    const int out_stride = ret_alpha ? 3 + S : 3;
+    float* attn = (out && ret_alpha && i == depth - 1) ? out + 3 : nullptr;      // query 0's attention row of the last layer (:200)
+    k_gnt_ray_attn<<<ray_grid, ray_block * rpc, sm_ray, st>>>(R, S, rpc, lp, qd, ck(i, 4), attn, out_stride);
     NFB_CHECK_LAUNCH("k_gnt_ray_attn");
     k_gnt_ffn<<<ffn_grid, 256, sm_ffn, st>>>(N, lp + L_R_LN2_W, ck(i, 4), ck(i, 5));
     NFB_CHECK_LAUNCH("k_gnt_ffn<ray>");
+  }
+  if (out) {
+    const size_t sm_head = (size_t)(S * 65 + D) * sizeof(float);
+    if ((rc = set_smem(k_gnt_head, sm_head, "k_gnt_head"))) return rc;
+    const int head_grid = R < sms * 4 ? R : sms * 4;
+    k_gnt_head<<<head_grid, ray_block < 64 ? 64 : ray_block, sm_head, st>>>(R, S, params + G_HEAD + (size_t)depth * L_SIZE, ck(depth, 0), out,
+                                                                         ret_alpha ? 3 + S : 3);
+    NFB_CHECK_LAUNCH("k_gnt_head");
   }
   return NFB_OK;
 }

@@ -24,14 +24,40 @@ extern "C" size_t nfb_gnt_bwd_workspace_bytes(int R, int S, int V, int depth) {
   return (rows * (2 * D + (size_t)depth * (D + 8)) + N * D * (size_t)(5 * depth + 1 + 1 + 7)) * sizeof(float);
 }
 
+// mode 0: checkpointing forward + reverse sweep (nfb_gnt_bwd) | 1: checkpointing forward only, writes `out` (nfb_gnt_fwd_save) |
+// 2: reverse sweep on a workspace filled by mode 1 (nfb_gnt_bwd_saved)
+static int gnt_grad_impl(int mode, int R, int S, int V, int depth, int ret_alpha, const float* rgb_feat, const float* ray_diff,
+                         const float* mask, const float* pts, const float* ray_d, const float* params, float* out, const float* d_out,
+                         float* d_rgb_feat, float* d_ray_diff, void* workspace, size_t workspace_bytes, void* stream);
+
 extern "C" int nfb_gnt_bwd(int R, int S, int V, int depth, int ret_alpha, const float* rgb_feat, const float* ray_diff,
                            const float* mask, const float* pts, const float* ray_d, const float* params, const float* d_out,
                            float* d_rgb_feat, float* d_ray_diff, void* workspace, size_t workspace_bytes, void* stream) {
+  return gnt_grad_impl(0, R, S, V, depth, ret_alpha, rgb_feat, ray_diff, mask, pts, ray_d, params, nullptr, d_out, d_rgb_feat, d_ray_diff,
+                       workspace, workspace_bytes, stream);
+}
+extern "C" int nfb_gnt_fwd_save(int R, int S, int V, int depth, int ret_alpha, const float* rgb_feat, const float* ray_diff,
+                                const float* mask, const float* pts, const float* ray_d, const float* params, float* out,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  return gnt_grad_impl(1, R, S, V, depth, ret_alpha, rgb_feat, ray_diff, mask, pts, ray_d, params, out, nullptr, nullptr, nullptr,
+                       workspace, workspace_bytes, stream);
+}
+extern "C" int nfb_gnt_bwd_saved(int R, int S, int V, int depth, int ret_alpha, const float* rgb_feat, const float* ray_diff,
+                                 const float* mask, const float* pts, const float* ray_d, const float* params, const float* d_out,
+                                 float* d_rgb_feat, float* d_ray_diff, void* workspace, size_t workspace_bytes, void* stream) {
+  return gnt_grad_impl(2, R, S, V, depth, ret_alpha, rgb_feat, ray_diff, mask, pts, ray_d, params, nullptr, d_out, d_rgb_feat, d_ray_diff,
+                       workspace, workspace_bytes, stream);
+}
+
+static int gnt_grad_impl(int mode, int R, int S, int V, int depth, int ret_alpha, const float* rgb_feat, const float* ray_diff,
+                         const float* mask, const float* pts, const float* ray_d, const float* params, float* out, const float* d_out,
+                         float* d_rgb_feat, float* d_ray_diff, void* workspace, size_t workspace_bytes, void* stream) {
   NFB_REQUIRE(R >= 0 && S >= 1 && V >= 1 && depth >= 1, NFB_EINVAL, "nfb_gnt_bwd: bad arguments (R=%d S=%d V=%d depth=%d)", R, S, V, depth);
   NFB_REQUIRE(S <= NFB_MAX_SAMPLES, NFB_EUNSUPPORTED, "nfb_gnt_bwd: S=%d > %d samples per ray", S, NFB_MAX_SAMPLES);
   NFB_REQUIRE(V <= NFB_MAX_VIEWS, NFB_EUNSUPPORTED, "nfb_gnt_bwd: V=%d > %d views", V, NFB_MAX_VIEWS);
   if (R == 0) return NFB_OK;
-  NFB_REQUIRE(rgb_feat && ray_diff && mask && pts && ray_d && params && d_out && d_rgb_feat && workspace, NFB_EINVAL, "nfb_gnt_bwd: NULL buffer");
+  NFB_REQUIRE(rgb_feat && ray_diff && mask && pts && ray_d && params && workspace && (mode == 1 ? out != nullptr : (d_out && d_rgb_feat)),
+              NFB_EINVAL, "nfb_gnt_bwd: NULL buffer");
   NFB_REQUIRE(workspace_bytes >= nfb_gnt_bwd_workspace_bytes(R, S, V, depth), NFB_EINVAL, "nfb_gnt_bwd: workspace too small (%zu < %zu bytes)",
               workspace_bytes, nfb_gnt_bwd_workspace_bytes(R, S, V, depth));
   NFB_REQUIRE(((uintptr_t)ray_diff % 16) == 0 && ((uintptr_t)workspace % 16) == 0 && ((uintptr_t)params % 16) == 0 &&
@@ -77,7 +103,9 @@ extern "C" int nfb_gnt_bwd(int R, int S, int V, int depth, int ret_alpha, const 
   const int rcore_ctas = (R + rpc_b - 1) / rpc_b, rcore_grid = rcore_ctas < sms * 2 ? rcore_ctas : sms * 2;
 
   // ---------------- checkpointing forward (fp32 kernels of nfb_gnt.cu) ----------------
-  if ((rc = gnt_forward_checkpoints(R, S, V, depth, rgb_feat, ray_diff, mask, pts, ray_d, params, F, CK, VPA, st))) return rc;
+  if (mode != 2 && (rc = gnt_forward_checkpoints(R, S, V, depth, rgb_feat, ray_diff, mask, pts, ray_d, params, F, CK, VPA, out, ret_alpha, st)))
+    return rc;
+  if (mode == 1) return NFB_OK;
 
   // ---------------- reverse sweep ----------------
   cudaError_t e = cudaMemsetAsync(dF, 0, rows * D * sizeof(float), st);

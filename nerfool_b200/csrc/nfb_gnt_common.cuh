@@ -125,8 +125,9 @@ __device__ __forceinline__ void posenc_axpy(float (&h)[D], const float (&x3)[3],
 
 // fp32 forward on the CUDA cores writing the running query after every block into ck[5 * i + j] (nfb_gnt.cu); F [rows][64],
 // the 5 * depth + 1 checkpoints [N][64] and, per layer, the view attention's per-row v + pos [rows][64] | ReLU(attn_fc.0) [rows][8]
-// (VPA: depth x rows x 72 floats) are the caller's
+// (VPA: depth x rows x 72 floats) are the caller's; out != NULL: also the network output [R][3 (+ S)] (head + attention row of query 0)
 int gnt_forward_checkpoints(int R, int S, int V, int depth, const float* rgb_feat, const float* ray_diff, const float* mask,
-                            const float* pts, const float* ray_d, const float* params, float* F, float* CK, float* VPA, cudaStream_t st);
+                            const float* pts, const float* ray_d, const float* params, float* F, float* CK, float* VPA,
+                            float* out, int ret_alpha, cudaStream_t st);
 
 }  // namespace nfbgnt

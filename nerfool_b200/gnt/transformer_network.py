@@ -98,19 +98,31 @@ BWD_WORKSPACE_GIB = float(__import__('os').environ.get('NFB_GNT_BWD_WS_GIB', '24
 
 
 class _GNTFn(torch.autograd.Function):
-    """out = nfb_gnt_fwd(...);  backward = nfb_gnt_bwd in ray chunks (rays are independent)."""
+    """out = GNT(rgb_feat, ray_diff, mask, pts, ray_d).  Without a gradient request: nfb_gnt_fwd (tensor-core forward).  With one, and if the
+    backward's workspace for all rays fits the cap: nfb_gnt_fwd_save (the fp32 checkpointing forward IS the forward) and nfb_gnt_bwd_saved
+    (reverse sweep on the kept workspace); otherwise nfb_gnt_fwd now and nfb_gnt_bwd (forward re-run + sweep) in ray chunks later."""
 
     @staticmethod
     def forward(ctx, rgb_feat, ray_diff, mask, pts, ray_d, blob, depth, ret_alpha):
         rf, rd, mk, pt, dd = f32c(rgb_feat.detach()), f32c(ray_diff.detach()), f32c(mask.detach()), f32c(pts.detach()), f32c(ray_d.detach())
         R, S, V = rf.shape[:3]
         dev = rf.device
+        lib = _lib.load()
         out = torch.empty(R, 3 + S if ret_alpha else 3, device=dev, dtype=torch.float32)
-        nbytes = int(_lib.load().nfb_gnt_workspace_bytes(R, S, V))
-        ws = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
+        ctx.ws = None
+        want_grad = rgb_feat.requires_grad or ray_diff.requires_grad
+        bwd_bytes = int(lib.nfb_gnt_bwd_workspace_bytes(R, S, V, depth)) if (want_grad and R > 0) else 0
         with torch.cuda.device(dev):
-            call('nfb_gnt_fwd', R, S, V, depth, int(bool(ret_alpha)), ptr(rf), ptr(rd), ptr(mk), ptr(pt), ptr(dd),
-                 ptr(blob), ptr(out), ptr(ws), ctypes.c_size_t(nbytes), _lib.precision_code(), stream_ptr(dev))
+            if want_grad and 0 < bwd_bytes <= BWD_WORKSPACE_GIB * 2 ** 30 and R * S * V < 2 ** 31:
+                ws = torch.empty(bwd_bytes, device=dev, dtype=torch.uint8)
+                call('nfb_gnt_fwd_save', R, S, V, depth, int(bool(ret_alpha)), ptr(rf), ptr(rd), ptr(mk), ptr(pt), ptr(dd),
+                     ptr(blob), ptr(out), ptr(ws), ctypes.c_size_t(bwd_bytes), stream_ptr(dev))
+                ctx.ws = ws
+            else:
+                nbytes = int(lib.nfb_gnt_workspace_bytes(R, S, V))
+                ws = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
+                call('nfb_gnt_fwd', R, S, V, depth, int(bool(ret_alpha)), ptr(rf), ptr(rd), ptr(mk), ptr(pt), ptr(dd),
+                     ptr(blob), ptr(out), ptr(ws), ctypes.c_size_t(nbytes), _lib.precision_code(), stream_ptr(dev))
         ctx.save_for_backward(rf, rd, mk, pt, dd, blob)
         ctx.meta = (depth, bool(ret_alpha), ray_diff.requires_grad)
         return out
@@ -125,11 +137,16 @@ class _GNTFn(torch.autograd.Function):
         d_rf = torch.empty_like(rf)
         d_rd = torch.empty_like(rd) if want_rd else None
         lib = _lib.load()
-        per_ray = max(int(lib.nfb_gnt_bwd_workspace_bytes(1, S, V, depth)), 1)
-        chunk = max(1, min(R, int(BWD_WORKSPACE_GIB * 2 ** 30) // per_ray, (2 ** 31 - 1) // (S * V)))
-        nbytes = int(lib.nfb_gnt_bwd_workspace_bytes(min(chunk, max(R, 1)), S, V, depth))
-        ws = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
+        ws, ctx.ws = ctx.ws, None            # the sweep consumes the saved workspace: a second backward re-runs the forward
         with torch.cuda.device(dev):
+            if ws is not None:
+                call('nfb_gnt_bwd_saved', R, S, V, depth, int(ret_alpha), ptr(rf), ptr(rd), ptr(mk), ptr(pt), ptr(dd), ptr(blob), ptr(g),
+                     ptr(d_rf), ptr(d_rd) if want_rd else None, ptr(ws), ctypes.c_size_t(ws.numel()), stream_ptr(dev))
+                return d_rf, d_rd, None, None, None, None, None, None
+            per_ray = max(int(lib.nfb_gnt_bwd_workspace_bytes(1, S, V, depth)), 1)
+            chunk = max(1, min(R, int(BWD_WORKSPACE_GIB * 2 ** 30) // per_ray, (2 ** 31 - 1) // (S * V)))
+            nbytes = int(lib.nfb_gnt_bwd_workspace_bytes(min(chunk, max(R, 1)), S, V, depth))
+            ws = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
             for r0 in range(0, R, chunk):
                 r1 = min(R, r0 + chunk)
                 call('nfb_gnt_bwd', r1 - r0, S, V, depth, int(ret_alpha), ptr(rf[r0:r1]), ptr(rd[r0:r1]), ptr(mk[r0:r1]), ptr(pt[r0:r1]),
