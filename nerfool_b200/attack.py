@@ -213,13 +213,18 @@ def delta_gradient_step(encoder, model, projector, ray_batch, delta, N_samples, 
             fc = ff = None
     if sharded:
         counts = [shard_slice(V, r, world)[1] - shard_slice(V, r, world)[0] for r in range(world)]
-        # shape and dtype of the encoder output, agreed over ranks (a rank without views has none of its own)
-        probe = torch.tensor([0, 0, 0, 0] if fc is None else list(fc.shape[1:]) + [_DTYPE_CODE[fc.dtype]], device=src.device)
-        dist.all_reduce(probe, op=dist.ReduceOp.MAX, group=group)
-        shape, dtype = tuple(int(v) for v in probe[:3]), _CODE_DTYPE[int(probe[3])]
-        empty = torch.zeros((0,) + shape, device=src.device, dtype=dtype)
-        full_c = _all_gather_views(fc.detach() if fc is not None else empty, counts, group)
-        full_f = _all_gather_views(ff.detach() if ff is not None else empty, counts, group)
+        # shape and dtype of the encoder output, agreed over ranks (a rank without views has none of its own); one small
+        # allreduce + host read per (source shape, world size), cached: it would otherwise stall the launch queue every step
+        key = (tuple(src.shape), str(src.dtype), world, str(src.device))
+        if key not in _ENC_SHAPE_CACHE:
+            probe = torch.tensor([0, 0, 0, 0] if fc is None else list(fc.shape[1:]) + [_DTYPE_CODE[fc.dtype]], device=src.device)
+            dist.all_reduce(probe, op=dist.ReduceOp.MAX, group=group)
+            _ENC_SHAPE_CACHE[key] = (tuple(int(v) for v in probe[:3]), _CODE_DTYPE[int(probe[3])])
+        shape, dtype = _ENC_SHAPE_CACHE[key]
+        # both levels in ONE all-gather (channels concatenated: [v, 2 C, h, w])
+        both = torch.cat([fc.detach(), ff.detach()], dim=1) if fc is not None else torch.zeros((0, 2 * shape[0]) + shape[1:], device=src.device, dtype=dtype)
+        full = _all_gather_views(both, counts, group)
+        full_c, full_f = full[:, :shape[0]], full[:, shape[0]:]
     else:
         full_c, full_f = fc.detach(), ff.detach()
     batch = dict(ray_batch)
@@ -242,6 +247,7 @@ def delta_gradient_step(encoder, model, projector, ray_batch, delta, N_samples, 
 
 
 _DTYPE_CODE = {torch.float32: 1, torch.float16: 2, torch.bfloat16: 3, torch.float64: 4}
+_ENC_SHAPE_CACHE = {}
 _CODE_DTYPE = {v: k for k, v in _DTYPE_CODE.items()}
 
 
