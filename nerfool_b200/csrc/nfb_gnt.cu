@@ -436,6 +436,107 @@ __global__ void __launch_bounds__(128) k_gnt_view_core(int N, int V, const float
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// fp32 view attention in row-parallel pieces (the checkpointing forward of nfb_gnt_bwd): one thread per sample for the query side
+// (k_gnt_pre, k_gnt_outfc), one thread per (sample, view) row for the key side (k_gnt_view_row_fwd: V x the parallelism of the fused
+// k_gnt_view_attn and a third of its live state), k_gnt_view_core for the softmax over views.  Same arithmetic per value.
+// ---------------------------------------------------------------------------------------------------
+// qq[n] = q_fc(LN(q[n]))
+__global__ void __launch_bounds__(128) k_gnt_pre(int N, const float* __restrict__ lp, const float* __restrict__ q_in, float* __restrict__ qq_out) {
+  extern __shared__ __align__(16) float sm[];
+  const int t = threadIdx.x, nt = blockDim.x;
+  load_vec_padded(sm, lp + L_V_LN1_W, D, D, t, nt);
+  load_vec_padded(sm + D, lp + L_V_LN1_B, D, D, t, nt);
+  load_wt_transposed(sm + 2 * D, lp + L_V_Q, D, D, D, t, nt);
+  __syncthreads();
+  for (int n = blockIdx.x * blockDim.x + t; n < N; n += gridDim.x * blockDim.x) {
+    float x[D], qq[D];
+    {
+      float q0[D];
+      load_row64(q_in + (size_t)n * D, q0);
+      layer_norm64(q0, sm, sm + D, LN_EPS_T, x);
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) qq[c] = 0.f;
+    dense_acc<D, D>(sm + 2 * D, x, qq);
+    store_row64(qq_out + (size_t)n * D, qq);
+  }
+}
+// q_out[n] = out_fc(x[n]) + bias + q_in[n]
+__global__ void __launch_bounds__(128) k_gnt_outfc(int N, const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ x_in,
+                                                    const float* q_in, float* q_out) {
+  extern __shared__ __align__(16) float sm[];
+  const int t = threadIdx.x, nt = blockDim.x;
+  load_wt_transposed(sm, w, D, D, D, t, nt);
+  load_vec_padded(sm + D * D, b, D, D, t, nt);
+  __syncthreads();
+  for (int n = blockIdx.x * blockDim.x + t; n < N; n += gridDim.x * blockDim.x) {
+    float x[D], o[D];
+    load_row64(x_in + (size_t)n * D, x);
+    load_bias<D>(o, sm + D * D);
+    dense_acc<D, D>(sm, x, o);
+    float q0[D];
+    load_row64(q_in + (size_t)n * D, q0);
+#pragma unroll
+    for (int c = 0; c < D; ++c) o[c] += q0[c];
+    store_row64(q_out + (size_t)n * D, o);
+  }
+}
+// per row: k = k_fc(F), v = v_fc(k), pos = pos_fc(ray_diff)  ->  VP = v + pos [64],  A8 = ReLU(attn_fc.0(k - qq + pos)) [8]
+__global__ void __launch_bounds__(128) k_gnt_view_row_fwd(size_t rows, int V, const float* __restrict__ F, const float* __restrict__ QQ,
+                                                           const float* __restrict__ ray_diff, const float* __restrict__ lp,
+                                                           float* __restrict__ VP, float* __restrict__ A8) {
+  extern __shared__ __align__(16) float sm[];
+  const int t = threadIdx.x, nt = blockDim.x;
+  load_wt_transposed(sm + VS_K, lp + L_V_K, D, D, D, t, nt);
+  load_wt_transposed(sm + VS_V, lp + L_V_V, D, D, D, t, nt);
+  load_wt_transposed(sm + VS_P0, lp + L_V_POS0_W, 8, 4, 8, t, nt);
+  load_vec_padded(sm + VS_P0_B, lp + L_V_POS0_B, 8, 8, t, nt);
+  load_wt_transposed(sm + VS_P2, lp + L_V_POS2_W, D, 8, D, t, nt);
+  load_vec_padded(sm + VS_P2_B, lp + L_V_POS2_B, D, D, t, nt);
+  load_wt_transposed(sm + VS_A0, lp + L_V_AT0_W, 8, D, 8, t, nt);
+  load_vec_padded(sm + VS_A0_B, lp + L_V_AT0_B, 8, 8, t, nt);
+  __syncthreads();
+  for (size_t row = (size_t)blockIdx.x * blockDim.x + t; row < rows; row += (size_t)gridDim.x * blockDim.x) {
+    float k[D], vv[D], pos[D];
+    {
+      float f[D];
+      load_row64(F + row * D, f);
+#pragma unroll
+      for (int c = 0; c < D; ++c) k[c] = 0.f;
+      dense_acc<D, D>(sm + VS_K, f, k);
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) vv[c] = 0.f;
+    dense_acc<D, D>(sm + VS_V, k, vv);
+    {
+      const float4 rd4 = __ldg(reinterpret_cast<const float4*>(ray_diff) + row);
+      const float rd[4] = {rd4.x, rd4.y, rd4.z, rd4.w};
+      float p8[8];
+      load_bias<8>(p8, sm + VS_P0_B);
+      dense_acc<4, 8>(sm + VS_P0, rd, p8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p8[j] = fmaxf(p8[j], 0.f);
+      load_bias<D>(pos, sm + VS_P2_B);
+      dense_acc<8, D>(sm + VS_P2, p8, pos);
+    }
+    float a8[8];
+    load_bias<8>(a8, sm + VS_A0_B);
+    {
+      float qq[D];
+      load_row64(QQ + (row / V) * D, qq);
+#pragma unroll
+      for (int c = 0; c < D; ++c) axpy_row<8>(a8, k[c] - qq[c] + pos[c], sm + VS_A0 + c * 8);
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) vv[c] += pos[c];
+    store_row64(VP + row * D, vv);
+    float4* o8 = reinterpret_cast<float4*>(A8 + row * 8);
+    o8[0] = make_float4(fmaxf(a8[0], 0.f), fmaxf(a8[1], 0.f), fmaxf(a8[2], 0.f), fmaxf(a8[3], 0.f));
+    o8[1] = make_float4(fmaxf(a8[4], 0.f), fmaxf(a8[5], 0.f), fmaxf(a8[6], 0.f), fmaxf(a8[7], 0.f));
+  }
+}
+
 // ray core: scaled-dot-product attention of the ray's samples given the projected Q, K, V [N][64]; o -> [N][64]
 // (same CTA / thread mapping as k_gnt_ray_attn; the projections and out_fc run in k_gnt_lin_tc)
 __global__ void __launch_bounds__(256, 1) k_gnt_ray_core(int R, int S, int rpc, const float* __restrict__ Q, const float* __restrict__ K,
@@ -744,7 +845,7 @@ extern "C" int nfb_gnt_fwd(int R, int S, int V, int depth, int ret_alpha, const 
 // fp32 forward with checkpoints (the first half of nfb_gnt_bwd, nfb_gnt_bwd.cu)
 int nfbgnt::gnt_forward_checkpoints(int R, int S, int V, int depth, const float* rgb_feat, const float* ray_diff, const float* mask,
                                     const float* pts, const float* ray_d, const float* params, float* F, float* CK, float* VPA,
-                                    float* out, int ret_alpha, cudaStream_t st) {
+                                    float* out, int ret_alpha, float* scratch, cudaStream_t st) {
   const int N = R * S;
   const size_t rows = (size_t)N * V, NB = (size_t)N * D;
   auto ck = [&](int i, int j) { return CK + NB * (size_t)(5 * i + j); };
@@ -763,6 +864,8 @@ int nfbgnt::gnt_forward_checkpoints(int R, int S, int V, int depth, const float*
   if ((rc = set_smem(k_gnt_ffn, sm_ffn, "k_gnt_ffn"))) return rc;
   if ((rc = set_smem(k_gnt_qfc, sm_qfc, "k_gnt_qfc"))) return rc;
   if ((rc = set_smem(k_gnt_ray_attn, sm_ray, "k_gnt_ray_attn"))) return rc;
+  const size_t sm_pre = (size_t)(2 * D + D * D) * sizeof(float);
+  if ((rc = set_smem(k_gnt_view_row_fwd, sm_view, "k_gnt_view_row_fwd"))) return rc;
   auto grid_n = [&](size_t n, int block, int per_sm) {
     size_t g = (n + block - 1) / block;
     if (g > (size_t)sms * per_sm) g = (size_t)sms * per_sm;
@@ -777,8 +880,23 @@ int nfbgnt::gnt_forward_checkpoints(int R, int S, int V, int depth, const float*
   for (int i = 0; i < depth; ++i) {
     const float* lp = params + G_HEAD + (size_t)i * L_SIZE;
     float* vp_i = VPA + (size_t)i * rows * (D + 8);           // layer i: VP [rows][64] then A8 [rows][8]
-    k_gnt_view_attn<<<grid_n(N, 128, 3), 128, sm_view, st>>>(N, V, F, ray_diff, mask, lp, ck(i, 0), ck(i, 1), vp_i, vp_i + rows * D);
-    NFB_CHECK_LAUNCH("k_gnt_view_attn");
+    if (scratch) {
+      float* qq = scratch;                                    // [N][64]
+      float* xa = scratch + NB;                               // [N][64]
+      k_gnt_pre<<<grid_n(N, 128, 6), 128, sm_pre, st>>>(N, lp, ck(i, 0), qq);
+      NFB_CHECK_LAUNCH("k_gnt_pre");
+      k_gnt_view_row_fwd<<<grid_n(rows, 128, 4), 128, sm_view, st>>>(rows, V, F, qq, ray_diff, lp, vp_i, vp_i + rows * D);
+      NFB_CHECK_LAUNCH("k_gnt_view_row_fwd");
+      int g = (N + 63) / 64;                                  // 2 threads per sample
+      if (g > sms * 8) g = sms * 8;
+      k_gnt_view_core<<<g, 128, 0, st>>>(N, V, vp_i + rows * D, vp_i, mask, lp, xa);
+      NFB_CHECK_LAUNCH("k_gnt_view_core");
+      k_gnt_outfc<<<grid_n(N, 128, 6), 128, sm_pre, st>>>(N, lp + L_V_O_W, lp + L_V_O_B, xa, ck(i, 0), ck(i, 1));
+      NFB_CHECK_LAUNCH("k_gnt_outfc");
+    } else {
+      k_gnt_view_attn<<<grid_n(N, 128, 3), 128, sm_view, st>>>(N, V, F, ray_diff, mask, lp, ck(i, 0), ck(i, 1), vp_i, vp_i + rows * D);
+      NFB_CHECK_LAUNCH("k_gnt_view_attn");
+    }
     k_gnt_ffn<<<ffn_grid, 256, sm_ffn, st>>>(N, lp + L_V_LN2_W, ck(i, 1), ck(i, 2));
     NFB_CHECK_LAUNCH("k_gnt_ffn<view>");
     const float* qd = ck(i, 2);

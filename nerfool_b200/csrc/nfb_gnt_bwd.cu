@@ -103,7 +103,7 @@ static int gnt_grad_impl(int mode, int R, int S, int V, int depth, int ret_alpha
   const int rcore_ctas = (R + rpc_b - 1) / rpc_b, rcore_grid = rcore_ctas < sms * 2 ? rcore_ctas : sms * 2;
 
   // ---------------- checkpointing forward (fp32 kernels of nfb_gnt.cu) ----------------
-  if (mode != 2 && (rc = gnt_forward_checkpoints(R, S, V, depth, rgb_feat, ray_diff, mask, pts, ray_d, params, F, CK, VPA, out, ret_alpha, st)))
+  if (mode != 2 && (rc = gnt_forward_checkpoints(R, S, V, depth, rgb_feat, ray_diff, mask, pts, ray_d, params, F, CK, VPA, out, ret_alpha, buf(0), st)))
     return rc;
   if (mode == 1) return NFB_OK;
 

@@ -128,6 +128,6 @@ __device__ __forceinline__ void posenc_axpy(float (&h)[D], const float (&x3)[3],
 // (VPA: depth x rows x 72 floats) are the caller's; out != NULL: also the network output [R][3 (+ S)] (head + attention row of query 0)
 int gnt_forward_checkpoints(int R, int S, int V, int depth, const float* rgb_feat, const float* ray_diff, const float* mask,
                             const float* pts, const float* ray_d, const float* params, float* F, float* CK, float* VPA,
-                            float* out, int ret_alpha, cudaStream_t st);
+                            float* out, int ret_alpha, float* scratch /* 2 x [N][64] or NULL: fused view attention */, cudaStream_t st);
 
 }  // namespace nfbgnt
