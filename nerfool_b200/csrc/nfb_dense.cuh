@@ -6,15 +6,25 @@
 #include "nfb_common.cuh"
 
 // out[0..NP) += x * Wt_row[0..NP)
+// The fused multiply-adds are issued as packed fp32x2 (FFMA2: two independent round-to-nearest FMAs per instruction, so the results
+// are bit-identical to four scalar FFMAs at half the issue slots; measured on the GNT reverse sweep: 35.3 -> 30.1 ms).
+// -DNFB_DENSE_SCALAR restores the scalar form.
 template <int NP>
 __device__ __forceinline__ void axpy_row(float (&out)[NP], float x, const float* __restrict__ wrow) {
 #pragma unroll
   for (int n = 0; n < NP; n += 4) {
     const float4 w = *reinterpret_cast<const float4*>(wrow + n);
+#ifndef NFB_DENSE_SCALAR
+    const float2 xx = make_float2(x, x);
+    const float2 r0 = __ffma2_rn(xx, make_float2(w.x, w.y), make_float2(out[n + 0], out[n + 1]));
+    const float2 r1 = __ffma2_rn(xx, make_float2(w.z, w.w), make_float2(out[n + 2], out[n + 3]));
+    out[n + 0] = r0.x; out[n + 1] = r0.y; out[n + 2] = r1.x; out[n + 3] = r1.y;
+#else
     out[n + 0] = fmaf(x, w.x, out[n + 0]);
     out[n + 1] = fmaf(x, w.y, out[n + 1]);
     out[n + 2] = fmaf(x, w.z, out[n + 2]);
     out[n + 3] = fmaf(x, w.w, out[n + 3]);
+#endif
   }
 }
 
@@ -37,6 +47,16 @@ __device__ __forceinline__ void dense_acc(const float* __restrict__ Wt, const fl
 // sum_n dy[n] * wrow[n]
 template <int NP>
 __device__ __forceinline__ float dot_row(const float (&dy)[NP], const float* __restrict__ wrow) {
+#ifndef NFB_DENSE_SCALAR
+  float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int n = 0; n < NP; n += 4) {
+    const float4 w = *reinterpret_cast<const float4*>(wrow + n);
+    a01 = __ffma2_rn(make_float2(dy[n + 0], dy[n + 1]), make_float2(w.x, w.y), a01);
+    a23 = __ffma2_rn(make_float2(dy[n + 2], dy[n + 3]), make_float2(w.z, w.w), a23);
+  }
+  return (a01.x + a01.y) + (a23.x + a23.y);
+#else
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
   for (int n = 0; n < NP; n += 4) {
@@ -47,6 +67,7 @@ __device__ __forceinline__ float dot_row(const float (&dy)[NP], const float* __r
     a3 = fmaf(dy[n + 3], w.w, a3);
   }
   return (a0 + a1) + (a2 + a3);
+#endif
 }
 
 // dx[k] = sum_n dy[n] * Wt[k][n]   (transpose product with the same smem layout)
