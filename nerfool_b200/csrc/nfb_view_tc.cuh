@@ -355,7 +355,10 @@ __device__ __forceinline__ void pool4(const float* __restrict__ row0, int V, int
       const float4 x = *reinterpret_cast<const float4*>(r + 4 * q);
       if (MODE != POOL_SUM) {
         const float wu = r[wslot] * scale;
-        m.x = fmaf(x.x, wu, m.x); m.y = fmaf(x.y, wu, m.y); m.z = fmaf(x.z, wu, m.z); m.w = fmaf(x.w, wu, m.w);
+        const float2 w2 = make_float2(wu, wu);                       // packed fp32x2: same FMAs, half the issue slots
+        const float2 a = __ffma2_rn(make_float2(x.x, x.y), w2, make_float2(m.x, m.y));
+        const float2 b = __ffma2_rn(make_float2(x.z, x.w), w2, make_float2(m.z, m.w));
+        m = make_float4(a.x, a.y, b.x, b.y);
       } else {
         m.x += x.x; m.y += x.y; m.z += x.z; m.w += x.w;
       }
@@ -367,8 +370,12 @@ __device__ __forceinline__ void pool4(const float* __restrict__ row0, int V, int
         const float* r = row0 + u * EXQ;
         const float4 x = *reinterpret_cast<const float4*>(r + 4 * q);
         const float wu = r[wslot] * scale;
-        const float dx = x.x - m.x, dy = x.y - m.y, dz = x.z - m.z, dw = x.w - m.w;
-        s2.x = fmaf(wu * dx, dx, s2.x); s2.y = fmaf(wu * dy, dy, s2.y); s2.z = fmaf(wu * dz, dz, s2.z); s2.w = fmaf(wu * dw, dw, s2.w);
+        const float2 w2 = make_float2(wu, wu), neg1 = make_float2(-1.f, -1.f);
+        const float2 d01 = __ffma2_rn(make_float2(m.x, m.y), neg1, make_float2(x.x, x.y));       // x - m (exact as a subtraction)
+        const float2 d23 = __ffma2_rn(make_float2(m.z, m.w), neg1, make_float2(x.z, x.w));
+        const float2 a = __ffma2_rn(__fmul2_rn(w2, d01), d01, make_float2(s2.x, s2.y));
+        const float2 b = __ffma2_rn(__fmul2_rn(w2, d23), d23, make_float2(s2.z, s2.w));
+        s2 = make_float4(a.x, a.y, b.x, b.y);
       }
     }
     emit(q, m, s2);
