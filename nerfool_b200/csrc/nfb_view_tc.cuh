@@ -700,10 +700,12 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       epi16_s<SAVE>(tl, 16 * kc, sf + F_B_BASE2 + 16 * kc, h, q);
       if (save) st_codes8(sp, SP_X1 + 2 * kc, q);
       float t[16];
+      const float2 w2 = make_float2(w, w);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        x1[16 * kc + j] = h[j];
-        t[j] = h[j] * w;
+      for (int j = 0; j < 16; j += 2) {
+        x1[16 * kc + j] = h[j]; x1[16 * kc + j + 1] = h[j + 1];
+        const float2 r = __fmul2_rn(make_float2(h[j], h[j + 1]), w2);
+        t[j] = r.x; t[j + 1] = r.y;
       }
       a_store16<NPASS>(tl, kc, t);
     }
@@ -750,10 +752,13 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
       epi16_s<SAVE>(tl, 16 * kc, sf + F_B_VIS2 + 16 * kc, h, q);
       if (save) st_codes8(sp, SP_XV + 2 * kc, q);
       float t[16];
+      const float2 v2 = make_float2(vis1, vis1);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        x1[16 * kc + j] += h[j];            // x1 now holds x2
-        t[j] = x1[16 * kc + j] * vis1;
+      for (int j = 0; j < 16; j += 2) {
+        const float2 s2 = __fadd2_rn(make_float2(x1[16 * kc + j], x1[16 * kc + j + 1]), make_float2(h[j], h[j + 1]));      // x1 now holds x2
+        x1[16 * kc + j] = s2.x; x1[16 * kc + j + 1] = s2.y;
+        const float2 r = __fmul2_rn(s2, v2);
+        t[j] = r.x; t[j + 1] = r.y;
       }
       if (save) {
 #pragma unroll
@@ -767,6 +772,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
     float vis2, sg2;
     {
       float z = sf[F_B_VISB2];
+      float2 za = make_float2(0.f, 0.f), zb = make_float2(0.f, 0.f);
 #if NFB_VTC_PAIR
       {
         float h[16], h2[16];
@@ -785,9 +791,15 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
         uint32_t q[8];
         epi16_s<SAVE>(tl, 16 * kc, sf + F_B_VISB0 + 16 * kc, h, q);
         if (save) st_codes8(sp, SP_HV2 + 2 * kc, q);
+        // 32-term dot product as four interleaved partial sums in two packed accumulators (a serial FFMA chain before)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) z = fmaf(h[j], sf[F_W_VISB2 + 16 * kc + j], z);
+        for (int j = 0; j < 16; j += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(sf + F_W_VISB2 + 16 * kc + j);
+          za = __ffma2_rn(make_float2(h[j], h[j + 1]), make_float2(w4.x, w4.y), za);
+          zb = __ffma2_rn(make_float2(h[j + 2], h[j + 3]), make_float2(w4.z, w4.w), zb);
+        }
       }
+      z += (za.x + za.y) + (zb.x + zb.y);
 #endif
       sg2 = sigmoid_f(z);
       vis2 = sg2 * mk;
