@@ -475,6 +475,22 @@ def test_gnt_module_interface_and_blob_layout():
         GNT(types.SimpleNamespace(netwidth=32, trans_depth=2), 32, 63, 63, True)
     with pytest.raises(RuntimeError, match='workspace'):
         _lib.call('nfb_gnt_fwd', 1, 4, 2, 2, 1, *[_lib.c_void_p(16)] * 8, _lib.ctypes.c_size_t(0), 1, None)
+    # data-gradient entry points: workspace formula (F, dF, per layer VP | A8 rows; 5 depth + 1 checkpoints + dq + 7 sample buffers),
+    # argument validation without a GPU, empty batch
+    R, S, V, depth = 2, 3, 4, 2
+    rows, N = R * S * V, R * S
+    assert lib.nfb_gnt_bwd_workspace_bytes(R, S, V, depth) == (rows * (2 * 64 + depth * 72) + N * 64 * (5 * depth + 1 + 1 + 7)) * 4
+    assert lib.nfb_gnt_bwd_workspace_bytes(0, S, V, depth) == 0
+    for entry, nptr in (('nfb_gnt_bwd', 10), ('nfb_gnt_bwd_saved', 10), ('nfb_gnt_fwd_save', 8)):
+        with pytest.raises(RuntimeError, match='workspace too small'):
+            _lib.call(entry, 1, 4, 2, 2, 1, *[_lib.c_void_p(16)] * nptr, _lib.ctypes.c_size_t(0), None)
+        with pytest.raises(RuntimeError, match='NULL buffer'):
+            _lib.call(entry, 1, 4, 2, 2, 1, *[None] * nptr, _lib.ctypes.c_size_t(1 << 30), None)
+        with pytest.raises(RuntimeError, match='samples per ray'):
+            _lib.call(entry, 1, 100000, 2, 2, 1, *[_lib.c_void_p(16)] * nptr, _lib.ctypes.c_size_t(0), None)
+        _lib.call(entry, 0, 4, 2, 2, 1, *[None] * nptr, _lib.ctypes.c_size_t(0), None)          # R = 0: nothing to do
+    with pytest.raises(RuntimeError, match='NULL buffer'):
+        _lib.call('nfb_project_grid_bwd', 4, 2, 2, 8, 8, 4, 4, *[_lib.c_void_p(16)] * 5, None, None, None, None, None)
 
 
 def test_graphed_step_refuses_stochastic_sampling():
