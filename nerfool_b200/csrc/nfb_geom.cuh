@@ -140,6 +140,68 @@ __device__ __forceinline__ void gather_row(const ViewGeom& g, int v, int H, int 
   }
 }
 
+// Warp-cooperative form of gather_row for kernels whose 32 lanes hold 32 different rows (nfb_view_tc.cuh).  A lane's own
+// LDG.128 covers 16 of the 128 bytes of a feature line, so a warp-wide load touches ~30 different lines for 512 useful bytes and
+// the same lines are revisited by the seven other loads of the tap: the L1 data pipe is the most loaded unit of the kernel
+// (l1tex__data_pipe_lsu_wavefronts 64 %) and the consumer of these loads holds the largest share of its stall samples.
+// Here the 8 lanes of a quarter-warp read one row's four feature lines TOGETHER (lane k the channels 4k..4k+3 of every tap): a
+// warp-wide load is 4 whole lines.  Tap offsets / weights of the row come from its owner lane by shuffle; after 8 rounds every
+// lane holds the channel quad k of the 8 rows of its quarter-warp, which are handed to the owners through `stage`
+// (row r: floats [4, 36), 16-byte aligned; any per-row scratch with that room, row stride `stride` floats).  Same taps, weights and
+// summation order as gather_row: bit-identical rows.  Every lane of the warp must call (inactive rows: active = false).
+__device__ __forceinline__ void gather_row_coop(bool active, const ViewGeom& g, int v, int H, int W, int fh, int fw,
+                                                const float* __restrict__ imgs, const float* __restrict__ feat,
+                                                float* __restrict__ stage, int stride, int my_row, float (&row)[NFB_ROW_CH]) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, k = lane & 7, q0 = lane & ~7;
+  row[0] = row[1] = row[2] = 0.f;
+  if (active) {
+    const Taps t = bilinear_taps(g.gx, g.gy, W, H);
+    const float* base = imgs + (size_t)v * H * W * 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (t.off[i] >= 0) {
+        const float* p = base + (size_t)t.off[i] * 3;
+        row[0] += __ldg(p + 0) * t.wt[i];
+        row[1] += __ldg(p + 1) * t.wt[i];
+        row[2] += __ldg(p + 2) * t.wt[i];
+      }
+    }
+  }
+  Taps t = bilinear_taps(active ? g.gx : 0.f, active ? g.gy : 0.f, fw, fh);
+  if (!active) { t.off[0] = t.off[1] = t.off[2] = t.off[3] = -1; }
+  // texel index inside the whole [V][fh][fw] map, so one shuffled integer addresses the line
+  const int plane = fh * fw;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (t.off[i] >= 0) t.off[i] += v * plane;
+  const float4* fbase = reinterpret_cast<const float4*>(feat) + k;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int src = q0 + it;
+    float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int off = __shfl_sync(FULL, t.off[i], src);
+      const float wgt = __shfl_sync(FULL, t.wt[i], src);
+      if (off >= 0) {
+        const float4 qv = __ldg(fbase + (size_t)off * (NFB_FEAT_CH / 4));
+        const float2 w2 = make_float2(wgt, wgt);
+        a01 = __ffma2_rn(make_float2(qv.x, qv.y), w2, a01);
+        a23 = __ffma2_rn(make_float2(qv.z, qv.w), w2, a23);
+      }
+    }
+    *reinterpret_cast<float4*>(stage + (size_t)(my_row - lane + src) * stride + 4 + 4 * k) = make_float4(a01.x, a01.y, a23.x, a23.y);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < NFB_FEAT_CH / 4; ++j) {
+    const float4 qv = *reinterpret_cast<const float4*>(stage + (size_t)my_row * stride + 4 + 4 * j);
+    row[3 + 4 * j + 0] = qv.x; row[3 + 4 * j + 1] = qv.y; row[3 + 4 * j + 2] = qv.z; row[3 + 4 * j + 3] = qv.w;
+  }
+  __syncwarp();                  // the staging rows are reused by the caller
+}
+
 // Scatter-add the cotangent of one gathered row back into d_feat / d_imgs (grid_sampler_2d backward
 // w.r.t. the input).  Each feature tap is 8 x RED.128 (vector float atomics, sm_90+).
 __device__ __forceinline__ void scatter_row(const ViewGeom& g, int v, int H, int W, int fh, int fw,

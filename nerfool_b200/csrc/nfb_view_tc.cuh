@@ -269,6 +269,9 @@ __device__ __forceinline__ void epi16_s(uint32_t tl, int col, const float* __res
 #ifndef NFB_VTC_PAIR
 #define NFB_VTC_PAIR 0
 #endif
+#ifndef NFB_VTC_COOP_GATHER
+#define NFB_VTC_COOP_GATHER 1     // quarter-warp cooperative feature gather (gather_row_coop, nfb_geom.cuh); 0 = one lane per row (gather_row): 140.9 vs 120.9 ms
+#endif
 template <bool SAVE>
 __device__ __forceinline__ void epi16_pair(uint32_t tl, int col, const float* __restrict__ bias, float (&y0)[16], float (&y1)[16],
                                            uint32_t (&q0)[8], uint32_t (&q1)[8]) {
@@ -495,6 +498,19 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
     float mk = 0.f;
     float ggx = 0.f, ggy = 0.f;
     if (FUSED) {
+#if NFB_VTC_COOP_GATHER
+      ViewGeom g;
+      g.gx = g.gy = g.mask = 0.f; g.rd[0] = g.rd[1] = g.rd[2] = g.rd[3] = 0.f;
+      if (active) {
+        float X, Y, Z;
+        load_point(a.pts, p, X, Y, Z);
+        g = view_geometry(X, Y, Z, s_cam + 16 * v, s_cam + 16 * V, Wm1, Hm1);
+      }
+      // the exchange rows are free here (the previous tile ended with a fence): they stage the quarter-warp transposition
+      gather_row_coop(active, g, v, a.H, a.W, a.fh, a.fw, a.imgs, a.feat, ex, EXQ, tg, x);
+      rd[0] = g.rd[0]; rd[1] = g.rd[1]; rd[2] = g.rd[2]; rd[3] = g.rd[3];
+      mk = g.mask; ggx = g.gx; ggy = g.gy;
+#else
       if (active) {
         float X, Y, Z;
         load_point(a.pts, p, X, Y, Z);
@@ -507,6 +523,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_fwd(ViewArgs a) {
         for (int c = 0; c < NFB_ROW_CH; ++c) x[c] = 0.f;
         rd[0] = rd[1] = rd[2] = rd[3] = 0.f;
       }
+#endif
     } else {
       // the tile's rows are contiguous in rgb_feat: coalesced copy through the exchange buffer
       const size_t row0 = (size_t)tile * TS * V;
