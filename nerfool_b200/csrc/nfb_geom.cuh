@@ -242,6 +242,55 @@ __device__ __forceinline__ void scatter_row(const ViewGeom& g, int v, int H, int
   }
 }
 
+// Warp-cooperative scatter, the mirror of gather_row_coop: the 8 lanes of a quarter-warp add one row's weighted cotangent to the
+// row's four feature lines TOGETHER (lane k the channels 4k..4k+3 of every tap), so a warp-wide RED.128 covers 4 whole 128-byte
+// lines of the gradient map instead of 16-byte pieces of ~30 different lines.  The cotangent rows are handed from their owners
+// to the quarter-warp through `stage` (row r: floats [4, 36)); tap offsets / weights by shuffle.  Every lane of the warp must call.
+__device__ __forceinline__ void scatter_row_coop(bool active, float gx, float gy, int v, int H, int W, int fh, int fw,
+                                                 const float (&d_row)[NFB_ROW_CH], float* __restrict__ d_feat, float* __restrict__ d_imgs,
+                                                 float* __restrict__ stage, int stride, int my_row) {
+  if (active && d_imgs) {
+    const Taps t = bilinear_taps(gx, gy, W, H);
+    float* base = d_imgs + (size_t)v * H * W * 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (t.off[i] >= 0) {
+        float* p = base + (size_t)t.off[i] * 3;
+        atomicAdd(p + 0, d_row[0] * t.wt[i]);
+        atomicAdd(p + 1, d_row[1] * t.wt[i]);
+        atomicAdd(p + 2, d_row[2] * t.wt[i]);
+      }
+    }
+  }
+  if (!d_feat) return;                                   // kernel argument: uniform
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, k = lane & 7, q0 = lane & ~7;
+#pragma unroll
+  for (int j = 0; j < NFB_FEAT_CH / 4; ++j)
+    *reinterpret_cast<float4*>(stage + (size_t)my_row * stride + 4 + 4 * j) =
+        make_float4(d_row[3 + 4 * j], d_row[4 + 4 * j], d_row[5 + 4 * j], d_row[6 + 4 * j]);
+  Taps t = bilinear_taps(active ? gx : 0.f, active ? gy : 0.f, fw, fh);
+  if (!active) { t.off[0] = t.off[1] = t.off[2] = t.off[3] = -1; }
+  const int plane = fh * fw;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (t.off[i] >= 0) t.off[i] += v * plane;
+  __syncwarp();
+  float4* fbase = reinterpret_cast<float4*>(d_feat) + k;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int src = q0 + it;
+    const float4 d4 = *reinterpret_cast<const float4*>(stage + (size_t)(my_row - lane + src) * stride + 4 + 4 * k);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int off = __shfl_sync(FULL, t.off[i], src);
+      const float wgt = __shfl_sync(FULL, t.wt[i], src);
+      if (off >= 0) atomicAdd(fbase + (size_t)off * (NFB_FEAT_CH / 4), make_float4(d4.x * wgt, d4.y * wgt, d4.z * wgt, d4.w * wgt));
+    }
+  }
+  __syncwarp();
+}
+
 // Scatter with pairwise de-duplication.  Consecutive samples of a ray fall into the same texel quad of a source view most
 // of the time (measured on the headline scene: 74 % at the coarse level, 87 % at the fine level).  The rows of a sample
 // pair (2k, 2k + 1) of one view are the lanes (l, l ^ V) of a warp when V is a power of two <= 16: if both hit the same

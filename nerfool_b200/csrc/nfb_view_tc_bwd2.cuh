@@ -14,6 +14,9 @@
 #pragma once
 #include "nfb_view_tc.cuh"
 
+#ifndef NFB_VTC_COOP_SCATTER
+#define NFB_VTC_COOP_SCATTER 1     // quarter-warp cooperative scatter (scatter_row_coop, nfb_geom.cuh); 0 = the pairwise de-duplicated per-lane scatter: 123.0 vs 110.4 ms
+#endif
 namespace nfbvtcs {
 using namespace nfbtc;
 using namespace nfbvtc;
@@ -511,6 +514,10 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       d_row[2] = fmaf(blend, d_r2, d_row[2]);
     }
     // (8) scatter (grid_sampler_2d backward w.r.t. the input)
+#if NFB_VTC_COOP_SCATTER
+    // the exchange rows are free here (fence above): they stage the hand-over of the cotangent rows to the quarter-warps
+    scatter_row_coop(active, gx, gy, v, a.H, a.W, a.fh, a.fw, d_row, a.d_feat, a.d_imgs, ex, EXQ, tg);
+#else
     if (warp_local && rm.spw >= 2) {
       // sample pairs (2k, 2k + 1) of a warp, same view: same texel quad -> one set of atomics for both
       scatter_row_paired(active, gx, gy, v, partner, pair_leader, a.H, a.W, a.fh, a.fw, d_row, a.d_feat, a.d_imgs);
@@ -519,6 +526,7 @@ __global__ void __launch_bounds__(GROUP * NG, 1) k_view_tc_bwd_stash(ViewArgs a)
       g.gx = gx; g.gy = gy;
       scatter_row(g, v, a.H, a.W, a.fh, a.fw, d_row, a.d_feat, a.d_imgs);
     }
+#endif
     named_bar_sync(bar_id, GROUP);          // exchange / statistics / staging buffers are reused by the next tile
   }
 
