@@ -262,18 +262,26 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
   const long long ntiles = (a.M + GROUP - 1) / GROUP;
 
   uint8_t* my_stage = s_stage + ((size_t)(MODE == LIN_KV ? grp : 0) * GROUP + tg) * ROW_STAGE_STRIDE;
-  if (MODE == LIN_KV) {                      // prologue: this thread's row of the group's first tile
-    const long long r0 = ((long long)blockIdx.x * NG + grp) * GROUP + tg;
-    if (r0 < a.M)
+  // LIN_KV input rows: the 32 rows of a warp are contiguous in memory (32 x 256 B), so the warp copies them as 16 fully
+  // coalesced 512-byte requests (lane l takes 16-byte piece 32 i + l) instead of every lane fetching its own row (32 different
+  // lines per request: the uncoalesced pattern that loaded the L1 data pipe of the IBRNet gather)
+  const int lane = tid & 31;
+  uint8_t* warp_stage = my_stage - (size_t)lane * ROW_STAGE_STRIDE;
+  auto stage_rows = [&](long long row0 /* first row of this warp */) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c) cp_async16(my_stage + 16 * c, a.x + r0 * TD + 4 * c);
-  }
+    for (int i = 0; i < 16; ++i) {
+      const int piece = 32 * i + lane, r = piece >> 4, c = piece & 15;
+      if (row0 + r < a.M) cp_async16(warp_stage + (size_t)r * ROW_STAGE_STRIDE + 16 * c, a.x + (row0 + r) * TD + 4 * c);
+    }
+  };
+  if (MODE == LIN_KV) stage_rows(((long long)blockIdx.x * NG + grp) * GROUP + tg - lane);     // prologue: the group's first tile
   for (long long tile = (long long)blockIdx.x * NG + grp; tile < ntiles; tile += (long long)gridDim.x * NG) {
     const long long row = tile * GROUP + tg;
     const bool active = row < a.M;
     float x[TD];
     if (MODE == LIN_KV) {
-      cp_async_wait_all();                   // own row only: no cross-thread dependence
+      cp_async_wait_all();
+      __syncwarp();                          // the row was copied by the lanes of this warp
 #pragma unroll
       for (int c = 0; c < TD; c += 4) {
         const float4 t4 = active ? *reinterpret_cast<const float4*>(my_stage + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -317,10 +325,8 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
       if (MODE == LIN_KV) {
         // x has been consumed (its TMEM stores completed before the barrier above), so the staging row is free: prefetch
         // this thread's row of the group's next tile while the MMAs and the epilogue of this one run
-        const long long rn = row + (long long)gridDim.x * NG * GROUP;
-        if (rn < a.M)
-#pragma unroll
-          for (int c = 0; c < 16; ++c) cp_async16(my_stage + 16 * c, a.x + rn * TD + 4 * c);
+        __syncwarp();                        // every lane of the warp has read its row out of the staging rows
+        stage_rows(row - lane + (long long)gridDim.x * NG * GROUP);
       }
       GNT_TC_WAIT();
       float y[TD];
