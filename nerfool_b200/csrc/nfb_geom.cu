@@ -65,6 +65,7 @@ k_project_gather_fwd(int N, int V, int H, int W, int fh, int fw, PointSrc psrc, 
                      const float* __restrict__ imgs, const float* __restrict__ feat,
                      float* __restrict__ rgb_feat, float* __restrict__ ray_diff, float* __restrict__ mask) {
   __shared__ float stage[PG_ROWS * NFB_ROW_CH];
+  __shared__ __align__(16) float coop[PG_ROWS * 36];       // transposition rows of the cooperative gather
   __shared__ float s_cam[16 * NFB_MAX_VIEWS + 4];
   for (int i = threadIdx.x; i < 16 * V + 3; i += blockDim.x) s_cam[i] = cam[i];
   __syncthreads();
@@ -74,17 +75,25 @@ k_project_gather_fwd(int N, int V, int H, int W, int fh, int fw, PointSrc psrc, 
   for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const size_t row0 = tile * PG_ROWS;
     const size_t row = row0 + threadIdx.x;
-    if (row < total) {
-      const int p = (int)(row / V), v = (int)(row % V);
-      float x, y, z;
-      load_point(psrc, p, x, y, z);
-      const ViewGeom g = view_geometry(x, y, z, s_cam + 16 * v, s_cam + 16 * V, Wm1, Hm1);
+    {
+      // quarter-warp cooperative gather (gather_row_coop): every lane of the warp takes part, rows past the end are inactive
+      const bool act = row < total;
+      const int p = act ? (int)(row / V) : 0, v = act ? (int)(row % V) : 0;
+      ViewGeom g;
+      g.gx = g.gy = g.mask = 0.f; g.rd[0] = g.rd[1] = g.rd[2] = g.rd[3] = 0.f;
+      if (act) {
+        float x, y, z;
+        load_point(psrc, p, x, y, z);
+        g = view_geometry(x, y, z, s_cam + 16 * v, s_cam + 16 * V, Wm1, Hm1);
+      }
       float r[NFB_ROW_CH];
-      gather_row(g, v, H, W, fh, fw, imgs, feat, r);
+      gather_row_coop(act, g, v, H, W, fh, fw, imgs, feat, coop, 36, (int)threadIdx.x, r);
+      if (act) {
 #pragma unroll
-      for (int c = 0; c < NFB_ROW_CH; ++c) stage[threadIdx.x * NFB_ROW_CH + c] = r[c];
-      reinterpret_cast<float4*>(ray_diff)[row] = make_float4(g.rd[0], g.rd[1], g.rd[2], g.rd[3]);
-      mask[row] = g.mask;
+        for (int c = 0; c < NFB_ROW_CH; ++c) stage[threadIdx.x * NFB_ROW_CH + c] = r[c];
+        reinterpret_cast<float4*>(ray_diff)[row] = make_float4(g.rd[0], g.rd[1], g.rd[2], g.rd[3]);
+        mask[row] = g.mask;
+      }
     }
     __syncthreads();
     const size_t rows_here = (total - row0 < (size_t)PG_ROWS) ? (total - row0) : (size_t)PG_ROWS;
