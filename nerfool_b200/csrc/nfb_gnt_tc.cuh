@@ -75,7 +75,8 @@ __device__ __forceinline__ void posenc64(const float (&x3)[3], float (&e)[TD]) {
 // into a shared-memory staging buffer with cp.async while the current tile is processed; row stride 272 B keeps the
 // 16-byte row reads of a warp conflict-free.
 constexpr int ROW_STAGE_STRIDE = 272;
-__host__ __device__ constexpr size_t stage_bytes(int mode) { return mode == LIN_KV ? (size_t)mode_groups(mode) * GROUP * ROW_STAGE_STRIDE : 0; }
+// every mode stages its 64-float rows through shared memory so that global loads / stores are warp-coalesced (see coop_row_load)
+__host__ __device__ constexpr size_t stage_bytes(int mode) { return (size_t)mode_groups(mode) * GROUP * ROW_STAGE_STRIDE; }
 
 template <int NPASS, int MODE>
 __host__ __device__ constexpr size_t lin_smem_bytes() {
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
   uint32_t phase = 0;
   const long long ntiles = (a.M + GROUP - 1) / GROUP;
 
-  uint8_t* my_stage = s_stage + ((size_t)(MODE == LIN_KV ? grp : 0) * GROUP + tg) * ROW_STAGE_STRIDE;
+  uint8_t* my_stage = s_stage + ((size_t)grp * GROUP + tg) * ROW_STAGE_STRIDE;
   // LIN_KV input rows: the 32 rows of a warp are contiguous in memory (32 x 256 B), so the warp copies them as 16 fully
   // coalesced 512-byte requests (lane l takes 16-byte piece 32 i + l) instead of every lane fetching its own row (32 different
   // lines per request: the uncoalesced pattern that loaded the L1 data pipe of the IBRNet gather)
@@ -273,6 +274,36 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
       const int piece = 32 * i + lane, r = piece >> 4, c = piece & 15;
       if (row0 + r < a.M) cp_async16(warp_stage + (size_t)r * ROW_STAGE_STRIDE + 16 * c, a.x + (row0 + r) * TD + 4 * c);
     }
+  };
+  // Row I/O of the other modes.  A thread's own 256-byte row is 16 LDG.128 / STG.128 that each touch 32 different lines across the warp
+  // (the uncoalesced pattern of the IBRNet gather); instead the warp moves its 32 contiguous rows as 16 fully coalesced 512-byte
+  // requests and the rows are transposed through the staging buffer.
+  auto coop_row_load = [&](const float* __restrict__ base, long long row0, bool act, float (&x)[TD]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int piece = 32 * i + lane, r = piece >> 4, c = piece & 15;
+      if (row0 + r < a.M) cp_async16(warp_stage + (size_t)r * ROW_STAGE_STRIDE + 16 * c, base + (row0 + r) * TD + 4 * c);
+    }
+    cp_async_wait_all();
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < TD; c += 4) {
+      const float4 t4 = act ? *reinterpret_cast<const float4*>(my_stage + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      x[c] = t4.x; x[c + 1] = t4.y; x[c + 2] = t4.z; x[c + 3] = t4.w;
+    }
+    __syncwarp();
+  };
+  auto coop_row_store = [&](float* __restrict__ base, long long row0, const float (&y)[TD]) {
+#pragma unroll
+    for (int c = 0; c < TD; c += 4) *reinterpret_cast<float4*>(my_stage + 4 * c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int piece = 32 * i + lane, r = piece >> 4, c = piece & 15;
+      if (row0 + r < a.M)
+        *reinterpret_cast<float4*>(base + (row0 + r) * TD + 4 * c) = *reinterpret_cast<const float4*>(warp_stage + (size_t)r * ROW_STAGE_STRIDE + 16 * c);
+    }
+    __syncwarp();
   };
   if (MODE == LIN_KV) stage_rows(((long long)blockIdx.x * NG + grp) * GROUP + tg - lane);     // prologue: the group's first tile
   for (long long tile = (long long)blockIdx.x * NG + grp; tile < ntiles; tile += (long long)gridDim.x * NG) {
@@ -290,11 +321,7 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
     } else if (MODE == LIN_EMBED) {
 #pragma unroll
       for (int c = 0; c < TD; ++c) x[c] = (active && c < NFB_ROW_CH) ? __ldg(a.x + row * NFB_ROW_CH + c) : 0.f;
-    } else if (active) row_load(a.x + row * TD, x);
-    else {
-#pragma unroll
-      for (int c = 0; c < TD; ++c) x[c] = 0.f;
-    }
+    } else coop_row_load(a.x, row - lane, active, x);
     if (MODE == LIN_PRE || MODE == LIN_QKV) row_layer_norm(x, s_ln, s_ln + 64);
     if (MODE == LIN_FFN) {
       float xn[TD];
@@ -318,7 +345,7 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
       d_load_row(tl, C_D1, y);
 #pragma unroll
       for (int c = 0; c < TD; ++c) y[c] += s_b1[c] + x[c];
-      if (active) row_store(a.y0 + row * TD, y);
+      coop_row_store(a.y0, row - lane, y);
     } else {
       a_store_row<NPASS>(tl, C_A, C_ALO, x);
       GNT_TC_ISSUE(C_D0, C_A, C_ALO, 0, false);
@@ -333,9 +360,9 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
       d_load_row(tl, C_D0, y);
       if (MODE == LIN_POST) {
         float r[TD];
-        if (active) row_load(a.res + row * TD, r);
+        coop_row_load(a.res, row - lane, active, r);
 #pragma unroll
-        for (int c = 0; c < TD; ++c) y[c] += s_b0[c] + (active ? r[c] : 0.f);
+        for (int c = 0; c < TD; ++c) y[c] += s_b0[c] + r[c];
       }
       if (MODE == LIN_QFC) {
         // two more K-rounds into the same accumulator: the positional encodings of the point and of the view direction
@@ -379,7 +406,7 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
 #pragma unroll
         for (int c = 0; c < TD; ++c) y[c] += s_b1[c];
       }
-      if (MODE != LIN_KV && active) row_store(a.y0 + row * TD, y);
+      if (MODE != LIN_KV) coop_row_store(a.y0, row - lane, y);
       if (MODE == LIN_KV) {
         a_store_row<NPASS>(tl, C_A, C_ALO, y);                     // v = v_fc(k): the projected k is the next input
         GNT_TC_ISSUE(C_D0, C_A, C_ALO, 1, false);
@@ -443,11 +470,11 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
         GNT_TC_ISSUE(C_D0, C_A, C_ALO, 1, false);                  // A (LN(x)) is unchanged
         GNT_TC_WAIT();
         d_load_row(tl, C_D0, y);
-        if (active) row_store(a.y1 + row * TD, y);
+        coop_row_store(a.y1, row - lane, y);
         GNT_TC_ISSUE(C_D0, C_A, C_ALO, 2, false);
         GNT_TC_WAIT();
         d_load_row(tl, C_D0, y);
-        if (active) row_store(a.y2 + row * TD, y);
+        coop_row_store(a.y2, row - lane, y);
       }
     }
   }
