@@ -71,9 +71,9 @@ __device__ __forceinline__ void posenc64(const float (&x3)[3], float (&e)[TD]) {
   e[63] = 0.f;
 }
 
-// LIN_KV (the per-(sample, view) row kernel, the largest of the network) prefetches the input rows of a group's NEXT tile
-// into a shared-memory staging buffer with cp.async while the current tile is processed; row stride 272 B keeps the
-// 16-byte row reads of a warp conflict-free.
+// Staging rows of the warp-coalesced row I/O (coop_row_load / coop_row_store): row stride 272 B keeps the 16-byte row reads of a
+// warp conflict-free.  (Round 1 used them to prefetch LIN_KV's next tile with cp.async, which measured +1 %; coalescing the loads
+// and the 256-byte v + pos stores through them is worth more.)
 constexpr int ROW_STAGE_STRIDE = 272;
 // every mode stages its 64-float rows through shared memory so that global loads / stores are warp-coalesced (see coop_row_load)
 __host__ __device__ constexpr size_t stage_bytes(int mode) { return (size_t)mode_groups(mode) * GROUP * ROW_STAGE_STRIDE; }
@@ -263,19 +263,9 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
   const long long ntiles = (a.M + GROUP - 1) / GROUP;
 
   uint8_t* my_stage = s_stage + ((size_t)grp * GROUP + tg) * ROW_STAGE_STRIDE;
-  // LIN_KV input rows: the 32 rows of a warp are contiguous in memory (32 x 256 B), so the warp copies them as 16 fully
-  // coalesced 512-byte requests (lane l takes 16-byte piece 32 i + l) instead of every lane fetching its own row (32 different
-  // lines per request: the uncoalesced pattern that loaded the L1 data pipe of the IBRNet gather)
   const int lane = tid & 31;
   uint8_t* warp_stage = my_stage - (size_t)lane * ROW_STAGE_STRIDE;
-  auto stage_rows = [&](long long row0 /* first row of this warp */) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int piece = 32 * i + lane, r = piece >> 4, c = piece & 15;
-      if (row0 + r < a.M) cp_async16(warp_stage + (size_t)r * ROW_STAGE_STRIDE + 16 * c, a.x + (row0 + r) * TD + 4 * c);
-    }
-  };
-  // Row I/O of the other modes.  A thread's own 256-byte row is 16 LDG.128 / STG.128 that each touch 32 different lines across the warp
+  // Row I/O.  A thread's own 256-byte row is 16 LDG.128 / STG.128 that each touch 32 different lines across the warp
   // (the uncoalesced pattern of the IBRNet gather); instead the warp moves its 32 contiguous rows as 16 fully coalesced 512-byte
   // requests and the rows are transposed through the staging buffer.
   auto coop_row_load = [&](const float* __restrict__ base, long long row0, bool act, float (&x)[TD]) {
@@ -305,20 +295,11 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
     }
     __syncwarp();
   };
-  if (MODE == LIN_KV) stage_rows(((long long)blockIdx.x * NG + grp) * GROUP + tg - lane);     // prologue: the group's first tile
   for (long long tile = (long long)blockIdx.x * NG + grp; tile < ntiles; tile += (long long)gridDim.x * NG) {
     const long long row = tile * GROUP + tg;
     const bool active = row < a.M;
     float x[TD];
-    if (MODE == LIN_KV) {
-      cp_async_wait_all();
-      __syncwarp();                          // the row was copied by the lanes of this warp
-#pragma unroll
-      for (int c = 0; c < TD; c += 4) {
-        const float4 t4 = active ? *reinterpret_cast<const float4*>(my_stage + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        x[c] = t4.x; x[c + 1] = t4.y; x[c + 2] = t4.z; x[c + 3] = t4.w;
-      }
-    } else if (MODE == LIN_EMBED) {
+    if (MODE == LIN_EMBED) {
 #pragma unroll
       for (int c = 0; c < TD; ++c) x[c] = (active && c < NFB_ROW_CH) ? __ldg(a.x + row * NFB_ROW_CH + c) : 0.f;
     } else coop_row_load(a.x, row - lane, active, x);
@@ -349,12 +330,6 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
     } else {
       a_store_row<NPASS>(tl, C_A, C_ALO, x);
       GNT_TC_ISSUE(C_D0, C_A, C_ALO, 0, false);
-      if (MODE == LIN_KV) {
-        // x has been consumed (its TMEM stores completed before the barrier above), so the staging row is free: prefetch
-        // this thread's row of the group's next tile while the MMAs and the epilogue of this one run
-        __syncwarp();                        // every lane of the warp has read its row out of the staging rows
-        stage_rows(row - lane + (long long)gridDim.x * NG * GROUP);
-      }
       GNT_TC_WAIT();
       float y[TD];
       d_load_row(tl, C_D0, y);
@@ -457,10 +432,10 @@ __global__ void __launch_bounds__(GROUP * mode_groups(MODE), 1) k_gnt_lin_tc(Lin
         }
         GNT_TC_WAIT();
         d_load_row(tl, C_D0, y);
-        if (active) {
 #pragma unroll
-          for (int c = 0; c < TD; ++c) y[c] += pos[c];
-          row_store(a.y0 + row * TD, y);
+        for (int c = 0; c < TD; ++c) y[c] += pos[c];
+        coop_row_store(a.y0, row - lane, y);          // v + pos: 256 B per row, coalesced through the staging rows
+        if (active) {
           float4* o8 = reinterpret_cast<float4*>(a.y1 + row * 8);
           o8[0] = make_float4(fmaxf(a8[0], 0.f), fmaxf(a8[1], 0.f), fmaxf(a8[2], 0.f), fmaxf(a8[3], 0.f));
           o8[1] = make_float4(fmaxf(a8[4], 0.f), fmaxf(a8[5], 0.f), fmaxf(a8[6], 0.f), fmaxf(a8[7], 0.f));
