@@ -385,54 +385,46 @@ __global__ void __launch_bounds__(256) k_gnt_head(int R, int S, const float* __r
 // Input per (sample, view) row from k_gnt_lin_tc<LIN_KV>: a8 = ReLU(attn_fc.0(k - qq + pos)) [8] and vp = v + pos [64].
 // Two adjacent lanes share a sample, each owns 32 of the 64 channels: a = attn_fc.2(a8) (masked), softmax over the
 // views per channel (online), x = sum_v vp a.
-__global__ void __launch_bounds__(128) k_gnt_view_core(int N, int V, const float* __restrict__ A8, const float* __restrict__ VP,
+__global__ void __launch_bounds__(256) k_gnt_view_core(int N, int V, const float* __restrict__ A8, const float* __restrict__ VP,
                                                         const float* __restrict__ mask, const float* __restrict__ lp,
                                                         float* __restrict__ xout) {
-  constexpr int HC = D / 2;
+  // Eight adjacent lanes share a sample, each owns 8 of the 64 channels: a warp-wide load of the v + pos rows is 4 whole
+  // 256-byte rows (with two lanes per sample it touched 16 rows for the same bytes), and the per-lane state is 24 registers.
+  constexpr int LC = 8;
   __shared__ __align__(16) float sm[8 * D + D];          // attn_fc.2 transposed [8][64], bias [64]
   const int t = threadIdx.x, nt = blockDim.x;
   load_wt_transposed(sm, lp + L_V_AT2_W, D, 8, D, t, nt);
   load_vec_padded(sm + 8 * D, lp + L_V_AT2_B, D, D, t, nt);
   __syncthreads();
-  const int c0 = (t & 1) * HC;
-  for (int n = blockIdx.x * (blockDim.x / 2) + (t >> 1); n < N; n += gridDim.x * (blockDim.x / 2)) {
-    float m[HC], l[HC], acc[HC];
+  const int c0 = (t & 7) * LC;
+  for (int n = blockIdx.x * (blockDim.x / 8) + (t >> 3); n < N; n += gridDim.x * (blockDim.x / 8)) {
+    float m[LC], l[LC], acc[LC];
 #pragma unroll
-    for (int c = 0; c < HC; ++c) { m[c] = -3.4e38f; l[c] = 0.f; acc[c] = 0.f; }
+    for (int c = 0; c < LC; ++c) { m[c] = -3.4e38f; l[c] = 0.f; acc[c] = 0.f; }
     for (int v = 0; v < V; ++v) {
       const size_t row = (size_t)n * V + v;
       const float4 h0 = __ldg(reinterpret_cast<const float4*>(A8 + row * 8)), h1 = __ldg(reinterpret_cast<const float4*>(A8 + row * 8) + 1);
       const float a8[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
       const bool valid = __ldg(mask + row) != 0.f;
-      const float4* vr = reinterpret_cast<const float4*>(VP + row * D + c0);
+      float a[LC];
+      load_bias<LC>(a, sm + 8 * D + c0);
 #pragma unroll
-      for (int cc = 0; cc < HC; cc += 16) {
-        float a[16];
-        load_bias<16>(a, sm + 8 * D + c0 + cc);
+      for (int j = 0; j < 8; ++j) axpy_row<LC>(a, a8[j], sm + j * D + c0);
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(VP + row * D + c0)), v1 = __ldg(reinterpret_cast<const float4*>(VP + row * D + c0) + 1);
+      const float vv[LC] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) axpy_row<16>(a, a8[j], sm + j * D + c0 + cc);
-        float vv[16];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 v4 = __ldg(vr + cc / 4 + j);
-          vv[4 * j] = v4.x; vv[4 * j + 1] = v4.y; vv[4 * j + 2] = v4.z; vv[4 * j + 3] = v4.w;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int c = cc + j;
-          const float s = valid ? a[j] : -1e9f;
-          const float mn = fmaxf(m[c], s);
-          const float sc = __expf(m[c] - mn), e = __expf(s - mn);
-          l[c] = fmaf(l[c], sc, e);
-          acc[c] = fmaf(acc[c], sc, vv[j] * e);
-          m[c] = mn;
-        }
+      for (int c = 0; c < LC; ++c) {
+        const float s_ = valid ? a[c] : -1e9f;
+        const float mn = fmaxf(m[c], s_);
+        const float sc = __expf(m[c] - mn), e = __expf(s_ - mn);
+        l[c] = fmaf(l[c], sc, e);
+        acc[c] = fmaf(acc[c], sc, vv[c] * e);
+        m[c] = mn;
       }
     }
-#pragma unroll
-    for (int c = 0; c < HC; c += 4)
-      *reinterpret_cast<float4*>(xout + (size_t)n * D + c0 + c) =
-          make_float4(acc[c] / l[c], acc[c + 1] / l[c + 1], acc[c + 2] / l[c + 2], acc[c + 3] / l[c + 3]);
+    float4* o = reinterpret_cast<float4*>(xout + (size_t)n * D + c0);
+    o[0] = make_float4(acc[0] / l[0], acc[1] / l[1], acc[2] / l[2], acc[3] / l[3]);
+    o[1] = make_float4(acc[4] / l[4], acc[5] / l[5], acc[6] / l[6], acc[7] / l[7]);
   }
 }
 
@@ -556,12 +548,13 @@ __global__ void __launch_bounds__(256, 1) k_gnt_ray_core(int R, int S, int rpc, 
     const size_t n = (size_t)(r < R ? r : 0) * S + (t < S ? t : 0);
     float qv[D];
     load_row64(Q + n * D, qv);
-    if (act) {
-      float tmp[D];
-      load_row64(K + n * D, tmp);
-      store_row64(sk + (size_t)t * D, tmp);
-      load_row64(Vp + n * D, tmp);
-      store_row64(sv + (size_t)t * D, tmp);
+    if (r < R) {
+      // the ray's K / V rows are contiguous in memory and laid out like sk / sv: coalesced block copy by the ray's threads
+      const float4* k4 = reinterpret_cast<const float4*>(K + (size_t)r * S * D);
+      const float4* v4 = reinterpret_cast<const float4*>(Vp + (size_t)r * S * D);
+      float4* sk4 = reinterpret_cast<float4*>(sk);
+      float4* sv4 = reinterpret_cast<float4*>(sv);
+      for (int i = t; i < S * (D / 4); i += rb) { sk4[i] = __ldg(k4 + i); sv4[i] = __ldg(v4 + i); }
     }
 #pragma unroll
     for (int c = 0; c < D; ++c) qv[c] *= 0.25f;          // 1 / sqrt(16)
@@ -613,21 +606,25 @@ __global__ void __launch_bounds__(256, 1) k_gnt_ray_core(int R, int S, int rpc, 
       for (int c = 0; c < 8; ++c) { o[16 * h + 2 * c] = a2[c].x * il; o[16 * h + 2 * c + 1] = a2[c].y * il; }
       if (t == 0) { sq0[RS_ST + h] = mx; sq0[RS_ST + 4 + h] = il; }
     }
-    if (act) store_row64(O + n * D, o);
-    if (attn_out) {
-      __syncthreads();
-      if (act) {
-        float pm = 0.f;
+    __syncthreads();                                       // every query of the ray is done with sv; query 0's statistics are published
+    if (act) store_row64(sv + (size_t)t * D, o);           // o rows leave through sv: coalesced block copy below
+    if (attn_out && act) {
+      float pm = 0.f;
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const float* kj = sk + (size_t)t * D + 16 * h;
-          float s = 0.f;
+      for (int h = 0; h < 4; ++h) {
+        const float* kj = sk + (size_t)t * D + 16 * h;
+        float s = 0.f;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) s = fmaf(sq0[RS_Q0 + 16 * h + c], kj[c], s);
-          pm += __expf(s - sq0[RS_ST + h]) * sq0[RS_ST + 4 + h];
-        }
-        attn_out[(size_t)r * attn_stride + t] = 0.25f * pm;
+        for (int c = 0; c < 16; ++c) s = fmaf(sq0[RS_Q0 + 16 * h + c], kj[c], s);
+        pm += __expf(s - sq0[RS_ST + h]) * sq0[RS_ST + 4 + h];
       }
+      attn_out[(size_t)r * attn_stride + t] = 0.25f * pm;
+    }
+    __syncthreads();
+    if (r < R) {
+      float4* o4 = reinterpret_cast<float4*>(O + (size_t)r * S * D);
+      const float4* sv4 = reinterpret_cast<const float4*>(sv);
+      for (int i = t; i < S * (D / 4); i += rb) o4[i] = sv4[i];
     }
     __syncthreads();
   }
@@ -706,9 +703,9 @@ static int gnt_layer_tc(int i, int R, int S, int V, const float* ray_diff, const
   a.a0_w = lp + L_V_AT0_W; a.a0_b = lp + L_V_AT0_B;
   if ((rc = launch_lin<NPASS, LIN_KV>(a, st, "k_gnt_lin_tc<kv>"))) return rc;
   {
-    int g = (N + 63) / 64;                      // 2 threads per sample
+    int g = (N + 31) / 32;                      // 8 threads per sample, 256 per CTA
     if (g > sms * 8) g = sms * 8;
-    k_gnt_view_core<<<g, 128, 0, st>>>(N, V, Kv, Vv, mask, lp, b1);
+    k_gnt_view_core<<<g, 256, 0, st>>>(N, V, Kv, Vv, mask, lp, b1);
     NFB_CHECK_LAUNCH("k_gnt_view_core");
   }
   a = LinArgs{};
@@ -887,9 +884,9 @@ int nfbgnt::gnt_forward_checkpoints(int R, int S, int V, int depth, const float*
       NFB_CHECK_LAUNCH("k_gnt_pre");
       k_gnt_view_row_fwd<<<grid_n(rows, 128, 4), 128, sm_view, st>>>(rows, V, F, qq, ray_diff, lp, vp_i, vp_i + rows * D);
       NFB_CHECK_LAUNCH("k_gnt_view_row_fwd");
-      int g = (N + 63) / 64;                                  // 2 threads per sample
+      int g = (N + 31) / 32;                                  // 8 threads per sample, 256 per CTA
       if (g > sms * 8) g = sms * 8;
-      k_gnt_view_core<<<g, 128, 0, st>>>(N, V, vp_i + rows * D, vp_i, mask, lp, xa);
+      k_gnt_view_core<<<g, 256, 0, st>>>(N, V, vp_i + rows * D, vp_i, mask, lp, xa);
       NFB_CHECK_LAUNCH("k_gnt_view_core");
       k_gnt_outfc<<<grid_n(N, 128, 6), 128, sm_pre, st>>>(N, lp + L_V_O_W, lp + L_V_O_B, xa, ck(i, 0), ck(i, 1));
       NFB_CHECK_LAUNCH("k_gnt_outfc");
