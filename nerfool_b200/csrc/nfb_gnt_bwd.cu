@@ -80,7 +80,7 @@ static int gnt_grad_impl(int mode, int R, int S, int V, int depth, int ret_alpha
 
   const int ray_block = ((S + 31) / 32) * 32;
   const size_t sm_proj = (size_t)(2 * D + 4 * D * D) * sizeof(float), sm_post = (size_t)(D + 3 * D * D) * sizeof(float),
-               sm_vbwd = (size_t)VB_TOTAL * sizeof(float),
+               sm_vbwd = (size_t)(VB_TOTAL + 4 * 32 * CS) * sizeof(float),
                sm_qb = (size_t)QB_TOTAL * sizeof(float), sm_eb = (size_t)EB_TOTAL * sizeof(float),
                sm_ffn = (size_t)(FS_B2 + 256 * D) * sizeof(float);     // k_gnt_ffn_bwd: weights + the per-thread dx columns
   int rpc_b = 256 / ray_block;

@@ -48,6 +48,38 @@ __device__ __forceinline__ void load_nat(float* __restrict__ dst, const float* _
   for (int i = tid; i < n; i += nt) dst[i] = __ldg(src + i);
 }
 
+// Warp-coalesced row I/O for the thread-per-row kernels: a thread's own 256-byte row is 16 requests that each touch 32 different
+// lines across the warp; here the warp moves its 32 contiguous rows as 16 whole-line requests and the rows change hands through a
+// per-warp staging block ws[32][CS] (CS = 68 floats: 272-byte stride, conflict-free 16-byte reads).  Every lane of the warp must call.
+constexpr int CS = 68;
+__device__ __forceinline__ void coop_load64(const float* __restrict__ base, size_t row0, size_t nrows, float* __restrict__ ws, int lane,
+                                            bool act, float (&x)[D]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int piece = 32 * i + lane, r = piece >> 4, c = piece & 15;
+    if (row0 + r < nrows) *reinterpret_cast<float4*>(ws + r * CS + 4 * c) = *(reinterpret_cast<const float4*>(base + (row0 + r) * D) + c);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < D; c += 4) {
+    const float4 t4 = act ? *reinterpret_cast<const float4*>(ws + lane * CS + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    x[c] = t4.x; x[c + 1] = t4.y; x[c + 2] = t4.z; x[c + 3] = t4.w;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void coop_store64(float* __restrict__ base, size_t row0, size_t nrows, float* __restrict__ ws, int lane,
+                                             const float (&y)[D]) {
+#pragma unroll
+  for (int c = 0; c < D; c += 4) *reinterpret_cast<float4*>(ws + lane * CS + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int piece = 32 * i + lane, r = piece >> 4, c = piece & 15;
+    if (row0 + r < nrows) *(reinterpret_cast<float4*>(base + (row0 + r) * D) + c) = *reinterpret_cast<const float4*>(ws + r * CS + 4 * c);
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------------
 // head (:303-305) backward: rgb = rgb_fc(mean_s LN(q)) -> dq[n] = LN'(q[n]) (rgb_fc^T d_rgb / S)
 // ---------------------------------------------------------------------------------------------------
@@ -366,10 +398,15 @@ __global__ void __launch_bounds__(128) k_gnt_view_row_bwd(size_t rows, const flo
   load_wt_transposed(sm + VB_P0T, lp + L_V_POS0_W, 8, 4, 8, t, nt);
   load_vec_padded(sm + VB_P0_B, lp + L_V_POS0_B, 8, 8, t, nt);
   __syncthreads();
-  for (size_t row = (size_t)blockIdx.x * blockDim.x + t; row < rows; row += (size_t)gridDim.x * blockDim.x) {
+  const int lane = t & 31;
+  float* ws = sm + VB_TOTAL + (t >> 5) * 32 * CS;            // this warp's staging block
+  for (size_t rbase = (size_t)blockIdx.x * blockDim.x; rbase < rows; rbase += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = rbase + t, row0 = row - lane;
+    const bool act = row < rows;
+    const size_t rs = act ? row : 0;
     float dt[D];
     {
-      const float4 h0 = __ldg(reinterpret_cast<const float4*>(DA8 + row * 8)), h1 = __ldg(reinterpret_cast<const float4*>(DA8 + row * 8) + 1);
+      const float4 h0 = __ldg(reinterpret_cast<const float4*>(DA8 + rs * 8)), h1 = __ldg(reinterpret_cast<const float4*>(DA8 + rs * 8) + 1);
       const float d8[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
       for (int c = 0; c < D; ++c) dt[c] = 0.f;
@@ -379,9 +416,9 @@ __global__ void __launch_bounds__(128) k_gnt_view_row_bwd(size_t rows, const flo
     float dk[D];
     {
       float dvp[D];
-      load_row64(DVP + row * D, dvp);
-      store_row64(DVP + row * D, dt);                       // DT
-      if (d_ray_diff) {
+      coop_load64(DVP, row0, rows, ws, lane, act, dvp);
+      coop_store64(DVP, row0, rows, ws, lane, dt);          // DT
+      if (d_ray_diff && act) {
         float dp8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) dp8[j] = 0.f;
@@ -406,10 +443,10 @@ __global__ void __launch_bounds__(128) k_gnt_view_row_bwd(size_t rows, const flo
       for (int k = 0; k < D; ++k) axpy_row<D>(dk, dvp[k], sm + VB_V + k * D);
     }
     float df[D];
-    load_row64(dF + row * D, df);
+    coop_load64(dF, row0, rows, ws, lane, act, df);
 #pragma unroll
     for (int k = 0; k < D; ++k) axpy_row<D>(df, dk[k], sm + VB_K + k * D);
-    store_row64(dF + row * D, df);
+    coop_store64(dF, row0, rows, ws, lane, df);
   }
 }
 
