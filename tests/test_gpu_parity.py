@@ -536,6 +536,10 @@ RENDER_CASES = [
     (10, 48, 64, 128, 'synthetic', 200, 200, True, True),
     (10, 64, 64, 64, 'llff', 378, 504, True, False),
     (3, 90, 16, 16, 'llff', 61, 83, False, False),
+    # contiguous row mapping (a sample's rows straddle warps: V = 7 -> 18 samples per tile, V = 17 -> 7): group-level fences around the
+    # cross-view exchanges and around the staging rows of the cooperative gather / scatter
+    (7, 44, 16, 16, 'llff', 61, 83, True, False),
+    (17, 21, 16, 8, 'llff', 61, 83, True, False),
 ]
 
 
